@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- the DMT hot path on N B200s of one node, one JSON line on stdout (rank 0).
+
+Metric (BASELINE.json): samples/s of the forward ranking path on BASELINE config 2 -- "DMT full
+3-seq fwd-only, d_model=64, 2 heads, 1 block, batch=4096, synthetic ids" -- per GPU, weak scaling
+(every rank runs its own 4096-sample batches; the path is data-parallel with no data-path
+collective in forward-only mode).
+
+  value      whole-job samples/s with the batch already resident in HBM, CUDA-event timed
+  e2e        the same metric through the plugin call (`Inference.inference`) from PINNED HOST
+             buffers: one packed H2D copy per step + the D2H read of the logits, inside the timing
+  roofline   the dominant kernel's algorithmic bytes (or FLOPs) / its live CUDA-event time, against
+             MEASURED_PEAKS.json
+  cpu_baseline   the CPU oracle (`oracle/dmt_oracle.py`, PyTorch CPU fp32, all host threads) on a
+             bounded sample of the same workload -- a reported baseline, not the target
+
+`--impl reference` times the reference's CPU path instead (the oracle port; TF-1.12 cannot be
+installed here) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+FALLBACK_BF16_TFLOPS = 1590.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (BASELINE config 2: 4096)")
+    ap.add_argument("--conf", default="dmt_d64.conf")
+    ap.add_argument("--id-mode", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--n-batches", type=int, default=4, help="distinct batches rotated through the timed loop")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small-tables", action="store_true", help="debug: tiny vocabularies")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": FALLBACK_BF16_TFLOPS, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args, device, rank):
+    import torch
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_tokens, SEED
+    from cikm2020_dmt_b200.plan import build_plan
+    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", args.conf)
+    plan = build_plan(conf)
+    rows = None
+    if args.small_tables:
+        rows = {"Sku": 20000, "Brand": 2000, "Shopid": 2000, "Cid3": 1000, "Cid2": 100}
+        for t in list(plan.tables.values()) + list(plan.bias_tables.values()):
+            if t.name in rows:
+                t.rows = rows[t.name]
+    batches = [synthetic_batch(plan, args.batch, seed=SEED + 1000 * rank + i, id_mode=args.id_mode, table_rows=rows)
+               for i in range(args.n_batches)]
+    return conf, plan, batches, rows
+
+
+def algorithmic_bytes_seq(plan, batch):
+    """SURVEY 8(d), fused K1-K4 boundary: per (sample, sequence) L*(sum D_f*e + 20) + (sum D_f*e + 20)
+    + 4 + d*a_out, fp32 tables (e=4) and fp32 interest vector (a_out=4)."""
+    total = 0
+    B = batch["features"].shape[0]
+    for seq in plan.sequences:
+        n_tok = int(batch[seq.user_features[-1]].offsets[-1])
+        row_bytes = sum(seq.dims) * 4 + 4 * len(seq.dims)
+        total += n_tok * row_bytes + B * (row_bytes + 4 + plan.d_model * 4)
+    return total
+
+
+def flops_seq(plan, batch):
+    d, dff = plan.d_model, plan.d_ff
+    total = 0
+    B = batch["features"].shape[0]
+    for seq in plan.sequences:
+        lens = (batch[seq.user_features[-1]].offsets[1:] - batch[seq.user_features[-1]].offsets[:-1]).double()
+        n_tok = float(lens.sum())
+        total += n_tok * (2 * d * 3 * d + 4 * d * dff) * plan.num_blocks_encode          # QKV + FF per token
+        total += float((lens * lens).sum()) * 4 * d * plan.num_blocks_encode              # QK^T + PV
+        total += (n_tok * (2 * d * 2 * d + 4 * d) + B * (2 * d * d + 4 * d * dff)) * plan.num_blocks_decode
+    return total
+
+
+def flops_mmoe(plan, B):
+    f, k = 0, plan.mmoe_in
+    for u in plan.hidden_units_bottom:
+        f += 2 * k * u
+        k = u
+    f *= plan.num_experts
+    f += 2 * plan.mmoe_in * plan.num_experts * plan.num_tasks
+    return f * B
+
+
+def cpu_oracle_throughput(plan, params_cpu, batch, seconds, lean=True):
+    """samples/s of the CPU oracle (PyTorch CPU fp32, all host threads) on `batch`."""
+    import torch
+    from oracle import dmt_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = batch["features"].shape[0]
+    with torch.no_grad():
+        O.inference(plan, params_cpu, batch, is_train=False, lean=lean)     # warm-up
+        times = []
+        t_end = time.perf_counter() + seconds
+        while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 200):
+            t0 = time.perf_counter()
+            O.inference(plan, params_cpu, batch, is_train=False, lean=lean)
+            times.append(time.perf_counter() - t0)
+    return B / statistics.median(times), len(times)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle port."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cikm2020_dmt_b200.data import synthetic_batch, SEED
+    from cikm2020_dmt_b200.params import ParamStore
+    from oracle import dmt_oracle as O
+    conf, plan, _, rows = build_workload(argparse.Namespace(**{**vars(args), "n_batches": 0}), "cpu", 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    store = ParamStore(plan, device="cpu")
+    P = O.params_from_store(store, torch.float32)
+    sample = synthetic_batch(plan, args.cpu_batch, seed=SEED, id_mode=args.id_mode, table_rows=rows)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            O.inference(plan, P, sample, is_train=False, lean=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.inference(plan, P, sample, is_train=False, lean=True)
+        dt = time.perf_counter() - t0
+    value = args.cpu_batch * args.steps / dt
+    desc = ("oracle port (PyTorch CPU fp32, lean lookups) fwd-only on %d-sample slices of the %d-sample batch"
+            % (args.cpu_batch, args.batch))
+    line = {
+        "impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, plan),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, plan):
+    return {"workload": "BASELINE config 2: DMT full 3-seq (clk50/ord50/cart10) fwd-only, d_model=%d, %d heads, "
+                        "%d+%d blocks, 615 dense + 23 pooled id features, MMoE %d experts / 2 tasks + bias tower, "
+                        "per-GPU batch %d, synthetic %s ids, Sku vocabulary %d"
+                        % (plan.d_model, plan.num_heads, plan.num_blocks_encode, plan.num_blocks_decode,
+                           plan.num_experts, args.batch, args.id_mode, plan.tables["Sku"].rows),
+            "conf": args.conf, "per_gpu_batch": args.batch, "precision": args.precision,
+            "l2": "inputs larger than L2: random rows of a %.0f MB Sku table + %d rotating batches"
+                  % (plan.tables["Sku"].rows * plan.tables["Sku"].dim * 4 / 1e6, args.n_batches)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from cikm2020_dmt_b200.data import PackedBatch, batch_to, batch_tokens
+    from cikm2020_dmt_b200.inference import Inference
+    from cikm2020_dmt_b200.params import ParamStore
+
+    conf, plan, batches, rows = build_workload(args, device, rank)
+    store = ParamStore(plan, device=device)
+    inf = Inference(conf, params=store, precision=args.precision) if not args.small_tables else None
+    if inf is None:
+        from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+        model = mmoe_transformer_unbias(plan, params=store, precision=args.precision)
+        infer = model.inference
+    else:
+        model = inf.model
+        infer = inf.inference
+    dev_batches = [batch_to(b, device) for b in batches]
+    packed = [PackedBatch(b) for b in batches]
+    B = args.batch
+    out_host = torch.empty(3, B, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(i):
+        infer(dev_batches[i % len(dev_batches)], is_train=False)
+
+    def step_e2e(i):
+        (yr, yb) = infer(packed[i % len(packed)], is_train=False)
+        out_host[0].copy_(yr[0].view(-1), non_blocking=True)
+        out_host[1].copy_(yr[1].view(-1), non_blocking=True)
+        out_host[2].copy_(yb.view(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller consumes the scores every step
+
+    # ---- warm-up, then the timed device-resident region (with per-stage events + clock sampling)
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    model.enable_stage_timing(True)
+    launches0 = model.launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    ms = timed(step_resident, args.steps)
+    gpu_launches = model.launches - launches0
+    torch.cuda.synchronize()
+    stage = model.stage_times_ms()
+    model.enable_stage_timing(False)
+    # untimed-by-stage pass: the headline value must not carry the event overhead
+    ms_clean = timed(step_resident, args.steps)
+    ms = min(ms, ms_clean)
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+
+    # ---- roofline of the dominant stage (live CUDA-event time inside the timed region)
+    stage_total = sum(t for t, _ in stage.values()) or 1.0
+    shares = {k: round(t / stage_total, 4) for k, (t, _) in stage.items()}
+    dom = max(stage, key=lambda k: stage[k][0])
+    steps_used = args.steps
+    mean_b = lambda fn: sum(fn(plan, batches[i % len(batches)]) for i in range(steps_used))
+    if dom == "seq_encode":
+        t_ms, n = stage["seq_encode"]
+        alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
+        achieved = alg / (t_ms / 1e3) / 1e9
+        roofline = {"kernel": "seq_encode_f32_kernel (fused gather->encoder->decoder, per sequence)",
+                    "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "launches": n, "avg_launch_ms": t_ms / n, "algorithmic_bytes_per_launch": alg / n,
+                    "flops_per_launch": mean_b(flops_seq) / n,
+                    "achieved_tflops": mean_b(flops_seq) / (t_ms / 1e3) / 1e12,
+                    "note": "fp32 CUDA-core path: compute-bound well below the HBM roofline (SURVEY 8d)"}
+    else:
+        t_ms, n = stage[dom]
+        fl = flops_mmoe(plan, B) * steps_used
+        achieved = fl / (t_ms / 1e3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "traffic": None,
+                    "peak_source": pk["source"], "launches": n, "avg_launch_ms": t_ms / n}
+    roofline["stage_share"] = shares
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from cikm2020_dmt_b200.data import SparseIds
+        from oracle import dmt_oracle as O
+        P = O.params_from_store(store, torch.float32)
+        nb = min(args.cpu_batch, B)
+        sub = {}
+        for k, v in batches[0].items():
+            if isinstance(v, SparseIds):
+                hi = int(v.offsets[nb])
+                sub[k] = SparseIds(v.values[:hi], v.offsets[:nb + 1], None if v.weights is None else v.weights[:hi])
+            else:
+                sub[k] = v[:nb]
+        sps, reps = cpu_oracle_throughput(plan, P, sub, args.cpu_seconds)
+        cpu_baseline = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "oracle port (PyTorch CPU fp32, lean lookups), first %d samples of batch 0, "
+                                  "median of %d forward passes" % (nb, reps)}
+        del P
+
+    h2d = sum(p.nbytes for p in packed) / len(packed)
+    line = {
+        "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args, plan),
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,146 @@
+"""ctypes binding of `libdmt_b200.so` (include/dmt_b200.h).
+
+The structures mirror the header field for field.  Loading fails loudly: there is no CPU or
+PyTorch fallback behind this module -- if the shared library is missing the product path
+raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
+MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
+PRECISION_F32, PRECISION_BF16 = 0, 1
+ABI_VERSION = 1
+
+_fp = C.c_void_p   # device pointers travel as integers
+
+
+class Dense(C.Structure):
+    _fields_ = [("w", _fp), ("b", _fp)]
+
+
+class LayerNorm(C.Structure):
+    _fields_ = [("gamma", _fp), ("beta", _fp)]
+
+
+class AttnWeights(C.Structure):
+    _fields_ = [("q", Dense), ("k", Dense), ("v", Dense), ("ln", LayerNorm)]
+
+
+class FFWeights(C.Structure):
+    _fields_ = [("w1", Dense), ("w2", Dense), ("ln", LayerNorm)]
+
+
+class SeqCfg(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("d_model", C.c_int32), ("d_ff", C.c_int32), ("num_heads", C.c_int32),
+                ("n_enc_blocks", C.c_int32), ("n_dec_blocks", C.c_int32), ("maxlen", C.c_int32),
+                ("zero_pad", C.c_int32), ("n_feats", C.c_int32), ("precision", C.c_int32)]
+
+
+class SeqInput(C.Structure):
+    _fields_ = [("table", _fp * MAX_SEQ_FEATS), ("rows", C.c_int64 * MAX_SEQ_FEATS),
+                ("dim", C.c_int32 * MAX_SEQ_FEATS), ("_pad", C.c_int32 * MAX_SEQ_FEATS),
+                ("ids", _fp * MAX_SEQ_FEATS), ("offsets", _fp * MAX_SEQ_FEATS),
+                ("item_ids", _fp * MAX_SEQ_FEATS)]
+
+
+class SeqWeights(C.Structure):
+    _fields_ = [("pos", _fp), ("enc_attn", AttnWeights * MAX_BLOCKS), ("dec_attn", AttnWeights * MAX_BLOCKS),
+                ("ff", FFWeights * MAX_BLOCKS)]
+
+
+class PoolFeat(C.Structure):
+    _fields_ = [("table", _fp), ("rows", C.c_int64), ("ids", _fp), ("offsets", _fp), ("weights", _fp),
+                ("dim", C.c_int32), ("out_col", C.c_int32)]
+
+
+class MmoeCfg(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("in_dim", C.c_int32), ("n_experts", C.c_int32), ("n_layers", C.c_int32),
+                ("units", C.c_int32 * MAX_LAYERS), ("n_tasks", C.c_int32), ("n_tower_layers", C.c_int32),
+                ("tower_units", C.c_int32 * MAX_LAYERS), ("precision", C.c_int32)]
+
+
+class MmoeWeights(C.Structure):
+    _fields_ = [("expert", (Dense * MAX_LAYERS) * MAX_EXPERTS), ("gate", Dense * MAX_TASKS),
+                ("tower", (Dense * MAX_LAYERS) * MAX_TASKS), ("tower_out", Dense * MAX_TASKS)]
+
+
+class BiasLossCfg(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("in_dim", C.c_int32), ("n_hidden", C.c_int32),
+                ("units", C.c_int32 * MAX_LAYERS), ("two_head_multiply", C.c_int32), ("ctr_rel", C.c_int32),
+                ("weight_ctr", C.c_float * 5), ("weight_ecvr", C.c_float * 5), ("loss_weight", C.c_float * 2)]
+
+
+class BiasWeights(C.Structure):
+    _fields_ = [("layer", Dense * (MAX_LAYERS + 1))]
+
+
+# name -> (restype, argtypes); must list every DMT_API symbol of include/dmt_b200.h
+PROTOTYPES = {
+    "dmt_abi_version": (C.c_int, []),
+    "dmt_last_error": (C.c_char_p, []),
+    "dmt_device_sm_count": (C.c_int, []),
+    "dmt_embed_gather": (C.c_int, [_fp, C.c_int64, C.c_int32, _fp, C.c_int64, C.c_int32, _fp, _fp]),
+    "dmt_seq_encode_workspace_bytes": (C.c_size_t, [C.POINTER(SeqCfg), C.c_int64]),
+    "dmt_seq_encode_fwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), _fp,
+                                     C.c_int64, _fp, C.c_size_t, _fp]),
+    "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
+    "dmt_copy_dense_features": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
+    "dmt_mmoe_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
+    "dmt_mmoe_fwd": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp, C.c_size_t,
+                               _fp]),
+    "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
+                                    _fp, _fp, _fp, _fp, _fp]),
+}
+
+
+class DmtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("dmt_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(rebuild=True):
+    """Load the shared library, (re)building it in-tree when nvcc is available and sources
+    changed.  Raises if it cannot be produced -- no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build() if rebuild else _build.LIB
+    if not os.path.exists(path):
+        raise RuntimeError("libdmt_b200.so is missing (%s); run `python -m cikm2020_dmt_b200.build`" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.dmt_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError("libdmt_b200.so ABI %d != binding ABI %d" % (got, ABI_VERSION))
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dmt_last_error()
+        raise DmtError(rc, msg.decode() if msg else "")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def dense(w, b):
+    return Dense(ptr(w), ptr(b))

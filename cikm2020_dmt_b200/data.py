@@ -1,0 +1,244 @@
+"""Batch container + seeded synthetic TFRecord-shaped batches.
+
+The reference hands the model a dict of `tf.SparseTensor`s, one per id feature,
+left-packed `[B, maxlen_in_batch]` (tfrecord_mask.py:23-84 + index_tables.py:37-45),
+plus `features` fp32 `[B, 615]`, `mask` fp32 `[B, 5]`, `label` fp32 `[B]`.  A
+left-packed SparseTensor is exactly a CSR row-partition, so the drop-in keeps the
+same keys and carries each feature as `SparseIds(values int32 [nnz], offsets int32
+[B+1])` (+ optional `weights`, the `<feature>Wts` tensor).
+
+`synthetic_batch` follows SURVEY 8(d): seed 20201019, length/id/label
+distributions measured on `jd_recsys_demo`.
+"""
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+SEED = 20201019
+LABEL_VALUES = (0, 1, 2, 4, 5)
+LABEL_PRIOR = (0.9322, 0.0088, 0.0569, 0.0015, 0.00065)   # jd_recsys_demo/stat/stat/part-00000
+
+
+@dataclass
+class SparseIds:
+    values: torch.Tensor             # int32 [nnz], post-lookup index in [0, V)
+    offsets: torch.Tensor            # int32 [B+1]
+    weights: Optional[torch.Tensor] = None   # fp32 [nnz] (`<feature>Wts`), None == all ones
+
+    @property
+    def batch_size(self):
+        return self.offsets.numel() - 1
+
+    def to(self, device, non_blocking=False):
+        return SparseIds(self.values.to(device, non_blocking=non_blocking),
+                         self.offsets.to(device, non_blocking=non_blocking),
+                         None if self.weights is None else self.weights.to(device, non_blocking=non_blocking))
+
+    def lengths(self):
+        return self.offsets[1:] - self.offsets[:-1]
+
+    def to_dense(self, pad=0):
+        """tf.sparse.to_dense of the left-packed tensor: [B, max_len]."""
+        lens = self.lengths().long()
+        B, T = lens.numel(), int(lens.max().item()) if lens.numel() else 0
+        out = torch.full((B, T), pad, dtype=torch.int64, device=self.values.device)
+        pos = torch.arange(T, device=self.values.device)[None, :]
+        m = pos < lens[:, None]
+        out[m] = self.values.long()
+        return out
+
+    @staticmethod
+    def from_lists(rows, weights=None):
+        lens = [len(r) for r in rows]
+        off = np.zeros(len(rows) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(lens)
+        vals = np.asarray([v for r in rows for v in r], dtype=np.int32)
+        w = None
+        if weights is not None:
+            w = torch.from_numpy(np.asarray([v for r in weights for v in r], dtype=np.float32))
+        return SparseIds(torch.from_numpy(vals), torch.from_numpy(off), w)
+
+
+def batch_to(batch: Dict, device, non_blocking=False) -> Dict:
+    out = {}
+    for k, v in batch.items():
+        out[k] = v.to(device, non_blocking=non_blocking) if hasattr(v, "to") else v
+    return out
+
+
+def _seq_lengths(rng, B, max_len, kind):
+    u = rng.random(B)
+    if kind == "clk":
+        lens = np.where(u < 0.45, max_len, rng.integers(1, max(max_len, 2), size=B))
+    elif kind == "near":
+        lens = np.where(u < 0.66, max_len, rng.integers(1, max(max_len, 2), size=B))
+    else:
+        mid = rng.integers(2, max(max_len, 3), size=B) if max_len > 2 else np.ones(B, dtype=np.int64)
+        lens = np.where(u < 0.6, max_len, np.where(u < 0.75, 1, mid))
+    return np.clip(lens, 1, max_len).astype(np.int64)
+
+
+def _draw_ids(rng, n, V, mode, oov_rows=0):
+    if V <= 2:
+        return np.zeros(n, dtype=np.int32)
+    if mode == "uniform":
+        return rng.integers(1, V, size=n).astype(np.int32)
+    # zipf over a fixed pseudo-random permutation of the in-vocab range, plus OOV buckets + index 0
+    hi = max(V - oov_rows, 2)
+    ranks = rng.zipf(1.05, size=n).astype(np.int64)
+    ranks = np.minimum(ranks, hi - 1) - 1
+    ids = 1 + (ranks * 2654435761 % (hi - 1))
+    if oov_rows > 0:
+        oov = rng.random(n) < 0.34
+        ids = np.where(oov, rng.integers(V - oov_rows, V, size=n), ids)
+    ids = np.where(rng.random(n) < 0.01, 0, ids)
+    return ids.astype(np.int32)
+
+
+def synthetic_batch(plan, batch_size, seed=SEED, id_mode="uniform", table_rows=None,
+                    seq_lens=None, full_length=False, near_len=6) -> Dict:
+    """One synthetic batch with the reference's feature names.
+
+    table_rows: optional {table name: V} override (vocab sweep, small test tables).
+    seq_lens:   optional per-sequence max length (defaults: the `_<N>` suffix of the
+                feature name, capped at maxlen_k).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B = batch_size
+    rows = {n: t.rows for n, t in plan.tables.items()}
+    rows.update({"bias:" + n: t.rows for n, t in plan.bias_tables.items()})
+    for n, v in (table_rows or {}).items():
+        if n in rows:
+            rows[n] = v
+        if "bias:" + n in rows:
+            rows["bias:" + n] = min(rows["bias:" + n], v)
+    batch: Dict = {}
+    dense = rng.normal(0.0, 0.2, size=(B, plan.feature_dim)).clip(-0.99, 0.99)
+    dense[rng.random(dense.shape) < 0.02] = 0.0
+    batch["features"] = torch.from_numpy(dense.astype(np.float32))
+    lab = rng.choice(len(LABEL_VALUES), size=B, p=np.asarray(LABEL_PRIOR) / sum(LABEL_PRIOR))
+    mask = np.zeros((B, len(LABEL_VALUES)), dtype=np.float32)
+    mask[np.arange(B), lab] = 1.0
+    batch["mask"] = torch.from_numpy(mask)
+    batch["label"] = torch.from_numpy(np.asarray(LABEL_VALUES, dtype=np.float32)[lab])
+
+    feat_table = {p.feature: p.table for p in plan.pooled}
+    done = set()
+    kinds = ("clk", "ord", "cart")
+    for seq in plan.sequences:
+        tail = seq.user_features[0].rsplit("_", 1)[-1]
+        L = int(tail) if tail.isdigit() else seq.maxlen
+        if seq_lens is not None:
+            L = seq_lens[seq.index]
+        L = min(L, seq.maxlen)
+        lens = np.full(B, L, dtype=np.int64) if full_length else \
+            _seq_lengths(rng, B, L, kinds[seq.index] if seq.index < 3 else "ord")
+        off = np.zeros(B + 1, dtype=np.int32)
+        off[1:] = np.cumsum(lens)
+        off_t = torch.from_numpy(off)
+        n = int(off[-1])
+        feats = list(seq.user_features) + ([seq.ts_feature] if seq.ts_feature else [])
+        for f in feats:
+            if f in done or f not in feat_table:
+                continue
+            V = rows[feat_table[f]]
+            oov = 302 if feat_table[f] == "Sku" and V > 100000 else 0
+            batch[f] = SparseIds(torch.from_numpy(_draw_ids(rng, n, V, id_mode, oov)), off_t)
+            done.add(f)
+    one = torch.arange(B + 1, dtype=torch.int32)
+    for p in plan.pooled:
+        if p.feature in done:
+            continue
+        if p.side == "i":
+            batch[p.feature] = SparseIds(torch.from_numpy(_draw_ids(rng, B, rows[p.table], id_mode)), one)
+        else:   # a pooled-only user feature that belongs to no sequence
+            lens = _seq_lengths(rng, B, 10, "ord")
+            off = np.zeros(B + 1, dtype=np.int32)
+            off[1:] = np.cumsum(lens)
+            batch[p.feature] = SparseIds(torch.from_numpy(_draw_ids(rng, int(off[-1]), rows[p.table], id_mode)),
+                                         torch.from_numpy(off))
+        done.add(p.feature)
+    for p in plan.bias_pooled:
+        if p.feature in done:
+            continue
+        lens = _seq_lengths(rng, B, near_len, "near")
+        off = np.zeros(B + 1, dtype=np.int32)
+        off[1:] = np.cumsum(lens)
+        V = min(rows["bias:" + p.table], rows.get(p.table, 1 << 60))
+        batch[p.feature] = SparseIds(torch.from_numpy(_draw_ids(rng, int(off[-1]), V, id_mode)),
+                                     torch.from_numpy(off))
+        done.add(p.feature)
+    return batch
+
+
+def batch_tokens(plan, batch) -> int:
+    """Valid tokens across the behaviour sequences (the unit of the gather roofline)."""
+    n = 0
+    for seq in plan.sequences:
+        n += int(batch[seq.user_features[-1]].offsets[-1])
+    return n
+
+
+class PackedBatch:
+    """A batch serialised into ONE pinned host buffer (what a data-loader worker hands over), so
+    the host->device step is a single async copy.  Arrays are 256-byte aligned; tensors that
+    share storage in the source batch (the offsets of the features of one sequence) are stored
+    once."""
+
+    ALIGN = 256
+
+    def __init__(self, batch: Dict, pin=True):
+        self.layout = []          # (key, kind, dtype, shape, byte offset); kind in {t, v, o, w}
+        blobs, seen, off = [], {}, 0
+
+        def add(key, kind, t):
+            nonlocal off
+            t = t.contiguous()
+            ident = (t.data_ptr(), t.dtype, tuple(t.shape))
+            if ident in seen and t.numel() > 0:
+                self.layout.append((key, kind, t.dtype, tuple(t.shape), seen[ident]))
+                return
+            seen[ident] = off
+            self.layout.append((key, kind, t.dtype, tuple(t.shape), off))
+            blobs.append((off, t))
+            off += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+
+        for k, v in batch.items():
+            if isinstance(v, SparseIds):
+                add(k, "v", v.values)
+                add(k, "o", v.offsets)
+                if v.weights is not None:
+                    add(k, "w", v.weights)
+            elif torch.is_tensor(v):
+                add(k, "t", v)
+        self.nbytes = max(off, self.ALIGN)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+        for o, t in blobs:
+            n = t.numel() * t.element_size()
+            if n:
+                self.host[o:o + n].copy_(t.view(-1).view(torch.uint8))
+
+    def unpack(self, buf: torch.Tensor) -> Dict:
+        """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device)."""
+        out, parts = {}, {}
+        for key, kind, dtype, shape, o in self.layout:
+            n = 1
+            for s in shape:
+                n *= s
+            nb = n * torch.empty((), dtype=dtype).element_size()
+            t = buf[o:o + nb].view(dtype).view(shape)
+            if kind == "t":
+                out[key] = t
+            else:
+                parts.setdefault(key, {})[kind] = t
+        for key, p in parts.items():
+            out[key] = SparseIds(p["v"], p["o"], p.get("w"))
+        return out
+
+    def to(self, device, out: Optional[torch.Tensor] = None) -> Dict:
+        if out is None:
+            out = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        out[:self.nbytes].copy_(self.host, non_blocking=True)
+        return self.unpack(out)

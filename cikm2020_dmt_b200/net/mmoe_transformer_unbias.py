@@ -1,0 +1,342 @@
+"""Host side of the DMT model plugin: same protocol as the reference's
+`model/net/mmoe_transformer_unbias.py` (class of the same name, `__init__(wnd_conf)`,
+`inference(inputs, is_train, is_predict)` :293-316), every operator executed by the
+hand-written CUDA library behind `include/dmt_b200.h`.
+
+This module only marshals pointers: it owns the device buffers (PyTorch tensors are the
+allocator), fills the POD descriptors and enqueues the C-ABI calls on the current CUDA
+stream.  There is no PyTorch math on the path and no CPU fallback.
+"""
+import ctypes as C
+
+import torch
+
+from .. import abi
+from ..data import PackedBatch, SparseIds
+from ..params import ParamStore, TASK_NAMES
+from ..plan import build_plan
+
+
+def _is_host(t):
+    return t.device.type == "cpu"
+
+
+class mmoe_transformer_unbias(object):
+    def __init__(self, wnd_conf, device=None, params=None, precision="f32", seed=20201019):
+        self.wnd_conf = wnd_conf
+        self.plan = wnd_conf if hasattr(wnd_conf, "mmoe_in") else build_plan(wnd_conf)
+        if not torch.cuda.is_available():
+            raise RuntimeError("dmt_b200 needs a CUDA device: the product path has no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.lib = abi.load()
+        self.precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16}[precision]
+        self.params = params if params is not None else ParamStore(self.plan, device=self.device, seed=seed)
+        if self.params.device != self.device:
+            raise ValueError("ParamStore lives on %s, model on %s" % (self.params.device, self.device))
+        self._buffers = {}
+        self._events = None          # bench hook: {stage: [(start, stop), ...]} CUDA events
+        self.launches = 0            # kernels of this library enqueued so far
+        self._bind_weights()
+
+    # ------------------------------------------------------------------ per-stage device timing
+    def enable_stage_timing(self, on=True):
+        self._events = {} if on else None
+
+    class _Stage(object):
+        def __init__(self, model, name, launches):
+            self.m, self.name, self.n = model, name, launches
+
+        def __enter__(self):
+            self.m.launches += self.n
+            if self.m._events is not None:
+                self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.ev[0].record(torch.cuda.current_stream(self.m.device))
+
+        def __exit__(self, *exc):
+            if self.m._events is not None:
+                self.ev[1].record(torch.cuda.current_stream(self.m.device))
+                self.m._events.setdefault(self.name, []).append(self.ev)
+            return False
+
+    def stage_times_ms(self):
+        """{stage: (total ms, launches)} -- call after a synchronize."""
+        out = {}
+        for name, evs in (self._events or {}).items():
+            out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        return out
+
+    # ------------------------------------------------------------------ weight descriptors
+    def _bind_weights(self):
+        plan, P = self.plan, self.params
+        self._seq_w = []
+        for seq in plan.sequences:
+            w = abi.SeqWeights()
+            S = seq.scope
+            w.pos = abi.ptr(P[S + "/positional_encoding_k_position_learn/embedding_position_learn"])
+
+            def attn(dst, base):
+                dst.q = abi.dense(P[base + "/dense/kernel"], P[base + "/dense/bias"])
+                dst.k = abi.dense(P[base + "/dense_1/kernel"], P[base + "/dense_1/bias"])
+                dst.v = abi.dense(P[base + "/dense_2/kernel"], P[base + "/dense_2/bias"])
+                dst.ln = abi.LayerNorm(abi.ptr(P[base + "/ln/gamma"]), abi.ptr(P[base + "/ln/beta"]))
+
+            for b in range(plan.num_blocks_encode):
+                attn(w.enc_attn[b], "%s/num_blocks_%d/self-attention" % (S, b))
+            for b in range(plan.num_blocks_decode):
+                attn(w.dec_attn[b], "%s/num_blocks_%d/vanilla_attention" % (S, b))
+            for b in range(max(plan.num_blocks_encode, plan.num_blocks_decode)):
+                base = "%s/num_blocks_%d/positionwise_feedforward" % (S, b)
+                w.ff[b].w1 = abi.dense(P[base + "/dense/kernel"], P[base + "/dense/bias"])
+                w.ff[b].w2 = abi.dense(P[base + "/dense_1/kernel"], P[base + "/dense_1/bias"])
+                w.ff[b].ln = abi.LayerNorm(abi.ptr(P[base + "/ln/gamma"]), abi.ptr(P[base + "/ln/beta"]))
+            self._seq_w.append(w)
+
+        mw = abi.MmoeWeights()
+        for e in range(plan.num_experts):
+            for l in range(len(plan.hidden_units_bottom)):
+                base = "DnnModel/mmoe_layers/expert-%d/expert-layer-%d" % (e, l)
+                mw.expert[e][l] = abi.dense(P[base + "/weights"], P[base + "/biases"])
+        for t in range(plan.num_tasks):
+            base = "DnnModel/mmoe_layers/gates-%d/gates-layer-0" % t
+            mw.gate[t] = abi.dense(P[base + "/weights"], P[base + "/biases"])
+            name = TASK_NAMES[t]
+            for l in range(len(plan.hidden_units_task)):
+                base = "DnnModel/%s/%s-fc-%d" % (name, name, l)
+                mw.tower[t][l] = abi.dense(P[base + "/weights"], P[base + "/biases"])
+            base = "DnnModel/%s/%s-output" % (name, name)
+            mw.tower_out[t] = abi.dense(P[base + "/weights"], P[base + "/biases"])
+        self._mmoe_w = mw
+
+        bw = abi.BiasWeights()
+        for l in range(len(plan.hidden_units_bias) + 1):
+            bw.layer[l] = abi.dense(P["DnnModel/layer_bias%d/kernel" % l], P["DnnModel/layer_bias%d/bias" % l])
+        self._bias_w = bw
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        t = self._buffers.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._buffers[key] = t
+        return t
+
+    def _dev(self, t):
+        if t is None:
+            return None
+        return t.to(self.device, non_blocking=True) if _is_host(t) else t
+
+    def stage_inputs(self, inputs):
+        """Bring a batch to the device exactly once.  A `PackedBatch` is one pinned buffer -> one
+        async copy; a plain dict is copied tensor by tensor (tensors shared between features, e.g.
+        the offsets of one sequence, are copied once)."""
+        if isinstance(inputs, PackedBatch):
+            buf = self._buf("packed_in", ((inputs.nbytes + 4095) // 4096 * 4096,), torch.uint8)
+            return inputs.to(self.device, out=buf)
+        if inputs.get("__staged__") is self:
+            return inputs
+        cache, out = {}, {"__staged__": self}
+
+        def dev(t):
+            if t is None or not _is_host(t):
+                return t
+            key = (t.data_ptr(), t.dtype, tuple(t.shape))
+            if key not in cache:
+                cache[key] = t.to(self.device, non_blocking=True)
+            return cache[key]
+
+        for k, v in inputs.items():
+            if isinstance(v, SparseIds):
+                out[k] = SparseIds(dev(v.values), dev(v.offsets), dev(v.weights))
+            elif torch.is_tensor(v):
+                out[k] = dev(v)
+            else:
+                out[k] = v
+        return out
+
+    def _sparse(self, inputs, name):
+        sp = inputs[name]
+        if not isinstance(sp, SparseIds):
+            raise TypeError("feature %r must be a SparseIds (CSR) value" % name)
+        w = sp.weights
+        wts = inputs.get(name + "Wts")
+        if wts is not None:
+            w = wts.values if isinstance(wts, SparseIds) else wts
+            if w.dtype != torch.float32:
+                w = w.float()
+        out = SparseIds(self._dev(sp.values), self._dev(sp.offsets), self._dev(w))
+        if out.values.dtype != torch.int32 or out.offsets.dtype != torch.int32:
+            raise TypeError("feature %r: ids/offsets must be int32" % name)
+        return out
+
+    # ------------------------------------------------------------------ forward pieces
+    def seq_encode(self, inputs, seq_index, out, out_ld, batch):
+        """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld)."""
+        plan = self.plan
+        seq = plan.sequences[seq_index]
+        cfg = abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
+                         plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
+                         len(seq.user_features), self.precision)
+        si = abi.SeqInput()
+        keep = []
+        for f, (uf, itf) in enumerate(zip(seq.user_features, seq.item_features)):
+            table = self.params.table(seq.tables[f])
+            u = self._sparse(inputs, uf)
+            it = self._sparse(inputs, itf)
+            if u.offsets.numel() != batch + 1:
+                raise ValueError("feature %r: offsets has %d entries, batch is %d" % (uf, u.offsets.numel(), batch))
+            if it.values.numel() != batch:
+                # the reference uses the flat .values of the item feature (:158): one id per sample
+                raise ValueError("item feature %r must hold exactly one id per sample" % itf)
+            keep += [u, it]
+            si.table[f] = abi.ptr(table)
+            si.rows[f] = table.shape[0]
+            si.dim[f] = table.shape[1]
+            si.ids[f] = abi.ptr(u.values)
+            si.offsets[f] = abi.ptr(u.offsets)
+            si.item_ids[f] = abi.ptr(it.values)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with self._Stage(self, "seq_encode", 1):
+            abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
+                                                  out, out_ld, None, 0, stream))
+        return keep
+
+    def pool_mean(self, inputs, specs, tables_bias, out, batch):
+        plan = self.plan
+        arr = (abi.PoolFeat * len(specs))()
+        keep = []
+        for i, p in enumerate(specs):
+            table = self.params.table(p.table, bias=tables_bias)
+            sp = self._sparse(inputs, p.feature)
+            if sp.offsets.numel() != batch + 1:
+                raise ValueError("feature %r: offsets has %d entries, batch is %d" % (p.feature, sp.offsets.numel(), batch))
+            keep.append(sp)
+            arr[i] = abi.PoolFeat(abi.ptr(table), table.shape[0], abi.ptr(sp.values), abi.ptr(sp.offsets),
+                                  abi.ptr(sp.weights), table.shape[1], p.col)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for s in range(0, len(specs), abi.MAX_POOL_FEATS):
+            n = min(abi.MAX_POOL_FEATS, len(specs) - s)
+            sub = C.cast(C.byref(arr, s * C.sizeof(abi.PoolFeat)), C.POINTER(abi.PoolFeat))
+            with self._Stage(self, "pool_mean", 1):
+                abi.check(self.lib.dmt_pool_mean_fwd(batch, n, sub, out.data_ptr(), out.stride(0), stream))
+        return keep
+
+    def mmoe(self, x, batch, logits):
+        plan = self.plan
+        cfg = abi.MmoeCfg()
+        cfg.batch, cfg.in_dim, cfg.n_experts = batch, plan.mmoe_in, plan.num_experts
+        cfg.n_layers = len(plan.hidden_units_bottom)
+        for i, u in enumerate(plan.hidden_units_bottom):
+            cfg.units[i] = u
+        cfg.n_tasks = plan.num_tasks
+        cfg.n_tower_layers = len(plan.hidden_units_task)
+        for i, u in enumerate(plan.hidden_units_task):
+            cfg.tower_units[i] = u
+        cfg.precision = self.precision
+        nbytes = self.lib.dmt_mmoe_workspace_bytes(C.byref(cfg))
+        ws = self._buf("mmoe_ws", (nbytes,), torch.uint8)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with self._Stage(self, "mmoe", cfg.n_layers + 1):
+            abi.check(self.lib.dmt_mmoe_fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),
+                                            logits.data_ptr(), ws.data_ptr(), nbytes, stream))
+
+    def _bias_cfg(self, batch, passthrough=False, loss_unbias_method=None, loss_ctr_rel_method=None):
+        plan = self.plan
+        cfg = abi.BiasLossCfg()
+        cfg.batch = batch
+        cfg.in_dim = 1 if passthrough else plan.bias_width
+        cfg.n_hidden = -1 if passthrough else len(plan.hidden_units_bias)
+        if not passthrough:
+            for i, u in enumerate(plan.hidden_units_bias):
+                cfg.units[i] = u
+        cfg.two_head_multiply = 1 if (loss_unbias_method or plan.loss_unbias_method) == "two_head_multiply" else 0
+        cfg.ctr_rel = 1 if (loss_ctr_rel_method or plan.loss_ctr_rel_method) == "ctr_rel" else 0
+        for i in range(5):
+            cfg.weight_ctr[i] = plan.weight_ctr[i]
+            cfg.weight_ecvr[i] = plan.weight_ecvr[i]
+        cfg.loss_weight[0], cfg.loss_weight[1] = plan.loss_weight[0], plan.loss_weight[1]
+        return cfg
+
+    # ------------------------------------------------------------------ plugin protocol
+    def inference(self, inputs, is_train=True, is_predict=False):
+        """mmoe_transformer_unbias.py:293-316.  Returns ((click_logit [B,1], order_logit [B,1]),
+        y_bias [B,1]) or, with is_predict, just the logit pair."""
+        plan = self.plan
+        if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
+            raise NotImplementedError("training-mode dropout is not built yet; call with is_train=False "
+                                      "or set the dropout rates to 0")
+        inputs = self.stage_inputs(inputs)
+        feats = inputs["features"] if plan.is_use_feature else None
+        first = inputs[plan.pooled[0].feature]
+        batch = first.offsets.numel() - 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        x_ld = (plan.mmoe_in + 3) // 4 * 4
+        x = self._buf("x", (batch, x_ld))
+        keep = []
+        if feats is not None:
+            if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
+                raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
+            feats = feats.contiguous()
+            with self._Stage(self, "copy_dense", 1):
+                abi.check(self.lib.dmt_copy_dense_features(feats.data_ptr(), batch, plan.feature_dim,
+                                                           x.data_ptr(), x_ld, stream))
+            keep.append(feats)
+        keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
+        for s in range(len(plan.sequences)):
+            col = plan.interest_col + s * plan.d_model
+            keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch)
+        logits = self._buf("logits", (plan.num_tasks, batch))
+        self.mmoe(x, batch, logits)
+        self._last = {"x": x, "batch": batch, "keep": keep}
+        y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
+        if is_predict:
+            return y_rel
+        bias_in = self._buf("bias_in", (batch, plan.bias_width))
+        keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
+        y_bias = self._buf("y_bias", (batch,))
+        cfg = self._bias_cfg(batch)
+        with self._Stage(self, "bias_tower", 1):
+            abi.check(self.lib.dmt_bias_loss_fwd(C.byref(cfg), C.byref(self._bias_w), bias_in.data_ptr(),
+                                                 bias_in.stride(0), logits.data_ptr(), None, y_bias.data_ptr(),
+                                                 None, None, None, None, stream))
+        return (y_rel, y_bias.view(batch, 1))
+
+    def loss(self, logits, mask, loss_unbias_method=None, loss_ctr_rel_method=None, want_probs=False,
+             want_grads=False):
+        """A12 on the outputs of `inference` (inference_mlp.py:173-223)."""
+        (click, order), y_bias = logits
+        batch = click.shape[0]
+        lg = self._buf("logits", (self.plan.num_tasks, batch))
+        if click.data_ptr() != lg[0].data_ptr() or order.data_ptr() != lg[1].data_ptr():
+            lg = self._buf("logits_in", (2, batch))
+            lg[0].copy_(click.reshape(-1))
+            lg[1].copy_(order.reshape(-1))
+        yb_in = y_bias.reshape(-1).contiguous()
+        mask = self._dev(mask)
+        if mask.dtype != torch.float32 or tuple(mask.shape) != (batch, 5):
+            raise ValueError("mask must be fp32 [%d, 5]" % batch)
+        mask = mask.contiguous()
+        cfg = self._bias_cfg(batch, passthrough=True, loss_unbias_method=loss_unbias_method,
+                             loss_ctr_rel_method=loss_ctr_rel_method)
+        yb_out = self._buf("y_bias_pass", (batch,))
+        loss = self._buf("loss", (1,))
+        probs = self._buf("probs", (2, batch)) if want_probs else None
+        dlog = self._buf("dlogits", (3, batch)) if want_grads else None
+        scratch = self._buf("loss_scratch", (self.lib.dmt_loss_scratch_bytes(batch),), torch.uint8)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with self._Stage(self, "loss", 2):
+            abi.check(self.lib.dmt_bias_loss_fwd(C.byref(cfg), C.byref(self._bias_w), yb_in.data_ptr(), 1,
+                                                 lg.data_ptr(), mask.data_ptr(), yb_out.data_ptr(),
+                                                 abi.ptr(probs), loss.data_ptr(), abi.ptr(dlog),
+                                                 scratch.data_ptr(), stream))
+        self._last_loss = {"mask": mask, "yb": yb_in}
+        out = loss[0]
+        if want_probs or want_grads:
+            return out, probs, dlog
+        return out
+
+    def l2_norm(self, inputs):
+        raise NotImplementedError("l2_norm is gated off by wnd_wd = 0.0 in dmt.conf (run_dnn.py:174)")
+
+    def embedding_update(self, sess=None):
+        raise NotImplementedError("update_emb is empty in dmt.conf (base.py:178-196 is unused)")

@@ -1,0 +1,237 @@
+/*
+ * dmt_b200.h -- C ABI of the B200-native DMT ranking hot path.
+ *
+ * The reference (guyulongcs/CIKM2020_DMT) has no FFI: every operator on this path is a
+ * stock TensorFlow-1.12 op reached through Python.  Each entry point below therefore
+ * replaces a *group of TF op calls* in the reference's Python; the file:line it replaces
+ * is cited on the declaration (paths relative to DMT_code/).  INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every export returns int: 0 = ok, < 0 = dmt_status code; dmt_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - no C++ types, no torch types: plain pointers, sizes and POD structs;
+ *   - every pointer inside the structs is a DEVICE pointer unless stated; the structs
+ *     themselves live in HOST memory and are read during the call;
+ *   - enqueue-only: work is launched on the caller's `stream` (a cudaStream_t passed as
+ *     void*); no allocation, no free, no hidden synchronisation, no global mutable state;
+ *   - the caller owns every buffer including the workspace (size it with the
+ *     *_workspace_bytes helpers);
+ *   - dense weights use the TF layout: kernel [in, out] row-major, y = x W + b;
+ *   - id features are CSR: values int32 [nnz] (post-lookup index in [0, V)), offsets
+ *     int32 [B+1] -- the left-packed tf.SparseTensor the reference's input pipeline
+ *     produces (data_feed/tfrecord_mask.py:23-84, data_feed/index_tables.py:37-45).
+ */
+#ifndef DMT_B200_H
+#define DMT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DMT_API __declspec(dllexport)
+#else
+#define DMT_API __attribute__((visibility("default")))
+#endif
+
+#define DMT_ABI_VERSION 1
+
+#define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
+#define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
+#define DMT_MAX_POOL_FEATS 64 /* pooled features per dmt_pool_mean_* launch        */
+#define DMT_MAX_EXPERTS 8
+#define DMT_MAX_TASKS 4
+#define DMT_MAX_LAYERS 4
+#define DMT_MAX_SEQ_LEN 64    /* fused encoder keeps one whole sequence on chip     */
+
+typedef enum dmt_status {
+  DMT_OK = 0,
+  DMT_ERR_INVALID_ARGUMENT = -1,
+  DMT_ERR_UNSUPPORTED_SHAPE = -2,
+  DMT_ERR_WORKSPACE_TOO_SMALL = -3,
+  DMT_ERR_CUDA = -4,
+  DMT_ERR_NO_DEVICE = -5
+} dmt_status;
+
+typedef enum dmt_precision {
+  DMT_PRECISION_F32 = 0,  /* fp32 CUDA-core math end to end (parity tolerance 1e-4)  */
+  DMT_PRECISION_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate  */
+} dmt_precision;
+
+/* one tf.layers.dense / base.dense_layer: kernel [in,out] + bias [out] */
+typedef struct dmt_dense {
+  const float* w;
+  const float* b;
+} dmt_dense;
+
+/* TransformerModel_util.py:58-78 */
+typedef struct dmt_layernorm {
+  const float* gamma;
+  const float* beta;
+} dmt_layernorm;
+
+/* TransformerModel_util.py:186-207: Q/K/V projections (no W_O) + LayerNorm */
+typedef struct dmt_attn_weights {
+  dmt_dense q, k, v;
+  dmt_layernorm ln;
+} dmt_attn_weights;
+
+/* TransformerModel_util.py:212-235; shared by encoder block i and decoder block i */
+typedef struct dmt_ff_weights {
+  dmt_dense w1, w2;
+  dmt_layernorm ln;
+} dmt_ff_weights;
+
+typedef struct dmt_seq_cfg {
+  int32_t batch;        /* B                                                          */
+  int32_t d_model;      /* transformer_d_model == sum of the pair dims                */
+  int32_t d_ff;         /* transformer_d_ff                                           */
+  int32_t num_heads;    /* transformer_num_heads; head j = columns [j*d_k,(j+1)*d_k)  */
+  int32_t n_enc_blocks; /* transformer_num_blocks_encode                              */
+  int32_t n_dec_blocks; /* transformer_num_blocks_decode                              */
+  int32_t maxlen;       /* transformer_maxlen_k: rows of the learned position table   */
+  int32_t zero_pad;     /* != 0: index i reads variable row i-1, 0 -> zero vector
+                           (base.py:87-89); 0: index i reads row i                    */
+  int32_t n_feats;      /* pairs in this sequence's attention_embed group             */
+  int32_t precision;    /* dmt_precision                                              */
+} dmt_seq_cfg;
+
+/* per-sequence inputs: generate_data(), mmoe_transformer_unbias.py:130-186 */
+typedef struct dmt_seq_input {
+  const float* table[DMT_MAX_SEQ_FEATS];     /* embedding variable [rows, dim] fp32    */
+  int64_t rows[DMT_MAX_SEQ_FEATS];
+  int32_t dim[DMT_MAX_SEQ_FEATS];
+  int32_t _pad[DMT_MAX_SEQ_FEATS];
+  const int32_t* ids[DMT_MAX_SEQ_FEATS];     /* user feature CSR values                */
+  const int32_t* offsets[DMT_MAX_SEQ_FEATS]; /* user feature CSR offsets [B+1]; the
+                                                LAST pair's lengths are the sequence
+                                                lengths (:141-146,183)                 */
+  const int32_t* item_ids[DMT_MAX_SEQ_FEATS];/* target item index, one per sample [B]  */
+} dmt_seq_input;
+
+typedef struct dmt_seq_weights {
+  const float* pos; /* positional_encoding_learn table [maxlen, d_model] (util:281-316) */
+  dmt_attn_weights enc_attn[DMT_MAX_BLOCKS]; /* num_blocks_i/self-attention            */
+  dmt_attn_weights dec_attn[DMT_MAX_BLOCKS]; /* num_blocks_i/vanilla_attention         */
+  dmt_ff_weights ff[DMT_MAX_BLOCKS];         /* num_blocks_i/positionwise_feedforward  */
+} dmt_seq_weights;
+
+/* one pooled feature: tf.nn.embedding_lookup_sparse(table, ids, weights, 'mean') */
+typedef struct dmt_pool_feat {
+  const float* table;     /* raw variable: index i reads row i (base.py:115-116)       */
+  int64_t rows;
+  const int32_t* ids;     /* CSR values                                                */
+  const int32_t* offsets; /* CSR offsets [B+1]                                         */
+  const float* weights;   /* `<feature>Wts` values [nnz] or NULL (all ones)            */
+  int32_t dim;
+  int32_t out_col;        /* first output column                                       */
+} dmt_pool_feat;
+
+typedef struct dmt_mmoe_cfg {
+  int32_t batch;
+  int32_t in_dim;                       /* 615 + pooled + n_seq*d_model (1199)         */
+  int32_t n_experts;                    /* num_experts                                 */
+  int32_t n_layers;                     /* len(hidden_units_bottom)                    */
+  int32_t units[DMT_MAX_LAYERS];        /* hidden_units_bottom                         */
+  int32_t n_tasks;                      /* 2: click, order                             */
+  int32_t n_tower_layers;               /* len(hidden_units_task)                      */
+  int32_t tower_units[DMT_MAX_LAYERS];  /* hidden_units_task                           */
+  int32_t precision;                    /* dmt_precision                               */
+} dmt_mmoe_cfg;
+
+typedef struct dmt_mmoe_weights {
+  dmt_dense expert[DMT_MAX_EXPERTS][DMT_MAX_LAYERS]; /* expert-e/expert-layer-l        */
+  dmt_dense gate[DMT_MAX_TASKS];                     /* gates-t/gates-layer-0 [in, E]  */
+  dmt_dense tower[DMT_MAX_TASKS][DMT_MAX_LAYERS];    /* <task>-fc-l                    */
+  dmt_dense tower_out[DMT_MAX_TASKS];                /* <task>-output [units, 1]       */
+} dmt_mmoe_weights;
+
+typedef struct dmt_bias_loss_cfg {
+  int32_t batch;
+  int32_t in_dim;                      /* sum of emb_bias dims (20)                    */
+  int32_t n_hidden;                    /* len(hidden_units_bias)                       */
+  int32_t units[DMT_MAX_LAYERS];       /* hidden_units_bias                            */
+  int32_t two_head_multiply;           /* loss_unbias_method == two_head_multiply      */
+  int32_t ctr_rel;                     /* loss_ctr_rel_method == ctr_rel               */
+  float weight_ctr[5];                 /* [class_weight] weight_ctr by ascending label */
+  float weight_ecvr[5];                /* [class_weight] weight_ecvr                   */
+  float loss_weight[2];                /* [parameter] loss_weight                      */
+} dmt_bias_loss_cfg;
+
+typedef struct dmt_bias_weights {
+  dmt_dense layer[DMT_MAX_LAYERS + 1]; /* layer_bias0..n_hidden (last one -> 1 unit)   */
+} dmt_bias_weights;
+
+/* ---- library ------------------------------------------------------------------- */
+DMT_API int dmt_abi_version(void);
+DMT_API const char* dmt_last_error(void);
+/* number of SMs of the current device (grid sizing); < 0 on error */
+DMT_API int dmt_device_sm_count(void);
+
+/* ---- A1/A2: raw row gather ------------------------------------------------------
+ * Replaces tf.nn.embedding_lookup(embedding(..., zero_pad), ids)
+ * (model/net/base.py:81-91; mmoe_transformer_unbias.py:153-158).  out[n, :] is the looked-up
+ * row of ids[n]; with zero_pad index 0 -> zeros and index i -> table row i-1.  Bit-exact.
+ * This is also the BASELINE config-5 vocabulary-sweep kernel. */
+DMT_API int dmt_embed_gather(const float* table, int64_t rows, int32_t dim, const int32_t* ids,
+                             int64_t n_ids, int32_t zero_pad, float* out, void* stream);
+
+/* ---- A2-A8: one behaviour sequence ------------------------------------------------
+ * Replaces generate_data (mmoe_transformer_unbias.py:130-186) + TransformerModel.encode_decode
+ * (TransformerModel.py:51-171) + multihead_attention / ff / ln
+ * (TransformerModel_util.py:11-108,160-235,281-316) for ONE sequence, eval mode
+ * (dropout sites inactive).  Writes the interest vector of sample b to
+ * out[b*out_ld + 0 .. d_model).  Samples are independent; padded positions are never
+ * computed (they are inert in the reference). */
+DMT_API size_t dmt_seq_encode_workspace_bytes(const dmt_seq_cfg* cfg, int64_t max_tokens);
+DMT_API int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in,
+                               const dmt_seq_weights* w, float* out, int64_t out_ld,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- A9/A11: pooled embeddings ----------------------------------------------------
+ * Replaces embedding_combiner (model/net/base.py:93-124) and embedding_combiner_bias
+ * (mmoe_transformer_unbias.py:235-257): out[b, out_col + j] = sum_t w_t row(ids_t)[j] / sum_t w_t.
+ * `feats` is a HOST array of n_feats <= DMT_MAX_POOL_FEATS descriptors. */
+DMT_API int dmt_pool_mean_fwd(int32_t batch, int32_t n_feats, const dmt_pool_feat* feats,
+                              float* out, int64_t out_ld, void* stream);
+
+/* strided 2-D copy of the dense `features` block into the MMoE input (base.py:95-96) */
+DMT_API int dmt_copy_dense_features(const float* features, int32_t batch, int32_t dim,
+                                    float* out, int64_t out_ld, void* stream);
+
+/* ---- A10: MMoE experts + gates + task towers --------------------------------------
+ * Replaces expert_gate + build_tower (mmoe_transformer_unbias.py:63-126,293-310).
+ * logits is [n_tasks][batch] (task-major): logits[0] = click_logit, logits[1] = order_logit. */
+DMT_API size_t dmt_mmoe_workspace_bytes(const dmt_mmoe_cfg* cfg);
+DMT_API int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x,
+                         int64_t x_ld, float* logits, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- A11/A12: bias tower + unbiased multi-task loss -------------------------------
+ * Replaces embedding_mlp_bias (mmoe_transformer_unbias.py:259-289, eval mode),
+ * cal_ctr_cvr_unibas (run_dnn.py:90-100) and logit_loss_unbias + cal_cross_entropy
+ * (model/inference_mlp.py:162-223).
+ *   bias_in  [B, in_dim] pooled bias embeddings (dmt_pool_mean_fwd output); with
+ *            cfg->n_hidden < 0 the tower is skipped and bias_in[b*bias_ld] IS y_bias
+ *            (loss on logits that were produced earlier)
+ *   logits   [2][B] from dmt_mmoe_fwd
+ *   mask     [B, 5] one-hot over labels (0,1,2,4,5), or NULL to skip the loss
+ *   y_bias   [B]   out
+ *   probs    [2][B] out: p_ctr, p_cvr (NULL to skip)
+ *   loss     device scalar out (NULL to skip); needs loss_scratch of
+ *            dmt_loss_scratch_bytes(batch) bytes
+ *   dlogits  [3][B] out: dLoss/d{click_logit, order_logit, y_bias} (NULL to skip) */
+DMT_API size_t dmt_loss_scratch_bytes(int32_t batch);
+DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weights* w,
+                              const float* bias_in, int64_t bias_ld, const float* logits,
+                              const float* mask, float* y_bias, float* probs, float* loss,
+                              float* dlogits, void* loss_scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMT_B200_H */

@@ -1,0 +1,88 @@
+"""The C-ABI shared library: builds for sm_100a, loads without a GPU, exports every symbol the header
+declares, and its POD structs have the layout the ctypes binding assumes.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "dmt_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"DMT_API\s+[\w\s\*]+?\b(dmt_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from cikm2020_dmt_b200 import abi
+    lib = abi.load()
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(abi.PROTOTYPES) == names, "binding table and header disagree"
+    assert lib.dmt_abi_version() == abi.ABI_VERSION
+    out = subprocess.run(["nm", "-D", "--defined-only", abi.lib_path()], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+    assert not any(s.startswith("_ZN3dmt") for s in exported), "internal symbols leak from the ABI"
+
+
+def test_library_contains_sm100a_code():
+    from cikm2020_dmt_b200 import abi
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", abi.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from cikm2020_dmt_b200 import abi
+    structs = {"dmt_seq_cfg": abi.SeqCfg, "dmt_seq_input": abi.SeqInput, "dmt_seq_weights": abi.SeqWeights,
+               "dmt_pool_feat": abi.PoolFeat, "dmt_mmoe_cfg": abi.MmoeCfg, "dmt_mmoe_weights": abi.MmoeWeights,
+               "dmt_bias_loss_cfg": abi.BiasLossCfg, "dmt_bias_weights": abi.BiasWeights,
+               "dmt_dense": abi.Dense, "dmt_attn_weights": abi.AttnWeights, "dmt_ff_weights": abi.FFWeights}
+    probes = {"dmt_seq_cfg": ["precision", "n_feats"], "dmt_seq_input": ["ids", "item_ids", "dim"],
+              "dmt_seq_weights": ["dec_attn", "ff"], "dmt_pool_feat": ["weights", "out_col"],
+              "dmt_mmoe_cfg": ["n_tasks", "tower_units", "precision"], "dmt_mmoe_weights": ["gate", "tower_out"],
+              "dmt_bias_loss_cfg": ["ctr_rel", "weight_ecvr", "loss_weight"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void){"]
+    for name in structs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in probes.get(name, []):
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ["return 0;}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        key, val = line.split()
+        if "." in key:
+            s, f = key.split(".")
+            assert getattr(structs[s], f).offset == int(val), key
+        else:
+            assert C.sizeof(structs[key]) == int(val), key
+
+
+def test_header_is_plain_c_and_cites_the_reference():
+    text = open(HEADER).read()
+    assert 'extern "C"' in text and "torch" not in text.replace("no torch types", "")
+    for cite in ("base.py:81-91", "mmoe_transformer_unbias.py:130-186", "TransformerModel.py:51-171",
+                 "inference_mlp.py:162-223", "mmoe_transformer_unbias.py:63-126"):
+        assert cite in text, cite
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cikm2020_dmt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
