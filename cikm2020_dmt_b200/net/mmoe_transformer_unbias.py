@@ -27,11 +27,14 @@ class mmoe_transformer_unbias(object):
         self.plan = wnd_conf if hasattr(wnd_conf, "mmoe_in") else build_plan(wnd_conf)
         if not torch.cuda.is_available():
             raise RuntimeError("dmt_b200 needs a CUDA device: the product path has no CPU fallback")
-        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = abi.load()
         self.precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16}[precision]
         self.params = params if params is not None else ParamStore(self.plan, device=self.device, seed=seed)
-        if self.params.device != self.device:
+        pdev = self.params.dense.device
+        if pdev.type != "cuda" or pdev.index != self.device.index:
             raise ValueError("ParamStore lives on %s, model on %s" % (self.params.device, self.device))
         self._buffers = {}
         self._events = None          # bench hook: {stage: [(start, stop), ...]} CUDA events
