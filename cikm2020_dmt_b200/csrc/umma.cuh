@@ -1,0 +1,157 @@
+// tcgen05 / TMEM / mbarrier building blocks (sm_100a inline PTX), shared by the bf16 tensor-core
+// kernels.  Conventions used throughout this library:
+//
+//   * one CTA = one 128-row accumulator tile: tcgen05.mma cta_group::1, M = 128, accumulator row i
+//     lives in TMEM lane i, accumulator column j in TMEM column base+j (fp32);
+//   * operands staged by ordinary stores use the NO-SWIZZLE canonical layouts
+//       K-major  [k/8][row][8 elems]   : 16-byte chunk (row, k/8) at (k/8)*ROWS*16 + row*16
+//                                        -> descriptor LBO = ROWS*16 (next 8 k), SBO = 128 (next 8 rows)
+//       MN-major [n/8][k][8 elems]     : the SAME physical image read as a B operand whose N index is
+//                                        the contiguous one -> SBO = KROWS*16 (next 8 n), LBO = 128 (next 8 k)
+//     which makes "one thread owns one row and writes 16-byte chunks" bank-conflict free;
+//   * operands loaded by TMA use SWIZZLE_128B K-major tiles of 64 elements (128 B) per row:
+//     SBO = 1024, start address advanced by 32 B per K=16 step.
+//
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace dmt {
+namespace umma {
+
+constexpr uint32_t kLayoutNone = 0;
+constexpr uint32_t kLayoutSW128 = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 64-bit shared-memory matrix descriptor: start address, leading / stride byte offsets (16-byte
+// units), version 1 (Blackwell), layout type.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7u) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, dense, M x N, operand majors.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false,
+                                                       bool b_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Arrive on `bar` when every tcgen05.mma issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM allocation: one full warp calls alloc / dealloc --------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- TMEM -> registers: each thread of the warp reads 16 / 32 consecutive fp32 columns of ITS lane
+//      (lane = 32*(warp%4) + laneid; the address carries the warp's base lane in bits 31:16) ----------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// address of (this warp's lane quarter, column) inside an allocation
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t col) {
+  return base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16) + col;
+}
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a descriptor / protocol bug must fail the launch (trap), never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+// ---- bulk async copy global -> shared (TMA engine, no tensor map): bytes % 16 == 0 ---------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- small numeric helpers ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace umma
+}  // namespace dmt

@@ -231,6 +231,14 @@ DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weigh
                               const float* mask, float* y_bias, float* probs, float* loss,
                               float* dlogits, void* loss_scratch, void* stream);
 
+/* ---- diagnostics -------------------------------------------------------------------
+ * One 128 x N x K bf16 tcgen05 GEMM through each shared-memory operand layout the tensor-core
+ * kernels use (mode 0: K-major/K-major no-swizzle, A [128,K], B [N,K]; mode 1: B MN-major,
+ * B [K,N]; mode 2: both SWIZZLE_128B K-major, K % 64 == 0).  C [128,N] fp32.  Exists so that the
+ * descriptor encodings are pinned by a unit test; not part of the model path. */
+DMT_API int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float* C, int32_t N,
+                              int32_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
