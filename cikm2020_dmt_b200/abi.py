@@ -12,7 +12,7 @@ from . import build as _build
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
 PRECISION_F32, PRECISION_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = C.c_void_p   # device pointers travel as integers
 
@@ -36,7 +36,8 @@ class FFWeights(C.Structure):
 class SeqCfg(C.Structure):
     _fields_ = [("batch", C.c_int32), ("d_model", C.c_int32), ("d_ff", C.c_int32), ("num_heads", C.c_int32),
                 ("n_enc_blocks", C.c_int32), ("n_dec_blocks", C.c_int32), ("maxlen", C.c_int32),
-                ("zero_pad", C.c_int32), ("n_feats", C.c_int32), ("precision", C.c_int32)]
+                ("zero_pad", C.c_int32), ("n_feats", C.c_int32), ("precision", C.c_int32),
+                ("slot_len", C.c_int32), ("_reserved", C.c_int32)]
 
 
 class SeqInput(C.Structure):
@@ -84,6 +85,7 @@ PROTOTYPES = {
     "dmt_device_sm_count": (C.c_int, []),
     "dmt_embed_gather": (C.c_int, [_fp, C.c_int64, C.c_int32, _fp, C.c_int64, C.c_int32, _fp, _fp]),
     "dmt_seq_encode_workspace_bytes": (C.c_size_t, [C.POINTER(SeqCfg), C.c_int64]),
+    "dmt_seq_prepare_weights": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqWeights), _fp, C.c_size_t, _fp]),
     "dmt_seq_encode_fwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), _fp,
                                      C.c_int64, _fp, C.c_size_t, _fp]),
     "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),

@@ -4,6 +4,11 @@
 namespace dmt {
 int seq_encode_f32_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                           int64_t out_ld, cudaStream_t st);
+size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg);
+bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why);
+int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st);
+int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
+                         int64_t out_ld, const void* prepared, cudaStream_t st);
 }
 
 static int validate_seq(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w) {
@@ -35,20 +40,36 @@ extern "C" {
 size_t dmt_seq_encode_workspace_bytes(const dmt_seq_cfg* cfg, int64_t max_tokens) {
   (void)max_tokens;
   if (!cfg) return 0;
+  if (cfg->precision == DMT_PRECISION_BF16) return dmt::seq_tc_prepared_bytes(cfg);   // resident weight images
   return 256;   // the fused fp32 path keeps every intermediate on chip
+}
+
+int dmt_seq_prepare_weights(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, size_t prepared_bytes,
+                            void* stream) {
+  DMT_REQUIRE(cfg && w && prepared, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_prepare_weights: null pointer");
+  DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_prepare_weights: only the bf16 path has prepared weights");
+  DMT_REQUIRE(prepared_bytes >= dmt::seq_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_prepare_weights: buffer %zu < %zu bytes", prepared_bytes, dmt::seq_tc_prepared_bytes(cfg));
+  DMT_REQUIRE(((uintptr_t)prepared & 15) == 0, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_prepare_weights: unaligned buffer");
+  return dmt::seq_tc_prepare(cfg, w, prepared, (cudaStream_t)stream);
 }
 
 int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                        int64_t out_ld, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   int rc = validate_seq(cfg, in, w);
   if (rc != DMT_OK) return rc;
   DMT_REQUIRE(out && out_ld >= cfg->d_model, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd: bad output");
   if (cfg->batch == 0) return DMT_OK;
-  DMT_REQUIRE(cfg->precision == DMT_PRECISION_F32, DMT_ERR_UNSUPPORTED_SHAPE,
-              "dmt_seq_encode_fwd: precision %d not built", cfg->precision);
-  return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, (cudaStream_t)stream);
+  if (cfg->precision == DMT_PRECISION_F32)
+    return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, (cudaStream_t)stream);
+  DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd: precision %d",
+              cfg->precision);
+  const char* why = nullptr;
+  DMT_REQUIRE(dmt::seq_tc_supported(cfg, in, &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd: %s", why);
+  DMT_REQUIRE(workspace && workspace_bytes >= dmt::seq_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_encode_fwd(bf16): workspace must hold the images written by dmt_seq_prepare_weights");
+  return dmt::seq_encode_tc_launch(cfg, in, w, out, out_ld, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -220,6 +220,16 @@ class PackedBatch:
             if n:
                 self.host[o:o + n].copy_(t.view(-1).view(torch.uint8))
 
+    def max_len(self, plan) -> Dict:
+        """{sequence index: longest sequence in this batch}, computed once from the host copy."""
+        if not hasattr(self, "_max_len"):
+            host = self.unpack(self.host)
+            self._max_len = {}
+            for seq in plan.sequences:
+                off = host[seq.user_features[-1]].offsets
+                self._max_len[seq.index] = int((off[1:] - off[:-1]).max()) if off.numel() > 1 else 0
+        return self._max_len
+
     def unpack(self, buf: torch.Tensor) -> Dict:
         """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device)."""
         out, parts = {}, {}

@@ -37,6 +37,8 @@ class mmoe_transformer_unbias(object):
         if pdev.type != "cuda" or pdev.index != self.device.index:
             raise ValueError("ParamStore lives on %s, model on %s" % (self.params.device, self.device))
         self._buffers = {}
+        self._prepared = {}          # seq index -> (params version, bf16 weight images)
+        self.params_version = 0      # bump (invalidate_prepared) whenever the parameters change
         self._events = None          # bench hook: {stage: [(start, stop), ...]} CUDA events
         self.launches = 0            # kernels of this library enqueued so far
         self._bind_weights()
@@ -135,7 +137,9 @@ class mmoe_transformer_unbias(object):
         the offsets of one sequence, are copied once)."""
         if isinstance(inputs, PackedBatch):
             buf = self._buf("packed_in", ((inputs.nbytes + 4095) // 4096 * 4096,), torch.uint8)
-            return inputs.to(self.device, out=buf)
+            out = inputs.to(self.device, out=buf)
+            out["__max_len__"] = inputs.max_len(self.plan)
+            return out
         if inputs.get("__staged__") is self:
             return inputs
         cache, out = {}, {"__staged__": self}
@@ -173,13 +177,44 @@ class mmoe_transformer_unbias(object):
         return out
 
     # ------------------------------------------------------------------ forward pieces
+    def invalidate_prepared(self):
+        """Call after the parameters changed (optimizer step, checkpoint load)."""
+        self.params_version += 1
+
+    def _seq_len_hint(self, inputs, seq):
+        """Upper bound on this sequence's lengths: exact when the offsets are host tensors (a data loader
+        knows them for free), otherwise the `_<N>` suffix of the reference's feature names
+        (clk_seq_*_7d_50, cart_seq_*_12m_10 -- dmt.conf:121) capped at transformer_maxlen_k."""
+        hint = inputs.get("__max_len__", {}).get(seq.index) if isinstance(inputs.get("__max_len__"), dict) else None
+        if hint is None:
+            tail = seq.user_features[-1].rsplit("_", 1)[-1]
+            hint = int(tail) if tail.isdigit() else seq.maxlen
+        return max(1, min(int(hint), seq.maxlen))
+
+    def _prepared_for(self, seq_index, cfg):
+        ver, buf = self._prepared.get(seq_index, (-1, None))
+        nbytes = self.lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0)
+        if buf is None:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if ver != self.params_version:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with self._Stage(self, "prepare_weights", 1):
+                abi.check(self.lib.dmt_seq_prepare_weights(C.byref(cfg), C.byref(self._seq_w[seq_index]),
+                                                           buf.data_ptr(), nbytes, stream))
+            self._prepared[seq_index] = (self.params_version, buf)
+        return buf, nbytes
+
     def seq_encode(self, inputs, seq_index, out, out_ld, batch):
         """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld)."""
         plan = self.plan
         seq = plan.sequences[seq_index]
         cfg = abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
                          plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
-                         len(seq.user_features), self.precision)
+                         len(seq.user_features), self.precision, self._seq_len_hint(inputs, seq), 0)
+        ws_ptr, ws_bytes = None, 0
+        if self.precision == abi.PRECISION_BF16:
+            ws, ws_bytes = self._prepared_for(seq_index, cfg)
+            ws_ptr = ws.data_ptr()
         si = abi.SeqInput()
         keep = []
         for f, (uf, itf) in enumerate(zip(seq.user_features, seq.item_features)):
@@ -201,7 +236,7 @@ class mmoe_transformer_unbias(object):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with self._Stage(self, "seq_encode", 1):
             abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
-                                                  out, out_ld, None, 0, stream))
+                                                  out, out_ld, ws_ptr, ws_bytes, stream))
         return keep
 
     def pool_mean(self, inputs, specs, tables_bias, out, batch):
@@ -235,7 +270,7 @@ class mmoe_transformer_unbias(object):
         cfg.n_tower_layers = len(plan.hidden_units_task)
         for i, u in enumerate(plan.hidden_units_task):
             cfg.tower_units[i] = u
-        cfg.precision = self.precision
+        cfg.precision = abi.PRECISION_F32      # the MMoE tower runs the fp32 kernels in either mode (for now)
         nbytes = self.lib.dmt_mmoe_workspace_bytes(C.byref(cfg))
         ws = self._buf("mmoe_ws", (nbytes,), torch.uint8)
         stream = torch.cuda.current_stream(self.device).cuda_stream

@@ -38,7 +38,7 @@ extern "C" {
 #define DMT_API __attribute__((visibility("default")))
 #endif
 
-#define DMT_ABI_VERSION 1
+#define DMT_ABI_VERSION 2
 
 #define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
 #define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
@@ -98,6 +98,10 @@ typedef struct dmt_seq_cfg {
                            (base.py:87-89); 0: index i reads row i                    */
   int32_t n_feats;      /* pairs in this sequence's attention_embed group             */
   int32_t precision;    /* dmt_precision                                              */
+  int32_t slot_len;     /* upper bound on the sequence lengths in THIS batch (0 = maxlen);
+                           the bf16 path packs 128/slot samples per tile (slot = 16/32/64)
+                           and truncates longer sequences to it                        */
+  int32_t _reserved;
 } dmt_seq_cfg;
 
 /* per-sequence inputs: generate_data(), mmoe_transformer_unbias.py:130-186 */
@@ -188,6 +192,12 @@ DMT_API int dmt_embed_gather(const float* table, int64_t rows, int32_t dim, cons
  * out[b*out_ld + 0 .. d_model).  Samples are independent; padded positions are never
  * computed (they are inert in the reference). */
 DMT_API size_t dmt_seq_encode_workspace_bytes(const dmt_seq_cfg* cfg, int64_t max_tokens);
+/* DMT_PRECISION_BF16 only: convert this sequence's transformer weights to the bf16 shared-memory
+ * images the tensor-core kernel keeps resident (call again whenever the weights change).  The
+ * `prepared` buffer (dmt_seq_encode_workspace_bytes bytes) is then passed as `workspace` to
+ * dmt_seq_encode_fwd. */
+DMT_API int dmt_seq_prepare_weights(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared,
+                                    size_t prepared_bytes, void* stream);
 DMT_API int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in,
                                const dmt_seq_weights* w, float* out, int64_t out_ld,
                                void* workspace, size_t workspace_bytes, void* stream);

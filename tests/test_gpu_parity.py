@@ -255,3 +255,86 @@ def test_abi_rejects_bad_arguments():
     assert lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(abi.SeqInput()), C.byref(abi.SeqWeights()), None, 64,
                                   None, 0, None) == -2
     assert b"maxlen" in lib.dmt_last_error()
+
+
+# ------------------------------------------------------------------ bf16 tensor-core path
+# Tolerance (SURVEY 8c, bf16 tensor-core path): interest vectors are LayerNorm outputs of O(1)
+# magnitude computed from bf16-rounded operands with fp32 accumulation: atol 6e-2, and the mean
+# absolute error must stay below 1e-2; logits atol 5e-2 / rtol 2e-2.
+ATOL_BF16, MEAN_BF16 = 6e-2, 1e-2
+
+
+def _bf16_model(plan, store):
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    return mmoe_transformer_unbias(plan, params=store, precision="bf16")
+
+
+@pytest.mark.parametrize("gen", [dict(), dict(full_length=True), dict(seq_lens=[16, 30, 10])])
+def test_seq_encode_bf16_matches_oracle(gen):
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 37, seed=31, **gen)
+    tc = _bf16_model(plan, model.params)
+    want = O.trans_core(plan, P, O.generate_data(plan, P, host), training=False)
+    B = 37
+    out = torch.zeros(B, len(plan.sequences) * plan.d_model, device="cuda")
+    ref = torch.zeros_like(out)
+    if "seq_lens" in gen:
+        dev["__max_len__"] = {i: l for i, l in enumerate(gen["seq_lens"])}
+    for s in range(len(plan.sequences)):
+        tc.seq_encode(dev, s, out.data_ptr() + 4 * s * plan.d_model, out.stride(0), B)
+        model.seq_encode(dev, s, ref.data_ptr() + 4 * s * plan.d_model, ref.stride(0), B)
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - want).abs()
+    assert err.max().item() < ATOL_BF16, "max abs err %.3e" % err.max().item()
+    assert err.mean().item() < MEAN_BF16, "mean abs err %.3e" % err.mean().item()
+    # and against the fp32 CUDA path (same inputs, same weights)
+    assert (out - ref).abs().max().item() < ATOL_BF16
+
+
+def test_seq_encode_bf16_edge_lengths_and_batch_tail():
+    """length-1 'unknow' sequences, full length, a batch that does not fill the last tile."""
+    from cikm2020_dmt_b200.data import SparseIds, batch_to
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 5, seed=35)
+    lens = [1, 50, 1, 17, 50]
+    g = torch.Generator().manual_seed(12)
+    off = torch.zeros(6, dtype=torch.int32)
+    off[1:] = torch.cumsum(torch.tensor(lens), 0)
+    seq = plan.sequences[0]
+    for f, uf in enumerate(seq.user_features):
+        V = plan.tables[seq.tables[f]].rows
+        vals = torch.randint(1, V, (int(off[-1]),), generator=g, dtype=torch.int32)
+        vals[0] = 0
+        host[uf] = SparseIds(vals, off)
+    dev = batch_to(host, "cuda")
+    tc = _bf16_model(plan, model.params)
+    want = O.trans_core(plan, P, O.generate_data(plan, P, host), training=False)
+    out = torch.zeros(5, len(plan.sequences) * plan.d_model, device="cuda")
+    for s in range(len(plan.sequences)):
+        tc.seq_encode(dev, s, out.data_ptr() + 4 * s * plan.d_model, out.stride(0), 5)
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - want).abs()
+    assert err.max().item() < ATOL_BF16 and err.mean().item() < MEAN_BF16, (err.max().item(), err.mean().item())
+
+
+def test_inference_bf16_matches_oracle():
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 300, seed=41)
+    tc = _bf16_model(plan, model.params)
+    (yr, yb) = tc.inference(dev, is_train=False)
+    (wr, wb) = O.inference(plan, P, host, is_train=False)
+    torch.cuda.synchronize()
+    _close(yr[0], wr[0], atol=5e-2, rtol=2e-2)
+    _close(yr[1], wr[1], atol=5e-2, rtol=2e-2)
+    _close(yb, wb, atol=1e-5)
+    loss = tc.loss((yr, yb), dev["mask"])
+    want = O.logit_loss_unbias(plan, (wr, wb), host["mask"])
+    assert abs(loss.item() - want.item()) <= 1e-2 * max(1.0, abs(want.item()))
+
+
+def test_bf16_rejects_unbuilt_shapes():
+    plan, model, host, dev, P, O = _setup("dmt.conf", 4, seed=1)
+    from cikm2020_dmt_b200 import abi
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    tc = mmoe_transformer_unbias(plan, params=model.params, precision="bf16")
+    out = torch.zeros(4, plan.d_model, device="cuda")
+    with pytest.raises(abi.DmtError) as ei:
+        tc.seq_encode(dev, 0, out.data_ptr(), out.stride(0), 4)
+    assert ei.value.code == -2
