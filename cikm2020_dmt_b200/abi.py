@@ -91,8 +91,10 @@ PROTOTYPES = {
     "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
     "dmt_copy_dense_features": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_mmoe_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
+    "dmt_mmoe_prepared_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
+    "dmt_mmoe_prepare_weights": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_size_t, _fp]),
     "dmt_mmoe_fwd": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp, C.c_size_t,
-                               _fp]),
+                               _fp, _fp]),
     "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
                                     _fp, _fp, _fp, _fp, _fp]),

@@ -1,5 +1,7 @@
 // dmt_mmoe_fwd, DMT_PRECISION_F32: expert MLPs as batched fp32 SIMT GEMMs with a fused
 // bias+ReLU epilogue, then one warp per sample for gates -> mixture -> task towers.
+#include <cuda_bf16.h>
+
 #include "dmt_common.cuh"
 
 namespace dmt {
@@ -86,7 +88,9 @@ struct HeadArgs {
   dmt_dense tower_out[DMT_MAX_TASKS];
   const float* x;
   int64_t x_ld;
-  const float* h_last;   // [E][B][H]
+  const void* h_last;    // [E][B][H] fp32, or bf16 when h_is_bf16
+  const float* gates;    // optional precomputed softmax gates [T][B][E] (NULL: computed here from x)
+  int32_t h_is_bf16;
   float* logits;         // [T][B]
   int32_t hdim;          // units of the last expert layer
   int32_t vec_floats;    // per-warp scratch floats (2 buffers)
@@ -109,33 +113,45 @@ __global__ void __launch_bounds__(kHeadWarps * 32) mmoe_head_kernel(const __grid
     float gl[DMT_MAX_EXPERTS];
 #pragma unroll
     for (int e = 0; e < DMT_MAX_EXPERTS; ++e) gl[e] = 0.f;
-    const float* __restrict__ Wg = a.gate[t].w;
-    for (int k = lane; k < K; k += 32) {
-      const float xv = __ldg(xr + k);
+    float inv = 1.0f;
+    if (a.gates) {
 #pragma unroll
       for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
-        if (e < E) gl[e] = fmaf(xv, __ldg(Wg + (int64_t)k * E + e), gl[e]);
+        if (e < E) gl[e] = __ldg(a.gates + ((int64_t)t * B + b) * E + e);
+    } else {
+      const float* __restrict__ Wg = a.gate[t].w;
+      for (int k = lane; k < K; k += 32) {
+        const float xv = __ldg(xr + k);
+#pragma unroll
+        for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+          if (e < E) gl[e] = fmaf(xv, __ldg(Wg + (int64_t)k * E + e), gl[e]);
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        if (e < E) {
+          gl[e] = warp_sum(gl[e]) + __ldg(a.gate[t].b + e);
+          mx = fmaxf(mx, gl[e]);
+        }
+      float den = 0.f;
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        if (e < E) {
+          gl[e] = expf(gl[e] - mx);
+          den += gl[e];
+        }
+      inv = 1.0f / den;
     }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
-      if (e < E) {
-        gl[e] = warp_sum(gl[e]) + __ldg(a.gate[t].b + e);
-        mx = fmaxf(mx, gl[e]);
-      }
-    float den = 0.f;
-#pragma unroll
-    for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
-      if (e < E) {
-        gl[e] = expf(gl[e] - mx);
-        den += gl[e];
-      }
-    const float inv = 1.0f / den;
     for (int c = lane; c < Hd; c += 32) {
       float acc = 0.f;
 #pragma unroll
       for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
-        if (e < E) acc = fmaf(gl[e] * inv, __ldg(a.h_last + ((int64_t)e * B + b) * Hd + c), acc);
+        if (e < E) {
+          const int64_t idx = ((int64_t)e * B + b) * Hd + c;
+          const float hv = a.h_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.h_last)[idx])
+                                       : __ldg(reinterpret_cast<const float*>(a.h_last) + idx);
+          acc = fmaf(gl[e] * inv, hv, acc);
+        }
       y0[c] = acc;
     }
     __syncwarp();
@@ -160,6 +176,34 @@ __global__ void __launch_bounds__(kHeadWarps * 32) mmoe_head_kernel(const __grid
     if (lane == 0) a.logits[(int64_t)t * B + b] = acc + __ldg(a.tower_out[t].b);
     __syncwarp();
   }
+}
+
+int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                     const void* h_last, int h_is_bf16, const float* gates, float* logits, cudaStream_t st) {
+  const int B = cfg->batch;
+  const int in_dim = cfg->units[cfg->n_layers - 1];
+  HeadArgs h;
+  h.cfg = *cfg;
+  for (int t = 0; t < cfg->n_tasks; ++t) {
+    h.gate[t] = w->gate[t];
+    for (int l = 0; l < cfg->n_tower_layers; ++l) h.tower[t][l] = w->tower[t][l];
+    h.tower_out[t] = w->tower_out[t];
+  }
+  h.x = x;
+  h.x_ld = x_ld;
+  h.h_last = h_last;
+  h.gates = gates;
+  h.h_is_bf16 = h_is_bf16;
+  h.logits = logits;
+  h.hdim = in_dim;
+  int mx = in_dim;
+  for (int l = 0; l < cfg->n_tower_layers; ++l) mx = cfg->tower_units[l] > mx ? cfg->tower_units[l] : mx;
+  h.vec_floats = 2 * ((mx + 31) / 32 * 32);
+  const size_t smem = (size_t)kHeadWarps * h.vec_floats * sizeof(float);
+  DMT_REQUIRE(smem <= 48 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_fwd: tower width %d too large", mx);
+  mmoe_head_kernel<<<(B + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, smem, st>>>(h);
+  DMT_CUDA_LAUNCH_CHECK("mmoe_head_kernel");
+  return DMT_OK;
 }
 
 int mmoe_f32_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
@@ -194,27 +238,15 @@ int mmoe_f32_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
     in_stride = (int64_t)B * units;
     layer_out += (int64_t)E * B * units;
   }
-  HeadArgs h;
-  h.cfg = *cfg;
-  for (int t = 0; t < cfg->n_tasks; ++t) {
-    h.gate[t] = w->gate[t];
-    for (int l = 0; l < cfg->n_tower_layers; ++l) h.tower[t][l] = w->tower[t][l];
-    h.tower_out[t] = w->tower_out[t];
-  }
-  h.x = x;
-  h.x_ld = x_ld;
-  h.h_last = in;
-  h.logits = logits;
-  h.hdim = in_dim;
-  int mx = in_dim;
-  for (int l = 0; l < cfg->n_tower_layers; ++l) mx = cfg->tower_units[l] > mx ? cfg->tower_units[l] : mx;
-  h.vec_floats = 2 * ((mx + 31) / 32 * 32);
-  const size_t smem = (size_t)kHeadWarps * h.vec_floats * sizeof(float);
-  DMT_REQUIRE(smem <= 48 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_fwd: tower width %d too large", mx);
-  mmoe_head_kernel<<<(B + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, smem, st>>>(h);
-  DMT_CUDA_LAUNCH_CHECK("mmoe_head_kernel");
-  return DMT_OK;
+  return mmoe_head_launch(cfg, w, x, x_ld, in, 0, nullptr, logits, st);
 }
+
+size_t mmoe_tc_prepared_bytes(const dmt_mmoe_cfg* cfg);
+size_t mmoe_tc_workspace_bytes(const dmt_mmoe_cfg* cfg);
+bool mmoe_tc_supported(const dmt_mmoe_cfg* cfg, const char** why);
+int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* prepared, cudaStream_t st);
+int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
+                   void* workspace, const void* prepared, cudaStream_t st);
 
 }  // namespace dmt
 
@@ -222,14 +254,34 @@ extern "C" {
 
 size_t dmt_mmoe_workspace_bytes(const dmt_mmoe_cfg* cfg) {
   if (!cfg) return 0;
+  if (cfg->precision == DMT_PRECISION_BF16) return dmt::mmoe_tc_workspace_bytes(cfg);
   size_t floats = 0;
   for (int l = 0; l < cfg->n_layers && l < DMT_MAX_LAYERS; ++l)
     floats += (size_t)cfg->n_experts * cfg->batch * cfg->units[l];
   return floats * sizeof(float) + 256;
 }
 
+size_t dmt_mmoe_prepared_bytes(const dmt_mmoe_cfg* cfg) {
+  if (!cfg || cfg->precision != DMT_PRECISION_BF16) return 0;
+  return dmt::mmoe_tc_prepared_bytes(cfg);
+}
+
+int dmt_mmoe_prepare_weights(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* prepared, size_t prepared_bytes,
+                             void* stream) {
+  DMT_REQUIRE(cfg && w && prepared, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_prepare_weights: null pointer");
+  DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_prepare_weights: only the bf16 path has prepared weights");
+  DMT_REQUIRE(cfg->n_experts > 0 && cfg->n_experts <= DMT_MAX_EXPERTS && cfg->n_layers > 0 &&
+                  cfg->n_layers <= DMT_MAX_LAYERS,
+              DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_prepare_weights: configuration out of range");
+  DMT_REQUIRE(prepared_bytes >= dmt::mmoe_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_mmoe_prepare_weights: buffer %zu < %zu bytes", prepared_bytes, dmt::mmoe_tc_prepared_bytes(cfg));
+  DMT_REQUIRE(((uintptr_t)prepared & 255) == 0, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_prepare_weights: unaligned buffer");
+  return dmt::mmoe_tc_prepare(cfg, w, prepared, (cudaStream_t)stream);
+}
+
 int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
-                 void* workspace, size_t workspace_bytes, void* stream) {
+                 void* workspace, size_t workspace_bytes, const void* prepared, void* stream) {
   DMT_REQUIRE(cfg && w && x && logits, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd: null pointer");
   DMT_REQUIRE(cfg->batch >= 0 && cfg->in_dim > 0 && cfg->n_experts > 0 && cfg->n_experts <= DMT_MAX_EXPERTS &&
                   cfg->n_layers > 0 && cfg->n_layers <= DMT_MAX_LAYERS && cfg->n_tasks > 0 &&
@@ -238,10 +290,18 @@ int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float
   DMT_REQUIRE(x_ld >= cfg->in_dim, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd: x_ld < in_dim");
   DMT_REQUIRE(workspace && workspace_bytes >= dmt_mmoe_workspace_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
               "dmt_mmoe_fwd: workspace %zu < %zu bytes", workspace_bytes, dmt_mmoe_workspace_bytes(cfg));
-  DMT_REQUIRE(cfg->precision == DMT_PRECISION_F32, DMT_ERR_UNSUPPORTED_SHAPE,
-              "dmt_mmoe_fwd: precision %d not built", cfg->precision);
   if (cfg->batch == 0) return DMT_OK;
-  return dmt::mmoe_f32_launch(cfg, w, x, x_ld, logits, (float*)workspace, (cudaStream_t)stream);
+  if (cfg->precision == DMT_PRECISION_F32)
+    return dmt::mmoe_f32_launch(cfg, w, x, x_ld, logits, (float*)workspace, (cudaStream_t)stream);
+  DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd: precision %d",
+              cfg->precision);
+  const char* why = nullptr;
+  DMT_REQUIRE(dmt::mmoe_tc_supported(cfg, &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_fwd: %s", why);
+  DMT_REQUIRE(prepared, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd(bf16): pass the buffer written by dmt_mmoe_prepare_weights");
+  DMT_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)prepared & 255) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd(bf16): workspace / prepared must be 256-byte aligned");
+  return dmt::mmoe_tc_launch(cfg, w, x, x_ld, logits, workspace, prepared, (cudaStream_t)stream);
 }
 
 }  // extern "C"

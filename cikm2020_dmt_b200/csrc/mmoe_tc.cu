@@ -1,0 +1,349 @@
+// dmt_mmoe_fwd, DMT_PRECISION_BF16: the expert MLPs as TMA-fed tcgen05 GEMMs.
+//
+//   cast+gate kernel : x fp32 -> bf16 (TMA-able, ld padded to 8 elements) and, in the same pass over x,
+//                      the 2 x 4 gate logits + softmax (mmoe_transformer_unbias.py:85-94)
+//   gemm_tc_kernel   : C[z] = relu(A[z] Bt[z]^T + bias[z]) per expert z, bf16 in / fp32 accumulate in
+//                      TMEM / bf16 out.  Warp-specialised: warp 0 = TMA producer (128B-swizzled 128x64
+//                      tiles, 3-stage mbarrier ring), warp 1 = MMA issuer, warps 2-5 = epilogue
+//   mmoe_head_kernel : gate mixture + task towers (shared with the fp32 path, mmoe_f32.cu)
+#include <cuda.h>
+
+#include "dmt_common.cuh"
+#include "umma.cuh"
+
+namespace dmt {
+
+using namespace umma;
+
+constexpr int GBM = 128, GBN = 128, GBK = 64, GSTAGES = 3;
+constexpr int kGemmThreads = 192;
+constexpr int kStageBytes = (GBM * GBK + GBN * GBK) * 2;
+
+struct GemmTcArgs {
+  CUtensorMap tmA, tmB;        // A: [rows, K] bf16 row-major; Bt: [rows, K] bf16 row-major (K-major B operand)
+  const float* bias;           // [z][N]
+  __nv_bfloat16* C;            // [z][M][ldc]
+  int32_t M, N, K;
+  int32_t a_rows_per_z;        // row offset of expert z inside the A tensor map (0: shared input)
+  int32_t b_rows_per_z;        // row offset of expert z inside the Bt tensor map
+  int64_t ldc, c_stride_z;
+  int32_t relu;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[GSTAGES], empty_bar[GSTAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM, z = blockIdx.z;
+  const int nkb = (g.K + GBK - 1) / GBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, GBN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GSTAGES;
+        mbar_wait(&empty_bar[s], ((kb / GSTAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + GBM * GBK * 2;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_2d(sa, &g.tmA, kb * GBK, z * g.a_rows_per_z + m0, &full_bar[s]);
+        tma_load_2d(sb, &g.tmB, kb * GBK, z * g.b_rows_per_z + n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(GBM, GBN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GSTAGES;
+        mbar_wait(&full_bar[s], (kb / GSTAGES) & 1);
+        fence_after_sync();
+        const uint32_t sa = smem_u32(smem + s * kStageBytes), sb = sa + GBM * GBK * 2;
+#pragma unroll
+        for (int k = 0; k < GBK / 16; ++k)
+          mma_bf16_ss(tbase, make_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128),
+                      make_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128), idesc, (kb | k) != 0);
+        commit(&empty_bar[s]);                 // frees the stage once these MMAs have read it
+      }
+      commit(&accum_bar);                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> +bias, relu -> bf16 -> global =====
+    mbar_wait(&accum_bar, 0);
+    fence_after_sync();
+    const int row = (warp & 3) * 32 + lane;
+    const int m = m0 + row;
+    const float* __restrict__ bias = g.bias + (int64_t)z * g.N;
+    __nv_bfloat16* crow = g.C + (int64_t)z * g.c_stride_z + (int64_t)m * g.ldc;
+#pragma unroll
+    for (int c0 = 0; c0 < GBN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, c0), r);
+      tmem_ld_wait();
+      if (m < g.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int n = n0 + c0 + j;
+          if (n + 8 <= g.N) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              y[e] = __uint_as_float(r[j + e]) + __ldg(bias + n + e);
+              if (g.relu) y[e] = fmaxf(y[e], 0.f);
+            }
+            uint4 v;
+            v.x = pack_bf16x2(y[0], y[1]);
+            v.y = pack_bf16x2(y[2], y[3]);
+            v.z = pack_bf16x2(y[4], y[5]);
+            v.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(crow + n) = v;
+          } else {
+            for (int e = 0; e < 8 && n + e < g.N; ++e) {
+              float yv = __uint_as_float(r[j + e]) + __ldg(bias + n + e);
+              if (g.relu) yv = fmaxf(yv, 0.f);
+              crow[n + e] = __float2bfloat16(yv);
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, GBN);
+}
+
+// One warp per sample: x fp32 -> bf16 row (zero-padded to ldx) + gate softmax for every task.
+__global__ void __launch_bounds__(256) mmoe_cast_gate_kernel(const float* __restrict__ x, int64_t x_ld, int B, int K,
+                                                             __nv_bfloat16* __restrict__ xb, int ldxb,
+                                                             dmt_dense g0, dmt_dense g1, dmt_dense g2, dmt_dense g3,
+                                                             int n_tasks, int E, float* __restrict__ gates) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  const dmt_dense gate[DMT_MAX_TASKS] = {g0, g1, g2, g3};
+  const float* __restrict__ xr = x + (int64_t)b * x_ld;
+  float acc[DMT_MAX_TASKS][DMT_MAX_EXPERTS];
+#pragma unroll
+  for (int t = 0; t < DMT_MAX_TASKS; ++t)
+#pragma unroll
+    for (int e = 0; e < DMT_MAX_EXPERTS; ++e) acc[t][e] = 0.f;
+  for (int k = lane; k < ldxb; k += 32) {
+    const float xv = k < K ? __ldg(xr + k) : 0.f;
+    xb[(int64_t)b * ldxb + k] = __float2bfloat16(xv);
+    if (k < K) {
+#pragma unroll
+      for (int t = 0; t < DMT_MAX_TASKS; ++t)
+        if (t < n_tasks) {
+#pragma unroll
+          for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+            if (e < E) acc[t][e] = fmaf(xv, __ldg(gate[t].w + (int64_t)k * E + e), acc[t][e]);
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < DMT_MAX_TASKS; ++t)
+    if (t < n_tasks) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        if (e < E) {
+          acc[t][e] = warp_sum(acc[t][e]) + __ldg(gate[t].b + e);
+          mx = fmaxf(mx, acc[t][e]);
+        }
+      float den = 0.f;
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        if (e < E) {
+          acc[t][e] = expf(acc[t][e] - mx);
+          den += acc[t][e];
+        }
+      if (lane == 0)
+        for (int e = 0; e < E; ++e) gates[((int64_t)t * B + b) * E + e] = acc[t][e] / den;
+    }
+}
+
+// Bt[z][n][k] = W_z[k][n] (bf16, K padded to ldk with zeros): the K-major B operand of layer l.
+__global__ void mmoe_prepare_kernel(dmt_mmoe_weights w, int layer, int E, int K, int N, int ldk,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)E * N * ldk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = i % ldk, n = (i / ldk) % N, z = i / ((int64_t)ldk * N);
+    out[i] = __float2bfloat16(k < K ? w.expert[z][layer].w[(int64_t)k * N + n] : 0.f);
+  }
+}
+__global__ void mmoe_prepare_bias_kernel(dmt_mmoe_weights w, int layer, int E, int N, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E * N) out[i] = w.expert[i / N][layer].b[i % N];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (row stride ld elements), box 64 x 128, 128-byte swizzle, OOB -> 0.
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  DMT_REQUIRE(fn, DMT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {GBK, GBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMT_REQUIRE(r == CUDA_SUCCESS, DMT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld",
+              (int)r, (long long)rows, (long long)cols, (long long)ld);
+  return DMT_OK;
+}
+
+static inline int pad8(int k) { return (k + 7) & ~7; }
+
+// prepared = [Bt_0 | Bt_1 | ... ] bf16 then [bias_0 | bias_1 | ...] fp32 (256-byte aligned sections)
+static size_t prepared_layout(const dmt_mmoe_cfg* cfg, size_t* w_off, size_t* b_off) {
+  size_t off = 0;
+  int K = cfg->in_dim;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    if (w_off) w_off[l] = off;
+    off += ((size_t)cfg->n_experts * cfg->units[l] * pad8(K) * 2 + 255) & ~(size_t)255;
+    K = cfg->units[l];
+  }
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    if (b_off) b_off[l] = off;
+    off += ((size_t)cfg->n_experts * cfg->units[l] * 4 + 255) & ~(size_t)255;
+  }
+  return off;
+}
+
+size_t mmoe_tc_prepared_bytes(const dmt_mmoe_cfg* cfg) { return prepared_layout(cfg, nullptr, nullptr) + 256; }
+
+// activations: xb | h_0 | h_1 | ... (bf16) | gates (fp32)
+static size_t workspace_layout(const dmt_mmoe_cfg* cfg, size_t* h_off, size_t* gate_off) {
+  size_t off = ((size_t)cfg->batch * pad8(cfg->in_dim) * 2 + 255) & ~(size_t)255;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    if (h_off) h_off[l] = off;
+    off += ((size_t)cfg->n_experts * cfg->batch * cfg->units[l] * 2 + 255) & ~(size_t)255;
+  }
+  if (gate_off) *gate_off = off;
+  off += ((size_t)cfg->n_tasks * cfg->batch * cfg->n_experts * 4 + 255) & ~(size_t)255;
+  return off;
+}
+
+size_t mmoe_tc_workspace_bytes(const dmt_mmoe_cfg* cfg) { return workspace_layout(cfg, nullptr, nullptr) + 256; }
+
+bool mmoe_tc_supported(const dmt_mmoe_cfg* cfg, const char** why) {
+  *why = nullptr;
+  for (int l = 0; l < cfg->n_layers; ++l)
+    if (cfg->units[l] % 8) *why = "bf16 MMoE path needs hidden_units_bottom that are multiples of 8";
+  return *why == nullptr;
+}
+
+int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* prepared, cudaStream_t st) {
+  size_t w_off[DMT_MAX_LAYERS], b_off[DMT_MAX_LAYERS];
+  prepared_layout(cfg, w_off, b_off);
+  uint8_t* base = (uint8_t*)prepared;
+  int K = cfg->in_dim;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    const int N = cfg->units[l], E = cfg->n_experts, ldk = pad8(K);
+    const int64_t total = (int64_t)E * N * ldk;
+    mmoe_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*w, l, E, K, N, ldk,
+                                                                         (__nv_bfloat16*)(base + w_off[l]));
+    mmoe_prepare_bias_kernel<<<(E * N + 255) / 256, 256, 0, st>>>(*w, l, E, N, (float*)(base + b_off[l]));
+    K = N;
+  }
+  DMT_CUDA_LAUNCH_CHECK("mmoe_prepare_kernel");
+  return DMT_OK;
+}
+
+int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                     const void* h_last, int h_is_bf16, const float* gates, float* logits, cudaStream_t st);
+
+int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
+                   void* workspace, const void* prepared, cudaStream_t st) {
+  size_t w_off[DMT_MAX_LAYERS], b_off[DMT_MAX_LAYERS], h_off[DMT_MAX_LAYERS], gate_off;
+  prepared_layout(cfg, w_off, b_off);
+  workspace_layout(cfg, h_off, &gate_off);
+  uint8_t* ws = (uint8_t*)workspace;
+  const uint8_t* pw = (const uint8_t*)prepared;
+  const int B = cfg->batch, E = cfg->n_experts;
+  __nv_bfloat16* xb = (__nv_bfloat16*)ws;
+  float* gates = (float*)(ws + gate_off);
+  const int ldx = pad8(cfg->in_dim);
+  mmoe_cast_gate_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, x_ld, B, cfg->in_dim, xb, ldx, w->gate[0], w->gate[1],
+                                                     w->gate[2], w->gate[3], cfg->n_tasks, E, gates);
+  DMT_CUDA_LAUNCH_CHECK("mmoe_cast_gate_kernel");
+
+  const int smem_bytes = GSTAGES * kStageBytes + 1024;
+  {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+  }
+  const __nv_bfloat16* a = xb;
+  int64_t a_rows = B;          // rows in the A tensor map
+  int a_rows_per_z = 0, K = cfg->in_dim, lda = ldx;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    const int N = cfg->units[l];
+    GemmTcArgs g;
+    int rc = make_map(&g.tmA, a, a_rows, K, lda);
+    if (rc != DMT_OK) return rc;
+    rc = make_map(&g.tmB, pw + w_off[l], (int64_t)E * N, K, pad8(K));
+    if (rc != DMT_OK) return rc;
+    g.bias = (const float*)(pw + b_off[l]);
+    g.C = (__nv_bfloat16*)(ws + h_off[l]);
+    g.M = B; g.N = N; g.K = K;
+    g.a_rows_per_z = a_rows_per_z;
+    g.b_rows_per_z = N;
+    g.ldc = N;
+    g.c_stride_z = (int64_t)B * N;
+    g.relu = 1;
+    dim3 grid((N + GBN - 1) / GBN, (B + GBM - 1) / GBM, E);
+    gemm_tc_kernel<<<grid, kGemmThreads, smem_bytes, st>>>(g);
+    DMT_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
+    a = g.C;
+    a_rows = (int64_t)E * B;
+    a_rows_per_z = B;
+    K = N;
+    lda = N;
+  }
+  return mmoe_head_launch(cfg, w, x, x_ld, ws + h_off[cfg->n_layers - 1], 1, gates, logits, st);
+}
+
+}  // namespace dmt

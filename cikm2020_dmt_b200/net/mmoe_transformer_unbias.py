@@ -270,13 +270,27 @@ class mmoe_transformer_unbias(object):
         cfg.n_tower_layers = len(plan.hidden_units_task)
         for i, u in enumerate(plan.hidden_units_task):
             cfg.tower_units[i] = u
-        cfg.precision = abi.PRECISION_F32      # the MMoE tower runs the fp32 kernels in either mode (for now)
+        cfg.precision = self.precision
         nbytes = self.lib.dmt_mmoe_workspace_bytes(C.byref(cfg))
-        ws = self._buf("mmoe_ws", (nbytes,), torch.uint8)
+        ws = self._buf("mmoe_ws", ((nbytes + 255) // 256 * 256,), torch.uint8)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        with self._Stage(self, "mmoe", cfg.n_layers + 1):
+        prep_ptr = None
+        launches = cfg.n_layers + 1
+        if self.precision == abi.PRECISION_BF16:
+            ver, prep = self._prepared.get("mmoe", (-1, None))
+            pbytes = self.lib.dmt_mmoe_prepared_bytes(C.byref(cfg))
+            if prep is None:
+                prep = torch.empty(pbytes, dtype=torch.uint8, device=self.device)
+            if ver != self.params_version:
+                with self._Stage(self, "prepare_weights", 2 * cfg.n_layers):
+                    abi.check(self.lib.dmt_mmoe_prepare_weights(C.byref(cfg), C.byref(self._mmoe_w),
+                                                                prep.data_ptr(), pbytes, stream))
+                self._prepared["mmoe"] = (self.params_version, prep)
+            prep_ptr = prep.data_ptr()
+            launches = cfg.n_layers + 2
+        with self._Stage(self, "mmoe", launches):
             abi.check(self.lib.dmt_mmoe_fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),
-                                            logits.data_ptr(), ws.data_ptr(), nbytes, stream))
+                                            logits.data_ptr(), ws.data_ptr(), nbytes, prep_ptr, stream))
 
     def _bias_cfg(self, batch, passthrough=False, loss_unbias_method=None, loss_ctr_rel_method=None):
         plan = self.plan

@@ -217,9 +217,15 @@ DMT_API int dmt_copy_dense_features(const float* features, int32_t batch, int32_
  * Replaces expert_gate + build_tower (mmoe_transformer_unbias.py:63-126,293-310).
  * logits is [n_tasks][batch] (task-major): logits[0] = click_logit, logits[1] = order_logit. */
 DMT_API size_t dmt_mmoe_workspace_bytes(const dmt_mmoe_cfg* cfg);
+/* DMT_PRECISION_BF16 only: bf16 K-major weight images of the expert layers for the tcgen05 GEMMs
+ * (call again whenever the weights change); 256-byte aligned buffer of dmt_mmoe_prepared_bytes. */
+DMT_API size_t dmt_mmoe_prepared_bytes(const dmt_mmoe_cfg* cfg);
+DMT_API int dmt_mmoe_prepare_weights(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w,
+                                     void* prepared, size_t prepared_bytes, void* stream);
+/* `prepared` is NULL for DMT_PRECISION_F32. */
 DMT_API int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x,
                          int64_t x_ld, float* logits, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         const void* prepared, void* stream);
 
 /* ---- A11/A12: bias tower + unbiased multi-task loss -------------------------------
  * Replaces embedding_mlp_bias (mmoe_transformer_unbias.py:259-289, eval mode),

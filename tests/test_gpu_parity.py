@@ -338,3 +338,22 @@ def test_bf16_rejects_unbuilt_shapes():
     with pytest.raises(abi.DmtError) as ei:
         tc.seq_encode(dev, 0, out.data_ptr(), out.stride(0), 4)
     assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("batch", [150, 1024])
+def test_mmoe_bf16_matches_oracle(batch):
+    """TMA + tcgen05 expert GEMMs (bf16 operands, fp32 accumulate): logits atol 5e-2 / rtol 2e-2."""
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 8, seed=9)
+    tc = _bf16_model(plan, model.params)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(batch, plan.mmoe_in, generator=g) * 0.3
+    tasks = O.expert_gate(plan, P, x.double())
+    want = torch.stack([O.build_tower(plan, P, t, O.TASK_NAMES[i]).squeeze(1) for i, t in enumerate(tasks)])
+    xd = x.cuda()
+    logits = torch.zeros(2, batch, device="cuda")
+    tc.mmoe(xd, batch, logits)
+    ref = torch.zeros(2, batch, device="cuda")
+    model.mmoe(xd, batch, ref)
+    torch.cuda.synchronize()
+    _close(logits, want, atol=5e-2, rtol=2e-2)
+    assert (logits - ref).abs().mean().item() < 1e-2
