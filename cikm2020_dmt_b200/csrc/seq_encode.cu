@@ -7,6 +7,7 @@ int seq_encode_f32_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const
 size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg);
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why);
 int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st);
+void seq_tc_set_profile(unsigned long long* p);
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                          int64_t out_ld, const void* prepared, cudaStream_t st);
 }
@@ -70,6 +71,11 @@ int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
   DMT_REQUIRE(workspace && workspace_bytes >= dmt::seq_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
               "dmt_seq_encode_fwd(bf16): workspace must hold the images written by dmt_seq_prepare_weights");
   return dmt::seq_encode_tc_launch(cfg, in, w, out, out_ld, workspace, (cudaStream_t)stream);
+}
+
+int dmt_debug_seq_profile(void* device_counters) {
+  dmt::seq_tc_set_profile((unsigned long long*)device_counters);
+  return DMT_OK;
 }
 
 }  // extern "C"

@@ -15,6 +15,8 @@
 // HBM traffic per (sample, sequence) is the algorithmic minimum: ids + embedding rows in, one
 // interest vector out.  Weights live in shared memory for the lifetime of the CTA (bf16 images
 // produced once by dmt_seq_prepare_weights).
+#include <limits.h>
+
 #include "dmt_common.cuh"
 #include "umma.cuh"
 
@@ -34,6 +36,7 @@ struct SeqTcArgs {
   float* out;
   int64_t out_ld;
   int32_t n_tiles;
+  unsigned long long* dbg;                            // diagnostics: per-phase SM cycles (thread 0), or NULL
   int32_t chunk_feat[32];                             // 16-byte chunk c of a token -> feature pair
   int32_t chunk_off[32];                              //                          -> first column inside that row
 };
@@ -43,27 +46,41 @@ constexpr int kTcThreads = 256;
 // element counts of the prepared images
 __host__ __device__ constexpr size_t prep_wqkv(int D) { return (size_t)3 * D * D; }
 __host__ __device__ constexpr size_t prep_w1(int D, int DFF) { return (size_t)D * DFF; }
-__host__ __device__ constexpr size_t prep_total(int D, int DFF) {
-  return prep_wqkv(D) + 2 * prep_w1(D, DFF) + (size_t)3 * D * D;
+// decoder block (bf16 units): G image (H*D outputs x D) | Wv image (D x D) | g fp32 [H*D]
+__host__ __device__ constexpr size_t prep_dec(int D, int H) { return (size_t)H * D * D + (size_t)D * D + 2 * (size_t)H * D; }
+__host__ __device__ constexpr size_t prep_total(int D, int DFF, int H) {
+  return prep_wqkv(D) + 2 * prep_w1(D, DFF) + prep_dec(D, H);
 }
 
 // Weight images (all bf16), "image(N, K)" = [k/8][n][8] with element (n, k) = W_tf[k][n] unless noted:
 //   wqkv  image(3D, D)   columns n = [Q | K | V]            (tcgen05 B operand, K-major)
 //   w1    image(DFF, D)                                      (tcgen05 B operand + decoder FF mat-vec)
 //   w2    image(D, DFF)                                      (tcgen05 B operand + decoder FF mat-vec)
-//   dq    image(D, D)    decoder Wq                          (mat-vec  qd = dvec Wq)
-//   dk    [c/8][k][8] = Wk[k][c]  (natural chunks)           (mat-vec  qt_h[k] = sum_{c in h} Wk[k][c] qd[c])
+//   G     image(H*D, D)  G[(h,k)][j] = sum_{c in head h} Wq[j][c] Wk[k][c]   -- the decoder's query and
+//                        key projections folded:  score_t = M_t . (dvec G_h + g_h)  (+ a constant per
+//                        (sample, head) that softmax ignores)
 //   dv    image(D, D)    decoder Wv                          (mat-vec  o = ctx Wv)
+//   g     fp32 [H*D]     g[(h,k)] = sum_{c in head h} bq[c] Wk[k][c]
 __global__ void seq_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
                                    const float* __restrict__ wv, const float* __restrict__ w1,
                                    const float* __restrict__ w2, const float* __restrict__ dq,
-                                   const float* __restrict__ dk, const float* __restrict__ dv,
-                                   __nv_bfloat16* __restrict__ out, int D, int DFF) {
-  const size_t n_qkv = prep_wqkv(D), n_w1 = prep_w1(D, DFF), n_dd = (size_t)D * D;
-  const size_t total = prep_total(D, DFF);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+                                   const float* __restrict__ dbq, const float* __restrict__ dk,
+                                   const float* __restrict__ dv, __nv_bfloat16* __restrict__ out, int D, int DFF,
+                                   int H) {
+  const size_t n_qkv = prep_wqkv(D), n_w1 = prep_w1(D, DFF), n_dd = (size_t)D * D, n_g = (size_t)H * D * D;
+  const size_t total_bf16 = n_qkv + 2 * n_w1 + n_g + n_dd;
+  const int DK = D / H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_bf16 + (size_t)H * D;
+       i += (size_t)gridDim.x * blockDim.x) {
     float v;
     size_t j = i;
+    if (i >= total_bf16) {                 // g[(h,k)] fp32, stored right after the bf16 images
+      const int hk = (int)(i - total_bf16), h = hk / D, k = hk % D;
+      float acc = 0.f;
+      for (int c = h * DK; c < (h + 1) * DK; ++c) acc = fmaf(dbq[c], dk[(size_t)k * D + c], acc);
+      reinterpret_cast<float*>(out + total_bf16)[hk] = acc;
+      continue;
+    }
     if (j < n_qkv) {                       // image(3D, D)
       const int e = j % 8, n = (j / 8) % (3 * D), kc = j / (8 * 3 * D), k = kc * 8 + e;
       const float* src = n < D ? wq : (n < 2 * D ? wk : wv);
@@ -74,14 +91,14 @@ __global__ void seq_prepare_kernel(const float* __restrict__ wq, const float* __
     } else if ((j -= n_w1) < n_w1) {       // image(D, DFF): W2 [DFF, D]
       const int e = j % 8, n = (j / 8) % D, kc = j / (8 * D), k = kc * 8 + e;
       v = w2[(size_t)k * D + n];
-    } else if ((j -= n_w1) < n_dd) {       // image(D, D): decoder Wq
-      const int e = j % 8, n = (j / 8) % D, kc = j / (8 * D), k = kc * 8 + e;
-      v = dq[(size_t)k * D + n];
-    } else if ((j -= n_dd) < n_dd) {       // [c/8][k][8] = Wk[k][c]
-      const int e = j % 8, k = (j / 8) % D, cc = j / (8 * D), c = cc * 8 + e;
-      v = dk[(size_t)k * D + c];
+    } else if ((j -= n_w1) < n_g) {        // image(H*D, D): G[(h,k)][jj]
+      const int e = j % 8, n = (j / 8) % (H * D), jc = j / (8 * H * D), jj = jc * 8 + e;
+      const int h = n / D, k = n % D;
+      float acc = 0.f;
+      for (int c = h * DK; c < (h + 1) * DK; ++c) acc = fmaf(dq[(size_t)jj * D + c], dk[(size_t)k * D + c], acc);
+      v = acc;
     } else {                               // image(D, D): decoder Wv
-      j -= n_dd;
+      j -= n_g;
       const int e = j % 8, n = (j / 8) % D, kc = j / (8 * D), k = kc * 8 + e;
       v = dv[(size_t)k * D + n];
     }
@@ -148,15 +165,26 @@ struct TcLayout {
   static constexpr int vDB = vLN + 6 * D;                     // decoder biases bq|bk|bv
   static constexpr int vDVEC = vDB + 3 * D;                   // [NS][D] scaled target embeddings
   static constexpr int vDEC = vDVEC + NS * D;                 // decoder scratch for 2 samples
-  static constexpr int dQD = 0, dQT = 2 * D, dCST = dQT + 2 * H * D, dSC = dCST + 2 * H + 4,
-                       dCTX = dSC + 2 * H * SLOT, dOV = dCTX + 2 * H * D, dAV = dOV + 2 * D, dHV = dAV + 2 * D,
-                       dPART = dHV + 2 * DFF, dEND = dPART + 4 * D;
+  static constexpr int dQT = 0, dSC = dQT + 2 * H * D, dCTX = dSC + 2 * H * SLOT, dOV = dCTX + 2 * H * D,
+                       dAV = dOV + 2 * D, dHV = dAV + 2 * D, dPART = dHV + 2 * DFF, dEND = dPART + 4 * D;
+  // decoder weights are bulk-copied per tile into the P0 buffer once the PV MMAs have consumed it
+  static constexpr int decBytes = (H * D * D + D * D) * 2 + H * D * 4;
+  static_assert(decBytes <= 128 * 128 * 2 && decBytes % 16 == 0, "decoder weights must fit the P0 buffer");
   static constexpr int nFV = vDEC + dEND;
   static constexpr int oLen = oFV + nFV * 4;                  // int32 [NS] lengths
   static constexpr int total = oLen + NS * 4 + 64;
   // TMEM columns
   static constexpr int tQKV = 0, tO = 192 < 3 * D ? 3 * D : 192, tS = 256, tFF1 = 0, tFF2 = 256;
 };
+
+#define DMT_TICK(idx)                                                   \
+  do {                                                                  \
+    if (a.dbg && tid == 0) {                                            \
+      const long long _now = clock64();                                 \
+      atomicAdd(a.dbg + (idx), (unsigned long long)(_now - t_last));    \
+      t_last = _now;                                                    \
+    }                                                                   \
+  } while (0)
 
 template <int D, int DFF, int H, int SLOT>
 __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __grid_constant__ SeqTcArgs a) {
@@ -168,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
   constexpr int CW = SLOT < 32 ? 32 : SLOT;        // score columns a warp loads (covers its rows' slots)
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   float* fv = reinterpret_cast<float*>(smem + L::oFV);
   int* slen = reinterpret_cast<int*>(smem + L::oLen);
@@ -184,6 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
     mbar_fence_init();
   }
   {
@@ -215,71 +244,147 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
   const uint32_t tbase = tmem_base_s;
   const uint32_t aWqkv = smem_u32(smem + L::oWqkv), aW1 = smem_u32(smem + L::oW1), aW2 = smem_u32(smem + L::oW2);
   const uint32_t aXA = smem_u32(sXA), aR2 = smem_u32(sR2), aP0 = smem_u32(sP0);
-  const __nv_bfloat16* gDq = a.prepared + prep_wqkv(D) + 2 * prep_w1(D, DFF);
-  const __nv_bfloat16* gDk = gDq + (size_t)D * D;
-  const __nv_bfloat16* gDv = gDk + (size_t)D * D;
+  // loop-invariant descriptor words: K-major images use LBO = one chunk column, SBO = 128 B
+  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
+  const uint32_t dXA = desc_lo(aXA, ROWB), dR2 = desc_lo(aR2, ROWB), dP0 = desc_lo(aP0, ROWB);
+  const uint32_t dWqkv = desc_lo(aWqkv, 3 * D * 16), dW1 = desc_lo(aW1, DFF * 16), dW2 = desc_lo(aW2, D * 16);
+  const __nv_bfloat16* gDec = a.prepared + prep_wqkv(D) + 2 * prep_w1(D, DFF);   // G | Wv | g
+  const uint8_t* sG = sP0;                                  // image(H*D, D)
+  const uint8_t* sDv = sP0 + H * D * D * 2;                 // image(D, D)
+  const float* sGb = reinterpret_cast<const float*>(sP0 + (H * D * D + D * D) * 2);
   const float sqrt_d = sqrtf((float)D);
   const float scale = 1.0f / sqrtf((float)DK);
   const int nf = a.cfg.n_feats;
   const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
-  uint32_t phase = 0;
+  uint32_t phase = 0, wphase = 0;
 
+  // ---- software-pipelined gather: the ids / embedding rows of tile t+1 are requested while tile t is
+  //      being computed (three dependent load levels -- offsets, ids, rows -- each issued just before one
+  //      of the MMA waits of the current tile), so P0 only converts registers that have already landed.
+  constexpr int NI = 128 * KC / kTcThreads;          // (row, chunk) items per thread; tile-invariant mapping
+  static_assert(128 * KC % kTcThreads == 0 && NS * KC <= kTcThreads, "gather item mapping");
+  constexpr int kInvalid = INT_MIN;
+  int pf_len = 0;                                    // tid < NS: length of slot tid in the next tile
+  int pf_o0[NI], pf_o1[NI], pf_l0[NI], pf_l1[NI];    // offsets of the chunk's feature / of the last feature
+  int pf_id[NI];
+  float4 pf_e0[NI], pf_e1[NI];
+  int pf_tid = 0;                                    // target item id (tid < NS*KC)
+  float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
+  uint32_t posr[NI][4];                              // learned positions of this thread's items, packed bf16
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const int i = tid + k * kTcThreads, c = i % KC, t = (i / KC) % SLOT;
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+    if (t < a.cfg.maxlen) {
+      p0 = ldg4(a.pos + t * D + c * 8);
+      p1 = ldg4(a.pos + t * D + c * 8 + 4);
+    }
+    posr[k][0] = pack_bf16x2(p0.x, p0.y); posr[k][1] = pack_bf16x2(p0.z, p0.w);
+    posr[k][2] = pack_bf16x2(p1.x, p1.y); posr[k][3] = pack_bf16x2(p1.z, p1.w);
+  }
+
+  auto stage_offsets = [&](int nt) {                 // level 1: CSR offsets
+    if (nt >= a.n_tiles) return;
+    const int nb0 = nt * NS;
+    if (tid < NS) {
+      const int b = nb0 + tid;
+      pf_len = 0;
+      if (b < B) pf_len = min(__ldg(a.in.offsets[nf - 1] + b + 1) - __ldg(a.in.offsets[nf - 1] + b), lmax);
+    }
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * kTcThreads, c = i % KC, r = i / KC, b = nb0 + r / SLOT;
+      pf_o0[k] = pf_o1[k] = pf_l0[k] = pf_l1[k] = 0;
+      if (b < B) {
+        const int f = a.chunk_feat[c];
+        pf_o0[k] = __ldg(a.in.offsets[f] + b);
+        pf_o1[k] = __ldg(a.in.offsets[f] + b + 1);
+        pf_l0[k] = __ldg(a.in.offsets[nf - 1] + b);
+        pf_l1[k] = __ldg(a.in.offsets[nf - 1] + b + 1);
+      }
+    }
+    if (tid < NS * KC) {
+      const int c = tid % KC, b = nb0 + tid / KC;
+      pf_tid = kInvalid;
+      if (b < B) pf_tid = __ldg(a.in.item_ids[a.chunk_feat[c]] + b);
+    }
+  };
+  auto stage_ids = [&](int nt) {                     // level 2: token ids
+    if (nt >= a.n_tiles) return;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * kTcThreads, c = i % KC, t = (i / KC) % SLOT;
+      pf_id[k] = kInvalid;                           // padded position: X row stays exactly zero
+      if (t < min(pf_l1[k] - pf_l0[k], lmax))
+        pf_id[k] = (t < pf_o1[k] - pf_o0[k]) ? __ldg(a.in.ids[a.chunk_feat[c]] + pf_o0[k] + t) : 0;
+    }
+  };
+  auto stage_rows = [&](int nt) {                    // level 3: embedding rows (the HBM traffic)
+    if (nt >= a.n_tiles) return;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int c = (tid + k * kTcThreads) % KC, f = a.chunk_feat[c];
+      pf_e0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_e1[k] = pf_e0[k];
+      const int64_t rw = (int64_t)pf_id[k] - (a.cfg.zero_pad ? 1 : 0);
+      if (pf_id[k] != kInvalid && rw >= 0 && rw < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
+        pf_e0[k] = ld_stream4(src);
+        pf_e1[k] = ld_stream4(src + 4);
+      }
+    }
+    if (tid < NS * KC) {
+      const int c = tid % KC, f = a.chunk_feat[c];
+      pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_t1 = pf_t0;
+      const int64_t rw = (int64_t)pf_tid - (a.cfg.zero_pad ? 1 : 0);
+      if (pf_tid != kInvalid && rw >= 0 && rw < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
+        pf_t0 = ld_stream4(src);
+        pf_t1 = ld_stream4(src + 4);
+      }
+    }
+  };
+  stage_offsets(blockIdx.x);
+  stage_ids(blockIdx.x);
+  stage_rows(blockIdx.x);
+
+  long long t_last = clock64();
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int b0 = tile * NS;
-    if (tid < NS) {
-      const int b = b0 + tid;
-      int len = 0;
-      if (b < B) len = __ldg(a.in.offsets[nf - 1] + b + 1) - __ldg(a.in.offsets[nf - 1] + b);
-      slen[tid] = min(len, lmax);
-    }
+    const int next_tile = tile + gridDim.x;
+    if (tid < NS) slen[tid] = pf_len;
     __syncthreads();
+    DMT_TICK(0);
 
-    // ---- P0: gather + concat + sqrt(d) scale + learned position -> X image (bf16) ----
-    for (int i = tid; i < 128 * KC; i += kTcThreads) {
-      const int c = i % KC, r = i / KC;
-      const int slot = r / SLOT, t = r % SLOT, b = b0 + slot;
+    // ---- P0: prefetched rows -> concat + sqrt(d) scale + learned position -> X image (bf16) ----
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * kTcThreads, c = i % KC, r = i / KC;
       float x[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) x[e] = 0.f;
-      if (b < B && t < slen[slot]) {
-        const int f = a.chunk_feat[c];
-        const int off = __ldg(a.in.offsets[f] + b);
-        const int len_f = __ldg(a.in.offsets[f] + b + 1) - off;
-        const int id = t < len_f ? __ldg(a.in.ids[f] + off + t) : 0;
-        const int64_t rw = (int64_t)id - (a.cfg.zero_pad ? 1 : 0);
-        const float4 p0 = ldg4(a.pos + t * D + c * 8), p1 = ldg4(a.pos + t * D + c * 8 + 4);
-        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
-        if (rw >= 0 && rw < a.in.rows[f]) {
-          const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
-          e0 = ld_stream4(src);
-          e1 = ld_stream4(src + 4);
-        }
-        x[0] = fmaf(e0.x, sqrt_d, p0.x); x[1] = fmaf(e0.y, sqrt_d, p0.y);
-        x[2] = fmaf(e0.z, sqrt_d, p0.z); x[3] = fmaf(e0.w, sqrt_d, p0.w);
-        x[4] = fmaf(e1.x, sqrt_d, p1.x); x[5] = fmaf(e1.y, sqrt_d, p1.y);
-        x[6] = fmaf(e1.z, sqrt_d, p1.z); x[7] = fmaf(e1.w, sqrt_d, p1.w);
+      if (pf_id[k] != kInvalid) {
+        const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(posr[k]);
+        const float2 q0 = __bfloat1622float2(pp[0]), q1 = __bfloat1622float2(pp[1]);
+        const float2 q2 = __bfloat1622float2(pp[2]), q3 = __bfloat1622float2(pp[3]);
+        x[0] = fmaf(pf_e0[k].x, sqrt_d, q0.x); x[1] = fmaf(pf_e0[k].y, sqrt_d, q0.y);
+        x[2] = fmaf(pf_e0[k].z, sqrt_d, q1.x); x[3] = fmaf(pf_e0[k].w, sqrt_d, q1.y);
+        x[4] = fmaf(pf_e1[k].x, sqrt_d, q2.x); x[5] = fmaf(pf_e1[k].y, sqrt_d, q2.y);
+        x[6] = fmaf(pf_e1[k].z, sqrt_d, q3.x); x[7] = fmaf(pf_e1[k].w, sqrt_d, q3.y);
       }
       *reinterpret_cast<uint4*>(sXA + c * ROWB + r * 16) = float8_to_bf16(x);
     }
-    for (int i = tid; i < NS * KC; i += kTcThreads) {   // target item rows -> decoder input (fp32)
-      const int c = i % KC, slot = i / KC, b = b0 + slot;
-      float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
-      if (b < B) {
-        const int f = a.chunk_feat[c];
-        const int64_t rw = (int64_t)__ldg(a.in.item_ids[f] + b) - (a.cfg.zero_pad ? 1 : 0);
-        if (rw >= 0 && rw < a.in.rows[f]) {
-          const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
-          e0 = ld_stream4(src);
-          e1 = ld_stream4(src + 4);
-        }
-      }
-      float* dv = fv + L::vDVEC + slot * D + c * 8;
-      dv[0] = e0.x * sqrt_d; dv[1] = e0.y * sqrt_d; dv[2] = e0.z * sqrt_d; dv[3] = e0.w * sqrt_d;
-      dv[4] = e1.x * sqrt_d; dv[5] = e1.y * sqrt_d; dv[6] = e1.z * sqrt_d; dv[7] = e1.w * sqrt_d;
+    if (tid < NS * KC) {                               // target item rows -> decoder input (fp32)
+      float* dv = fv + L::vDVEC + (tid / KC) * D + (tid % KC) * 8;
+      dv[0] = pf_t0.x * sqrt_d; dv[1] = pf_t0.y * sqrt_d; dv[2] = pf_t0.z * sqrt_d; dv[3] = pf_t0.w * sqrt_d;
+      dv[4] = pf_t1.x * sqrt_d; dv[5] = pf_t1.y * sqrt_d; dv[6] = pf_t1.z * sqrt_d; dv[7] = pf_t1.w * sqrt_d;
     }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    DMT_TICK(1);
+    stage_offsets(next_tile);
 
     // ---- P1: [Q|K|V] = X Wqkv ----
     if (tid == 0) {
@@ -287,14 +392,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
       constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tQKV, make_smem_desc(aXA + ks * 2 * ROWB, ROWB, 128, kLayoutNone),
-                    make_smem_desc(aWqkv + ks * 2 * (3 * D * 16), 3 * D * 16, 128, kLayoutNone), idesc, ks > 0);
+        mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
       commit(&bar);
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
 
+    DMT_TICK(2);
     // ---- P2: + bias, bf16, Q / K / V images ([chunk][row][8] each) ----
     {
       constexpr int colsPerHalf = 3 * D / 2;
@@ -319,6 +425,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    DMT_TICK(3);
+    stage_ids(next_tile);
 
     // ---- P3: S_h = Q_h K_h^T for both heads ----
     if (tid == 0) {
@@ -329,8 +437,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
 #pragma unroll
         for (int ks = 0; ks < DK / 16; ++ks) {
           const uint32_t ch = (h * DK) / 8 + ks * 2;
-          mma_bf16_ss(tbase + L::tS + h * 128, make_smem_desc(aR2 + ch * ROWB, ROWB, 128, kLayoutNone),
-                      make_smem_desc(aR2 + 128 * D * 2 + ch * ROWB, ROWB, 128, kLayoutNone), idesc, ks > 0);
+          mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dR2 + ch * (ROWB / 16), dHi),
+                      desc_join(dR2 + (128 * D * 2 + ch * ROWB) / 16, dHi), idesc, ks > 0);
         }
       commit(&bar);
     }
@@ -338,34 +446,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     phase ^= 1;
     fence_after_sync();
 
+    DMT_TICK(4);
     // ---- P4: masked softmax, one thread = one (row, head); P images ----
     {
       const int h = half;
       const int slot = row / SLOT;
       const int len = slen[slot];
       const int col0 = (row / CW) * CW;               // warp-uniform: rows of a warp share the CW window
-      float p[CW];
+      const int lo = slot * SLOT - col0;              // this row's keys are window columns [lo, lo + len)
+      const float sl2 = scale * 1.4426950408889634f;  // softmax(s*scale) through exp2
+      uint32_t r[CW];
 #pragma unroll
-      for (int blk = 0; blk < CW / 32; ++blk) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0 + blk * 32), r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) p[blk * 32 + e] = __uint_as_float(r[e]);
-      }
+      for (int blk = 0; blk < CW / 32; ++blk) tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0 + blk * 32), r + blk * 32);
+      tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
-        const int key = col0 + j;
-        const bool ok = (key / SLOT == slot) && (key % SLOT < len);
-        p[j] = ok ? p[j] * scale : -INFINITY;
-        mx = fmaxf(mx, p[j]);
+        const bool ok = (unsigned)(j - lo) < (unsigned)len;
+        const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
+        r[j] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
       }
+      const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
-        p[j] = (p[j] == -INFINITY) ? 0.f : __expf(p[j] - mx);
-        sum += p[j];
+        const float e = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));   // exp2(-inf) == 0 for masked keys
+        r[j] = __float_as_uint(e);
+        sum += e;
       }
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
       uint8_t* dstP = (h == 0) ? sP0 : sR2;            // head 1 reuses the (dead) Q|K images
@@ -373,10 +481,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
       const int kc0 = col0 / 8;
 #pragma unroll
       for (int jj = 0; jj < CW / 8; ++jj) {           // the CW keys this row can attend to
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = p[jj * 8 + e] * inv;
-        *reinterpret_cast<uint4*>(dstP + (kc0 + jj) * ROWB + row * 16) = float8_to_bf16(y);
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r[jj * 8 + 0]) * inv, __uint_as_float(r[jj * 8 + 1]) * inv);
+        v.y = pack_bf16x2(__uint_as_float(r[jj * 8 + 2]) * inv, __uint_as_float(r[jj * 8 + 3]) * inv);
+        v.z = pack_bf16x2(__uint_as_float(r[jj * 8 + 4]) * inv, __uint_as_float(r[jj * 8 + 5]) * inv);
+        v.w = pack_bf16x2(__uint_as_float(r[jj * 8 + 6]) * inv, __uint_as_float(r[jj * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dstP + (kc0 + jj) * ROWB + row * 16) = v;
       }
 #pragma unroll
       for (int kc = 0; kc < 16; ++kc)                 // every other key block of the tile: exact zeros
@@ -386,18 +496,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     fence_before_sync();
     __syncthreads();
 
+    DMT_TICK(5);
     // ---- P5: O_h = P_h V_h (V read as an MN-major B operand straight from its image) ----
     if (tid == 0) {
       fence_after_sync();
       constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        const uint32_t aP = (h == 0) ? aP0 : aR2;
-        const uint32_t aV = aR2 + 2 * (128 * D * 2) + ((h * DK) / 8) * ROWB;
+        const uint32_t dP = (h == 0) ? dP0 : dR2;
+        const uint32_t dV = desc_lo(aR2 + 2 * (128 * D * 2) + ((h * DK) / 8) * ROWB, 128);   // MN-major: LBO = next 8 keys
 #pragma unroll
         for (int ks = 0; ks < 128 / 16; ++ks)
-          mma_bf16_ss(tbase + L::tO + h * DK, make_smem_desc(aP + ks * 2 * ROWB, ROWB, 128, kLayoutNone),
-                      make_smem_desc(aV + ks * 256, 128, ROWB, kLayoutNone), idesc, ks > 0);
+          mma_bf16_ss(tbase + L::tO + h * DK, desc_join(dP + ks * (2 * ROWB / 16), dHi),
+                      desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
       }
       commit(&bar);
     }
@@ -405,7 +516,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     phase ^= 1;
     fence_after_sync();
 
+    DMT_TICK(6);
     // ---- P6: A = LN(O + X) (self-attention LayerNorm), written over X ----
+    if (tid == 0) {   // P0 is dead until the next tile's softmax: stream the decoder weights into it (async)
+      mbar_expect_tx(&wbar, L::decBytes);
+      bulk_g2s(sP0, gDec, L::decBytes, &wbar);
+    }
     if (half == 0) {
       float y[D];
 #pragma unroll
@@ -430,6 +546,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    DMT_TICK(7);
+    stage_rows(next_tile);
 
     // ---- P7: hidden = A W1 ----
     if (tid == 0) {
@@ -437,14 +555,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
       constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
 #pragma unroll
       for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tFF1, make_smem_desc(aXA + ks * 2 * ROWB, ROWB, 128, kLayoutNone),
-                    make_smem_desc(aW1 + ks * 2 * (DFF * 16), DFF * 16, 128, kLayoutNone), idesc, ks > 0);
+        mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
       commit(&bar);
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
 
+    DMT_TICK(8);
     // ---- P8: relu(+b1) -> H image ----
     {
       constexpr int colsPerHalf = DFF / 2;
@@ -468,20 +587,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     fence_before_sync();
     __syncthreads();
 
+    DMT_TICK(9);
     // ---- P9: F = H W2 ----
     if (tid == 0) {
       fence_after_sync();
       constexpr uint32_t idesc = make_idesc_bf16(128, D);
 #pragma unroll
       for (int ks = 0; ks < DFF / 16; ++ks)
-        mma_bf16_ss(tbase + L::tFF2, make_smem_desc(aR2 + ks * 2 * ROWB, ROWB, 128, kLayoutNone),
-                    make_smem_desc(aW2 + ks * 2 * (D * 16), D * 16, 128, kLayoutNone), idesc, ks > 0);
+        mma_bf16_ss(tbase + L::tFF2, desc_join(dR2 + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dW2 + ks * (2 * D), dHi), idesc, ks > 0);
       commit(&bar);
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
 
+    DMT_TICK(10);
     // ---- P10: memory = LN(F + b2 + A) (feed-forward LayerNorm), fp32 row-major over the H image ----
     if (half == 0) {
       float y[D];
@@ -509,45 +630,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
     fence_before_sync();
     __syncthreads();
 
+    DMT_TICK(11);
     // ---- P11: decoder, two samples at a time (TransformerModel.py:125-171).  K/V projections of the
     //      memory are folded:  score_j = M_j . (Wk_h qd_h) + bk_h . qd_h ,  o_h = (sum_j p_j M_j) Wv_h + bv_h ----
     const float* Mem = reinterpret_cast<const float*>(sR2);
     float* dec = fv + L::vDEC;
+    mbar_wait(&wbar, wphase);
+    wphase ^= 1;
     for (int g0 = 0; g0 < NS; g0 += 2) {
-      // a: qd = dvec Wq + bq
-      if (tid < 2 * D) {
-        const int s = tid / D, n = tid % D;
-        const float* dv = fv + L::vDVEC + (g0 + s) * D;
-        float acc = fv[L::vDB + n];
-#pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-          float w[8];
-          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(gDq + ((size_t)kc * D + n) * 8)), w);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc = fmaf(dv[kc * 8 + e], w[e], acc);
-        }
-        dec[L::dQD + s * D + n] = acc;
-      }
-      __syncthreads();
-      // b: qt[s][h][k] = sum_{c in h} Wk[k][c] qd[c] ; cst[s][h] = sum_{c in h} bk[c] qd[c]
+      // a: qt[s][h][k] = dvec[s] . G[(h,k)] + g[(h,k)]   (query and key projections folded)
       for (int i = tid; i < 2 * H * D; i += kTcThreads) {
-        const int k = i % D, h = (i / D) % H, s = i / (D * H);
-        const float* qd = dec + L::dQD + s * D + h * DK;
-        float acc = 0.f;
+        const int n = i % (H * D), s = i / (H * D);
+        const float* dv = fv + L::vDVEC + (g0 + s) * D;
+        float acc = sGb[n];
 #pragma unroll
-        for (int cc = 0; cc < DK / 8; ++cc) {
+        for (int jc = 0; jc < KC; ++jc) {
           float w[8];
-          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(gDk + ((size_t)((h * DK) / 8 + cc) * D + k) * 8)), w);
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(sG + (jc * H * D + n) * 16), w);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc = fmaf(qd[cc * 8 + e], w[e], acc);
+          for (int e = 0; e < 8; ++e) acc = fmaf(dv[jc * 8 + e], w[e], acc);
         }
-        dec[L::dQT + (s * H + h) * D + k] = acc;
-      }
-      if (tid < 2 * H) {
-        const int h = tid % H, s = tid / H;
-        float acc = 0.f;
-        for (int c = 0; c < DK; ++c) acc = fmaf(fv[L::vDB + D + h * DK + c], dec[L::dQD + s * D + h * DK + c], acc);
-        dec[L::dCST + s * H + h] = acc;
+        dec[L::dQT + s * H * D + n] = acc;
       }
       __syncthreads();
       // c: scores over the slot's valid keys
@@ -557,7 +660,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
         if (j < slen[g0 + s]) {
           const float* m = Mem + ((g0 + s) * SLOT + j) * MLD;
           const float* qt = dec + L::dQT + (s * H + h) * D;
-          float acc = dec[L::dCST + s * H + h];
+          float acc = 0.f;   // the per-(sample, head) constant bk_h . qd_h cancels in the softmax
 #pragma unroll
           for (int k = 0; k < D; k += 4) {
             const float4 mv = *reinterpret_cast<const float4*>(m + k);
@@ -590,10 +693,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
         const int k = i % D, h = (i / D) % H, s = i / (D * H);
         const float* pr = dec + L::dSC + (s * H + h) * SLOT;
         const float* m = Mem + ((g0 + s) * SLOT) * MLD + k;
-        const int len = slen[g0 + s];
-        float acc = 0.f;
-        for (int j = 0; j < len; ++j) acc = fmaf(pr[j], m[j * MLD], acc);
-        dec[L::dCTX + (s * H + h) * D + k] = acc;
+        // p_j is exactly 0 beyond the sequence length and every memory row is finite, so the loop runs
+        // over the whole slot: fixed trip count, four independent accumulators
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < SLOT; j += 4) {
+          a0 = fmaf(pr[j], m[j * MLD], a0);
+          a1 = fmaf(pr[j + 1], m[(j + 1) * MLD], a1);
+          a2 = fmaf(pr[j + 2], m[(j + 2) * MLD], a2);
+          a3 = fmaf(pr[j + 3], m[(j + 3) * MLD], a3);
+        }
+        dec[L::dCTX + (s * H + h) * D + k] = (a0 + a1) + (a2 + a3);
       }
       __syncthreads();
       // f: o = ctx_h Wv_h + bv (sum_j p_j == 1; an empty sequence contributes o = 0) ; y = o + dvec
@@ -604,7 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
           float w[8];
-          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(gDv + ((size_t)kc * D + c) * 8)), w);
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(sDv + (kc * D + c) * 16), w);
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc = fmaf(ctx[kc * 8 + e], w[e], acc);
         }
@@ -696,6 +806,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) seq_encode_tc_kernel(const __gr
       }
       __syncthreads();
     }
+    DMT_TICK(12);
   }
 
   fence_before_sync();
@@ -717,7 +828,12 @@ static int launch_tc(const SeqTcArgs& a, cudaStream_t st) {
   return DMT_OK;
 }
 
-size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg) { return prep_total(cfg->d_model, cfg->d_ff) * 2 + 256; }
+static unsigned long long* g_seq_profile = nullptr;   // diagnostics only (dmt_debug_seq_profile)
+void seq_tc_set_profile(unsigned long long* p) { g_seq_profile = p; }
+
+size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg) {
+  return prep_total(cfg->d_model, cfg->d_ff, cfg->num_heads) * 2 + 256;
+}
 
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why) {
   *why = nullptr;
@@ -732,12 +848,13 @@ bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const cha
 }
 
 int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st) {
-  const size_t total = prep_total(cfg->d_model, cfg->d_ff);
+  const size_t total = prep_total(cfg->d_model, cfg->d_ff, cfg->num_heads);
   const int blocks = (int)((total + 255) / 256);
   const dmt_attn_weights& e = w->enc_attn[0];
   const dmt_attn_weights& d = w->dec_attn[0];
-  seq_prepare_kernel<<<blocks, 256, 0, st>>>(e.q.w, e.k.w, e.v.w, w->ff[0].w1.w, w->ff[0].w2.w, d.q.w, d.k.w, d.v.w,
-                                            (__nv_bfloat16*)prepared, cfg->d_model, cfg->d_ff);
+  seq_prepare_kernel<<<blocks, 256, 0, st>>>(e.q.w, e.k.w, e.v.w, w->ff[0].w1.w, w->ff[0].w2.w, d.q.w, d.q.b, d.k.w,
+                                            d.v.w, (__nv_bfloat16*)prepared, cfg->d_model, cfg->d_ff,
+                                            cfg->num_heads);
   DMT_CUDA_LAUNCH_CHECK("seq_prepare_kernel");
   return DMT_OK;
 }
@@ -754,6 +871,7 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
   a.b1 = w->ff[0].w1.b; a.b2 = w->ff[0].w2.b; a.ln2_g = w->ff[0].ln.gamma; a.ln2_b = w->ff[0].ln.beta;
   a.dbq = d.q.b; a.dbk = d.k.b; a.dbv = d.v.b; a.ln3_g = d.ln.gamma; a.ln3_b = d.ln.beta;
   a.prepared = (const __nv_bfloat16*)prepared;
+  a.dbg = g_seq_profile;
   a.out = out;
   a.out_ld = out_ld;
   int c = 0;

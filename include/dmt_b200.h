@@ -255,6 +255,11 @@ DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weigh
 DMT_API int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float* C, int32_t N,
                               int32_t K, void* stream);
 
+/* Diagnostics: when `device_counters` (16 x uint64 on the device) is non-NULL, the bf16 sequence kernel
+ * adds the SM cycles thread 0 of every CTA spends in each of its phases (gather-convert, QKV MMA, QKV
+ * epilogue, ... decoder).  Pass NULL to switch it off.  Process-wide debug switch, not for production. */
+DMT_API int dmt_debug_seq_profile(void* device_counters);
+
 #ifdef __cplusplus
 }
 #endif
