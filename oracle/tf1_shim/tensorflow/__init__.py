@@ -66,6 +66,29 @@ class Tensor(torch.Tensor):
     def get_shape(self):
         return _Shape(torch.Tensor.size(self))
 
+    # tf.Tensor.__mul__ etc. run convert_to_tensor on Python lists (`mask * [1.0, 15.0, ...]`)
+    @staticmethod
+    def _c(o):
+        return torch.as_tensor(o, dtype=torch.float64) if isinstance(o, (list, tuple)) else o
+
+    def __mul__(self, o):
+        return torch.Tensor.__mul__(self, Tensor._c(o))
+
+    def __rmul__(self, o):
+        return torch.Tensor.__rmul__(self, Tensor._c(o))
+
+    def __add__(self, o):
+        return torch.Tensor.__add__(self, Tensor._c(o))
+
+    def __radd__(self, o):
+        return torch.Tensor.__radd__(self, Tensor._c(o))
+
+    def __sub__(self, o):
+        return torch.Tensor.__sub__(self, Tensor._c(o))
+
+    def __truediv__(self, o):
+        return torch.Tensor.__truediv__(self, Tensor._c(o))
+
     # graph semantics: `x *= s` rebinds the Python name, it never mutates the producer's value
     def __imul__(self, o):
         return self * o
