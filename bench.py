@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (BASELINE config 2: 4096)")
     ap.add_argument("--conf", default="dmt_d64.conf")
     ap.add_argument("--id-mode", default="uniform", choices=["uniform", "zipf"])
-    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--n-batches", type=int, default=4, help="distinct batches rotated through the timed loop")
     ap.add_argument("--cpu-batch", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
@@ -323,13 +323,15 @@ def main():
         t_ms, n = stage["seq_encode"]
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
         achieved = alg / (t_ms / 1e3) / 1e9
-        roofline = {"kernel": "seq_encode_f32_kernel (fused gather->encoder->decoder, per sequence)",
+        roofline = {"kernel": ("seq_encode_tc_kernel (bf16 tcgen05" if args.precision == "bf16" else
+                               "seq_encode_f32_kernel (fp32 CUDA cores") + ", fused gather->encoder->decoder, per sequence)",
                     "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                     "launches": n, "avg_launch_ms": t_ms / n, "algorithmic_bytes_per_launch": alg / n,
                     "flops_per_launch": mean_b(flops_seq) / n,
                     "achieved_tflops": mean_b(flops_seq) / (t_ms / 1e3) / 1e12,
-                    "note": "fp32 CUDA-core path: compute-bound well below the HBM roofline (SURVEY 8d)"}
+                    "note": "fully fused kernel: 432 FLOP/B vs a 209 FLOP/B ridge, latency-bound at L<=50 "
+                            "(DESIGN.md 4.1); the HBM-bound gather is reported under embed_gather"}
     else:
         t_ms, n = stage[dom]
         fl = flops_mmoe(plan, B) * steps_used
@@ -358,6 +360,34 @@ def main():
                                   "median of %d forward passes" % (nb, reps)}
         del P
 
+    # ---- BASELINE metric part 2: stand-alone embedding gather (Sku rows of this workload) vs HBM peak
+    embed_gather = None
+    try:
+        from cikm2020_dmt_b200 import abi as _abi
+        sku = store.table("Sku")
+        n_ids = 4096 * 50
+        gsets = [torch.randint(1, sku.shape[0] + 1, (n_ids,), device=device, dtype=torch.int32) for _ in range(4)]
+        gout = torch.empty(n_ids, sku.shape[1], device=device)
+        st = torch.cuda.current_stream().cuda_stream
+        for i in range(3):
+            _abi.check(model.lib.dmt_embed_gather(sku.data_ptr(), sku.shape[0], sku.shape[1], gsets[i].data_ptr(),
+                                                  n_ids, 1, gout.data_ptr(), st))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(20):
+            _abi.check(model.lib.dmt_embed_gather(sku.data_ptr(), sku.shape[0], sku.shape[1],
+                                                  gsets[i % 4].data_ptr(), n_ids, 1, gout.data_ptr(), st))
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 20
+        gbytes = n_ids * (sku.shape[1] * 4 + 4) + n_ids * sku.shape[1] * 4
+        embed_gather = {"kernel": "embed_gather_kernel (B=4096, L=50, Sku %dx%d fp32, uniform ids)" % tuple(sku.shape),
+                        "bound": "hbm", "achieved": gbytes / (gms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbytes / (gms / 1e3) / 1e9 / pk["hbm_gbs"], "avg_launch_ms": gms,
+                        "algorithmic_bytes_per_launch": gbytes}
+    except Exception as exc:   # diagnostics only; never fail the bench line
+        embed_gather = {"error": str(exc)}
+
     h2d = sum(p.nbytes for p in packed) / len(packed)
     line = {
         "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -367,6 +397,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "embed_gather": embed_gather,
         "gpu_launches": int(gpu_launches), "clocks": clocks,
         "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
     }
