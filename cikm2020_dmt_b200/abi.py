@@ -78,6 +78,19 @@ class BiasWeights(C.Structure):
     _fields_ = [("layer", Dense * (MAX_LAYERS + 1))]
 
 
+class AdamCfg(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("step", C.c_int32), ("_pad", C.c_int32)]
+
+
+class GradSource(C.Structure):
+    _fields_ = [("ids", _fp), ("offsets", _fp), ("weights", _fp), ("grad", _fp), ("n", C.c_int64),
+                ("grad_ld", C.c_int64), ("grad_col", C.c_int32), ("id_offset", C.c_int32), ("batch", C.c_int32),
+                ("mean", C.c_int32)]
+
+MAX_GRAD_SOURCES = 16
+
+
 # name -> (restype, argtypes); must list every DMT_API symbol of include/dmt_b200.h
 PROTOTYPES = {
     "dmt_abi_version": (C.c_int, []),
@@ -98,6 +111,11 @@ PROTOTYPES = {
     "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
                                     _fp, _fp, _fp, _fp, _fp]),
+    "dmt_adam_dense": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp]),
+    "dmt_embed_grad_expand": (C.c_int, [C.c_int32, C.POINTER(GradSource), C.c_int64, _fp, _fp, _fp, _fp]),
+    "dmt_embed_adam_sorted": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32,
+                                        C.POINTER(GradSource), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp, _fp]),
+    "dmt_adam_rows_untouched": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),
 }

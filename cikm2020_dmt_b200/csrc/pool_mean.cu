@@ -27,7 +27,27 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const __grid_constant__ 
     const int j = c - a.col_first[f];
     const int beg = __ldg(pf.offsets + b), end = __ldg(pf.offsets + b + 1);
     float num = 0.f, den = 0.f;
-    for (int t = beg; t < end; ++t) {
+    int t = beg;
+    // four tokens per trip: the id -> row dependent loads of different tokens overlap (the kernel is
+    // latency-bound otherwise); accumulation order stays token order
+    for (; t + 4 <= end; t += 4) {
+      int64_t row[4];
+      float w[4], e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        row[u] = __ldg(pf.ids + t + u);
+        w[u] = pf.weights ? __ldg(pf.weights + t + u) : 1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        e[u] = (row[u] >= 0 && row[u] < pf.rows) ? __ldg(pf.table + row[u] * pf.dim + j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        num = fmaf(w[u], e[u], num);
+        den += w[u];
+      }
+    }
+    for (; t < end; ++t) {
       const int64_t row = __ldg(pf.ids + t);
       const float w = pf.weights ? __ldg(pf.weights + t) : 1.0f;
       const float e = (row >= 0 && row < pf.rows) ? __ldg(pf.table + row * pf.dim + j) : 0.f;

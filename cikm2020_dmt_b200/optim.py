@@ -1,15 +1,102 @@
-"""TF-1 Adam over the DMT parameter store (tf.train.AdamOptimizer, inference_mlp.py:272-273).
+"""TF-1 Adam over the DMT parameter store (`tf.train.AdamOptimizer`, inference_mlp.py:272-273;
+applied to tower-averaged gradients, run_dnn.py:203-207).
 
-Placeholder until the fused Adam kernel (K10) lands: constructing it is allowed so that
-`Inference.get_optimizer` keeps the reference's surface, stepping raises.
+Host side only: owns the m / v buffers (PyTorch tensors are the allocator), builds the POD descriptors
+and enqueues the C-ABI kernels.  The one library call on the path is the key sort between
+`dmt_embed_grad_expand` and `dmt_embed_adam_sorted` (`torch.sort`, i.e. CUB) -- plumbing, like the
+allocator; the arithmetic (segmented gradient reduction + the Adam update) is ours.
 """
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import abi
+
+
+@dataclass
+class LookupGrad:
+    """One group of lookups into a table + where their gradient rows live (dmt_grad_source)."""
+    ids: torch.Tensor                      # int32 [n]
+    grad: torch.Tensor                     # fp32 [rows, ld]
+    grad_col: int = 0
+    id_offset: int = 0                     # -1: zero-pad path (base.py:87-89)
+    offsets: Optional[torch.Tensor] = None  # int32 [B+1]: gradient rows are per sample
+    weights: Optional[torch.Tensor] = None
+    mean: bool = False
+
+    def to_c(self):
+        g = abi.GradSource()
+        g.ids = abi.ptr(self.ids)
+        g.offsets = abi.ptr(self.offsets)
+        g.weights = abi.ptr(self.weights)
+        g.grad = abi.ptr(self.grad)
+        g.n = self.ids.numel()
+        g.grad_ld = self.grad.stride(0)
+        g.grad_col = self.grad_col
+        g.id_offset = self.id_offset
+        g.batch = 0 if self.offsets is None else self.offsets.numel() - 1
+        g.mean = 1 if self.mean else 0
+        return g
 
 
 class TFAdam(object):
     def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
-        self.model, self.learning_rate = model, learning_rate
+        self.model = model
+        self.store = model.params
+        self.lib = model.lib
+        self.learning_rate = learning_rate
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.t = 0
+        dev = self.store.dense.device
+        self.m_dense = torch.zeros_like(self.store.dense)
+        self.v_dense = torch.zeros_like(self.store.dense)
+        self.m_tab = {k: torch.zeros_like(t) for k, t in self.store.tables.items()}
+        self.v_tab = {k: torch.zeros_like(t) for k, t in self.store.tables.items()}
+        self.touched = {k: torch.zeros(t.shape[0], dtype=torch.uint8, device=dev) for k, t in self.store.tables.items()}
 
-    def step(self, grads, lr=None):
-        raise NotImplementedError("dmt_adam_* kernels are not built yet")
+    def _cfg(self, lr):
+        lr = self.learning_rate if lr is None else lr
+        if isinstance(lr, (list, tuple)):
+            lr = lr[0]
+        return abi.AdamCfg(float(lr), self.beta1, self.beta2, self.epsilon, int(self.t), 0)
+
+    def begin_step(self):
+        self.t += 1
+
+    def step_dense(self, grad_flat, lr=None, grad_scale=1.0):
+        cfg = self._cfg(lr)
+        stream = torch.cuda.current_stream(grad_flat.device).cuda_stream
+        self.model.launches += 1
+        abi.check(self.lib.dmt_adam_dense(C.byref(cfg), self.store.dense.data_ptr(), self.m_dense.data_ptr(),
+                                          self.v_dense.data_ptr(), grad_flat.data_ptr(), grad_flat.numel(),
+                                          float(grad_scale), stream))
+
+    def step_table(self, name, sources: List[LookupGrad], lr=None, grad_scale=1.0):
+        """`name` is the TF variable name of the table; `sources` every lookup of this step into it."""
+        table = self.store.tables[name]
+        cfg = self._cfg(lr)
+        stream = torch.cuda.current_stream(table.device).cuda_stream
+        rows, dim = table.shape
+        if sources:
+            arr = (abi.GradSource * len(sources))(*[s.to_c() for s in sources])
+            total = sum(s.ids.numel() for s in sources)
+            keys = torch.empty(total, dtype=torch.int32, device=table.device)
+            refs = torch.empty(total, dtype=torch.int64, device=table.device)
+            scale = torch.empty(total, dtype=torch.float32, device=table.device)
+            abi.check(self.lib.dmt_embed_grad_expand(len(sources), arr, rows, keys.data_ptr(), refs.data_ptr(),
+                                                     scale.data_ptr(), stream))
+            skeys, perm = torch.sort(keys, stable=True)
+            abi.check(self.lib.dmt_embed_adam_sorted(C.byref(cfg), table.data_ptr(), self.m_tab[name].data_ptr(),
+                                                     self.v_tab[name].data_ptr(), rows, dim, len(sources), arr,
+                                                     skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),
+                                                     scale.data_ptr(), total, float(grad_scale),
+                                                     self.touched[name].data_ptr(), stream))
+            self.model.launches += 2
+            self._keep = (arr, keys, refs, scale, skeys, perm, sources)
+        abi.check(self.lib.dmt_adam_rows_untouched(C.byref(cfg), table.data_ptr(), self.m_tab[name].data_ptr(),
+                                                   self.v_tab[name].data_ptr(), rows, dim,
+                                                   self.touched[name].data_ptr(), stream))
+        self.model.launches += 1
+        self.model.invalidate_prepared()

@@ -47,6 +47,7 @@ extern "C" {
 #define DMT_MAX_TASKS 4
 #define DMT_MAX_LAYERS 4
 #define DMT_MAX_SEQ_LEN 64    /* fused encoder keeps one whole sequence on chip     */
+#define DMT_MAX_GRAD_SOURCES 16 /* lookups feeding one table per step (3 seq + 3 target + pooled) */
 
 typedef enum dmt_status {
   DMT_OK = 0,
@@ -246,6 +247,56 @@ DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weigh
                               const float* bias_in, int64_t bias_ld, const float* logits,
                               const float* mask, float* y_bias, float* probs, float* loss,
                               float* dlogits, void* loss_scratch, void* stream);
+
+/* ---- A13: optimizer ----------------------------------------------------------------
+ * tf.train.AdamOptimizer(lr) (model/inference_mlp.py:272-273) applied to the tower-averaged gradients
+ * (run_dnn.py:45-80,203,207).  TF-1 form: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps),
+ * DENSE over every row of every table (the reference densifies IndexedSlices, run_dnn.py:63-72). */
+typedef struct dmt_adam_cfg {
+  float lr;       /* piecewise_constant(global_step, step_boundary, learning_rate), run_dnn.py:125-126 */
+  float beta1;    /* 0.9   */
+  float beta2;    /* 0.999 */
+  float epsilon;  /* 1e-8  */
+  int32_t step;   /* t >= 1 */
+  int32_t _pad;
+} dmt_adam_cfg;
+
+/* One group of lookups into a table whose gradient is needed: the backward of tf.nn.embedding_lookup
+ * (sequence / target path, base.py:81-91: id_offset = -1 with zero_pad, index 0 has no gradient) or of
+ * tf.nn.embedding_lookup_sparse(combiner='mean') (pooled path, base.py:116: id_offset = 0, mean = 1). */
+typedef struct dmt_grad_source {
+  const int32_t* ids;     /* [n] lookup indices                                                     */
+  const int32_t* offsets; /* CSR offsets [batch+1] when `grad` holds ONE ROW PER SAMPLE (pooled and
+                             target lookups); NULL when it holds one row per lookup (sequence tokens) */
+  const float* weights;   /* `<feature>Wts` [n] or NULL (pooled path)                               */
+  const float* grad;      /* gradient rows, row stride grad_ld floats; this table's slice starts at
+                             column grad_col                                                         */
+  int64_t n;
+  int64_t grad_ld;
+  int32_t grad_col;
+  int32_t id_offset;      /* variable row = id + id_offset; rows outside [0, V) carry no gradient   */
+  int32_t batch;
+  int32_t mean;           /* != 0: scale each lookup by w / sum_w of its sample                     */
+} dmt_grad_source;
+
+/* theta/m/v/grad: flat fp32 buffers of n elements (16-byte aligned); g = grad * grad_scale. */
+DMT_API int dmt_adam_dense(const dmt_adam_cfg* cfg, float* param, float* m, float* v, const float* grad,
+                           int64_t n, float grad_scale, void* stream);
+/* K9 step 1: expand every lookup into (row key | INT32_MAX if none, gradient-row reference, scale).
+ * keys/refs/scale have sum(sources[i].n) entries, in source order.  `sources` is a HOST array. */
+DMT_API int dmt_embed_grad_expand(int32_t n_sources, const dmt_grad_source* sources, int64_t rows,
+                                  int32_t* keys, int64_t* refs, float* scale, void* stream);
+/* K9 step 2 + K10: `sorted_keys` ascending with `perm` (sorted position -> expanded position) from any
+ * stable device sort; one warp per run of equal keys sums the gradient rows in sorted order
+ * (deterministic) and applies the Adam update; touched[row] = 1. */
+DMT_API int dmt_embed_adam_sorted(const dmt_adam_cfg* cfg, float* table, float* m, float* v, int64_t rows,
+                                  int32_t dim, int32_t n_sources, const dmt_grad_source* sources,
+                                  const int32_t* sorted_keys, const int64_t* perm, const int64_t* refs,
+                                  const float* scale, int64_t n, float grad_scale, uint8_t* touched,
+                                  void* stream);
+/* K10 for the rows without a gradient this step (g = 0 still moves them); clears `touched`. */
+DMT_API int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float* m, float* v,
+                                    int64_t rows, int32_t dim, uint8_t* touched, void* stream);
 
 /* ---- diagnostics -------------------------------------------------------------------
  * One 128 x N x K bf16 tcgen05 GEMM through each shared-memory operand layout the tensor-core

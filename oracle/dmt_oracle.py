@@ -341,14 +341,17 @@ class TFAdam:
 
     def __init__(self, params: Dict[str, torch.Tensor], lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8):
         self.params = params
-        self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, epsilon
+        # the hyper-parameters reach TF's ApplyAdam kernel as float32 scalars: (1 - beta2) is
+        # 1 - float32(0.999) = 0.00099998713, not 0.001
+        f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))
+        self.lr, self.b1, self.b2, self.eps = f32(lr), f32(beta1), f32(beta2), f32(epsilon)
         self.t = 0
         self.m = {k: torch.zeros_like(v) for k, v in params.items()}
         self.v = {k: torch.zeros_like(v) for k, v in params.items()}
 
     def step(self, grads: Dict[str, torch.Tensor], lr=None):
         self.t += 1
-        lr = self.lr if lr is None else lr
+        lr = self.lr if lr is None else float(torch.tensor(lr, dtype=torch.float32))
         lr_t = lr * math.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
         with torch.no_grad():
             for k, p in self.params.items():

@@ -43,7 +43,7 @@ def test_library_contains_sm100a_code():
 
 def test_struct_layouts_match_header(tmp_path):
     from cikm2020_dmt_b200 import abi
-    structs = {"dmt_seq_cfg": abi.SeqCfg, "dmt_seq_input": abi.SeqInput, "dmt_seq_weights": abi.SeqWeights,
+    structs = {"dmt_adam_cfg": abi.AdamCfg, "dmt_grad_source": abi.GradSource, "dmt_seq_cfg": abi.SeqCfg, "dmt_seq_input": abi.SeqInput, "dmt_seq_weights": abi.SeqWeights,
                "dmt_pool_feat": abi.PoolFeat, "dmt_mmoe_cfg": abi.MmoeCfg, "dmt_mmoe_weights": abi.MmoeWeights,
                "dmt_bias_loss_cfg": abi.BiasLossCfg, "dmt_bias_weights": abi.BiasWeights,
                "dmt_dense": abi.Dense, "dmt_attn_weights": abi.AttnWeights, "dmt_ff_weights": abi.FFWeights}
