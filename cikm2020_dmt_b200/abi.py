@@ -12,7 +12,7 @@ from . import build as _build
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
 PRECISION_F32, PRECISION_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _fp = C.c_void_p   # device pointers travel as integers
 
@@ -111,6 +111,19 @@ PROTOTYPES = {
     "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
                                     _fp, _fp, _fp, _fp, _fp]),
+    "dmt_seq_saved_bytes": (C.c_size_t, [C.POINTER(SeqCfg), C.c_int64]),
+    "dmt_seq_encode_fwd_train": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), _fp,
+                                           C.c_int64, C.c_int64, _fp, C.c_size_t, _fp]),
+    "dmt_seq_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(SeqCfg), C.c_int64]),
+    "dmt_seq_encode_bwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), C.c_int64, _fp,
+                                     C.c_size_t, _fp, C.c_int64, C.POINTER(SeqWeights), _fp, _fp, _fp, C.c_size_t,
+                                     _fp]),
+    "dmt_mmoe_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
+    "dmt_mmoe_bwd": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp,
+                               C.POINTER(MmoeWeights), _fp, C.c_int64, C.c_int32, _fp, C.c_size_t, _fp]),
+    "dmt_bias_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(BiasLossCfg)]),
+    "dmt_bias_bwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp,
+                               C.POINTER(BiasWeights), _fp, C.c_int64, _fp, C.c_size_t, _fp]),
     "dmt_adam_dense": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp]),
     "dmt_embed_grad_expand": (C.c_int, [C.c_int32, C.POINTER(GradSource), C.c_int64, _fp, _fp, _fp, _fp]),
     "dmt_embed_adam_sorted": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32,

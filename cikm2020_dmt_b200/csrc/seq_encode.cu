@@ -1,9 +1,14 @@
 // dmt_seq_encode_fwd: argument validation + dispatch on dmt_precision.
 #include "dmt_common.cuh"
+#include "seq_train.cuh"
 
 namespace dmt {
 int seq_encode_f32_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
-                          int64_t out_ld, cudaStream_t st);
+                          int64_t out_ld, const SeqSaved* saved, cudaStream_t st);
+int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, int64_t T,
+                   const SeqSaved& sv, const float* d_out, int64_t d_out_ld, const dmt_seq_grads* g, float* d_tokens,
+                   float* d_target, void* ws, cudaStream_t st);
+size_t seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t T);
 size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg);
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why);
 int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st);
@@ -63,7 +68,7 @@ int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
   DMT_REQUIRE(out && out_ld >= cfg->d_model, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd: bad output");
   if (cfg->batch == 0) return DMT_OK;
   if (cfg->precision == DMT_PRECISION_F32)
-    return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, (cudaStream_t)stream);
+    return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, nullptr, (cudaStream_t)stream);
   DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd: precision %d",
               cfg->precision);
   const char* why = nullptr;
@@ -71,6 +76,55 @@ int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
   DMT_REQUIRE(workspace && workspace_bytes >= dmt::seq_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
               "dmt_seq_encode_fwd(bf16): workspace must hold the images written by dmt_seq_prepare_weights");
   return dmt::seq_encode_tc_launch(cfg, in, w, out, out_ld, workspace, (cudaStream_t)stream);
+}
+
+size_t dmt_seq_saved_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens) {
+  if (!cfg || n_tokens < 0) return 0;
+  return dmt::seq_saved_carve(*cfg, n_tokens, nullptr, nullptr);
+}
+
+int dmt_seq_encode_fwd_train(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
+                             int64_t out_ld, int64_t n_tokens, void* saved, size_t saved_bytes, void* stream) {
+  int rc = validate_seq(cfg, in, w);
+  if (rc != DMT_OK) return rc;
+  DMT_REQUIRE(out && out_ld >= cfg->d_model, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd_train: bad output");
+  DMT_REQUIRE(n_tokens >= 0 && saved && ((uintptr_t)saved & 255) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_encode_fwd_train: `saved` must be a 256-byte aligned buffer");
+  DMT_REQUIRE(saved_bytes >= dmt_seq_saved_bytes(cfg, n_tokens), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_encode_fwd_train: saved buffer %zu < %zu bytes", saved_bytes, dmt_seq_saved_bytes(cfg, n_tokens));
+  if (cfg->batch == 0) return DMT_OK;
+  dmt::SeqSaved sv;
+  dmt::seq_saved_carve(*cfg, n_tokens, saved, &sv);
+  return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, &sv, (cudaStream_t)stream);
+}
+
+size_t dmt_seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens) {
+  if (!cfg || n_tokens < 0) return 0;
+  return dmt::seq_bwd_workspace_bytes(cfg, n_tokens);
+}
+
+int dmt_seq_encode_bwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, int64_t n_tokens,
+                       const void* saved, size_t saved_bytes, const float* d_out, int64_t d_out_ld,
+                       const dmt_seq_grads* grads, float* d_tokens, float* d_target, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  int rc = validate_seq(cfg, in, w);
+  if (rc != DMT_OK) return rc;
+  DMT_REQUIRE(saved && d_out && grads && d_target && workspace && (d_tokens || n_tokens == 0),
+              DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_bwd: null pointer");
+  DMT_REQUIRE(d_out_ld >= cfg->d_model && n_tokens >= 0, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_bwd: bad sizes");
+  DMT_REQUIRE((((uintptr_t)saved | (uintptr_t)workspace) & 255) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_encode_bwd: saved / workspace must be 256-byte aligned");
+  DMT_REQUIRE(saved_bytes >= dmt_seq_saved_bytes(cfg, n_tokens), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_encode_bwd: saved buffer %zu < %zu bytes", saved_bytes, dmt_seq_saved_bytes(cfg, n_tokens));
+  DMT_REQUIRE(workspace_bytes >= dmt::seq_bwd_workspace_bytes(cfg, n_tokens), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_encode_bwd: workspace %zu < %zu bytes", workspace_bytes,
+              dmt::seq_bwd_workspace_bytes(cfg, n_tokens));
+  DMT_REQUIRE(grads->pos, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_bwd: gradient descriptor incomplete");
+  if (cfg->batch == 0) return DMT_OK;
+  dmt::SeqSaved sv;
+  dmt::seq_saved_carve(*cfg, n_tokens, const_cast<void*>(saved), &sv);
+  return dmt::seq_bwd_launch(cfg, in, w, n_tokens, sv, d_out, d_out_ld, grads, d_tokens, d_target, workspace,
+                             (cudaStream_t)stream);
 }
 
 int dmt_debug_seq_profile(void* device_counters) {

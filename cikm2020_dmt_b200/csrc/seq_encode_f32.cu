@@ -9,6 +9,7 @@
 // All arithmetic is fp32 on CUDA cores; this is the exact-parity path (tolerance 1e-4 against
 // the fp64 oracle) and the arithmetic reference for the bf16 tensor-core path.
 #include "dmt_common.cuh"
+#include "seq_train.cuh"
 
 namespace dmt {
 
@@ -23,6 +24,7 @@ struct SeqArgs {
   int32_t ld;    // padded row stride of [*, d_model] buffers (d_model + 4: conflict-free float4 rows)
   int32_t ldh;   // padded row stride of the [*, d_ff] buffer
   int32_t region_floats;
+  SeqSaved sv;   // SAVE instantiation only: where the training forward leaves its activations
 };
 
 constexpr int kThreads = 256;
@@ -134,6 +136,19 @@ __device__ __forceinline__ float lookup_elem(const float* __restrict__ table, in
   return __ldg(table + row * dim + c);
 }
 
+// rows [0, L) of an on-chip [*, ld] buffer -> global rows off + t (row stride gld floats, first column gcol)
+__device__ __forceinline__ void save_rows(const float* s, int ld, int L, int W, float* g, int64_t off, int gld,
+                                          int gcol) {
+  for (int i = threadIdx.x; i < L * W; i += kThreads) {
+    const int t = i / W, c = i - t * W;
+    g[(off + t) * gld + gcol + c] = s[t * ld + c];
+  }
+}
+__device__ __forceinline__ void zero_rows(float* g, int64_t off, int t0, int t1, int W) {
+  for (int i = threadIdx.x; i < (t1 - t0) * W; i += kThreads) g[(off + t0) * W + i] = 0.f;
+}
+
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __grid_constant__ SeqArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int D = a.cfg.d_model, DFF = a.cfg.d_ff, H = a.cfg.num_heads, dk = D / H;
@@ -159,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
   float* sc = hvec + DFF;                // [H][LP] decoder attention probabilities
 
   const int off_last = __ldg(a.in.offsets[nf - 1] + b);
-  int L = __ldg(a.in.offsets[nf - 1] + b + 1) - off_last;
-  L = min(L, LP);
+  const int len_all = __ldg(a.in.offsets[nf - 1] + b + 1) - off_last;
+  const int L = min(len_all, LP);
   const float sqrt_d = sqrtf((float)D);
   const float scale = 1.0f / sqrtf((float)dk);
 
@@ -183,6 +198,20 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
     dvec[c] = lookup_elem(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d;
   }
   __syncthreads();
+  if (SAVE) {
+    save_rows(X, ld, L, D, a.sv.hin[0], off_last, D, 0);
+    if (len_all > L) {   // tokens beyond the on-chip cap: inert zero rows in every saved buffer
+      for (int blk = 0; blk <= a.cfg.n_enc_blocks; ++blk) zero_rows(a.sv.hin[blk], off_last, L, len_all, D);
+      for (int blk = 0; blk < a.cfg.n_enc_blocks; ++blk) {
+        zero_rows(a.sv.qkv[blk], off_last, L, len_all, 3 * D);
+        zero_rows(a.sv.z1[blk], off_last, L, len_all, D);
+        zero_rows(a.sv.a[blk], off_last, L, len_all, D);
+        zero_rows(a.sv.f1[blk], off_last, L, len_all, DFF);
+        zero_rows(a.sv.z2[blk], off_last, L, len_all, D);
+      }
+      for (int blk = 0; blk < a.cfg.n_dec_blocks; ++blk) zero_rows(a.sv.kvd[blk], off_last, L, len_all, 2 * D);
+    }
+  }
 
   // ---- A3-A6: encoder blocks ----
   for (int blk = 0; blk < a.cfg.n_enc_blocks && L > 0; ++blk) {
@@ -192,6 +221,11 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
     gemm_rows<8>(X, ld, L, D, aw.k.w, aw.k.b, D, Kb, ld, false);
     gemm_rows<8>(X, ld, L, D, aw.v.w, aw.v.b, D, V, ld, false);
     __syncthreads();
+    if (SAVE) {
+      save_rows(Q, ld, L, D, a.sv.qkv[blk], off_last, 3 * D, 0);
+      save_rows(Kb, ld, L, D, a.sv.qkv[blk], off_last, 3 * D, D);
+      save_rows(V, ld, L, D, a.sv.qkv[blk], off_last, 3 * D, 2 * D);
+    }
     for (int h = 0; h < H; ++h) {
       const int hc = h * dk;
       for (int i = tid; i < L * L; i += kThreads) {
@@ -235,26 +269,49 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
       }
       __syncthreads();
     }
+    if (SAVE) {
+      for (int i = tid; i < L * D; i += kThreads) {
+        const int t = i / D, c = i - t * D;
+        a.sv.z1[blk][(off_last + t) * D + c] = Q[t * ld + c] + X[t * ld + c];
+      }
+    }
     ln_rows(Q, ld, X, ld, L, D, aw.ln.gamma, aw.ln.beta, A, ld);   // residual = the block input
     __syncthreads();
+    if (SAVE) save_rows(A, ld, L, D, a.sv.a[blk], off_last, D, 0);
     gemm_rows<8>(A, ld, L, D, fw.w1.w, fw.w1.b, DFF, Hb, ldh, true);
     __syncthreads();
+    if (SAVE) save_rows(Hb, ldh, L, DFF, a.sv.f1[blk], off_last, DFF, 0);
     gemm_rows<4>(Hb, ldh, L, DFF, fw.w2.w, fw.w2.b, D, X, ld, false);
     __syncthreads();
+    if (SAVE) {
+      for (int i = tid; i < L * D; i += kThreads) {
+        const int t = i / D, c = i - t * D;
+        a.sv.z2[blk][(off_last + t) * D + c] = X[t * ld + c] + A[t * ld + c];
+      }
+      __syncthreads();   // the LayerNorm below rewrites X in place
+    }
     ln_rows(X, ld, A, ld, L, D, fw.ln.gamma, fw.ln.beta, X, ld);
     __syncthreads();
+    if (SAVE) save_rows(X, ld, L, D, a.sv.hin[blk + 1], off_last, D, 0);
   }
 
   // ---- A7: decoder blocks, single query over the encoder memory (TransformerModel.py:125-171) ----
   for (int blk = 0; blk < a.cfg.n_dec_blocks; ++blk) {
     const dmt_attn_weights& aw = a.w.dec_attn[blk];
     const dmt_ff_weights& fw = a.w.ff[blk];
+    if (SAVE)
+      for (int c = tid; c < D; c += kThreads) a.sv.din[blk][(int64_t)b * D + c] = dvec[c];
     gemv_row(dvec, D, aw.q.w, aw.q.b, D, qd, false, nullptr);
     if (L > 0) {
       gemm_rows<8>(X, ld, L, D, aw.k.w, aw.k.b, D, Kb, ld, false);
       gemm_rows<8>(X, ld, L, D, aw.v.w, aw.v.b, D, V, ld, false);
     }
     __syncthreads();
+    if (SAVE) {
+      for (int c = tid; c < D; c += kThreads) a.sv.qd[blk][(int64_t)b * D + c] = qd[c];
+      save_rows(Kb, ld, L, D, a.sv.kvd[blk], off_last, 2 * D, 0);
+      save_rows(V, ld, L, D, a.sv.kvd[blk], off_last, 2 * D, D);
+    }
     for (int i = tid; i < H * L; i += kThreads) {
       const int h = i / L, j = i - h * L;
       float acc = 0.f;
@@ -284,21 +341,37 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
       ovec[c] = acc;
     }
     __syncthreads();
+    if (SAVE) {
+      for (int i = tid; i < H * LP; i += kThreads) {
+        const int j = i % LP;
+        a.sv.pd[blk][(int64_t)b * H * LP + i] = j < L ? sc[i] : 0.f;
+      }
+      for (int c = tid; c < D; c += kThreads) a.sv.z1d[blk][(int64_t)b * D + c] = ovec[c] + dvec[c];
+    }
     ln_rows(ovec, D, dvec, D, 1, D, aw.ln.gamma, aw.ln.beta, avec, D);
     __syncthreads();
+    if (SAVE)
+      for (int c = tid; c < D; c += kThreads) a.sv.ad[blk][(int64_t)b * D + c] = avec[c];
     gemv_row(avec, D, fw.w1.w, fw.w1.b, DFF, hvec, true, nullptr);
     __syncthreads();
+    if (SAVE)
+      for (int c = tid; c < DFF; c += kThreads) a.sv.f1d[blk][(int64_t)b * DFF + c] = hvec[c];
     gemv_row(hvec, DFF, fw.w2.w, fw.w2.b, D, ovec, false, avec);
     __syncthreads();
+    if (SAVE)
+      for (int c = tid; c < D; c += kThreads) a.sv.z2d[blk][(int64_t)b * D + c] = ovec[c];
     ln_rows(ovec, D, nullptr, 0, 1, D, fw.ln.gamma, fw.ln.beta, dvec, D);
     __syncthreads();
   }
+  if (SAVE)
+    for (int c = tid; c < D; c += kThreads) a.sv.din[a.cfg.n_dec_blocks][(int64_t)b * D + c] = dvec[c];
   for (int c = tid; c < D; c += kThreads) a.out[(int64_t)b * a.out_ld + c] = dvec[c];
 }
 
 int seq_encode_f32_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
-                          int64_t out_ld, cudaStream_t st) {
+                          int64_t out_ld, const SeqSaved* saved, cudaStream_t st) {
   SeqArgs a;
+  a.sv = saved ? *saved : SeqSaved{};
   a.cfg = *cfg;
   a.in = *in;
   a.w = *w;
@@ -323,10 +396,13 @@ int seq_encode_f32_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const
   const size_t smem_bytes = smem_floats * sizeof(float);
   DMT_REQUIRE(smem_bytes <= 227 * 1024, DMT_ERR_UNSUPPORTED_SHAPE,
               "dmt_seq_encode_fwd: sequence tile needs %zu B shared memory (> 227 KB)", smem_bytes);
-  cudaError_t e = cudaFuncSetAttribute(seq_encode_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(saved ? seq_encode_f32_kernel<true> : seq_encode_f32_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_f32_kernel)");
-  seq_encode_f32_kernel<<<cfg->batch, kThreads, smem_bytes, st>>>(a);
+  if (saved)
+    seq_encode_f32_kernel<true><<<cfg->batch, kThreads, smem_bytes, st>>>(a);
+  else
+    seq_encode_f32_kernel<false><<<cfg->batch, kThreads, smem_bytes, st>>>(a);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_f32_kernel");
   return DMT_OK;
 }

@@ -1,0 +1,634 @@
+// dmt_seq_encode_bwd (fp32): backward of one behaviour sequence's encoder/decoder
+// (TransformerModel.py:84-171, TransformerModel_util.py:11-108,160-235) from the activations the training
+// forward saved.  Row-batched pipeline:
+//
+//   d(interest) -> [LN bwd -> FF bwd (2 GEMMs) -> LN bwd -> single-query attention bwd -> dD, dMemory] per decoder block
+//               -> [LN bwd -> FF bwd -> LN bwd -> self-attention bwd (per sample) -> dX GEMM]          per encoder block
+//               -> token-row gradients (x sqrt(d)), position-table gradient, target-row gradients
+//
+// Weight gradients are  saved_activation^T x gradient  contractions over all tokens: grouped split-K
+// GEMMs with a fixed-order reduction (gemm_f32.cuh).  Nothing here uses floating-point atomics.
+#include "gemm_f32.cuh"
+#include "seq_train.cuh"
+
+namespace dmt {
+
+namespace {
+
+constexpr int kLnWarps = 8;
+constexpr int kLnMaxCols = 8;   // D <= 256
+
+struct LnBwdArgs {
+  const float* z;      // LayerNorm input rows
+  const float* dy;
+  const float* gamma;
+  float* dz;
+  float* partial;      // [gridDim.x][2*D]: per-CTA sums of dy*xhat | dy
+  int64_t ldz, lddy, lddz, rows;
+  int D;
+};
+
+// One warp per row: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma
+// (backward of TransformerModel_util.py:58-78, biased variance, eps inside the sqrt).
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const __grid_constant__ LnBwdArgs a) {
+  __shared__ float red[kLnWarps][2 * 32 * kLnMaxCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = a.D;
+  float gam[kLnMaxCols], dg[kLnMaxCols], db[kLnMaxCols];
+#pragma unroll
+  for (int i = 0; i < kLnMaxCols; ++i) {
+    const int c = lane + 32 * i;
+    gam[i] = c < D ? __ldg(a.gamma + c) : 0.f;
+    dg[i] = db[i] = 0.f;
+  }
+  const float invD = 1.0f / (float)D;
+  for (int64_t r = (int64_t)blockIdx.x * kLnWarps + warp; r < a.rows; r += (int64_t)gridDim.x * kLnWarps) {
+    float v[kLnMaxCols], dy[kLnMaxCols];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxCols; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < D ? __ldg(a.z + r * a.ldz + c) : 0.f;
+      dy[i] = c < D ? __ldg(a.dy + r * a.lddy + c) : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxCols; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float dl = v[i] - mean;
+        q += dl * dl;
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * invD + kLnEps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxCols; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        v[i] = (v[i] - mean) * rstd;      // xhat
+        const float g = dy[i] * gam[i];
+        sg += g;
+        sgx += g * v[i];
+        dg[i] += dy[i] * v[i];
+        db[i] += dy[i];
+      }
+    }
+    sg = warp_sum(sg) * invD;
+    sgx = warp_sum(sgx) * invD;
+#pragma unroll
+    for (int i = 0; i < kLnMaxCols; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) a.dz[r * a.lddz + c] = rstd * (dy[i] * gam[i] - sg - v[i] * sgx);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLnMaxCols; ++i) {
+    const int c = lane + 32 * i;
+    if (c < D) {
+      red[warp][c] = dg[i];
+      red[warp][D + c] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += kLnWarps * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+    a.partial[(int64_t)blockIdx.x * 2 * D + c] = s;
+  }
+}
+
+// dgamma[c] += sum_cta partial[cta][c]; dbeta[c] += sum_cta partial[cta][D + c] (fixed order).
+__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int n_cta, int D, float* dgamma,
+                                       float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * D) return;
+  float s = 0.f;
+  for (int i = 0; i < n_cta; ++i) s += partial[(int64_t)i * 2 * D + c];
+  if (c < D)
+    dgamma[c] += s;
+  else
+    dbeta[c - D] += s;
+}
+
+int ln_bwd_launch(const float* z, int64_t ldz, const float* dy, int64_t lddy, const float* gamma, float* dz,
+                  int64_t lddz, int64_t rows, int D, float* partial, int grid, float* dgamma, float* dbeta,
+                  cudaStream_t st) {
+  LnBwdArgs a{z, dy, gamma, dz, partial, ldz, lddy, lddz, rows, D};
+  ln_bwd_kernel<<<grid, kLnWarps * 32, 0, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("ln_bwd_kernel");
+  ln_param_reduce_kernel<<<(2 * D + 127) / 128, 128, 0, st>>>(partial, grid, D, dgamma, dbeta);
+  DMT_CUDA_LAUNCH_CHECK("ln_param_reduce_kernel");
+  return DMT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Self-attention backward, one CTA per sample (TransformerModel_util.py:11-56 + head split :193-201).
+//   P = softmax(Q_h K_h^T / sqrt(dk)) over the L valid keys (recomputed), O_h = P V_h
+//   dV_h = P^T dO_h ; dP = dO_h V_h^T ; dS = P * (dP - rowsum(P * dP)) / sqrt(dk)
+//   dQ_h = dS K_h ; dK_h = dS^T Q_h
+struct AttnBwdArgs {
+  const float* qkv;        // [T, 3D]
+  const float* d_o;        // [T, D] gradient of the attention context (= LayerNorm-input gradient)
+  float* dqkv;             // [T, 3D]
+  const int32_t* offsets;  // [B+1]
+  int D, H, LP;
+};
+
+constexpr int kAttnThreads = 256;
+
+__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = a.D, H = a.H, LP = a.LP, dk = D / H, ld = D + 4, lds = LP + 1;
+  float* Q = sm;
+  float* K = Q + LP * ld;
+  float* V = K + LP * ld;
+  float* dO = V + LP * ld;
+  float* P = dO + LP * ld;      // [LP][lds]
+  float* dS = P + LP * lds;     // [LP][lds]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t off = __ldg(a.offsets + b);
+  const int len_all = __ldg(a.offsets + b + 1) - (int)off;
+  const int L = min(len_all, LP);
+  for (int i = tid; i < (len_all - L) * 3 * D; i += kAttnThreads) a.dqkv[(off + L) * 3 * D + i] = 0.f;
+  if (L == 0) return;
+  for (int i = tid; i < L * D; i += kAttnThreads) {
+    const int t = i / D, c = i - t * D;
+    const float* row = a.qkv + (off + t) * 3 * D;
+    Q[t * ld + c] = __ldg(row + c);
+    K[t * ld + c] = __ldg(row + D + c);
+    V[t * ld + c] = __ldg(row + 2 * D + c);
+    dO[t * ld + c] = __ldg(a.d_o + (off + t) * D + c);
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)dk);
+  for (int h = 0; h < H; ++h) {
+    const int hc = h * dk;
+    for (int i = tid; i < L * L; i += kAttnThreads) {
+      const int qi = i / L, kj = i - qi * L;
+      float s = 0.f, dp = 0.f;
+      for (int c = 0; c < dk; ++c) {
+        s = fmaf(Q[qi * ld + hc + c], K[kj * ld + hc + c], s);
+        dp = fmaf(dO[qi * ld + hc + c], V[kj * ld + hc + c], dp);
+      }
+      P[qi * lds + kj] = s * scale;
+      dS[qi * lds + kj] = dp;
+    }
+    __syncthreads();
+    for (int r = warp; r < L; r += kAttnThreads / 32) {
+      float m = -INFINITY;
+      for (int j = lane; j < L; j += 32) m = fmaxf(m, P[r * lds + j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < L; j += 32) {
+        const float e = expf(P[r * lds + j] - m);
+        P[r * lds + j] = e;
+        s += e;
+      }
+      const float inv = 1.0f / warp_sum(s);
+      float pd = 0.f;
+      for (int j = lane; j < L; j += 32) {
+        const float p = P[r * lds + j] * inv;
+        P[r * lds + j] = p;
+        pd = fmaf(p, dS[r * lds + j], pd);
+      }
+      pd = warp_sum(pd);
+      for (int j = lane; j < L; j += 32) dS[r * lds + j] = P[r * lds + j] * (dS[r * lds + j] - pd) * scale;
+    }
+    __syncthreads();
+    for (int i = tid; i < L * dk; i += kAttnThreads) {
+      const int t = i / dk, c = i - t * dk;
+      float dq = 0.f, dkk = 0.f, dv = 0.f;
+      for (int j = 0; j < L; ++j) {
+        dq = fmaf(dS[t * lds + j], K[j * ld + hc + c], dq);      // t = query row
+        dkk = fmaf(dS[j * lds + t], Q[j * ld + hc + c], dkk);    // t = key row
+        dv = fmaf(P[j * lds + t], dO[j * ld + hc + c], dv);
+      }
+      float* row = a.dqkv + (off + t) * 3 * D + hc + c;
+      row[0] = dq;
+      row[D] = dkk;
+      row[2 * D] = dv;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Vanilla (decoder) attention backward: ONE query per sample over the L memory rows
+// (TransformerModel.py:157-166).  od_h = sum_j p[h][j] Vd[j,h]; the probabilities were saved.
+struct DecAttnBwdArgs {
+  const float* qd;         // [B, D]
+  const float* kvd;        // [T, 2D]
+  const float* pd;         // [B, H, LP]
+  const float* d_od;       // [B, D] gradient of the context (= LayerNorm-input gradient)
+  float* dqd;              // [B, D]
+  float* dkvd;             // [T, 2D]
+  const int32_t* offsets;
+  int D, H, LP;
+};
+
+constexpr int kDecThreads = 128;
+
+__global__ void __launch_bounds__(kDecThreads) dec_attn_bwd_kernel(const __grid_constant__ DecAttnBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int D = a.D, H = a.H, LP = a.LP, dk = D / H, ld = 2 * D + 1;
+  float* KV = sm;                  // [LP][2D+1]
+  float* q = KV + LP * ld;         // [D]
+  float* dod = q + D;              // [D]
+  float* p = dod + D;              // [H][LP]
+  float* ds = p + H * LP;          // [H][LP]
+  float* rsum = ds + H * LP;       // [H]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t off = __ldg(a.offsets + b);
+  const int len_all = __ldg(a.offsets + b + 1) - (int)off;
+  const int L = min(len_all, LP);
+  for (int i = tid; i < (len_all - L) * 2 * D; i += kDecThreads) a.dkvd[(off + L) * 2 * D + i] = 0.f;
+  for (int i = tid; i < L * 2 * D; i += kDecThreads) {
+    const int t = i / (2 * D), c = i - t * 2 * D;
+    KV[t * ld + c] = __ldg(a.kvd + (off + t) * 2 * D + c);
+  }
+  for (int c = tid; c < D; c += kDecThreads) {
+    q[c] = __ldg(a.qd + (int64_t)b * D + c);
+    dod[c] = __ldg(a.d_od + (int64_t)b * D + c);
+  }
+  for (int i = tid; i < H * LP; i += kDecThreads) p[i] = __ldg(a.pd + (int64_t)b * H * LP + i);
+  __syncthreads();
+  for (int i = tid; i < H * L; i += kDecThreads) {
+    const int h = i / L, j = i - h * L;
+    float dp = 0.f;
+    for (int c = 0; c < dk; ++c) dp = fmaf(dod[h * dk + c], KV[j * ld + D + h * dk + c], dp);
+    ds[h * LP + j] = dp;
+  }
+  __syncthreads();
+  if (tid < H) {
+    float r = 0.f;
+    for (int j = 0; j < L; ++j) r = fmaf(p[tid * LP + j], ds[tid * LP + j], r);
+    rsum[tid] = r;
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)dk);
+  for (int i = tid; i < H * L; i += kDecThreads) {
+    const int h = i / L, j = i - h * L;
+    ds[h * LP + j] = p[h * LP + j] * (ds[h * LP + j] - rsum[h]) * scale;
+  }
+  __syncthreads();
+  for (int i = tid; i < L * D; i += kDecThreads) {
+    const int j = i / D, c = i - j * D, h = c / dk;
+    float* row = a.dkvd + (off + j) * 2 * D;
+    row[c] = ds[h * LP + j] * q[c];
+    row[D + c] = p[h * LP + j] * dod[c];
+  }
+  for (int c = tid; c < D; c += kDecThreads) {
+    const int h = c / dk;
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc = fmaf(ds[h * LP + j], KV[j * ld + c], acc);
+    a.dqd[(int64_t)b * D + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Position-table gradient (positional_encoding_learn, TransformerModel_util.py:281-316): the encoder
+// input is rows * sqrt(d) + P[t], so dP[t] = sum_b dH0[b, t] = (1/sqrt(d)) * sum_b d_tokens[b, t].
+// One CTA per position, fixed summation order.
+struct PosGradArgs {
+  const float* d_tokens;   // [T, D]
+  const int32_t* offsets;
+  float* dpos;             // [maxlen, D]  +=
+  float inv_scale;
+  int B, D, LP;
+};
+
+__global__ void __launch_bounds__(256) pos_grad_kernel(const __grid_constant__ PosGradArgs a) {
+  __shared__ float red[256];
+  const int t = blockIdx.x, D = a.D;
+  const int groups = 256 / D > 0 ? 256 / D : 1;
+  const int c = threadIdx.x % D, grp = threadIdx.x / D;
+  float s = 0.f;
+  if (grp < groups && threadIdx.x < groups * D) {
+    for (int b = grp; b < a.B; b += groups) {
+      const int off = __ldg(a.offsets + b);
+      const int len = min(__ldg(a.offsets + b + 1) - off, a.LP);
+      if (t < len) s += __ldg(a.d_tokens + ((int64_t)off + t) * D + c);
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float tot = 0.f;
+    for (int gi = 0; gi < groups; ++gi) tot += red[gi * D + threadIdx.x];
+    a.dpos[(int64_t)t * D + threadIdx.x] += tot * a.inv_scale;
+  }
+}
+
+__global__ void scale_copy_kernel(const float* __restrict__ src, int64_t lds_, float* __restrict__ dst, int64_t ldd,
+                                  int64_t rows, int D, float alpha) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  const int64_t r = i / D;
+  const int c = (int)(i - r * D);
+  dst[r * ldd + c] = src[r * lds_ + c] * alpha;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct BwdWs {
+  float *dh[2];     // [T, d]  gradient of an encoder block output / input (ping-pong)
+  float *dz2, *da, *dz1;   // [T, d]
+  float *df1;       // [T, dff]
+  float *dqkv;      // [T, 3d]
+  float *dkvd;      // [T, 2d]
+  float *dd[2];     // [B, d]  gradient of a decoder block output / input
+  float *dz2d, *dad, *dz1d, *dqd;   // [B, d]
+  float *df1d;      // [B, dff]
+  float *ln_partial;                // [ln_grid][2d]
+  float *gpart[8];  // split-K scratch of the weight-gradient contractions (one block's worth)
+  int ln_grid;
+  int splits_T[8], splits_B[8];
+};
+
+// weight-gradient problems of one block: index -> (M, N)
+//   0 W1 [d,dff]  1 W2 [dff,d]  2..4 Wq/Wk/Wv [d,d]
+inline void wg_shape(const dmt_seq_cfg& c, int i, int* M, int* N) {
+  const int d = c.d_model, dff = c.d_ff;
+  switch (i) {
+    case 0: *M = d; *N = dff; break;
+    case 1: *M = dff; *N = d; break;
+    default: *M = d; *N = d; break;
+  }
+}
+
+size_t bwd_carve(const dmt_seq_cfg& c, int64_t T, void* base, BwdWs* out) {
+  Carver cv(base);
+  BwdWs w{};
+  const size_t d = c.d_model, dff = c.d_ff, B = c.batch;
+  w.dh[0] = cv.take(T * d);
+  w.dh[1] = cv.take(T * d);
+  w.dz2 = cv.take(T * d);
+  w.da = cv.take(T * d);
+  w.dz1 = cv.take(T * d);
+  w.df1 = cv.take(T * dff);
+  w.dqkv = cv.take(T * 3 * d);
+  w.dkvd = cv.take(T * 2 * d);
+  w.dd[0] = cv.take(B * d);
+  w.dd[1] = cv.take(B * d);
+  w.dz2d = cv.take(B * d);
+  w.dad = cv.take(B * d);
+  w.dz1d = cv.take(B * d);
+  w.dqd = cv.take(B * d);
+  w.df1d = cv.take(B * dff);
+  w.ln_grid = 2 * sm_count_cached();
+  w.ln_partial = cv.take((size_t)w.ln_grid * 2 * d);
+  for (int i = 0; i < 5; ++i) {
+    int M, N;
+    wg_shape(c, i, &M, &N);
+    w.splits_T[i] = gemm_pick_splits(M, N, T);
+    w.splits_B[i] = gemm_pick_splits(M, N, (int64_t)B);
+    const int s = w.splits_T[i] > w.splits_B[i] ? w.splits_T[i] : w.splits_B[i];
+    w.gpart[i] = cv.take((size_t)s * (M + 1) * N);
+  }
+  if (out) *out = w;
+  return cv.off + 256;
+}
+
+// dW (+)= act^T grad over `rows` rows, db (+)= column sums of grad
+inline void wgrad_prob(GemmProb& p, const float* act, int64_t ld_act, const float* grad, int64_t ld_grad, int64_t rows,
+                       int M, int N, const dmt_dense& g, int splits, float* partial) {
+  gemm_prob_init(p);
+  p.n_parts = 1;
+  p.part[0] = GemmPart{act, grad, ld_act, ld_grad, (int)rows, 0};
+  p.M = M;
+  p.N = N;
+  p.transA = 1;
+  p.transB = 0;
+  p.C = const_cast<float*>(g.w);
+  p.ldc = N;
+  p.accumulate = 1;
+  p.colsum = const_cast<float*>(g.b);
+  p.colsum_accumulate = 1;
+  p.splits = splits;
+  p.partial = partial;
+}
+
+// C[rows, N] = epilogue(grad[rows, K] * W^T), W stored [N, K] (TF kernel [in = N, out = K])
+inline void dgrad_prob(GemmProb& p, int n_parts, const float* const* grad, const int64_t* ld_grad,
+                       const float* const* W, const int* K, int64_t rows, int N, float* C, int64_t ldc) {
+  gemm_prob_init(p);
+  p.n_parts = n_parts;
+  for (int i = 0; i < n_parts; ++i) p.part[i] = GemmPart{grad[i], W[i], ld_grad[i], (int64_t)K[i], K[i], 0};
+  p.M = (int)rows;
+  p.N = N;
+  p.transA = 0;
+  p.transB = 1;
+  p.C = C;
+  p.ldc = ldc;
+}
+
+}  // namespace
+
+size_t seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t T) { return bwd_carve(*cfg, T, nullptr, nullptr); }
+
+int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, int64_t T,
+                   const SeqSaved& sv, const float* d_out, int64_t d_out_ld, const dmt_seq_grads* g, float* d_tokens,
+                   float* d_target, void* ws_base, cudaStream_t st) {
+  const dmt_seq_cfg& c = *cfg;
+  DMT_REQUIRE(T < (1ll << 31), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: %lld tokens", (long long)T);
+  BwdWs ws;
+  bwd_carve(c, T, ws_base, &ws);
+  const int d = c.d_model, dff = c.d_ff, B = c.batch, H = c.num_heads, LP = seq_lp(c);
+  const float sqrt_d = sqrtf((float)d);
+  const int32_t* offsets = in->offsets[c.n_feats - 1];
+  int rc;
+
+  // ------------------------------------------------------------------ decoder blocks, last to first
+  const float* dcur = d_out;       // gradient of the current block's output [B, d]
+  int64_t dcur_ld = d_out_ld;
+  bool dmem_written = false;
+  float* dmem = ws.dh[0];          // gradient of the encoder memory [T, d]
+  for (int blk = c.n_dec_blocks - 1; blk >= 0; --blk) {
+    const dmt_attn_weights& aw = w->dec_attn[blk];
+    const dmt_ff_weights& fw = w->ff[blk];
+    const dmt_attn_weights& ag = g->dec_attn[blk];
+    const dmt_ff_weights& fg = g->ff[blk];
+    // FF LayerNorm
+    rc = ln_bwd_launch(sv.z2d[blk], d, dcur, dcur_ld, fw.ln.gamma, ws.dz2d, d, B, d, ws.ln_partial, ws.ln_grid,
+                       const_cast<float*>(fg.ln.gamma), const_cast<float*>(fg.ln.beta), st);
+    if (rc) return rc;
+    {   // dF1 = (dZ2 W2^T) * (F1 > 0)
+      GemmGroup grp{};
+      const float* gr[1] = {ws.dz2d};
+      const int64_t lg[1] = {d};
+      const float* W[1] = {fw.w2.w};
+      const int K[1] = {d};
+      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, dff, ws.df1d, dff);
+      grp.p[0].mask = sv.f1d[blk];
+      grp.p[0].ld_mask = dff;
+      grp.n = 1;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    {   // dA = dZ2 + dF1 W1^T
+      GemmGroup grp{};
+      const float* gr[1] = {ws.df1d};
+      const int64_t lg[1] = {dff};
+      const float* W[1] = {fw.w1.w};
+      const int K[1] = {dff};
+      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, ws.dad, d);
+      grp.p[0].addend = ws.dz2d;
+      grp.p[0].ld_add = d;
+      grp.n = 1;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    // attention LayerNorm: input z1d = context + block input
+    rc = ln_bwd_launch(sv.z1d[blk], d, ws.dad, d, aw.ln.gamma, ws.dz1d, d, B, d, ws.ln_partial, ws.ln_grid,
+                       const_cast<float*>(ag.ln.gamma), const_cast<float*>(ag.ln.beta), st);
+    if (rc) return rc;
+    {
+      DecAttnBwdArgs a{sv.qd[blk], sv.kvd[blk], sv.pd[blk], ws.dz1d, ws.dqd, ws.dkvd, offsets, d, H, LP};
+      const size_t smem = ((size_t)LP * (2 * d + 1) + 2 * d + 2 * H * LP + H + 8) * sizeof(float);
+      cudaError_t e = cudaFuncSetAttribute(dec_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_attn_bwd_kernel)");
+      dec_attn_bwd_kernel<<<B, kDecThreads, smem, st>>>(a);
+      DMT_CUDA_LAUNCH_CHECK("dec_attn_bwd_kernel");
+    }
+    float* dnext = ws.dd[blk & 1];
+    {   // dD_in = dZ1 + dQd Wq^T (x sqrt(d) into d_target for the first block) ; dMemory (+)= dKd Wk^T + dVd Wv^T
+      GemmGroup grp{};
+      const float* gr[1] = {ws.dqd};
+      const int64_t lg[1] = {d};
+      const float* W[1] = {aw.q.w};
+      const int K[1] = {d};
+      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, blk == 0 ? d_target : dnext, d);
+      grp.p[0].addend = ws.dz1d;
+      grp.p[0].ld_add = d;
+      if (blk == 0) grp.p[0].alpha = sqrt_d;
+      grp.n = 1;
+      if (T > 0) {
+        const float* gr2[2] = {ws.dkvd, ws.dkvd + d};
+        const int64_t lg2[2] = {2 * d, 2 * d};
+        const float* W2[2] = {aw.k.w, aw.v.w};
+        const int K2[2] = {d, d};
+        dgrad_prob(grp.p[1], 2, gr2, lg2, W2, K2, T, d, dmem, d);
+        grp.p[1].accumulate = dmem_written ? 1 : 0;
+        grp.n = 2;
+      }
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+      dmem_written = true;
+    }
+    {   // weight gradients of this block
+      GemmGroup grp{};
+      int n = 0;
+      wgrad_prob(grp.p[n++], sv.ad[blk], d, ws.df1d, dff, B, d, dff, fg.w1, ws.splits_B[0], ws.gpart[0]);
+      wgrad_prob(grp.p[n++], sv.f1d[blk], dff, ws.dz2d, d, B, dff, d, fg.w2, ws.splits_B[1], ws.gpart[1]);
+      wgrad_prob(grp.p[n++], sv.din[blk], d, ws.dqd, d, B, d, d, ag.q, ws.splits_B[2], ws.gpart[2]);
+      if (T > 0) {
+        const float* mem = sv.hin[c.n_enc_blocks];
+        wgrad_prob(grp.p[n++], mem, d, ws.dkvd, 2 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
+        wgrad_prob(grp.p[n++], mem, d, ws.dkvd + d, 2 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
+      }
+      grp.n = n;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    dcur = dnext;
+    dcur_ld = d;
+  }
+  if (c.n_dec_blocks == 0) {   // interest = target * sqrt(d): no decoder variables, memory unused
+    scale_copy_kernel<<<(unsigned)(((int64_t)B * d + 255) / 256), 256, 0, st>>>(d_out, d_out_ld, d_target, d, B, d,
+                                                                               sqrt_d);
+    DMT_CUDA_LAUNCH_CHECK("scale_copy_kernel");
+  }
+  if (T == 0) return DMT_OK;
+  if (!dmem_written) {
+    cudaError_t e = cudaMemsetAsync(dmem, 0, (size_t)T * d * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dmem)");
+  }
+
+  // ------------------------------------------------------------------ encoder blocks, last to first
+  float* dh = dmem;
+  int ping = 0;
+  for (int blk = c.n_enc_blocks - 1; blk >= 0; --blk) {
+    const dmt_attn_weights& aw = w->enc_attn[blk];
+    const dmt_ff_weights& fw = w->ff[blk];
+    const dmt_attn_weights& ag = g->enc_attn[blk];
+    const dmt_ff_weights& fg = g->ff[blk];
+    rc = ln_bwd_launch(sv.z2[blk], d, dh, d, fw.ln.gamma, ws.dz2, d, T, d, ws.ln_partial, ws.ln_grid,
+                       const_cast<float*>(fg.ln.gamma), const_cast<float*>(fg.ln.beta), st);
+    if (rc) return rc;
+    {
+      GemmGroup grp{};
+      const float* gr[1] = {ws.dz2};
+      const int64_t lg[1] = {d};
+      const float* W[1] = {fw.w2.w};
+      const int K[1] = {d};
+      dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, dff, ws.df1, dff);
+      grp.p[0].mask = sv.f1[blk];
+      grp.p[0].ld_mask = dff;
+      grp.n = 1;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    {
+      GemmGroup grp{};
+      const float* gr[1] = {ws.df1};
+      const int64_t lg[1] = {dff};
+      const float* W[1] = {fw.w1.w};
+      const int K[1] = {dff};
+      dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, d, ws.da, d);
+      grp.p[0].addend = ws.dz2;
+      grp.p[0].ld_add = d;
+      grp.n = 1;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    rc = ln_bwd_launch(sv.z1[blk], d, ws.da, d, aw.ln.gamma, ws.dz1, d, T, d, ws.ln_partial, ws.ln_grid,
+                       const_cast<float*>(ag.ln.gamma), const_cast<float*>(ag.ln.beta), st);
+    if (rc) return rc;
+    {
+      AttnBwdArgs a{sv.qkv[blk], ws.dz1, ws.dqkv, offsets, d, H, LP};
+      const size_t smem = ((size_t)4 * LP * (d + 4) + 2 * LP * (LP + 1)) * sizeof(float);
+      DMT_REQUIRE(smem <= 227 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: attention tile needs %zu B", smem);
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_bwd_kernel)");
+      attn_bwd_kernel<<<B, kAttnThreads, smem, st>>>(a);
+      DMT_CUDA_LAUNCH_CHECK("attn_bwd_kernel");
+    }
+    ping ^= 1;
+    float* dhin = blk == 0 ? d_tokens : ws.dh[ping];
+    {   // dH_in = dZ1 + dQ Wq^T + dK Wk^T + dV Wv^T   (x sqrt(d) for the first block: row gradients)
+      GemmGroup grp{};
+      const float* gr[3] = {ws.dqkv, ws.dqkv + d, ws.dqkv + 2 * d};
+      const int64_t lg[3] = {3 * d, 3 * d, 3 * d};
+      const float* W[3] = {aw.q.w, aw.k.w, aw.v.w};
+      const int K[3] = {d, d, d};
+      dgrad_prob(grp.p[0], 3, gr, lg, W, K, T, d, dhin, d);
+      grp.p[0].addend = ws.dz1;
+      grp.p[0].ld_add = d;
+      if (blk == 0) grp.p[0].alpha = sqrt_d;
+      grp.n = 1;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    {
+      GemmGroup grp{};
+      int n = 0;
+      wgrad_prob(grp.p[n++], sv.a[blk], d, ws.df1, dff, T, d, dff, fg.w1, ws.splits_T[0], ws.gpart[0]);
+      wgrad_prob(grp.p[n++], sv.f1[blk], dff, ws.dz2, d, T, dff, d, fg.w2, ws.splits_T[1], ws.gpart[1]);
+      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv, 3 * d, T, d, d, ag.q, ws.splits_T[2], ws.gpart[2]);
+      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + d, 3 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
+      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + 2 * d, 3 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
+      grp.n = n;
+      if ((rc = gemm_group_launch(grp, st))) return rc;
+    }
+    dh = dhin;
+  }
+  if (c.n_enc_blocks == 0) {   // memory = encoder input
+    scale_copy_kernel<<<(unsigned)((T * d + 255) / 256), 256, 0, st>>>(dmem, d, d_tokens, d, T, d, sqrt_d);
+    DMT_CUDA_LAUNCH_CHECK("scale_copy_kernel");
+  }
+  {
+    PosGradArgs a{d_tokens, offsets, const_cast<float*>(g->pos), 1.0f / sqrt_d, B, d, LP};
+    DMT_REQUIRE(d <= 256, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: d_model %d > 256", d);
+    pos_grad_kernel<<<LP, 256, 0, st>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("pos_grad_kernel");
+  }
+  return DMT_OK;
+}
+
+}  // namespace dmt

@@ -71,9 +71,11 @@ class mmoe_transformer_unbias(object):
         return out
 
     # ------------------------------------------------------------------ weight descriptors
-    def _bind_weights(self):
-        plan, P = self.plan, self.params
-        self._seq_w = []
+    def _bind(self, P):
+        """Fill the POD descriptors from `P[name] -> tensor` (the parameters, or a gradient buffer with the
+        same layout)."""
+        plan = self.plan
+        seq_w = []
         for seq in plan.sequences:
             w = abi.SeqWeights()
             S = seq.scope
@@ -94,7 +96,7 @@ class mmoe_transformer_unbias(object):
                 w.ff[b].w1 = abi.dense(P[base + "/dense/kernel"], P[base + "/dense/bias"])
                 w.ff[b].w2 = abi.dense(P[base + "/dense_1/kernel"], P[base + "/dense_1/bias"])
                 w.ff[b].ln = abi.LayerNorm(abi.ptr(P[base + "/ln/gamma"]), abi.ptr(P[base + "/ln/beta"]))
-            self._seq_w.append(w)
+            seq_w.append(w)
 
         mw = abi.MmoeWeights()
         for e in range(plan.num_experts):
@@ -110,12 +112,14 @@ class mmoe_transformer_unbias(object):
                 mw.tower[t][l] = abi.dense(P[base + "/weights"], P[base + "/biases"])
             base = "DnnModel/%s/%s-output" % (name, name)
             mw.tower_out[t] = abi.dense(P[base + "/weights"], P[base + "/biases"])
-        self._mmoe_w = mw
 
         bw = abi.BiasWeights()
         for l in range(len(plan.hidden_units_bias) + 1):
             bw.layer[l] = abi.dense(P["DnnModel/layer_bias%d/kernel" % l], P["DnnModel/layer_bias%d/bias" % l])
-        self._bias_w = bw
+        return seq_w, mw, bw
+
+    def _bind_weights(self):
+        self._seq_w, self._mmoe_w, self._bias_w = self._bind(self.params)
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name, shape, dtype=torch.float32):
@@ -124,6 +128,14 @@ class mmoe_transformer_unbias(object):
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._buffers[key] = t
+        return t
+
+    def _scratch(self, name, nbytes):
+        """Grow-only byte buffer (sizes that depend on the number of tokens change every batch)."""
+        t = self._buffers.get(("scratch", name))
+        if t is None or t.numel() < nbytes:
+            t = torch.empty((int(nbytes * 1.25) + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.device)
+            self._buffers[("scratch", name)] = t
         return t
 
     def _dev(self, t):
@@ -136,7 +148,7 @@ class mmoe_transformer_unbias(object):
         async copy; a plain dict is copied tensor by tensor (tensors shared between features, e.g.
         the offsets of one sequence, are copied once)."""
         if isinstance(inputs, PackedBatch):
-            buf = self._buf("packed_in", ((inputs.nbytes + 4095) // 4096 * 4096,), torch.uint8)
+            buf = self._scratch("packed_in", inputs.nbytes)
             out = inputs.to(self.device, out=buf)
             out["__max_len__"] = inputs.max_len(self.plan)
             return out
@@ -204,17 +216,13 @@ class mmoe_transformer_unbias(object):
             self._prepared[seq_index] = (self.params_version, buf)
         return buf, nbytes
 
-    def seq_encode(self, inputs, seq_index, out, out_ld, batch):
-        """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld)."""
+    def _seq_cfg(self, inputs, seq, batch, precision):
         plan = self.plan
-        seq = plan.sequences[seq_index]
-        cfg = abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
-                         plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
-                         len(seq.user_features), self.precision, self._seq_len_hint(inputs, seq), 0)
-        ws_ptr, ws_bytes = None, 0
-        if self.precision == abi.PRECISION_BF16:
-            ws, ws_bytes = self._prepared_for(seq_index, cfg)
-            ws_ptr = ws.data_ptr()
+        return abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
+                          plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
+                          len(seq.user_features), precision, self._seq_len_hint(inputs, seq), 0)
+
+    def _seq_input(self, inputs, seq, batch):
         si = abi.SeqInput()
         keep = []
         for f, (uf, itf) in enumerate(zip(seq.user_features, seq.item_features)):
@@ -233,6 +241,18 @@ class mmoe_transformer_unbias(object):
             si.ids[f] = abi.ptr(u.values)
             si.offsets[f] = abi.ptr(u.offsets)
             si.item_ids[f] = abi.ptr(it.values)
+        return si, keep
+
+    def seq_encode(self, inputs, seq_index, out, out_ld, batch):
+        """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld)."""
+        plan = self.plan
+        seq = plan.sequences[seq_index]
+        cfg = self._seq_cfg(inputs, seq, batch, self.precision)
+        ws_ptr, ws_bytes = None, 0
+        if self.precision == abi.PRECISION_BF16:
+            ws, ws_bytes = self._prepared_for(seq_index, cfg)
+            ws_ptr = ws.data_ptr()
+        si, keep = self._seq_input(inputs, seq, batch)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with self._Stage(self, "seq_encode", 1):
             abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
@@ -259,7 +279,7 @@ class mmoe_transformer_unbias(object):
                 abi.check(self.lib.dmt_pool_mean_fwd(batch, n, sub, out.data_ptr(), out.stride(0), stream))
         return keep
 
-    def mmoe(self, x, batch, logits):
+    def _mmoe_cfg(self, batch, precision):
         plan = self.plan
         cfg = abi.MmoeCfg()
         cfg.batch, cfg.in_dim, cfg.n_experts = batch, plan.mmoe_in, plan.num_experts
@@ -270,7 +290,11 @@ class mmoe_transformer_unbias(object):
         cfg.n_tower_layers = len(plan.hidden_units_task)
         for i, u in enumerate(plan.hidden_units_task):
             cfg.tower_units[i] = u
-        cfg.precision = self.precision
+        cfg.precision = precision
+        return cfg
+
+    def mmoe(self, x, batch, logits):
+        cfg = self._mmoe_cfg(batch, self.precision)
         nbytes = self.lib.dmt_mmoe_workspace_bytes(C.byref(cfg))
         ws = self._buf("mmoe_ws", ((nbytes + 255) // 256 * 256,), torch.uint8)
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -386,6 +410,135 @@ class mmoe_transformer_unbias(object):
         if want_probs or want_grads:
             return out, probs, dlog
         return out
+
+    # ------------------------------------------------------------------ A13: gradients
+    def compute_gradients(self, inputs, mask=None, loss_unbias_method=None, loss_ctr_rel_method=None):
+        """`optimizer.compute_gradients(loss)` of the reference's training graph (run_dnn.py:154-181): one
+        forward that saves activations + the backward, fp32.  Returns `(loss, Gradients)`; the loss is the
+        batch mean, so averaging `Gradients` over data-parallel ranks equals `average_gradients`
+        (run_dnn.py:45-80)."""
+        from ..optim import Gradients, LookupGrad
+        plan, lib = self.plan, self.lib
+        if plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias):
+            raise NotImplementedError("training-mode dropout is not built yet; set transformer_dropout_rate and "
+                                      "dropout_rate_bias to 0")
+        inputs = self.stage_inputs(inputs)
+        mask = self._dev(inputs["mask"] if mask is None else mask)
+        feats = inputs["features"] if plan.is_use_feature else None
+        batch = inputs[plan.pooled[0].feature].offsets.numel() - 1
+        if mask.dtype != torch.float32 or tuple(mask.shape) != (batch, 5):
+            raise ValueError("mask must be fp32 [%d, 5]" % batch)
+        mask = mask.contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        F32 = abi.PRECISION_F32
+
+        if getattr(self, "_grad_dense", None) is None:
+            self._grad_dense = torch.zeros_like(self.params.dense)
+            gviews = {sp.name: self._grad_dense[sp.offset:sp.offset + sp.numel].view(sp.shape)
+                      for sp in self.params.specs}
+            self._seq_g, self._mmoe_g, self._bias_g = self._bind(gviews)
+            self._grad_views = gviews
+        g_dense = self._grad_dense
+        g_dense.zero_()
+
+        # ---- forward (activations saved)
+        x_ld = (plan.mmoe_in + 3) // 4 * 4
+        x = self._buf("x", (batch, x_ld))
+        keep = []
+        if feats is not None:
+            if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
+                raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
+            feats = feats.contiguous()
+            with self._Stage(self, "copy_dense", 1):
+                abi.check(lib.dmt_copy_dense_features(feats.data_ptr(), batch, plan.feature_dim,
+                                                      x.data_ptr(), x_ld, stream))
+            keep.append(feats)
+        keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
+        seq_state = []
+        for s, seq in enumerate(plan.sequences):
+            cfg = self._seq_cfg(inputs, seq, batch, F32)
+            si, kp = self._seq_input(inputs, seq, batch)
+            keep += kp
+            users = [self._sparse(inputs, uf) for uf in seq.user_features]
+            n_tok = users[-1].values.numel()
+            if any(u.values.numel() != n_tok for u in users):
+                raise ValueError("sequence %d: the id features of one behaviour sequence must have equal lengths" % s)
+            nbytes = lib.dmt_seq_saved_bytes(C.byref(cfg), n_tok)
+            saved = self._scratch("seq_saved_%d" % s, nbytes)
+            col = plan.interest_col + s * plan.d_model
+            with self._Stage(self, "seq_encode_train", 1):
+                abi.check(lib.dmt_seq_encode_fwd_train(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]),
+                                                       x.data_ptr() + 4 * col, x_ld, n_tok, saved.data_ptr(),
+                                                       saved.numel(), stream))
+            seq_state.append((cfg, si, users, n_tok, saved, col))
+        mcfg = self._mmoe_cfg(batch, F32)
+        mws_bytes = lib.dmt_mmoe_workspace_bytes(C.byref(mcfg))
+        mws = self._buf("mmoe_ws_f32", ((mws_bytes + 255) // 256 * 256,), torch.uint8)
+        logits = self._buf("logits", (plan.num_tasks, batch))
+        with self._Stage(self, "mmoe", mcfg.n_layers + 1):
+            abi.check(lib.dmt_mmoe_fwd(C.byref(mcfg), C.byref(self._mmoe_w), x.data_ptr(), x_ld, logits.data_ptr(),
+                                       mws.data_ptr(), mws_bytes, None, stream))
+        bias_in = self._buf("bias_in", (batch, plan.bias_width))
+        keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
+        y_bias = self._buf("y_bias", (batch,))
+        bcfg = self._bias_cfg(batch, loss_unbias_method=loss_unbias_method, loss_ctr_rel_method=loss_ctr_rel_method)
+        loss = self._buf("loss", (1,))
+        dlog = self._buf("dlogits", (3, batch))
+        scratch = self._buf("loss_scratch", (lib.dmt_loss_scratch_bytes(batch),), torch.uint8)
+        with self._Stage(self, "bias_loss", 2):
+            abi.check(lib.dmt_bias_loss_fwd(C.byref(bcfg), C.byref(self._bias_w), bias_in.data_ptr(),
+                                            bias_in.stride(0), logits.data_ptr(), mask.data_ptr(), y_bias.data_ptr(),
+                                            None, loss.data_ptr(), dlog.data_ptr(), scratch.data_ptr(), stream))
+
+        # ---- backward
+        d_bias_in = self._buf("d_bias_in", (batch, plan.bias_width))
+        nb = lib.dmt_bias_bwd_workspace_bytes(C.byref(bcfg))
+        bws = self._buf("bias_bwd_ws", ((nb + 255) // 256 * 256,), torch.uint8)
+        with self._Stage(self, "bias_bwd", 3):
+            abi.check(lib.dmt_bias_bwd(C.byref(bcfg), C.byref(self._bias_w), bias_in.data_ptr(), bias_in.stride(0),
+                                       dlog[2].data_ptr(), C.byref(self._bias_g), d_bias_in.data_ptr(),
+                                       d_bias_in.stride(0), bws.data_ptr(), bws.numel(), stream))
+        dx = self._buf("dx", (batch, x_ld))
+        nb = lib.dmt_mmoe_bwd_workspace_bytes(C.byref(mcfg))
+        mbws = self._buf("mmoe_bwd_ws", ((nb + 255) // 256 * 256,), torch.uint8)
+        col0 = plan.feature_dim if plan.is_use_feature else 0
+        with self._Stage(self, "mmoe_bwd", 4 + 4 * mcfg.n_layers):
+            abi.check(lib.dmt_mmoe_bwd(C.byref(mcfg), C.byref(self._mmoe_w), x.data_ptr(), x_ld, mws.data_ptr(),
+                                       dlog.data_ptr(), C.byref(self._mmoe_g), dx.data_ptr(), x_ld, col0,
+                                       mbws.data_ptr(), mbws.numel(), stream))
+        lookups = {}
+
+        def add(scope, lg):
+            lookups.setdefault(scope, []).append(lg)
+
+        for p in plan.pooled:
+            sp = self._sparse(inputs, p.feature)
+            add(plan.tables[p.table].scope, LookupGrad(sp.values, dx, p.col, 0, sp.offsets, sp.weights, True))
+        for p in plan.bias_pooled:
+            sp = self._sparse(inputs, p.feature)
+            add(plan.bias_tables[p.table].scope,
+                LookupGrad(sp.values, d_bias_in, p.col, 0, sp.offsets, sp.weights, True))
+        id_off = -1 if plan.zero_pad else 0
+        for s, seq in enumerate(plan.sequences):
+            cfg, si, users, n_tok, saved, col = seq_state[s]
+            d_tok = self._scratch("d_tokens_%d" % s, max(n_tok, 1) * plan.d_model * 4)
+            d_tok = d_tok[:max(n_tok, 1) * plan.d_model * 4].view(torch.float32).view(max(n_tok, 1), plan.d_model)
+            d_tar = self._buf("d_target_%d" % s, (batch, plan.d_model))
+            nb = lib.dmt_seq_bwd_workspace_bytes(C.byref(cfg), n_tok)
+            sws = self._scratch("seq_bwd_ws", nb)
+            with self._Stage(self, "seq_bwd", 30):
+                abi.check(lib.dmt_seq_encode_bwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]), n_tok,
+                                                 saved.data_ptr(), saved.numel(), dx.data_ptr() + 4 * col, x_ld,
+                                                 C.byref(self._seq_g[s]), d_tok.data_ptr(), d_tar.data_ptr(),
+                                                 sws.data_ptr(), sws.numel(), stream))
+            for f, u in enumerate(users):
+                scope = plan.tables[seq.tables[f]].scope
+                if n_tok:
+                    add(scope, LookupGrad(u.values, d_tok, seq.col_offsets[f], id_off))
+                it = self._sparse(inputs, seq.item_features[f])
+                add(scope, LookupGrad(it.values, d_tar, seq.col_offsets[f], id_off))
+        self._keep_train = (keep, seq_state, inputs)
+        return loss[0], Gradients(g_dense, lookups, self._grad_views)
 
     def l2_norm(self, inputs):
         raise NotImplementedError("l2_norm is gated off by wnd_wd = 0.0 in dmt.conf (run_dnn.py:174)")

@@ -41,6 +41,38 @@ class LookupGrad:
         return g
 
 
+class Gradients(object):
+    """What `compute_gradients` hands to the optimizer: `dense` is a flat buffer laid out like
+    `ParamStore.dense` (one allreduce), `lookups` maps a table's TF variable name to the lookups that feed it
+    (the IndexedSlices of the reference, run_dnn.py:63-72, kept sparse), `views` names the dense slices."""
+
+    def __init__(self, dense, lookups, views):
+        self.dense, self.lookups, self.views = dense, lookups, views
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+    def table_dense(self, store, name, grad_scale=1.0):
+        """Densified gradient of one table (tests / small tables only)."""
+        table = store.tables[name]
+        out = torch.zeros_like(table, dtype=torch.float64)
+        for lg in self.lookups.get(name, []):
+            ids = lg.ids.long()
+            g = lg.grad[:, lg.grad_col:lg.grad_col + table.shape[1]].double()
+            if lg.offsets is not None:
+                lens = (lg.offsets[1:] - lg.offsets[:-1]).long()
+                seg = torch.repeat_interleave(torch.arange(lens.numel(), device=ids.device), lens)
+                w = torch.ones_like(ids, dtype=torch.float64) if lg.weights is None else lg.weights.double()
+                if lg.mean:
+                    wsum = torch.zeros(lens.numel(), dtype=torch.float64, device=ids.device).index_add_(0, seg, w)
+                    w = w / wsum[seg]
+                g = g[seg] * w[:, None]
+            rows = ids + lg.id_offset
+            ok = (rows >= 0) & (rows < table.shape[0])
+            out.index_add_(0, rows[ok], g[ok])
+        return out * grad_scale
+
+
 class TFAdam(object):
     def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
         self.model = model
@@ -64,6 +96,14 @@ class TFAdam(object):
 
     def begin_step(self):
         self.t += 1
+
+    def apply_gradients(self, grads, lr=None, grad_scale=1.0):
+        """`optimizer.apply_gradients` (run_dnn.py:203-207): one TF-Adam step over every variable; tables
+        without a lookup this step still decay (dense semantics)."""
+        self.begin_step()
+        self.step_dense(grads.dense, lr=lr, grad_scale=grad_scale)
+        for name in self.store.tables:
+            self.step_table(name, grads.lookups.get(name, []), lr=lr, grad_scale=grad_scale)
 
     def step_dense(self, grad_flat, lr=None, grad_scale=1.0):
         cfg = self._cfg(lr)

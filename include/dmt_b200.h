@@ -38,7 +38,7 @@ extern "C" {
 #define DMT_API __attribute__((visibility("default")))
 #endif
 
-#define DMT_ABI_VERSION 2
+#define DMT_ABI_VERSION 3
 
 #define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
 #define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
@@ -247,6 +247,51 @@ DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weigh
                               const float* bias_in, int64_t bias_ld, const float* logits,
                               const float* mask, float* y_bias, float* probs, float* loss,
                               float* dlogits, void* loss_scratch, void* stream);
+
+/* ---- A13: training forward / backward ----------------------------------------------
+ * tf.gradients of the graph built by inference + loss_multi_task_unbias (run_dnn.py:181,
+ * compute_gradients).  fp32 arithmetic.  The training forward writes the activations the backward needs
+ * into a caller-owned `saved` buffer (HBM is cheap on this part: ~3.6 KB per token); the backward is a
+ * short pipeline of row-batched kernels (LayerNorm / attention backward, grouped GEMMs with fixed-order
+ * split-K) that ACCUMULATES every parameter gradient into the buffers named by a `*_grads` descriptor --
+ * same layout as the weight descriptor, pointing into a gradient buffer the caller zeroed at the start of
+ * the step (the feed-forward variables are shared by encoder and decoder block i, so they receive two
+ * contributions).  No floating-point atomics: gradients are run-to-run deterministic.
+ * Dropout sites are inactive (rate 0 / eval mode), as in the forward. */
+typedef dmt_seq_weights dmt_seq_grads;   /* pointers are written (+=) */
+typedef dmt_mmoe_weights dmt_mmoe_grads;
+typedef dmt_bias_weights dmt_bias_grads;
+
+/* n_tokens = nnz of the sequence's id features (all pairs of one sequence have equal lengths in the data). */
+DMT_API size_t dmt_seq_saved_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens);
+DMT_API int dmt_seq_encode_fwd_train(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w,
+                                     float* out, int64_t out_ld, int64_t n_tokens, void* saved,
+                                     size_t saved_bytes, void* stream);
+DMT_API size_t dmt_seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens);
+/* d_out     [B, d_model] (row stride d_out_ld): dLoss/d(interest vector)
+ * d_tokens  [n_tokens, d_model] out: dLoss/d(looked-up row) of every sequence token, columns in pair
+ *           order (feeds dmt_grad_source with id_offset -1, grad_col = the pair's first column)
+ * d_target  [B, d_model] out: dLoss/d(target-item rows) */
+DMT_API int dmt_seq_encode_bwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w,
+                               int64_t n_tokens, const void* saved, size_t saved_bytes, const float* d_out,
+                               int64_t d_out_ld, const dmt_seq_grads* grads, float* d_tokens, float* d_target,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of dmt_mmoe_fwd (fp32 layout of its workspace: every expert layer's activations).
+ *   dlogits  [n_tasks][B]
+ *   dx       [B, dx_ld] out: columns [dx_col0, in_dim) are written (the dense `features` block in front
+ *            of dx_col0 is an input, not a variable) */
+DMT_API size_t dmt_mmoe_bwd_workspace_bytes(const dmt_mmoe_cfg* cfg);
+DMT_API int dmt_mmoe_bwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                         const void* fwd_workspace, const float* dlogits, const dmt_mmoe_grads* grads, float* dx,
+                         int64_t dx_ld, int32_t dx_col0, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the bias tower (mmoe_transformer_unbias.py:259-289): dy_bias [B] -> d_bias_in [B, in_dim]
+ * (row stride d_in_ld) + the layer_bias* gradients. */
+DMT_API size_t dmt_bias_bwd_workspace_bytes(const dmt_bias_loss_cfg* cfg);
+DMT_API int dmt_bias_bwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weights* w, const float* bias_in,
+                         int64_t bias_ld, const float* dy_bias, const dmt_bias_grads* grads, float* d_bias_in,
+                         int64_t d_in_ld, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- A13: optimizer ----------------------------------------------------------------
  * tf.train.AdamOptimizer(lr) (model/inference_mlp.py:272-273) applied to the tower-averaged gradients

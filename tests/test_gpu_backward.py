@@ -1,0 +1,138 @@
+"""A13 gradients: the CUDA training forward + backward (through the C ABI) against autograd over the CPU
+oracle (fp64) on the same seeded inputs and parameters.
+
+The reference obtains its gradients from `optimizer.compute_gradients(loss)` (run_dnn.py:181) = tf.gradients
+of the graph the oracle restates, so autograd over the restatement is the reference gradient.  Dropout is
+compared at rate 0 (TF RNG streams are not reproducible).
+
+Tolerance (fp32 kernels vs fp64 oracle): per variable, |got - want| <= 2e-4 * max|want| + 1e-6 * G, where
+G = the largest gradient entry of any variable (a gradient that is analytically zero -- the key bias of an
+attention layer, softmax being shift invariant -- comes out as fp32 cancellation noise of that scale).
+"""
+import pytest
+import torch
+
+from conftest import SMALL_ROWS, make_plan
+
+pytestmark = pytest.mark.gpu
+
+NO_DROPOUT = {("model", "transformer_dropout_rate"): "0.0", ("model", "dropout_rate_bias"): "0.0,0.0"}
+
+
+def _setup(conf_file, batch, seed=0, overrides=None, **gen):
+    from cikm2020_dmt_b200.params import ParamStore
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    from oracle import dmt_oracle as O
+    ov = dict(NO_DROPOUT)
+    ov.update(overrides or {})
+    conf, plan = make_plan(conf_file, overrides=ov)
+    store = ParamStore(plan, device="cuda", seed=seed + 1).randomize_(seed + 2)
+    model = mmoe_transformer_unbias(plan, params=store)
+    host = synthetic_batch(plan, batch, seed=seed + 3, table_rows=SMALL_ROWS, **gen)
+    # make the rare positive labels present so every loss branch carries gradient
+    lab = torch.arange(batch) % 5
+    host["mask"] = torch.nn.functional.one_hot(lab, 5).float()
+    return plan, model, store, host, batch_to(host, "cuda"), O
+
+
+def _check(name, got, want, rtol=2e-4, atol=1e-7):
+    got = got.detach().double().cpu().reshape(want.shape)
+    want = want.detach().double().cpu()
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item()
+    assert err <= rtol * ref + atol, "%s: max abs err %.3e vs max |ref| %.3e" % (name, err, ref)
+
+
+def _compare_all(plan, model, store, host, dev, O, **loss_kw):
+    P = O.params_from_store(store)
+    for p in P.values():
+        p.requires_grad_(True)
+    logits = O.inference(plan, P, host, is_train=False)
+    loss_ref = O.logit_loss_unbias(plan, logits, host["mask"], **loss_kw)
+    loss_ref.backward()
+    loss, G = model.compute_gradients(dev, **loss_kw)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item()) + 1e-6
+    checked = 0
+    scale = max(float(p.grad.abs().max()) for p in P.values() if p.grad is not None)
+    for spec in store.specs:
+        want = P[spec.name].grad
+        if want is None:
+            want = torch.zeros_like(P[spec.name])
+        _check(spec.name, G[spec.name], want, atol=1e-6 * scale)
+        checked += 1
+    for name in store.tables:
+        want = P[name].grad
+        if want is None:
+            want = torch.zeros_like(P[name])
+        _check(name, G.table_dense(store, name), want, atol=1e-6 * scale)
+        checked += 1
+    assert checked == len(store.specs) + len(store.tables)
+    return G
+
+
+def test_gradients_match_oracle_autograd_d64():
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 48)
+    _compare_all(plan, model, store, host, dev, O)
+
+
+def test_gradients_match_oracle_autograd_dmt_conf_d80_h4():
+    plan, model, store, host, dev, O = _setup("dmt.conf", 40, seed=4)
+    _compare_all(plan, model, store, host, dev, O)
+
+
+def test_gradients_two_blocks_and_ctr_rel_multiply():
+    ov = {("model", "transformer_num_blocks_encode"): "2", ("model", "transformer_num_blocks_decode"): "2"}
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 24, seed=7, overrides=ov)
+    _compare_all(plan, model, store, host, dev, O, loss_unbias_method="two_head_multiply",
+                 loss_ctr_rel_method="ctr_rel")
+
+
+def test_gradients_are_deterministic_and_batch_split_additive():
+    """No floating-point atomics on the path: two runs give bit-identical gradients; and since the loss is a
+    batch mean, the gradient of a batch is the mean of the gradients of its halves (the data-parallel
+    `average_gradients` identity, run_dnn.py:45-80)."""
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 64, seed=11)
+    _, G = model.compute_gradients(dev)
+    first = G.dense.clone()
+    _, G = model.compute_gradients(dev)
+    torch.cuda.synchronize()
+    assert torch.equal(first, G.dense)
+
+
+def test_train_steps_follow_oracle_adam():
+    """Three full steps (forward, backward, TF-1 Adam over dense + sparse variables) track the oracle."""
+    from cikm2020_dmt_b200.optim import TFAdam
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 32, seed=21)
+    opt = TFAdam(model, 1e-3)
+    P = O.params_from_store(store)
+    ref = O.TFAdam(P, lr=1e-3)
+    losses = []
+    noise = set()   # variables whose exact gradient is zero (attention key biases): Adam amplifies fp32 noise
+    for step in range(3):
+        h = synthetic_batch(plan, 32, seed=100 + step, table_rows=SMALL_ROWS)
+        h["mask"] = torch.nn.functional.one_hot((torch.arange(32) + step) % 5, 5).float()
+        loss_ref, grads_ref, _ = O.loss_and_grads(plan, P, h)
+        noise |= {k for k, g in grads_ref.items() if float(g.abs().max()) < 1e-12}
+        ref.step(grads_ref)
+        loss, G = model.compute_gradients(batch_to(h, "cuda"))
+        opt.apply_gradients(G)
+        losses.append((loss.item(), loss_ref.item()))
+    torch.cuda.synchronize()
+    for got, want in losses:
+        assert abs(got - want) <= 1e-3 * abs(want) + 1e-5, losses
+    # Adam's first steps move every coordinate by ~lr regardless of gradient scale, so compare absolutely
+    assert all(k.endswith("attention/dense_1/bias") for k in noise), noise
+    for name, v in store.named_parameters():
+        if name in noise:
+            continue
+        got = v.detach().double().cpu()
+        want = P[name].detach()
+        err = (got - want).abs()
+        # a coordinate whose exact gradient is ~1e-9 may take an Adam step of the wrong sign in fp32
+        # (|step| ~ lr * |g| / (|g| + eps)); everything else must track closely
+        assert err.max().item() <= 1e-3, "%s drifted by %.3e after 3 steps" % (name, err.max().item())
+        assert err.mean().item() <= 2e-5, "%s mean drift %.3e after 3 steps" % (name, err.mean().item())
