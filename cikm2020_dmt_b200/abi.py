@@ -12,7 +12,7 @@ from . import build as _build
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
 PRECISION_F32, PRECISION_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _fp = C.c_void_p   # device pointers travel as integers
 
@@ -126,8 +126,14 @@ PROTOTYPES = {
                                C.POINTER(BiasWeights), _fp, C.c_int64, _fp, C.c_size_t, _fp]),
     "dmt_adam_dense": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp]),
     "dmt_embed_grad_expand": (C.c_int, [C.c_int32, C.POINTER(GradSource), C.c_int64, _fp, _fp, _fp, _fp]),
+    "dmt_embed_sorted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "dmt_embed_adam_sorted": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_int32,
-                                        C.POINTER(GradSource), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp, _fp]),
+                                        C.POINTER(GradSource), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp, _fp,
+                                        C.c_size_t, _fp]),
+    "dmt_embed_grad_densify_sorted": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(GradSource), _fp, _fp, _fp,
+                                                _fp, C.c_int64, C.c_float, _fp, _fp, C.c_size_t, _fp]),
+    "dmt_embed_grad_scatter_rows": (C.c_int, [C.c_int32, C.POINTER(GradSource), _fp, _fp, _fp, C.c_int64, C.c_int32,
+                                              _fp, _fp]),
     "dmt_adam_rows_untouched": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),

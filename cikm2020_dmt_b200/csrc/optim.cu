@@ -10,9 +10,9 @@
 //   1. dmt_embed_grad_expand      every lookup of the step (sequence tokens, target items, pooled features)
 //                                 becomes a (row key, gradient-row reference, scale) triple;
 //   2. the caller sorts the keys (stable; any device sort -- plumbing);
-//   3. dmt_embed_adam_sorted      one warp per run of equal keys sums the referenced gradient rows in sorted
-//                                 order (deterministic, no atomics) and applies the Adam update to that row,
-//                                 marking it touched;
+//   3. dmt_embed_adam_sorted      chunked two-pass segmented reduction of the referenced gradient rows in
+//                                 sorted order (deterministic, no atomics, hot rows do not serialise) + the
+//                                 Adam update of each touched row;
 //   4. dmt_adam_rows_untouched    one streaming pass applies the g = 0 update to every other row (pure HBM:
 //                                 6 * V * D * 4 bytes) and clears the marks.
 #include "dmt_common.cuh"
@@ -119,31 +119,31 @@ struct SortedAdamArgs {
   uint8_t* touched;
   float gscale;
   AdamScalars s;
+  float* dense_out;         // non-null: write the summed gradient row here instead of applying Adam
+  float* carry;             // [chunks][2][dim] partial sums of the sub-runs that cross a chunk boundary
 };
 
-// One warp per position; the warp whose position starts a run of equal keys owns that row.
-__global__ void __launch_bounds__(256) adam_sorted_kernel(const __grid_constant__ SortedAdamArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= a.n) return;
-  const int32_t key = __ldg(a.keys + w);
-  if (key == INT32_MAX) return;
-  if (w > 0 && __ldg(a.keys + w - 1) == key) return;   // not the head of its run
+// Deterministic segmented reduction over the sorted lookups, robust to hot rows (a 23-row time table or the
+// 302 OOV bucket rows of Sku receive 10^4..10^5 lookups each): the sorted positions are cut into fixed chunks
+// of kChunk; pass 1 (one warp per chunk) sums every sub-run of equal keys inside its chunk in sorted order --
+// a run that lies inside one chunk is finished on the spot, a sub-run that continues from / into a neighbour
+// chunk is parked in `carry`; pass 2 (the warp of the chunk where such a run starts) adds the parked partials
+// chunk by chunk.  Fixed chunking + fixed order => run-to-run identical sums, no atomics; the serial depth of a
+// run of length r is kChunk + r / kChunk instead of r.
+constexpr int kChunk = 128;
+constexpr int kMaxCols = 4;   // D <= 128: columns lane, lane+32, ...
+
+__device__ __forceinline__ void finish_row(const SortedAdamArgs& a, int32_t key, const float (&acc)[kMaxCols], int lane) {
   const int D = a.dim;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};                  // columns lane, lane+32, ... (D <= 128)
-  for (int64_t i = w; i < a.n && __ldg(a.keys + i) == key; ++i) {
-    const int64_t e = __ldg(a.perm + i);
-    const int64_t ref = __ldg(a.refs + e);
-    const dmt_grad_source& g = a.src[ref >> 40];
-    const float sc = __ldg(a.scale + e);
-    const float* gr = g.grad + (ref & 0xFFFFFFFFFFll) * g.grad_ld + g.grad_col;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (lane + 32 * c < D) acc[c] = fmaf(sc, __ldg(gr + lane + 32 * c), acc[c]);
-  }
   const int64_t base = (int64_t)key * D;
+  if (a.dense_out) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kMaxCols; ++c)
+      if (lane + 32 * c < D) a.dense_out[base + lane + 32 * c] = acc[c] * a.gscale;
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) {
     const int col = lane + 32 * c;
     if (col < D) {
       float p = a.table[base + col], m = a.m[base + col], v = a.v[base + col];
@@ -156,24 +156,170 @@ __global__ void __launch_bounds__(256) adam_sorted_kernel(const __grid_constant_
   if (lane == 0) a.touched[key] = 1;
 }
 
+__global__ void __launch_bounds__(256) adam_sorted_pass1_kernel(const __grid_constant__ SortedAdamArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t beg = chunk * kChunk;
+  if (beg >= a.n) return;
+  const int64_t end = min(a.n, beg + (int64_t)kChunk);
+  const int D = a.dim;
+  const int32_t prev_key = beg > 0 ? __ldg(a.keys + beg - 1) : -1;
+  const int32_t next_key = end < a.n ? __ldg(a.keys + end) : -1;
+  float acc[kMaxCols] = {0.f, 0.f, 0.f, 0.f};
+  int32_t cur = __ldg(a.keys + beg);
+  bool starts_here = cur != prev_key;
+  for (int64_t i0 = beg; i0 < end; i0 += 32) {
+    // lanes fetch 32 (key, gradient-row address, scale) triples at once, then the warp walks them in order
+    const int64_t i = i0 + lane;
+    int32_t k = -1;
+    const float* gr = nullptr;
+    float sc = 0.f;
+    if (i < end) {
+      k = __ldg(a.keys + i);
+      const int64_t e = __ldg(a.perm + i);
+      const int64_t ref = __ldg(a.refs + e);
+      const dmt_grad_source& g = a.src[ref >> 40];
+      sc = __ldg(a.scale + e);
+      gr = g.grad + (ref & 0xFFFFFFFFFFll) * g.grad_ld + g.grad_col;
+    }
+    const int cnt = (int)min((int64_t)32, end - i0);
+    for (int j = 0; j < cnt; ++j) {
+      const int32_t kj = __shfl_sync(0xffffffffu, k, j);
+      const float scj = __shfl_sync(0xffffffffu, sc, j);
+      const float* grj = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gr, j));
+      if (kj != cur) {
+        if (cur != INT32_MAX) {
+          if (starts_here) {
+            finish_row(a, cur, acc, lane);      // the run began and ended inside this chunk
+          } else {
+#pragma unroll
+            for (int c = 0; c < kMaxCols; ++c)
+              if (lane + 32 * c < D) a.carry[(chunk * 2 + 0) * D + lane + 32 * c] = acc[c];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) acc[c] = 0.f;
+        cur = kj;
+        starts_here = true;
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxCols; ++c)
+        if (lane + 32 * c < D) acc[c] = fmaf(scj, __ldg(grj + lane + 32 * c), acc[c]);
+    }
+  }
+  if (cur == INT32_MAX) return;
+  const bool ends_here = cur != next_key;
+  if (starts_here && ends_here) {
+    finish_row(a, cur, acc, lane);
+  } else {
+    const int slot = starts_here ? 1 : 0;   // 1: head of a run that continues; 0: continuation (maybe whole chunk)
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c)
+      if (lane + 32 * c < D) a.carry[(chunk * 2 + slot) * D + lane + 32 * c] = acc[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_sorted_pass2_kernel(const __grid_constant__ SortedAdamArgs a) {
+  const int lane = threadIdx.x & 31;
+  int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t beg = chunk * kChunk;
+  if (beg >= a.n) return;
+  int64_t end = min(a.n, beg + (int64_t)kChunk);
+  if (end >= a.n) return;                                     // nothing continues past the last chunk
+  const int32_t key = __ldg(a.keys + end - 1);
+  if (key == INT32_MAX || __ldg(a.keys + end) != key) return;  // the trailing run ends here
+  // this chunk owns the run iff the run starts inside it
+  if (__ldg(a.keys + beg) == key && beg > 0 && __ldg(a.keys + beg - 1) == key) return;
+  const int D = a.dim;
+  float acc[kMaxCols];
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) acc[c] = lane + 32 * c < D ? a.carry[(chunk * 2 + 1) * D + lane + 32 * c] : 0.f;
+  for (;;) {
+    ++chunk;
+    const int64_t b2 = chunk * kChunk;
+    const int64_t e2 = min(a.n, b2 + (int64_t)kChunk);
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c)
+      if (lane + 32 * c < D) acc[c] += a.carry[(chunk * 2 + 0) * D + lane + 32 * c];
+    if (e2 >= a.n || __ldg(a.keys + e2 - 1) != key || __ldg(a.keys + e2) != key) break;
+  }
+  finish_row(a, key, acc, lane);
+}
+
+// out[key, :] = scale * gradient row, for lookups whose keys are UNIQUE (the compact table of a row-sharded
+// embedding: one compact row per lookup).  One warp per lookup.
+struct ScatterRowsArgs {
+  dmt_grad_source src[DMT_MAX_GRAD_SOURCES];
+  const int32_t* keys;
+  const int64_t* refs;
+  const float* scale;
+  int64_t n;
+  int32_t dim;
+  float* out;
+};
+
+__global__ void __launch_bounds__(256) grad_scatter_rows_kernel(const __grid_constant__ ScatterRowsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= a.n) return;
+  const int32_t key = __ldg(a.keys + w);
+  if (key == INT32_MAX) return;
+  const int64_t ref = __ldg(a.refs + w);
+  const dmt_grad_source& g = a.src[ref >> 40];
+  const float sc = __ldg(a.scale + w);
+  const float* gr = g.grad + (ref & 0xFFFFFFFFFFll) * g.grad_ld + g.grad_col;
+  for (int c = lane; c < a.dim; c += 32) a.out[(int64_t)key * a.dim + c] = sc * __ldg(gr + c);
+}
+
+// VEC floats per thread (4 when dim % 4 == 0): one 16-byte load/store per array, one `touched` byte per chunk.
+template <int VEC>
 __global__ void __launch_bounds__(256) adam_untouched_kernel(float* __restrict__ table, float* __restrict__ m,
                                                              float* __restrict__ v, int64_t rows, int dim,
-                                                             uint8_t* __restrict__ touched, AdamScalars s) {
-  const int64_t total = rows * dim;
+                                                             const uint8_t* __restrict__ touched, AdamScalars s) {
+  const int chunks = dim / VEC;
+  const int64_t total = rows * chunks;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / dim;
+    const int64_t r = total < (1ll << 32) ? (int64_t)((uint32_t)i / (uint32_t)chunks) : i / chunks;
     if (touched[r]) continue;
-    float p = table[i], mm = m[i], vv = v[i];
-    adam_update(p, mm, vv, 0.f, s);
-    table[i] = p;
-    m[i] = mm;
-    v[i] = vv;
+    if (VEC == 4) {
+      float4 p = *reinterpret_cast<float4*>(table + i * 4), mm = *reinterpret_cast<float4*>(m + i * 4);
+      float4 vv = *reinterpret_cast<float4*>(v + i * 4);
+      adam_update(p.x, mm.x, vv.x, 0.f, s);
+      adam_update(p.y, mm.y, vv.y, 0.f, s);
+      adam_update(p.z, mm.z, vv.z, 0.f, s);
+      adam_update(p.w, mm.w, vv.w, 0.f, s);
+      *reinterpret_cast<float4*>(table + i * 4) = p;
+      *reinterpret_cast<float4*>(m + i * 4) = mm;
+      *reinterpret_cast<float4*>(v + i * 4) = vv;
+    } else {
+      float p = table[i], mm = m[i], vv = v[i];
+      adam_update(p, mm, vv, 0.f, s);
+      table[i] = p;
+      m[i] = mm;
+      v[i] = vv;
+    }
   }
+}
+
+static int sorted_launch(const SortedAdamArgs& a, cudaStream_t st) {
+  const int64_t chunks = (a.n + kChunk - 1) / kChunk;
+  const int64_t blocks = (chunks * 32 + 255) / 256;
+  adam_sorted_pass1_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("adam_sorted_pass1_kernel");
+  adam_sorted_pass2_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("adam_sorted_pass2_kernel");
+  return DMT_OK;
 }
 
 }  // namespace dmt
 
 extern "C" {
+
+size_t dmt_embed_sorted_workspace_bytes(int64_t n, int32_t dim) {
+  if (n <= 0 || dim <= 0) return 256;
+  return (size_t)((n + dmt::kChunk - 1) / dmt::kChunk) * 2 * dim * sizeof(float) + 256;
+}
+
 
 int dmt_adam_dense(const dmt_adam_cfg* cfg, float* param, float* m, float* v, const float* grad, int64_t n,
                    float grad_scale, void* stream) {
@@ -222,7 +368,7 @@ int dmt_embed_grad_expand(int32_t n_sources, const dmt_grad_source* sources, int
 int dmt_embed_adam_sorted(const dmt_adam_cfg* cfg, float* table, float* m, float* v, int64_t rows, int32_t dim,
                           int32_t n_sources, const dmt_grad_source* sources, const int32_t* sorted_keys,
                           const int64_t* perm, const int64_t* refs, const float* scale, int64_t n, float grad_scale,
-                          uint8_t* touched, void* stream) {
+                          uint8_t* touched, void* workspace, size_t workspace_bytes, void* stream) {
   DMT_REQUIRE(cfg && table && m && v && sources && sorted_keys && perm && refs && scale && touched,
               DMT_ERR_INVALID_ARGUMENT, "dmt_embed_adam_sorted: null pointer");
   DMT_REQUIRE(dim > 0 && dim <= 128 && n_sources > 0 && n_sources <= DMT_MAX_GRAD_SOURCES && cfg->step >= 1,
@@ -236,9 +382,49 @@ int dmt_embed_adam_sorted(const dmt_adam_cfg* cfg, float* table, float* m, float
   a.keys = sorted_keys; a.perm = perm; a.refs = refs; a.scale = scale;
   a.n = n; a.touched = touched; a.gscale = grad_scale;
   a.s = dmt::adam_scalars(cfg);
+  a.dense_out = nullptr;
+  DMT_REQUIRE(workspace && workspace_bytes >= dmt_embed_sorted_workspace_bytes(n, dim), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_embed_adam_sorted: workspace %zu < %zu bytes", workspace_bytes, dmt_embed_sorted_workspace_bytes(n, dim));
+  a.carry = (float*)workspace;
+  return dmt::sorted_launch(a, (cudaStream_t)stream);
+}
+
+int dmt_embed_grad_densify_sorted(int64_t rows, int32_t dim, int32_t n_sources, const dmt_grad_source* sources,
+                                  const int32_t* sorted_keys, const int64_t* perm, const int64_t* refs,
+                                  const float* scale, int64_t n, float grad_scale, float* dense_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  DMT_REQUIRE(sources && sorted_keys && perm && refs && scale && dense_out, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_embed_grad_densify_sorted: null pointer");
+  DMT_REQUIRE(dim > 0 && dim <= 128 && n_sources > 0 && n_sources <= DMT_MAX_GRAD_SOURCES, DMT_ERR_UNSUPPORTED_SHAPE,
+              "dmt_embed_grad_densify_sorted: dim=%d n_sources=%d", dim, n_sources);
+  if (n == 0) return DMT_OK;
+  dmt::SortedAdamArgs a{};
+  for (int s = 0; s < n_sources; ++s) a.src[s] = sources[s];
+  a.rows = rows; a.dim = dim;
+  a.keys = sorted_keys; a.perm = perm; a.refs = refs; a.scale = scale;
+  a.n = n; a.gscale = grad_scale;
+  a.dense_out = dense_out;
+  DMT_REQUIRE(workspace && workspace_bytes >= dmt_embed_sorted_workspace_bytes(n, dim), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_embed_grad_densify_sorted: workspace %zu < %zu bytes", workspace_bytes,
+              dmt_embed_sorted_workspace_bytes(n, dim));
+  a.carry = (float*)workspace;
+  return dmt::sorted_launch(a, (cudaStream_t)stream);
+}
+
+int dmt_embed_grad_scatter_rows(int32_t n_sources, const dmt_grad_source* sources, const int32_t* keys,
+                                const int64_t* refs, const float* scale, int64_t n, int32_t dim, float* out,
+                                void* stream) {
+  DMT_REQUIRE(sources && keys && refs && scale && out, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_embed_grad_scatter_rows: null pointer");
+  DMT_REQUIRE(dim > 0 && n_sources > 0 && n_sources <= DMT_MAX_GRAD_SOURCES, DMT_ERR_UNSUPPORTED_SHAPE,
+              "dmt_embed_grad_scatter_rows: dim=%d n_sources=%d", dim, n_sources);
+  if (n == 0) return DMT_OK;
+  dmt::ScatterRowsArgs a{};
+  for (int s = 0; s < n_sources; ++s) a.src[s] = sources[s];
+  a.keys = keys; a.refs = refs; a.scale = scale; a.n = n; a.dim = dim; a.out = out;
   const int64_t blocks = (n * 32 + 255) / 256;
-  dmt::adam_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  DMT_CUDA_LAUNCH_CHECK("adam_sorted_kernel");
+  dmt::grad_scatter_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("grad_scatter_rows_kernel");
   return DMT_OK;
 }
 
@@ -247,11 +433,16 @@ int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float* m, flo
   DMT_REQUIRE(cfg && table && m && v && touched && cfg->step >= 1, DMT_ERR_INVALID_ARGUMENT,
               "dmt_adam_rows_untouched: bad arguments");
   if (rows == 0) return DMT_OK;
-  int64_t blocks = (rows * dim + 255) / 256;
+  const bool vec = dim % 4 == 0 && (((uintptr_t)table | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  int64_t blocks = (rows * (vec ? dim / 4 : dim) + 255) / 256;
   const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
   if (blocks > cap) blocks = cap;
-  dmt::adam_untouched_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, m, v, rows, dim, touched,
-                                                                                dmt::adam_scalars(cfg));
+  if (vec)
+    dmt::adam_untouched_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, m, v, rows, dim, touched,
+                                                                                     dmt::adam_scalars(cfg));
+  else
+    dmt::adam_untouched_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, m, v, rows, dim, touched,
+                                                                                     dmt::adam_scalars(cfg));
   DMT_CUDA_LAUNCH_CHECK("adam_untouched_kernel");
   cudaError_t e = cudaMemsetAsync(touched, 0, (size_t)rows, (cudaStream_t)stream);
   if (e != cudaSuccess) return dmt::cuda_fail(e, "cudaMemsetAsync(touched)");

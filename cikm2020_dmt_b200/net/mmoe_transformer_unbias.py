@@ -173,8 +173,14 @@ class mmoe_transformer_unbias(object):
                 out[k] = v
         return out
 
-    def _sparse(self, inputs, name):
-        sp = inputs[name]
+    def _sparse(self, inputs, name, role="pool"):
+        """`role` distinguishes the lookups of one feature: 'pool' (embedding_combiner, row = id) and 'seq<i>'
+        (generate_data of sequence i, row = id-1).  A row-sharded table re-maps them to different compact rows
+        (`inputs['__remap__'][(role, name)]`, see shard.py / train.py); otherwise all read `inputs[name]`."""
+        remap = inputs.get("__remap__")
+        sp = remap.get((role, name)) if remap else None
+        if sp is None:
+            sp = inputs[name]
         if not isinstance(sp, SparseIds):
             raise TypeError("feature %r must be a SparseIds (CSR) value" % name)
         w = sp.weights
@@ -227,8 +233,8 @@ class mmoe_transformer_unbias(object):
         keep = []
         for f, (uf, itf) in enumerate(zip(seq.user_features, seq.item_features)):
             table = self.params.table(seq.tables[f])
-            u = self._sparse(inputs, uf)
-            it = self._sparse(inputs, itf)
+            u = self._sparse(inputs, uf, "seq%d" % seq.index)
+            it = self._sparse(inputs, itf, "seq%d" % seq.index)
             if u.offsets.numel() != batch + 1:
                 raise ValueError("feature %r: offsets has %d entries, batch is %d" % (uf, u.offsets.numel(), batch))
             if it.values.numel() != batch:
@@ -412,6 +418,16 @@ class mmoe_transformer_unbias(object):
         return out
 
     # ------------------------------------------------------------------ A13: gradients
+    def bind_grad_buffer(self, flat):
+        """Use `flat` (fp32, laid out like `params.dense`, e.g. the front of a data-parallel allreduce bucket)
+        as the dense gradient buffer."""
+        if flat.numel() != self.params.dense.numel() or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("gradient buffer must be a contiguous fp32 tensor of %d elements" % self.params.dense.numel())
+        self._grad_dense = flat
+        gviews = {sp.name: flat[sp.offset:sp.offset + sp.numel].view(sp.shape) for sp in self.params.specs}
+        self._seq_g, self._mmoe_g, self._bias_g = self._bind(gviews)
+        self._grad_views = gviews
+
     def compute_gradients(self, inputs, mask=None, loss_unbias_method=None, loss_ctr_rel_method=None):
         """`optimizer.compute_gradients(loss)` of the reference's training graph (run_dnn.py:154-181): one
         forward that saves activations + the backward, fp32.  Returns `(loss, Gradients)`; the loss is the
@@ -433,11 +449,7 @@ class mmoe_transformer_unbias(object):
         F32 = abi.PRECISION_F32
 
         if getattr(self, "_grad_dense", None) is None:
-            self._grad_dense = torch.zeros_like(self.params.dense)
-            gviews = {sp.name: self._grad_dense[sp.offset:sp.offset + sp.numel].view(sp.shape)
-                      for sp in self.params.specs}
-            self._seq_g, self._mmoe_g, self._bias_g = self._bind(gviews)
-            self._grad_views = gviews
+            self.bind_grad_buffer(torch.zeros_like(self.params.dense))
         g_dense = self._grad_dense
         g_dense.zero_()
 
@@ -459,7 +471,7 @@ class mmoe_transformer_unbias(object):
             cfg = self._seq_cfg(inputs, seq, batch, F32)
             si, kp = self._seq_input(inputs, seq, batch)
             keep += kp
-            users = [self._sparse(inputs, uf) for uf in seq.user_features]
+            users = [self._sparse(inputs, uf, "seq%d" % seq.index) for uf in seq.user_features]
             n_tok = users[-1].values.numel()
             if any(u.values.numel() != n_tok for u in users):
                 raise ValueError("sequence %d: the id features of one behaviour sequence must have equal lengths" % s)
@@ -535,7 +547,7 @@ class mmoe_transformer_unbias(object):
                 scope = plan.tables[seq.tables[f]].scope
                 if n_tok:
                     add(scope, LookupGrad(u.values, d_tok, seq.col_offsets[f], id_off))
-                it = self._sparse(inputs, seq.item_features[f])
+                it = self._sparse(inputs, seq.item_features[f], "seq%d" % seq.index)
                 add(scope, LookupGrad(it.values, d_tar, seq.col_offsets[f], id_off))
         self._keep_train = (keep, seq_state, inputs)
         return loss[0], Gradients(g_dense, lookups, self._grad_views)

@@ -128,12 +128,14 @@ class TFAdam(object):
             abi.check(self.lib.dmt_embed_grad_expand(len(sources), arr, rows, keys.data_ptr(), refs.data_ptr(),
                                                      scale.data_ptr(), stream))
             skeys, perm = torch.sort(keys, stable=True)
+            ws = self.model._scratch("sorted_ws", self.lib.dmt_embed_sorted_workspace_bytes(total, dim))
             abi.check(self.lib.dmt_embed_adam_sorted(C.byref(cfg), table.data_ptr(), self.m_tab[name].data_ptr(),
                                                      self.v_tab[name].data_ptr(), rows, dim, len(sources), arr,
                                                      skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),
                                                      scale.data_ptr(), total, float(grad_scale),
-                                                     self.touched[name].data_ptr(), stream))
-            self.model.launches += 2
+                                                     self.touched[name].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     stream))
+            self.model.launches += 3
             self._keep = (arr, keys, refs, scale, skeys, perm, sources)
         abi.check(self.lib.dmt_adam_rows_untouched(C.byref(cfg), table.data_ptr(), self.m_tab[name].data_ptr(),
                                                    self.v_tab[name].data_ptr(), rows, dim,

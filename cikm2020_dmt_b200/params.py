@@ -149,7 +149,9 @@ class ParamStore:
     `views`   {TF variable name: view} over both
     """
 
-    def __init__(self, plan, device="cpu", seed=20201019, init=True, table_rows_override=None):
+    def __init__(self, plan, device="cpu", seed=20201019, init=True, table_rows_override=None, row_shards=None):
+        """row_shards: {TF variable name: (lo, hi)} -- keep only rows [lo, hi) of that table on this rank (the
+        values are those of the full table's initialisation, so N ranks together hold exactly the 1-GPU table)."""
         self.plan = plan
         self.device = torch.device(device)
         self.specs = dense_param_specs(plan)
@@ -167,6 +169,9 @@ class ParamStore:
             t = torch.empty(s.shape, dtype=torch.float32)
             if init:
                 _fill(t, s, gen)
+            if row_shards and s.name in row_shards:
+                lo, hi = row_shards[s.name]
+                t = t[lo:hi].clone()
             tables[s.name] = t
         for s in self.specs:
             v = dense[s.offset:s.offset + s.numel].view(s.shape)

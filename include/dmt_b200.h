@@ -38,7 +38,7 @@ extern "C" {
 #define DMT_API __attribute__((visibility("default")))
 #endif
 
-#define DMT_ABI_VERSION 3
+#define DMT_ABI_VERSION 4
 
 #define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
 #define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
@@ -332,13 +332,30 @@ DMT_API int dmt_adam_dense(const dmt_adam_cfg* cfg, float* param, float* m, floa
 DMT_API int dmt_embed_grad_expand(int32_t n_sources, const dmt_grad_source* sources, int64_t rows,
                                   int32_t* keys, int64_t* refs, float* scale, void* stream);
 /* K9 step 2 + K10: `sorted_keys` ascending with `perm` (sorted position -> expanded position) from any
- * stable device sort; one warp per run of equal keys sums the gradient rows in sorted order
- * (deterministic) and applies the Adam update; touched[row] = 1. */
+ * stable device sort; the gradient rows of every run of equal keys are summed in sorted order by a chunked
+ * two-pass segmented reduction (deterministic; a row hit 10^5 times does not serialise) and the Adam update
+ * is applied to that row; touched[row] = 1.  workspace: dmt_embed_sorted_workspace_bytes(n, dim). */
+DMT_API size_t dmt_embed_sorted_workspace_bytes(int64_t n, int32_t dim);
 DMT_API int dmt_embed_adam_sorted(const dmt_adam_cfg* cfg, float* table, float* m, float* v, int64_t rows,
                                   int32_t dim, int32_t n_sources, const dmt_grad_source* sources,
                                   const int32_t* sorted_keys, const int64_t* perm, const int64_t* refs,
                                   const float* scale, int64_t n, float grad_scale, uint8_t* touched,
-                                  void* stream);
+                                  void* workspace, size_t workspace_bytes, void* stream);
+/* Data-parallel variants of K9.
+ * densify: same segmented reduction as dmt_embed_adam_sorted, but the summed gradient row (x grad_scale) is
+ *   written to dense_out [rows, dim] (zeroed by the caller) -- the replicated small tables join the dense
+ *   allreduce bucket this way, exactly what average_gradients does (run_dnn.py:63-72).
+ * scatter_rows: out[key, :] = scale * gradient row for lookups with UNIQUE keys (keys/refs/scale straight from
+ *   dmt_embed_grad_expand, unsorted): the per-row gradients of a row-sharded table's compact copy, ready for
+ *   the all-to-all back to the owning ranks. */
+DMT_API int dmt_embed_grad_densify_sorted(int64_t rows, int32_t dim, int32_t n_sources,
+                                          const dmt_grad_source* sources, const int32_t* sorted_keys,
+                                          const int64_t* perm, const int64_t* refs, const float* scale, int64_t n,
+                                          float grad_scale, float* dense_out, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+DMT_API int dmt_embed_grad_scatter_rows(int32_t n_sources, const dmt_grad_source* sources, const int32_t* keys,
+                                        const int64_t* refs, const float* scale, int64_t n, int32_t dim, float* out,
+                                        void* stream);
 /* K10 for the rows without a gradient this step (g = 0 still moves them); clears `touched`. */
 DMT_API int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float* m, float* v,
                                     int64_t rows, int32_t dim, uint8_t* touched, void* stream);
