@@ -35,6 +35,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=0.0)
     ap.add_argument("--small-tables", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="debug: gradients only")
+    ap.add_argument("--train-gemm", default="bf16x3", choices=["f32", "bf16", "bf16x3"],
+                    help="engine of the training-path GEMMs: fp32 SIMT | tcgen05 bf16 | tcgen05 split-bf16 (fp32-grade)")
     return ap.parse_args()
 
 
@@ -74,7 +76,8 @@ def main():
     batches = [synthetic_batch(plan, args.batch, seed=SEED + 1000 * rank + i, id_mode=args.id_mode, table_rows=rows)
                for i in range(args.n_batches)]
     trainer = Trainer(plan, device=device, learning_rate=conf.learning_rate if hasattr(conf, "learning_rate") else 1e-3,
-                      world=world, rank=rank, seed=SEED)
+                      world=world, rank=rank, seed=SEED, precision="f32" if args.train_gemm == "f32" else "bf16",
+                      train_gemm=args.train_gemm)
     model = trainer.model
     dev_batches = [batch_to(b, device) for b in batches]
 
@@ -120,7 +123,10 @@ def main():
     line = {
         "metric": "training samples/sec", "value": world * args.batch * args.steps / (ms / 1e3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak",
+        "dtype": {"f32": "f32", "bf16": "bf16 GEMM operands / fp32 accumulate+storage",
+                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate+storage"}[args.train_gemm],
+        "data": "synthetic",
         "config": {"workload": "BASELINE config %d: DMT training step (fwd + bwd + TF-1 Adam, dense over every row), "
                                "615 dense + all id sequences, MMoE 2 tasks, per-GPU batch %d, d_model=%d, %d heads, "
                                "Sku vocabulary %d %s" % (4 if world > 1 else 3, args.batch, plan.d_model, plan.num_heads,

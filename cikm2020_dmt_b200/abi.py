@@ -11,8 +11,8 @@ from . import build as _build
 
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
-PRECISION_F32, PRECISION_BF16 = 0, 1
-ABI_VERSION = 4
+PRECISION_F32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
+ABI_VERSION = 5
 
 _fp = C.c_void_p   # device pointers travel as integers
 
@@ -117,6 +117,9 @@ PROTOTYPES = {
     "dmt_seq_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(SeqCfg), C.c_int64]),
     "dmt_seq_encode_bwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), C.c_int64, _fp,
                                      C.c_size_t, _fp, C.c_int64, C.POINTER(SeqWeights), _fp, _fp, _fp, C.c_size_t,
+                                     _fp]),
+    "dmt_mmoe_train_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
+    "dmt_mmoe_fwd_train": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp, C.c_size_t,
                                      _fp]),
     "dmt_mmoe_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
     "dmt_mmoe_bwd": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp,

@@ -170,7 +170,17 @@ size_t gemm_partial_bytes(const GemmProb& p) {
   return (size_t)p.splits * (p.M + (p.colsum ? 1 : 0)) * p.N * sizeof(float);
 }
 
-int gemm_pick_splits(int M, int N, int64_t K) {
+int gemm_pick_splits_tc(int M, int N, int64_t K, bool colsum);
+int gemm_tc_group_launch(GemmGroup& g, cudaStream_t st, int (*reduce)(GemmGroup&, cudaStream_t));
+
+static int launch_reduce(GemmGroup& g, cudaStream_t st) {
+  gemm_group_reduce_kernel<<<g.total_red, 256, 0, st>>>(g);
+  DMT_CUDA_LAUNCH_CHECK("gemm_group_reduce_kernel");
+  return DMT_OK;
+}
+
+int gemm_pick_splits(int M, int N, int64_t K, bool use_tc, bool colsum) {
+  if (use_tc) return gemm_pick_splits_tc(M, N, K, colsum);
   const int tiles = ((M + 63) / 64) * ((N + BN - 1) / BN);
   const int target = 2 * sm_count_cached();
   int64_t s = target / (tiles > 0 ? tiles : 1);
@@ -198,6 +208,7 @@ int gemm_group_launch(GemmGroup& g, cudaStream_t st) {
     DMT_REQUIRE(!p.colsum || p.n_parts == 1, DMT_ERR_INVALID_ARGUMENT, "gemm group: colsum needs a single part");
   }
   if (empty) return DMT_OK;
+  if (g.use_tc) return gemm_tc_group_launch(g, st, launch_reduce);
   const int TM = min_m >= 2048 ? 8 : 4;
   const int BM = 16 * TM;
   int cta = 0, red = 0;

@@ -45,6 +45,7 @@ struct GemmProb {
   float* partial;        // [splits][M + (colsum ? 1 : 0)][N] scratch when splits > 1
   // filled by the launcher
   int tiles_m, tiles_n, cta0, red0;
+  int tc_bn;             // tensor-core path: tile width of this problem
 };
 
 struct GemmGroup {
@@ -52,7 +53,16 @@ struct GemmGroup {
   int n;
   int total_ctas;
   int total_red;
+  int tc_nmax;  // filled by the tensor-core launcher: widest 16-padded tile of the group
+  int tc_stages;   //                               shared-memory stages (1 when no CTA walks more than one K chunk)
+  int use_tc;   // 0: fp32 SIMT; 1: bf16 operands on tcgen05 (gemm_tc.cu), fp32 accumulate; 3: bf16x3 split
+                // operands (hi*hi + hi*lo + lo*hi) on tcgen05 -- fp32-grade results
 };
+
+// dmt_precision -> GemmGroup::use_tc
+inline int gemm_engine(int precision) {
+  return precision == DMT_PRECISION_BF16 ? 1 : (precision == DMT_PRECISION_BF16X3 ? 3 : 0);
+}
 
 inline void gemm_prob_init(GemmProb& p) {
   p = GemmProb{};
@@ -63,7 +73,8 @@ inline void gemm_prob_init(GemmProb& p) {
 // bytes of split-K scratch problem `p` needs (0 when splits == 1)
 size_t gemm_partial_bytes(const GemmProb& p);
 // choose a split count for a [M,N] += A^T B contraction over K rows so that the launch fills the chip
-int gemm_pick_splits(int M, int N, int64_t K);
+// (the two engines tile differently, so the choice depends on which one will run the problem)
+int gemm_pick_splits(int M, int N, int64_t K, bool use_tc = false, bool colsum = true);
 int gemm_group_launch(GemmGroup& g, cudaStream_t st);
 
 }  // namespace dmt

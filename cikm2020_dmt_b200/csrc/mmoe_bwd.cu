@@ -175,6 +175,7 @@ struct MmoeBwdWs {
 size_t mmoe_bwd_carve(const dmt_mmoe_cfg& c, void* base, MmoeBwdWs* out) {
   Carver cv(base);
   MmoeBwdWs w{};
+  const bool tc = gemm_engine(c.precision) != 0;
   const size_t B = c.batch, E = c.n_experts, T = c.n_tasks;
   const int Hd = c.units[c.n_layers - 1];
   for (int l = 0; l < c.n_layers; ++l) w.dH[l] = cv.take(E * B * c.units[l]);
@@ -187,18 +188,18 @@ size_t mmoe_bwd_carve(const dmt_mmoe_cfg& c, void* base, MmoeBwdWs* out) {
   size_t worst = 0;
   int in_dim = c.in_dim;
   for (int l = 0; l < c.n_layers; ++l) {
-    w.splits_layer[l] = gemm_pick_splits(in_dim, c.units[l], (int64_t)B);
+    w.splits_layer[l] = gemm_pick_splits(in_dim, c.units[l], (int64_t)B, tc);
     const size_t need = (size_t)w.splits_layer[l] * (in_dim + 1) * c.units[l];
     if (need > worst) worst = need;
     in_dim = c.units[l];
   }
   for (size_t e = 0; e < E; ++e) w.part_expert[e] = cv.take(worst);
-  w.splits_gate = gemm_pick_splits(c.in_dim, (int)E, (int64_t)B);
+  w.splits_gate = gemm_pick_splits(c.in_dim, (int)E, (int64_t)B, tc);
   for (size_t t = 0; t < T; ++t) w.part_gate[t] = cv.take((size_t)w.splits_gate * (c.in_dim + 1) * E);
   in_dim = Hd;
   for (int l = 0; l <= c.n_tower_layers; ++l) {
     const int units = l < c.n_tower_layers ? c.tower_units[l] : 1;
-    w.splits_tower[l] = gemm_pick_splits(in_dim, units, (int64_t)B);
+    w.splits_tower[l] = gemm_pick_splits(in_dim, units, (int64_t)B, tc);
     for (size_t t = 0; t < T; ++t) w.part_tower[t][l] = cv.take((size_t)w.splits_tower[l] * (in_dim + 1) * units);
     in_dim = units;
   }
@@ -233,6 +234,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
   const int Hd = c.units[NL - 1];
   MmoeBwdWs ws;
   mmoe_bwd_carve(c, ws_base, &ws);
+  const int use_tc = gemm_engine(c.precision);
   // forward activations: [l][E][B][units_l]
   const float* H[DMT_MAX_LAYERS];
   {
@@ -276,6 +278,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
   // tower + gate weight gradients (contractions over the batch)
   for (int t = 0; t < NT; ++t) {
     GemmGroup grp{};
+      grp.use_tc = use_tc;
     int n = 0;
     int in_dim = Hd;
     const float* in = ws.zt + (int64_t)t * B * Hd;
@@ -299,6 +302,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
     const int in_dim = l == 0 ? c.in_dim : c.units[l - 1];
     {
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       for (int e = 0; e < E; ++e) {
         const float* in = l == 0 ? x : H[l - 1] + (int64_t)e * B * in_dim;
         wgrad(grp.p[e], in, l == 0 ? x_ld : in_dim, ws.dH[l] + (int64_t)e * B * units, units, B, in_dim, units,
@@ -309,6 +313,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
     }
     if (l > 0) {
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       for (int e = 0; e < E; ++e) {
         GemmProb& p = grp.p[e];
         gemm_prob_init(p);
@@ -328,6 +333,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
       DMT_REQUIRE(E + NT <= kGemmMaxParts, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_bwd: experts + tasks = %d > %d", E + NT,
                   kGemmMaxParts);
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       GemmProb& p = grp.p[0];
       gemm_prob_init(p);
       int n = 0;
@@ -350,6 +356,47 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
 }
 
 size_t mmoe_bwd_workspace_bytes(const dmt_mmoe_cfg* cfg) { return mmoe_bwd_carve(*cfg, nullptr, nullptr); }
+
+int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                     const void* h_last, int h_is_bf16, const float* gates, float* logits, cudaStream_t st);
+
+// Training forward: expert layers through the grouped GEMM (fp32 activations kept for the backward; bf16
+// tensor-core operands when cfg->precision says so), then the shared head kernel.
+int mmoe_fwd_train_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                          float* logits, float* ws, cudaStream_t st) {
+  const dmt_mmoe_cfg& c = *cfg;
+  const int B = c.batch, E = c.n_experts;
+  const float* in = x;
+  int64_t in_ld = x_ld, in_stride = 0;
+  int in_dim = c.in_dim;
+  float* out = ws;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const int units = c.units[l];
+    GemmGroup grp{};
+    grp.use_tc = gemm_engine(c.precision);
+    for (int e = 0; e < E; ++e) {
+      GemmProb& p = grp.p[e];
+      gemm_prob_init(p);
+      p.n_parts = 1;
+      p.part[0] = GemmPart{in + in_stride * e, w->expert[e][l].w, in_ld, units, in_dim, 0};
+      p.M = B;
+      p.N = units;
+      p.C = out + (int64_t)e * B * units;
+      p.ldc = units;
+      p.bias = w->expert[e][l].b;
+      p.relu = 1;
+    }
+    grp.n = E;
+    int rc = gemm_group_launch(grp, st);
+    if (rc) return rc;
+    in = out;
+    in_ld = units;
+    in_dim = units;
+    in_stride = (int64_t)B * units;
+    out += (int64_t)E * B * units;
+  }
+  return mmoe_head_launch(cfg, w, x, x_ld, in, 0, nullptr, logits, st);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Bias tower backward (mmoe_transformer_unbias.py:259-289): one thread per sample recomputes the tiny MLP
@@ -461,8 +508,6 @@ int dmt_mmoe_bwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float
                   cfg->n_layers > 0 && cfg->n_layers <= DMT_MAX_LAYERS && cfg->n_tasks > 0 &&
                   cfg->n_tasks <= DMT_MAX_TASKS && cfg->n_tower_layers >= 0 && cfg->n_tower_layers <= DMT_MAX_LAYERS,
               DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_bwd: configuration out of range");
-  DMT_REQUIRE(cfg->precision == DMT_PRECISION_F32, DMT_ERR_UNSUPPORTED_SHAPE,
-              "dmt_mmoe_bwd: needs the fp32 forward workspace (every expert layer's activations in fp32)");
   DMT_REQUIRE(x_ld >= cfg->in_dim && (!dx || dx_ld >= cfg->in_dim) && dx_col0 >= 0, DMT_ERR_INVALID_ARGUMENT,
               "dmt_mmoe_bwd: bad strides");
   DMT_REQUIRE(((uintptr_t)workspace & 255) == 0 && workspace_bytes >= dmt::mmoe_bwd_workspace_bytes(cfg),
@@ -471,6 +516,28 @@ int dmt_mmoe_bwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float
   if (cfg->batch == 0) return DMT_OK;
   return dmt::mmoe_bwd_launch(cfg, w, x, x_ld, (const float*)fwd_workspace, dlogits, grads, dx, dx_ld, dx_col0,
                               workspace, (cudaStream_t)stream);
+}
+
+size_t dmt_mmoe_train_workspace_bytes(const dmt_mmoe_cfg* cfg) {
+  if (!cfg) return 0;
+  size_t floats = 0;
+  for (int l = 0; l < cfg->n_layers && l < DMT_MAX_LAYERS; ++l)
+    floats += (size_t)cfg->n_experts * cfg->batch * cfg->units[l];
+  return floats * sizeof(float) + 256;
+}
+
+int dmt_mmoe_fwd_train(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  DMT_REQUIRE(cfg && w && x && logits && workspace, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd_train: null pointer");
+  DMT_REQUIRE(cfg->batch >= 0 && cfg->in_dim > 0 && cfg->n_experts > 0 && cfg->n_experts <= DMT_MAX_EXPERTS &&
+                  cfg->n_layers > 0 && cfg->n_layers <= DMT_MAX_LAYERS && cfg->n_tasks > 0 &&
+                  cfg->n_tasks <= DMT_MAX_TASKS && cfg->n_tower_layers >= 0 && cfg->n_tower_layers <= DMT_MAX_LAYERS,
+              DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd_train: configuration out of range");
+  DMT_REQUIRE(x_ld >= cfg->in_dim, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd_train: x_ld < in_dim");
+  DMT_REQUIRE(workspace_bytes >= dmt_mmoe_train_workspace_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_mmoe_fwd_train: workspace %zu < %zu bytes", workspace_bytes, dmt_mmoe_train_workspace_bytes(cfg));
+  if (cfg->batch == 0) return DMT_OK;
+  return dmt::mmoe_fwd_train_launch(cfg, w, x, x_ld, logits, (float*)workspace, (cudaStream_t)stream);
 }
 
 size_t dmt_bias_bwd_workspace_bytes(const dmt_bias_loss_cfg* cfg) {

@@ -9,6 +9,8 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
                    const SeqSaved& sv, const float* d_out, int64_t d_out_ld, const dmt_seq_grads* g, float* d_tokens,
                    float* d_target, void* ws, cudaStream_t st);
 size_t seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t T);
+int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
+                           int64_t out_ld, int64_t T, const SeqSaved& sv, cudaStream_t st);
 size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg);
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why);
 int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st);
@@ -95,6 +97,8 @@ int dmt_seq_encode_fwd_train(const dmt_seq_cfg* cfg, const dmt_seq_input* in, co
   if (cfg->batch == 0) return DMT_OK;
   dmt::SeqSaved sv;
   dmt::seq_saved_carve(*cfg, n_tokens, saved, &sv);
+  if (cfg->precision != DMT_PRECISION_F32)   // row-batched pipeline on the tensor-core GEMM engine
+    return dmt::seq_fwd_train_pipeline(cfg, in, w, out, out_ld, n_tokens, sv, (cudaStream_t)stream);
   return dmt::seq_encode_f32_launch(cfg, in, w, out, out_ld, &sv, (cudaStream_t)stream);
 }
 

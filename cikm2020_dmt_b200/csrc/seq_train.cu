@@ -142,7 +142,7 @@ constexpr int kAttnThreads = 256;
 
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int D = a.D, H = a.H, LP = a.LP, dk = D / H, ld = D + 4, lds = LP + 1;
+  const int D = a.D, H = a.H, LP = a.LP, dk = D / H, ld = D + 1, lds = LP + 1;   // odd strides: conflict-free
   float* Q = sm;
   float* K = Q + LP * ld;
   float* V = K + LP * ld;
@@ -293,22 +293,26 @@ __global__ void __launch_bounds__(kDecThreads) dec_attn_bwd_kernel(const __grid_
 // Position-table gradient (positional_encoding_learn, TransformerModel_util.py:281-316): the encoder
 // input is rows * sqrt(d) + P[t], so dP[t] = sum_b dH0[b, t] = (1/sqrt(d)) * sum_b d_tokens[b, t].
 // One CTA per position, fixed summation order.
+constexpr int kPosSplits = 16;
+
 struct PosGradArgs {
   const float* d_tokens;   // [T, D]
   const int32_t* offsets;
+  float* partial;          // [kPosSplits][LP][D]
   float* dpos;             // [maxlen, D]  +=
   float inv_scale;
   int B, D, LP;
 };
 
+// grid (LP, kPosSplits): CTA (t, s) sums position t over samples b = s, s + kPosSplits, ... (fixed order)
 __global__ void __launch_bounds__(256) pos_grad_kernel(const __grid_constant__ PosGradArgs a) {
   __shared__ float red[256];
-  const int t = blockIdx.x, D = a.D;
+  const int t = blockIdx.x, split = blockIdx.y, D = a.D;
   const int groups = 256 / D > 0 ? 256 / D : 1;
   const int c = threadIdx.x % D, grp = threadIdx.x / D;
   float s = 0.f;
-  if (grp < groups && threadIdx.x < groups * D) {
-    for (int b = grp; b < a.B; b += groups) {
+  if (threadIdx.x < groups * D) {
+    for (int b = split + grp * kPosSplits; b < a.B; b += groups * kPosSplits) {
       const int off = __ldg(a.offsets + b);
       const int len = min(__ldg(a.offsets + b + 1) - off, a.LP);
       if (t < len) s += __ldg(a.d_tokens + ((int64_t)off + t) * D + c);
@@ -319,8 +323,16 @@ __global__ void __launch_bounds__(256) pos_grad_kernel(const __grid_constant__ P
   if (threadIdx.x < D) {
     float tot = 0.f;
     for (int gi = 0; gi < groups; ++gi) tot += red[gi * D + threadIdx.x];
-    a.dpos[(int64_t)t * D + threadIdx.x] += tot * a.inv_scale;
+    a.partial[((int64_t)split * a.LP + t) * D + threadIdx.x] = tot;
   }
+}
+
+__global__ void pos_grad_reduce_kernel(const __grid_constant__ PosGradArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.LP * a.D) return;
+  float tot = 0.f;
+  for (int s = 0; s < kPosSplits; ++s) tot += a.partial[(int64_t)s * a.LP * a.D + i];
+  a.dpos[i] += tot * a.inv_scale;
 }
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, int64_t lds_, float* __restrict__ dst, int64_t ldd,
@@ -343,6 +355,7 @@ struct BwdWs {
   float *dz2d, *dad, *dz1d, *dqd;   // [B, d]
   float *df1d;      // [B, dff]
   float *ln_partial;                // [ln_grid][2d]
+  float *pos_partial;               // [kPosSplits][LP][d]
   float *gpart[8];  // split-K scratch of the weight-gradient contractions (one block's worth)
   int ln_grid;
   int splits_T[8], splits_B[8];
@@ -380,11 +393,13 @@ size_t bwd_carve(const dmt_seq_cfg& c, int64_t T, void* base, BwdWs* out) {
   w.df1d = cv.take(B * dff);
   w.ln_grid = 2 * sm_count_cached();
   w.ln_partial = cv.take((size_t)w.ln_grid * 2 * d);
+  w.pos_partial = cv.take((size_t)kPosSplits * seq_lp(c) * d);
   for (int i = 0; i < 5; ++i) {
     int M, N;
     wg_shape(c, i, &M, &N);
-    w.splits_T[i] = gemm_pick_splits(M, N, T);
-    w.splits_B[i] = gemm_pick_splits(M, N, (int64_t)B);
+    const bool tc = gemm_engine(c.precision) != 0;
+    w.splits_T[i] = gemm_pick_splits(M, N, T, tc);
+    w.splits_B[i] = gemm_pick_splits(M, N, (int64_t)B, tc);
     const int s = w.splits_T[i] > w.splits_B[i] ? w.splits_T[i] : w.splits_B[i];
     w.gpart[i] = cv.take((size_t)s * (M + 1) * N);
   }
@@ -438,6 +453,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
   bwd_carve(c, T, ws_base, &ws);
   const int d = c.d_model, dff = c.d_ff, B = c.batch, H = c.num_heads, LP = seq_lp(c);
   const float sqrt_d = sqrtf((float)d);
+  const int use_tc = gemm_engine(c.precision);   // GEMMs on tcgen05 (bf16 operands, fp32 accumulate)
   const int32_t* offsets = in->offsets[c.n_feats - 1];
   int rc;
 
@@ -457,6 +473,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     if (rc) return rc;
     {   // dF1 = (dZ2 W2^T) * (F1 > 0)
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[1] = {ws.dz2d};
       const int64_t lg[1] = {d};
       const float* W[1] = {fw.w2.w};
@@ -469,6 +486,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     }
     {   // dA = dZ2 + dF1 W1^T
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[1] = {ws.df1d};
       const int64_t lg[1] = {dff};
       const float* W[1] = {fw.w1.w};
@@ -494,6 +512,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     float* dnext = ws.dd[blk & 1];
     {   // dD_in = dZ1 + dQd Wq^T (x sqrt(d) into d_target for the first block) ; dMemory (+)= dKd Wk^T + dVd Wv^T
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[1] = {ws.dqd};
       const int64_t lg[1] = {d};
       const float* W[1] = {aw.q.w};
@@ -517,6 +536,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     }
     {   // weight gradients of this block
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       int n = 0;
       wgrad_prob(grp.p[n++], sv.ad[blk], d, ws.df1d, dff, B, d, dff, fg.w1, ws.splits_B[0], ws.gpart[0]);
       wgrad_prob(grp.p[n++], sv.f1d[blk], dff, ws.dz2d, d, B, dff, d, fg.w2, ws.splits_B[1], ws.gpart[1]);
@@ -556,6 +576,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     if (rc) return rc;
     {
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[1] = {ws.dz2};
       const int64_t lg[1] = {d};
       const float* W[1] = {fw.w2.w};
@@ -568,6 +589,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     }
     {
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[1] = {ws.df1};
       const int64_t lg[1] = {dff};
       const float* W[1] = {fw.w1.w};
@@ -583,7 +605,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     if (rc) return rc;
     {
       AttnBwdArgs a{sv.qkv[blk], ws.dz1, ws.dqkv, offsets, d, H, LP};
-      const size_t smem = ((size_t)4 * LP * (d + 4) + 2 * LP * (LP + 1)) * sizeof(float);
+      const size_t smem = ((size_t)4 * LP * (d + 1) + 2 * LP * (LP + 1)) * sizeof(float);
       DMT_REQUIRE(smem <= 227 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: attention tile needs %zu B", smem);
       cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_bwd_kernel)");
@@ -594,6 +616,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     float* dhin = blk == 0 ? d_tokens : ws.dh[ping];
     {   // dH_in = dZ1 + dQ Wq^T + dK Wk^T + dV Wv^T   (x sqrt(d) for the first block: row gradients)
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       const float* gr[3] = {ws.dqkv, ws.dqkv + d, ws.dqkv + 2 * d};
       const int64_t lg[3] = {3 * d, 3 * d, 3 * d};
       const float* W[3] = {aw.q.w, aw.k.w, aw.v.w};
@@ -607,6 +630,7 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     }
     {
       GemmGroup grp{};
+      grp.use_tc = use_tc;
       int n = 0;
       wgrad_prob(grp.p[n++], sv.a[blk], d, ws.df1, dff, T, d, dff, fg.w1, ws.splits_T[0], ws.gpart[0]);
       wgrad_prob(grp.p[n++], sv.f1[blk], dff, ws.dz2, d, T, dff, d, fg.w2, ws.splits_T[1], ws.gpart[1]);
@@ -623,10 +647,12 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     DMT_CUDA_LAUNCH_CHECK("scale_copy_kernel");
   }
   {
-    PosGradArgs a{d_tokens, offsets, const_cast<float*>(g->pos), 1.0f / sqrt_d, B, d, LP};
+    PosGradArgs a{d_tokens, offsets, ws.pos_partial, const_cast<float*>(g->pos), 1.0f / sqrt_d, B, d, LP};
     DMT_REQUIRE(d <= 256, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: d_model %d > 256", d);
-    pos_grad_kernel<<<LP, 256, 0, st>>>(a);
+    pos_grad_kernel<<<dim3(LP, kPosSplits), 256, 0, st>>>(a);
     DMT_CUDA_LAUNCH_CHECK("pos_grad_kernel");
+    pos_grad_reduce_kernel<<<(LP * d + 255) / 256, 256, 0, st>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("pos_grad_reduce_kernel");
   }
   return DMT_OK;
 }

@@ -22,7 +22,10 @@ def _is_host(t):
 
 
 class mmoe_transformer_unbias(object):
-    def __init__(self, wnd_conf, device=None, params=None, precision="f32", seed=20201019):
+    def __init__(self, wnd_conf, device=None, params=None, precision="f32", seed=20201019, train_gemm=None):
+        """precision: 'f32' (CUDA cores, exact-parity path) | 'bf16' (tcgen05 inference kernels).
+        train_gemm: engine of the GEMMs of the TRAINING path -- 'f32' (SIMT), 'bf16' (tcgen05, bf16 operands) or
+        'bf16x3' (tcgen05, split hi+lo operands: fp32-grade).  Default: 'f32' with precision 'f32', else 'bf16x3'."""
         self.wnd_conf = wnd_conf
         self.plan = wnd_conf if hasattr(wnd_conf, "mmoe_in") else build_plan(wnd_conf)
         if not torch.cuda.is_available():
@@ -32,6 +35,10 @@ class mmoe_transformer_unbias(object):
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = abi.load()
         self.precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16}[precision]
+        if train_gemm is None:
+            train_gemm = "f32" if precision == "f32" else "bf16x3"
+        self.train_precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16,
+                                "bf16x3": abi.PRECISION_BF16X3}[train_gemm]
         self.params = params if params is not None else ParamStore(self.plan, device=self.device, seed=seed)
         pdev = self.params.dense.device
         if pdev.type != "cuda" or pdev.index != self.device.index:
@@ -153,6 +160,9 @@ class mmoe_transformer_unbias(object):
             out["__max_len__"] = inputs.max_len(self.plan)
             return out
         if inputs.get("__staged__") is self:
+            ready = inputs.get("__ready__")
+            if ready is not None:     # produced by prefetch(): order the consumer after the copy
+                torch.cuda.current_stream(self.device).wait_event(ready)
             return inputs
         cache, out = {}, {"__staged__": self}
 
@@ -171,6 +181,33 @@ class mmoe_transformer_unbias(object):
                 out[k] = dev(v)
             else:
                 out[k] = v
+        return out
+
+    def prefetch(self, packed):
+        """Start the host->device copy of a `PackedBatch` on a side stream and return the staged batch; pass
+        it to `inference` / `compute_gradients` later.  The copy overlaps whatever the compute stream is doing
+        (what a data-loader prefetch thread does for the reference's tf.data pipeline,
+        tfrecord_mask.py:140-157).  Three rotating device buffers: a buffer is rewritten only after the
+        compute enqueued before this call -- which includes its previous consumer -- has finished."""
+        if not isinstance(packed, PackedBatch):
+            raise TypeError("prefetch takes a PackedBatch (one pinned host buffer)")
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._pf_slot = 0
+        cur = torch.cuda.current_stream(self.device)
+        self._pf_slot = (self._pf_slot + 1) % 3
+        buf = self._scratch("prefetch_%d" % self._pf_slot, packed.nbytes)
+        buf.record_stream(self._copy_stream)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._copy_stream.wait_event(done)
+        with torch.cuda.stream(self._copy_stream):
+            out = packed.to(self.device, out=buf)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        out["__max_len__"] = packed.max_len(self.plan)
+        out["__staged__"] = self
+        out["__ready__"] = ready
         return out
 
     def _sparse(self, inputs, name, role="pool"):
@@ -446,7 +483,7 @@ class mmoe_transformer_unbias(object):
             raise ValueError("mask must be fp32 [%d, 5]" % batch)
         mask = mask.contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        F32 = abi.PRECISION_F32
+        F32 = self.train_precision   # engine of the training-path GEMMs (activations / gradients stay fp32)
 
         if getattr(self, "_grad_dense", None) is None:
             self.bind_grad_buffer(torch.zeros_like(self.params.dense))
@@ -484,12 +521,12 @@ class mmoe_transformer_unbias(object):
                                                        saved.numel(), stream))
             seq_state.append((cfg, si, users, n_tok, saved, col))
         mcfg = self._mmoe_cfg(batch, F32)
-        mws_bytes = lib.dmt_mmoe_workspace_bytes(C.byref(mcfg))
+        mws_bytes = lib.dmt_mmoe_train_workspace_bytes(C.byref(mcfg))
         mws = self._buf("mmoe_ws_f32", ((mws_bytes + 255) // 256 * 256,), torch.uint8)
         logits = self._buf("logits", (plan.num_tasks, batch))
         with self._Stage(self, "mmoe", mcfg.n_layers + 1):
-            abi.check(lib.dmt_mmoe_fwd(C.byref(mcfg), C.byref(self._mmoe_w), x.data_ptr(), x_ld, logits.data_ptr(),
-                                       mws.data_ptr(), mws_bytes, None, stream))
+            abi.check(lib.dmt_mmoe_fwd_train(C.byref(mcfg), C.byref(self._mmoe_w), x.data_ptr(), x_ld,
+                                             logits.data_ptr(), mws.data_ptr(), mws_bytes, stream))
         bias_in = self._buf("bias_in", (batch, plan.bias_width))
         keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
         y_bias = self._buf("y_bias", (batch,))

@@ -31,7 +31,7 @@ from .shard import RowExchange, RowShard, remap_ids
 
 class Trainer(object):
     def __init__(self, plan, device, learning_rate=1e-3, world=1, rank=0, seed=20201019, sharded_tables=("Sku",),
-                 group=None, randomize=None, force_dp_path=False):
+                 group=None, randomize=None, force_dp_path=False, precision="f32", train_gemm=None):
         """force_dp_path: run the data-parallel code path (compact tables, densified replicas, bucket) even
         with world == 1 -- the single-GPU test of that path."""
         self.plan, self.device = plan, torch.device(device)
@@ -52,7 +52,8 @@ class Trainer(object):
             for scope, (lo, hi) in row_shards.items():
                 store.tables[scope] = store.tables[scope][lo:hi].clone()
         store = _store_to(store, self.device)
-        self.model = mmoe_transformer_unbias(plan, device=self.device, params=store, precision="f32")
+        self.model = mmoe_transformer_unbias(plan, device=self.device, params=store, precision=precision,
+                                             train_gemm=train_gemm)
         self.store = store
         self.opt = TFAdam(self.model, learning_rate)
         self.learning_rate = learning_rate

@@ -38,7 +38,7 @@ extern "C" {
 #define DMT_API __attribute__((visibility("default")))
 #endif
 
-#define DMT_ABI_VERSION 4
+#define DMT_ABI_VERSION 5
 
 #define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
 #define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
@@ -60,7 +60,10 @@ typedef enum dmt_status {
 
 typedef enum dmt_precision {
   DMT_PRECISION_F32 = 0,  /* fp32 CUDA-core math end to end (parity tolerance 1e-4)  */
-  DMT_PRECISION_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate  */
+  DMT_PRECISION_BF16 = 1, /* bf16 operands on tcgen05 tensor cores, fp32 accumulate  */
+  DMT_PRECISION_BF16X3 = 2 /* training entry points only (fwd_train / bwd): every GEMM operand is split
+                              x = hi + lo into two bf16 images and each product is hi*hi + hi*lo + lo*hi on
+                              tcgen05 -- fp32-grade gradients at tensor-core speed                       */
 } dmt_precision;
 
 /* one tf.layers.dense / base.dense_layer: kernel [in,out] + bias [out] */
@@ -250,7 +253,8 @@ DMT_API int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weigh
 
 /* ---- A13: training forward / backward ----------------------------------------------
  * tf.gradients of the graph built by inference + loss_multi_task_unbias (run_dnn.py:181,
- * compute_gradients).  fp32 arithmetic.  The training forward writes the activations the backward needs
+ * compute_gradients).  fp32 arithmetic (DMT_PRECISION_F32) or fp32 storage with the GEMMs on bf16 tensor
+ * cores (DMT_PRECISION_BF16).  The training forward writes the activations the backward needs
  * into a caller-owned `saved` buffer (HBM is cheap on this part: ~3.6 KB per token); the backward is a
  * short pipeline of row-batched kernels (LayerNorm / attention backward, grouped GEMMs with fixed-order
  * split-K) that ACCUMULATES every parameter gradient into the buffers named by a `*_grads` descriptor --
@@ -277,7 +281,14 @@ DMT_API int dmt_seq_encode_bwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, 
                                int64_t d_out_ld, const dmt_seq_grads* grads, float* d_tokens, float* d_target,
                                void* workspace, size_t workspace_bytes, void* stream);
 
-/* Backward of dmt_mmoe_fwd (fp32 layout of its workspace: every expert layer's activations).
+/* Training forward of the MMoE block: like dmt_mmoe_fwd, but every expert layer's activations stay in
+ * `workspace` as fp32 [layer][expert][B][units] for the backward; with DMT_PRECISION_BF16 the GEMMs of the
+ * training path (forward and backward) run on tcgen05 with bf16 operands / fp32 accumulation. */
+DMT_API size_t dmt_mmoe_train_workspace_bytes(const dmt_mmoe_cfg* cfg);
+DMT_API int dmt_mmoe_fwd_train(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                               float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of dmt_mmoe_fwd_train (`fwd_workspace` = its workspace).
  *   dlogits  [n_tasks][B]
  *   dx       [B, dx_ld] out: columns [dx_col0, in_dim) are written (the dense `features` block in front
  *            of dx_col0 is an input, not a variable) */

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 NO_DROPOUT = {("model", "transformer_dropout_rate"): "0.0", ("model", "dropout_rate_bias"): "0.0,0.0"}
 
 
-def _setup(conf_file, batch, seed=0, overrides=None, **gen):
+def _setup(conf_file, batch, seed=0, overrides=None, precision="f32", train_gemm=None, **gen):
     from cikm2020_dmt_b200.params import ParamStore
     from cikm2020_dmt_b200.data import synthetic_batch, batch_to
     from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
@@ -28,7 +28,7 @@ def _setup(conf_file, batch, seed=0, overrides=None, **gen):
     ov.update(overrides or {})
     conf, plan = make_plan(conf_file, overrides=ov)
     store = ParamStore(plan, device="cuda", seed=seed + 1).randomize_(seed + 2)
-    model = mmoe_transformer_unbias(plan, params=store)
+    model = mmoe_transformer_unbias(plan, params=store, precision=precision, train_gemm=train_gemm)
     host = synthetic_batch(plan, batch, seed=seed + 3, table_rows=SMALL_ROWS, **gen)
     # make the rare positive labels present so every loss branch carries gradient
     lab = torch.arange(batch) % 5
@@ -87,6 +87,51 @@ def test_gradients_two_blocks_and_ctr_rel_multiply():
     plan, model, store, host, dev, O = _setup("dmt_d64.conf", 24, seed=7, overrides=ov)
     _compare_all(plan, model, store, host, dev, O, loss_unbias_method="two_head_multiply",
                  loss_ctr_rel_method="ctr_rel")
+
+
+@pytest.mark.parametrize("conf_file,batch,engine,rel_tol,cos_tol",
+                         [("dmt_d64.conf", 200, "bf16x3", 2e-3, 0.99999), ("dmt.conf", 72, "bf16x3", 2e-3, 0.99999),
+                          ("dmt_d64.conf", 200, "bf16", 1e-1, 0.995)])
+def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol):
+    """Training with every GEMM of the path (MMoE forward, all dgrad / wgrad contractions) on tcgen05, fp32
+    accumulation, everything else fp32.
+      * 'bf16x3' (the default of the bf16 model): operands split hi + lo, three MMAs per product -> per variable
+        relative Frobenius error <= 2e-3 and cosine >= 0.99999 against the fp64 oracle gradient;
+      * 'bf16': plain bf16 operands (2^-9 rounding per operand through a chain of up to eight GEMMs and a
+        loss whose class weights reach 400): relative error <= 1e-1, cosine >= 0.995.
+    Variables whose exact gradient is ~0 are compared absolutely."""
+    plan, model, store, host, dev, O = _setup(conf_file, batch, seed=31, precision="bf16", train_gemm=engine)
+    P = O.params_from_store(store)
+    loss_ref, grads_ref, _ = O.loss_and_grads(plan, P, host)
+    loss, G = model.compute_gradients(dev)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= (1e-2 if engine == "bf16" else 1e-4) * abs(loss_ref.item())
+    scale = max(float(g.abs().max()) for g in grads_ref.values())
+    bad = []
+    for name in [s.name for s in store.specs] + list(store.tables):
+        want = grads_ref.get(name)
+        want = torch.zeros_like(P[name]) if want is None else want.double()
+        got = (G[name] if name in G.views and name not in store.tables else G.table_dense(store, name))
+        got = got.detach().double().cpu().reshape(want.shape)
+        wn = want.norm().item()
+        if wn <= 1e-5 * scale * want.numel() ** 0.5:          # analytically (near) zero gradient
+            if (got - want).abs().max().item() > 2e-3 * scale:
+                bad.append((name, "abs", (got - want).abs().max().item()))
+            continue
+        rel = (got - want).norm().item() / wn
+        cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-300))
+        if rel > rel_tol or cos < cos_tol:
+            bad.append((name[-50:], round(rel, 4), round(cos, 5)))
+    assert not bad, bad
+
+
+def test_bf16_gemm_gradients_are_deterministic():
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 300, seed=5, precision="bf16")
+    _, G = model.compute_gradients(dev)
+    first = G.dense.clone()
+    _, G = model.compute_gradients(dev)
+    torch.cuda.synchronize()
+    assert torch.equal(first, G.dense)
 
 
 def test_gradients_are_deterministic_and_batch_split_additive():
