@@ -23,8 +23,10 @@ using namespace umma;
 namespace {
 
 constexpr int kTcThreads = 256;
-constexpr int BM = 128, BN = 256, BKC = 64;       // tile rows, max tile columns, K per stage
-constexpr int kStageA = BM * BKC * 2;             // 16 KB: one bf16 image of an A chunk
+constexpr int BM = 128, BN = 256;                 // tile rows, max tile columns
+// K per shared-memory stage: 64, or 32 in the split (x3) mode whose two images per operand would otherwise
+// double the footprint and halve the CTAs per SM (these GEMMs live on occupancy, not on MMA rate)
+__host__ __device__ constexpr int stage_k(bool x3) { return x3 ? 32 : 64; }
 // one bf16 image of a B chunk is Nmax * 128 bytes, Nmax = the widest (16-padded) tile of the group
 
 __device__ __forceinline__ uint4 pack8(const float* f) {
@@ -55,15 +57,6 @@ __device__ __forceinline__ void load8(const float* __restrict__ base, int64_t ld
   }
 }
 
-__device__ __forceinline__ float epi(const GemmProb& P, float v, int m, int n) {
-  if (P.addend) v += __ldg(P.addend + (int64_t)m * P.ld_add + n);
-  v *= P.alpha;
-  if (P.bias) v += __ldg(P.bias + n);
-  if (P.relu) v = fmaxf(v, 0.f);
-  if (P.mask && !(__ldg(P.mask + (int64_t)m * P.ld_mask + n) > 0.f)) v = 0.f;
-  return v;
-}
-
 // hi / lo split of 8 values: hi = bf16(x), lo = bf16(x - hi)
 __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   float l[8];
@@ -82,8 +75,23 @@ __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   lo = pack8(l);
 }
 
+// one 16-byte chunk (8 bf16) of an operand image; with X3 also the low-order image `lo_off` bytes behind it
 template <int X3>
-__global__ void __launch_bounds__(kTcThreads) gemm_tc_group_kernel(const __grid_constant__ GemmGroup g) {
+__device__ __forceinline__ void store_chunk(uint8_t* dst, int lo_off, const float* f) {
+  if (X3) {
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+  } else {
+    *reinterpret_cast<uint4*>(dst) = pack8(f);
+  }
+}
+
+template <int X3>
+__global__ void __launch_bounds__(kTcThreads, 4) gemm_tc_group_kernel(const __grid_constant__ GemmGroup g) {
+  constexpr int BKC = stage_k(X3 != 0);
+  constexpr int kStageA = BM * BKC * 2;                 // one bf16 image of an A chunk
   const int kStage = kStageA + g.tc_nmax * (BKC * 2);   // bytes of one (A, B) image pair
   const int kStageAll = (X3 ? 2 : 1) * kStage;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -116,8 +124,14 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_group_kernel(const __grid_
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_base_s;
-  const uint32_t idesc = make_idesc_bf16(BM, Npad);
-  const uint32_t dHi = desc_hi(128, kLayoutNone);
+  // operand images: K contiguous in memory -> canonical K-major [k/8][row][8] (LBO = rows*16 to the next 8 k,
+  // SBO = 128 to the next 8 rows); row index contiguous in memory (the token-contracting weight-gradient
+  // operands, the [K,N] weights of a forward GEMM) -> MN-major [row/8][k][8] (LBO = 128 to the next 8 k,
+  // SBO = 64*16 to the next 8 rows), staged without any transposition.
+  const bool a_mn = P.transA != 0, b_mn = P.transB == 0;
+  const uint32_t idesc = make_idesc_bf16(BM, Npad, a_mn, b_mn);
+  const uint32_t dHiA = a_mn ? desc_hi(BKC * 16, kLayoutNone) : desc_hi(128, kLayoutNone);
+  const uint32_t dHiB = b_mn ? desc_hi(BKC * 16, kLayoutNone) : desc_hi(128, kLayoutNone);
 
   int it = 0;
   for (int part = 0; part < P.n_parts; ++part) {
@@ -131,9 +145,9 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_group_kernel(const __grid_
       kbeg = min(K, split * chunk);
       kend = min(K, kbeg + chunk);
     }
-    const bool a_contig = !P.transA, b_contig = P.transB != 0;
-    const bool a_vec = a_contig && (lda % 4 == 0) && (((uintptr_t)A & 15) == 0) && (kbeg % 4 == 0);
-    const bool b_vec = b_contig && (ldb % 4 == 0) && (((uintptr_t)Bm & 15) == 0) && (kbeg % 4 == 0);
+    // 16-byte loads need: aligned base, row stride a multiple of 4 floats and a 4-aligned first element
+    const bool a_vec = (lda % 4 == 0) && (((uintptr_t)A & 15) == 0) && ((a_mn ? m0 : kbeg) % 4 == 0);
+    const bool b_vec = (ldb % 4 == 0) && (((uintptr_t)Bm & 15) == 0) && ((b_mn ? n0 : kbeg) % 4 == 0);
     for (int k0 = kbeg; k0 < kend; k0 += BKC, ++it) {
       const int s = g.tc_stages > 1 ? (it & 1) : 0;
       if (g.tc_stages > 1) {
@@ -143,46 +157,99 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_group_kernel(const __grid_
       }
       uint8_t* sA = smem + s * kStageAll;      // [A hi | B hi | A lo | B lo]
       uint8_t* sB = sA + kStageA;
-      // ---- A: 128 rows x 8 chunks
+      // ---- A: 128 rows x 64 k
+      if (!a_mn) {      // K contiguous in memory -> K-major image [k/8][row][8]
 #pragma unroll
-      for (int j = 0; j < BM * (BKC / 8) / kTcThreads; ++j) {
-        const int i = tid + j * kTcThreads, row = i % BM, kc = i / BM;
-        const int m = m0 + row, k = k0 + kc * 8;
-        float f[8];
-        if (m < M && k < kend) {
-          load8(A, lda, a_contig, m, k, kend, a_vec, f);
-        } else {
-          const bool one = ones_row && m == M;       // the bias-gradient row
+        for (int j = 0; j < BM * (BKC / 8) / kTcThreads; ++j) {
+          const int i = tid + j * kTcThreads, row = i % BM, kc = i / BM;
+          const int m = m0 + row, k = k0 + kc * 8;
+          float f[8];
+          if (m < M && k < kend) {
+            load8(A, lda, true, m, k, kend, a_vec, f);
+          } else {
+            const bool one = ones_row && m == M;       // the bias-gradient row
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (one && k + e < kend) ? 1.0f : 0.f;
+            for (int e = 0; e < 8; ++e) f[e] = (one && k + e < kend) ? 1.0f : 0.f;
+          }
+          store_chunk<X3>(sA + kc * (BM * 16) + row * 16, kStage, f);
         }
-        if (X3) {
-          uint4 hi, lo;
-          split8(f, hi, lo);
-          *reinterpret_cast<uint4*>(sA + kc * (BM * 16) + row * 16) = hi;
-          *reinterpret_cast<uint4*>(sA + kStage + kc * (BM * 16) + row * 16) = lo;
-        } else {
-          *reinterpret_cast<uint4*>(sA + kc * (BM * 16) + row * 16) = pack8(f);
-        }
-      }
-      // ---- B: Npad rows x 8 chunks
-      for (int i = tid; i < Npad * (BKC / 8); i += kTcThreads) {
-        const int n = i % Npad, kc = i / Npad;
-        const int k = k0 + kc * 8;
-        float f[8];
-        if (n < N && k < kend) {
-          load8(Bm, ldb, b_contig, n0 + n, k, kend, b_vec, f);
-        } else {
+      } else {          // M contiguous in memory -> MN-major image [m/8][k][8], no transposition needed
+#pragma unroll
+        for (int j = 0; j < (BM / 8) * BKC / kTcThreads; ++j) {
+          const int blk = warp + j * (kTcThreads / 32);              // 4 row-octets x 8 k per warp-instruction
+          const int o = (blk & 3) * 4 + (lane >> 3), kk = (blk >> 2) * 8 + (lane & 7);
+          const int m = m0 + o * 8, k = k0 + kk;
+          float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = 0.f;
+          if (k < kend) {
+            if (m + 8 <= M && a_vec) {
+              const float4 x = ldg4(A + (int64_t)k * lda + m), y = ldg4(A + (int64_t)k * lda + m + 4);
+              f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (m + e < M) f[e] = __ldg(A + (int64_t)k * lda + m + e);
+                else if (ones_row && m + e == M) f[e] = 1.0f;
+              }
+            }
+          }
+          store_chunk<X3>(sA + o * (BKC * 16) + kk * 16, kStage, f);
         }
-        if (X3) {
-          uint4 hi, lo;
-          split8(f, hi, lo);
-          *reinterpret_cast<uint4*>(sB + kc * (Npad * 16) + n * 16) = hi;
-          *reinterpret_cast<uint4*>(sB + kStage + kc * (Npad * 16) + n * 16) = lo;
-        } else {
-          *reinterpret_cast<uint4*>(sB + kc * (Npad * 16) + n * 16) = pack8(f);
+      }
+      // ---- B: Npad rows x 64 k.  Four items per trip: all their (independent) global loads are issued before
+      //      the first conversion, otherwise every trip of this runtime-bounded loop costs one DRAM latency.
+      if (!b_mn) {
+        const int total = Npad * (BKC / 8);
+        for (int i0 = tid; i0 < total; i0 += 4 * kTcThreads) {
+          float f[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            const int n = i % Npad, kc = i / Npad, k = k0 + kc * 8;
+            if (i < total && n < N && k < kend) {
+              load8(Bm, ldb, true, n0 + n, k, kend, b_vec, f[u]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[u][e] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kTcThreads;
+            if (i < total) store_chunk<X3>(sB + (i / Npad) * (Npad * 16) + (i % Npad) * 16, kStage, f[u]);
+          }
+        }
+      } else {
+        const int n_oct = Npad / 8, groups = (n_oct + 3) / 4, total = groups * (BKC / 8);
+        for (int b0 = warp; b0 < total; b0 += 4 * (kTcThreads / 32)) {
+          float f[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int blk = b0 + u * (kTcThreads / 32);
+            const int o = (blk % groups) * 4 + (lane >> 3), kk = (blk / groups) * 8 + (lane & 7);
+            const int n = o * 8, k = k0 + kk;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[u][e] = 0.f;
+            if (blk < total && o < n_oct && k < kend) {
+              const float* p = Bm + (int64_t)k * ldb + n0 + n;
+              if (n + 8 <= N && b_vec) {
+                const float4 x = ldg4(p), y = ldg4(p + 4);
+                f[u][0] = x.x; f[u][1] = x.y; f[u][2] = x.z; f[u][3] = x.w;
+                f[u][4] = y.x; f[u][5] = y.y; f[u][6] = y.z; f[u][7] = y.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (n + e < N) f[u][e] = __ldg(p + e);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int blk = b0 + u * (kTcThreads / 32);
+            const int o = (blk % groups) * 4 + (lane >> 3), kk = (blk / groups) * 8 + (lane & 7);
+            if (blk < total && o < n_oct) store_chunk<X3>(sB + o * (BKC * 16) + kk * 16, kStage, f[u]);
+          }
         }
       }
       fence_proxy_async();
@@ -190,14 +257,16 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_group_kernel(const __grid_
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
-        const uint32_t dA = desc_lo(smem_u32(sA), BM * 16), dB = desc_lo(smem_u32(sB), Npad * 16);
+        const uint32_t dA = desc_lo(smem_u32(sA), a_mn ? 128 : BM * 16);
+        const uint32_t dB = desc_lo(smem_u32(sB), b_mn ? 128 : Npad * 16);
+        const uint32_t stepA = a_mn ? 16 : 2 * BM, stepB = b_mn ? 16 : 2 * Npad;   // 16 k further, in 16-byte units
 #pragma unroll
         for (int ks = 0; ks < BKC / 16; ++ks) {
-          const uint64_t ah = desc_join(dA + ks * (2 * BM), dHi), bh = desc_join(dB + ks * (2 * Npad), dHi);
+          const uint64_t ah = desc_join(dA + ks * stepA, dHiA), bh = desc_join(dB + ks * stepB, dHiB);
           mma_bf16_ss(tbase, ah, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
           if (X3) {   // + hi*lo + lo*hi (the lo images sit kStage bytes behind the hi images)
-            const uint64_t al = desc_join(dA + kStage / 16 + ks * (2 * BM), dHi);
-            const uint64_t bl = desc_join(dB + kStage / 16 + ks * (2 * Npad), dHi);
+            const uint64_t al = desc_join(dA + kStage / 16 + ks * stepA, dHiA);
+            const uint64_t bl = desc_join(dB + kStage / 16 + ks * stepB, dHiB);
             mma_bf16_ss(tbase, ah, bl, idesc, 1u);
             mma_bf16_ss(tbase, al, bh, idesc, 1u);
           }
@@ -319,6 +388,7 @@ int gemm_tc_group_launch(GemmGroup& g, cudaStream_t st, int (*reduce)(GemmGroup&
   g.total_red = red;
   if (!any) return DMT_OK;
   const bool x3 = g.use_tc == 3;
+  const int kc = stage_k(x3);
   int nmax = 16, stages = 1;
   for (int i = 0; i < g.n; ++i) {
     const GemmProb& p = g.p[i];
@@ -326,12 +396,12 @@ int gemm_tc_group_launch(GemmGroup& g, cudaStream_t st, int (*reduce)(GemmGroup&
     const int w = p.N < p.tc_bn ? p.N : p.tc_bn;
     if (((w + 15) & ~15) > nmax) nmax = (w + 15) & ~15;
     int64_t chunks = 0;                      // K chunks one CTA walks
-    for (int q = 0; q < p.n_parts; ++q) chunks += (p.part[q].K / (p.splits > 1 ? p.splits : 1) + BKC - 1) / BKC;
+    for (int q = 0; q < p.n_parts; ++q) chunks += (p.part[q].K / (p.splits > 1 ? p.splits : 1) + kc - 1) / kc;
     if (chunks > 1) stages = 2;
   }
   g.tc_nmax = nmax;
   g.tc_stages = stages;
-  int smem = stages * (x3 ? 2 : 1) * (kStageA + nmax * (BKC * 2));
+  int smem = stages * (x3 ? 2 : 1) * (BM * kc * 2 + nmax * (kc * 2));
   if (smem < 8 * 32 * 33 * 4) smem = 8 * 32 * 33 * 4;     // the epilogue's transposition buffers
   cudaError_t e = cudaFuncSetAttribute(x3 ? gemm_tc_group_kernel<1> : gemm_tc_group_kernel<0>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
