@@ -354,6 +354,17 @@ def main():
                     "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"], "traffic": None,
                     "peak_source": pk["source"], "launches": n, "avg_launch_ms": t_ms / n}
     roofline["stage_share"] = shares
+    # DRAM bytes per launch of the same kernel from the committed ncu capture (when the workload matches)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tr = json.load(fh).get("seq_encode_tc_kernel")
+        wl = tr["workload"]
+        if (dom == "seq_encode" and wl["conf"] == args.conf and wl["per_gpu_batch"] == args.batch
+                and wl["precision"] == args.precision and wl["id_mode"] == args.id_mode and not args.small_tables):
+            roofline["traffic"] = tr["mean_dram_bytes_per_launch"]
+            roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
