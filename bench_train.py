@@ -35,6 +35,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=0.0)
     ap.add_argument("--small-tables", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="debug: gradients only")
+    ap.add_argument("--no-dropout", action="store_true", help="set the conf's dropout rates to 0")
     ap.add_argument("--train-gemm", default="bf16x3", choices=["f32", "bf16", "bf16x3"],
                     help="engine of the training-path GEMMs: fp32 SIMT | tcgen05 bf16 | tcgen05 split-bf16 (fp32-grade)")
     return ap.parse_args()
@@ -65,7 +66,8 @@ def main():
     from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
     from cikm2020_dmt_b200.train import Trainer
 
-    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", args.conf, overrides=NO_DROPOUT)
+    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", args.conf,
+                overrides=NO_DROPOUT if args.no_dropout else None)
     plan = build_plan(conf)
     rows = None
     if args.small_tables:
@@ -132,7 +134,9 @@ def main():
                                "Sku vocabulary %d %s" % (4 if world > 1 else 3, args.batch, plan.d_model, plan.num_heads,
                                                          plan.tables["Sku"].rows,
                                                          "row-sharded over %d ranks" % world if world > 1 else ""),
-                   "conf": args.conf, "dropout": "rate 0 (not built yet)"},
+                   "conf": args.conf,
+                   "dropout": "off" if args.no_dropout else "training mode: transformer %.2g, bias tower %s"
+                              % (plan.dropout_rate, list(plan.dropout_rate_bias))},
         "stage_ms_per_step": {k: round(t / args.steps, 4) for k, (t, _) in sorted(stage.items())},
         "stage_share": {k: round(t / total, 4) for k, (t, _) in sorted(stage.items())},
         "gpu_launches": int(launches),

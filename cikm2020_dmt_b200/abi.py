@@ -12,7 +12,7 @@ from . import build as _build
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
 PRECISION_F32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _fp = C.c_void_p   # device pointers travel as integers
 
@@ -37,7 +37,8 @@ class SeqCfg(C.Structure):
     _fields_ = [("batch", C.c_int32), ("d_model", C.c_int32), ("d_ff", C.c_int32), ("num_heads", C.c_int32),
                 ("n_enc_blocks", C.c_int32), ("n_dec_blocks", C.c_int32), ("maxlen", C.c_int32),
                 ("zero_pad", C.c_int32), ("n_feats", C.c_int32), ("precision", C.c_int32),
-                ("slot_len", C.c_int32), ("_reserved", C.c_int32)]
+                ("slot_len", C.c_int32), ("_reserved", C.c_int32), ("dropout_rate", C.c_float),
+                ("dropout_seed", C.c_uint32)]
 
 
 class SeqInput(C.Structure):
@@ -71,7 +72,8 @@ class MmoeWeights(C.Structure):
 class BiasLossCfg(C.Structure):
     _fields_ = [("batch", C.c_int32), ("in_dim", C.c_int32), ("n_hidden", C.c_int32),
                 ("units", C.c_int32 * MAX_LAYERS), ("two_head_multiply", C.c_int32), ("ctr_rel", C.c_int32),
-                ("weight_ctr", C.c_float * 5), ("weight_ecvr", C.c_float * 5), ("loss_weight", C.c_float * 2)]
+                ("weight_ctr", C.c_float * 5), ("weight_ecvr", C.c_float * 5), ("loss_weight", C.c_float * 2),
+                ("dropout_rate", C.c_float * MAX_LAYERS), ("dropout_seed", C.c_uint32)]
 
 
 class BiasWeights(C.Structure):

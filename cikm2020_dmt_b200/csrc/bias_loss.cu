@@ -1,6 +1,7 @@
 // dmt_bias_loss_fwd: neighbouring-bias tower (A11) + unbiased two-task loss and its logit
 // gradients (A12), fused: one thread per sample, the tiny MLP weights staged in shared memory.
 #include "dmt_common.cuh"
+#include "dropout.cuh"
 
 namespace dmt {
 
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(128) bias_loss_kernel(const __grid_constant__ 
       for (int k = 0; k < in_dim; ++k) acc = fmaf(cur[k], W[k * units + n], acc);
       acc += bb[n];
       nxt[n] = (l < a.cfg.n_hidden) ? fmaxf(acc, 0.f) : acc;   // relu hidden, identity output (:263-287)
+      if (l < a.cfg.n_hidden && a.cfg.dropout_rate[l] > 0.f)   // training mode (:272,280)
+        nxt[n] *= Dropout(a.cfg.dropout_rate[l], a.cfg.dropout_seed, kSiteBias + l).mult((uint32_t)(b * units + n));
     }
     for (int n = 0; n < units; ++n) cur[n] = nxt[n];
     base += in_dim * units + units;

@@ -5,6 +5,7 @@
 //   grouped GEMMs          expert layers last to first: dW = in^T dH (split-K over the batch), dH_prev =
 //                          (dH W^T) * relu'(H_prev); the first layer and both gates contract into dx in ONE
 //                          multi-part problem, so dx is written once.
+#include "dropout.cuh"
 #include "gemm_f32.cuh"
 #include "seq_train.cuh"   // Carver
 
@@ -434,7 +435,9 @@ __global__ void __launch_bounds__(128) bias_bwd_kernel(const __grid_constant__ B
     for (int n = 0; n < units; ++n) {
       float acc = 0.f;
       for (int k = 0; k < dims[l]; ++k) acc = fmaf(acts[l][k], __ldg(W + k * units + n), acc);
-      const float y = fmaxf(acc + __ldg(a.w.layer[l].b + n), 0.f);
+      float y = fmaxf(acc + __ldg(a.w.layer[l].b + n), 0.f);
+      if (a.cfg.dropout_rate[l] > 0.f)
+        y *= Dropout(a.cfg.dropout_rate[l], a.cfg.dropout_seed, kSiteBias + l).mult((uint32_t)(b * units + n));
       acts[l + 1][n] = y;
       a.act[l][(int64_t)b * units + n] = y;
     }
@@ -449,7 +452,10 @@ __global__ void __launch_bounds__(128) bias_bwd_kernel(const __grid_constant__ B
   for (int l = nh - 1; l >= 0; --l) {
     const int units = dims[l + 1];
     for (int n = 0; n < units; ++n) {
-      const float dp = acts[l + 1][n] > 0.f ? dcur[n] : 0.f;
+      // out = relu(z) * M: a dropped or inactive unit carries no gradient, a kept one scales it by M
+      float dp = acts[l + 1][n] > 0.f ? dcur[n] : 0.f;
+      if (a.cfg.dropout_rate[l] > 0.f)
+        dp *= Dropout(a.cfg.dropout_rate[l], a.cfg.dropout_seed, kSiteBias + l).mult((uint32_t)(b * units + n));
       dcur[n] = dp;
       a.dpre[l][(int64_t)b * units + n] = dp;
     }

@@ -9,6 +9,7 @@
 // All arithmetic is fp32 on CUDA cores; this is the exact-parity path (tolerance 1e-4 against
 // the fp64 oracle) and the arithmetic reference for the bf16 tensor-core path.
 #include "dmt_common.cuh"
+#include "dropout.cuh"
 #include "seq_train.cuh"
 
 namespace dmt {
@@ -178,6 +179,9 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
   const int L = min(len_all, LP);
   const float sqrt_d = sqrtf((float)D);
   const float scale = 1.0f / sqrtf((float)dk);
+  // training forward only (SAVE): the dropout sites of B12; rate 0 / eval -> every multiplier is 1
+  const float drate = SAVE ? a.cfg.dropout_rate : 0.f;
+  const Dropout drop_enc(drate, a.cfg.dropout_seed, kSiteEncIn), drop_dec(drate, a.cfg.dropout_seed, kSiteDecIn);
 
   // ---- A2/A3: gather + concat + scale + learned position (mmoe_transformer_unbias.py:153-158,181;
   //      TransformerModel.py:97-100) ----
@@ -189,13 +193,14 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
     const int len_f = __ldg(a.in.offsets[f] + b + 1) - off;
     const int id = (t < len_f) ? __ldg(a.in.ids[f] + off + t) : 0;
     const float e = lookup_elem(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad);
-    X[t * ld + c] = e * sqrt_d + __ldg(a.w.pos + t * D + c);
+    X[t * ld + c] = (e * sqrt_d + __ldg(a.w.pos + t * D + c)) * drop_enc.mult((uint32_t)((off_last + t) * D + c));
   }
   for (int c = tid; c < D; c += kThreads) {
     int f = 0;
     while (f + 1 < nf && c >= a.col_off[f + 1]) ++f;
     const int id = __ldg(a.in.item_ids[f] + b);
-    dvec[c] = lookup_elem(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d;
+    dvec[c] = lookup_elem(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d *
+              drop_dec.mult((uint32_t)(b * D + c));
   }
   __syncthreads();
   if (SAVE) {
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
       save_rows(Kb, ld, L, D, a.sv.qkv[blk], off_last, 3 * D, D);
       save_rows(V, ld, L, D, a.sv.qkv[blk], off_last, 3 * D, 2 * D);
     }
+    const Dropout drop_p(drate, a.cfg.dropout_seed, kSiteSelfProbs + blk);
     for (int h = 0; h < H; ++h) {
       const int hc = h * dk;
       for (int i = tid; i < L * L; i += kThreads) {
@@ -257,7 +263,8 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
           s += e;
         }
         const float inv = 1.0f / warp_sum(s);
-        for (int j = lane; j < L; j += 32) S[r * lds + j] *= inv;
+        for (int j = lane; j < L; j += 32)
+          S[r * lds + j] *= inv * drop_p.mult((uint32_t)(((b * H + h) * LP + r) * LP + j));
       }
       __syncthreads();
       // context; overwrites this head's Q columns (dead after the scores)
@@ -334,10 +341,12 @@ __global__ void __launch_bounds__(kThreads, 2) seq_encode_f32_kernel(const __gri
       for (int j = lane; j < L; j += 32) sc[h * LP + j] *= inv;
     }
     __syncthreads();
+    const Dropout drop_v(drate, a.cfg.dropout_seed, kSiteVanillaProbs + blk);
     for (int c = tid; c < D; c += kThreads) {
       const int h = c / dk;
       float acc = 0.f;
-      for (int j = 0; j < L; ++j) acc = fmaf(sc[h * LP + j], V[j * ld + c], acc);
+      for (int j = 0; j < L; ++j)
+        acc = fmaf(sc[h * LP + j] * drop_v.mult((uint32_t)((b * H + h) * LP + j)), V[j * ld + c], acc);
       ovec[c] = acc;
     }
     __syncthreads();

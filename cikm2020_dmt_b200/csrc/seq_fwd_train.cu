@@ -13,6 +13,7 @@
 //
 // Same arithmetic as TransformerModel.py:84-171 / TransformerModel_util.py:11-108,160-235 (see
 // seq_encode_f32.cu for the fused fp32 statement); only the GEMM operands are rounded (bf16 or split-bf16).
+#include "dropout.cuh"
 #include "gemm_f32.cuh"
 #include "seq_train.cuh"
 
@@ -43,6 +44,8 @@ __global__ void __launch_bounds__(256) seq_gather_kernel(const __grid_constant__
   const int len_all = __ldg(a.in.offsets[nf - 1] + b + 1) - off_last;
   const int L = min(len_all, a.LP);
   const float sqrt_d = sqrtf((float)D);
+  const Dropout drop_enc(a.cfg.dropout_rate, a.cfg.dropout_seed, kSiteEncIn);
+  const Dropout drop_dec(a.cfg.dropout_rate, a.cfg.dropout_seed, kSiteDecIn);
   for (int i = threadIdx.x; i < len_all * D; i += 256) {
     const int t = i / D, c = i - t * D;
     float v = 0.f;
@@ -54,6 +57,7 @@ __global__ void __launch_bounds__(256) seq_gather_kernel(const __grid_constant__
       const int id = (t < len_f) ? __ldg(a.in.ids[f] + off + t) : 0;
       v = lookup(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d +
           __ldg(a.pos + t * D + c);
+      v *= drop_enc.mult((uint32_t)((off_last + t) * D + c));      // TransformerModel.py:101
     }
     a.h0[((int64_t)off_last + t) * D + c] = v;
   }
@@ -62,7 +66,8 @@ __global__ void __launch_bounds__(256) seq_gather_kernel(const __grid_constant__
     while (f + 1 < nf && c >= a.col_off[f + 1]) ++f;
     const int id = __ldg(a.in.item_ids[f] + b);
     a.d0[(int64_t)b * D + c] =
-        lookup(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d;
+        lookup(a.in.table[f], a.in.rows[f], a.in.dim[f], id, c - a.col_off[f], a.cfg.zero_pad) * sqrt_d *
+        drop_dec.mult((uint32_t)(b * D + c));                        // TransformerModel.py:151
   }
 }
 
@@ -122,6 +127,7 @@ struct AttnFwdArgs {
   float* a;           // [T, D]
   const int32_t* offsets;
   int D, H, LP;
+  Dropout drop;       // attention-probability dropout of this block (TransformerModel_util.py:51)
 };
 
 // One CTA per sample: softmax(Q_h K_h^T / sqrt(dk)) V_h over the L valid keys, + residual, LayerNorm.
@@ -165,7 +171,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
         s += e;
       }
       const float inv = 1.0f / warp_sum(s);
-      for (int j = lane; j < L; j += 32) S[r * lds + j] *= inv;
+      for (int j = lane; j < L; j += 32)
+        S[r * lds + j] *= inv * a.drop.mult((uint32_t)(((b * H + h) * LP + r) * LP + j));
     }
     __syncthreads();
     for (int i = tid; i < L * dk; i += 256) {
@@ -201,6 +208,7 @@ struct DecAttnFwdArgs {
   float* ad;          // [B, D]
   const int32_t* offsets;
   int D, H, LP;
+  Dropout drop;
 };
 
 __global__ void __launch_bounds__(128) dec_attn_fwd_kernel(const __grid_constant__ DecAttnFwdArgs a) {
@@ -246,7 +254,8 @@ __global__ void __launch_bounds__(128) dec_attn_fwd_kernel(const __grid_constant
   for (int c = tid; c < D; c += 128) {
     const int h = c / dk;
     float acc = 0.f;
-    for (int j = 0; j < L; ++j) acc = fmaf(p[h * LP + j], KV[j * ld + D + c], acc);
+    for (int j = 0; j < L; ++j)
+      acc = fmaf(p[h * LP + j] * a.drop.mult((uint32_t)((b * H + h) * LP + j)), KV[j * ld + D + c], acc);
     const float z = acc + __ldg(a.din + (int64_t)b * D + c);
     o[c] = z;
     a.z1d[(int64_t)b * D + c] = z;
@@ -345,7 +354,8 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
       if ((rc = gemm_group_launch(grp, st))) return rc;
     }
     {
-      AttnFwdArgs a{sv.qkv[blk], sv.hin[blk], aw.ln.gamma, aw.ln.beta, sv.z1[blk], sv.a[blk], offsets, d, H, LP};
+      AttnFwdArgs a{sv.qkv[blk], sv.hin[blk], aw.ln.gamma, aw.ln.beta, sv.z1[blk], sv.a[blk], offsets, d, H, LP,
+                    Dropout(c.dropout_rate, c.dropout_seed, kSiteSelfProbs + blk)};
       const size_t smem = ((size_t)3 * LP * (d + 1) + LP * (LP + 1)) * sizeof(float);
       DMT_REQUIRE(smem <= 227 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd_train: attention tile %zu B", smem);
       cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -388,7 +398,7 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
     }
     {
       DecAttnFwdArgs a{sv.qd[blk], sv.kvd[blk], sv.din[blk], aw.ln.gamma, aw.ln.beta, sv.pd[blk], sv.z1d[blk], sv.ad[blk],
-                       offsets, d, H, LP};
+                       offsets, d, H, LP, Dropout(c.dropout_rate, c.dropout_seed, kSiteVanillaProbs + blk)};
       const size_t smem = ((size_t)LP * (2 * d + 1) + d + H * LP + 256 + 8) * sizeof(float);
       cudaError_t e = cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_attn_fwd_kernel)");

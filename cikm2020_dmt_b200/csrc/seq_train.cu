@@ -8,6 +8,7 @@
 //
 // Weight gradients are  saved_activation^T x gradient  contractions over all tokens: grouped split-K
 // GEMMs with a fixed-order reduction (gemm_f32.cuh).  Nothing here uses floating-point atomics.
+#include "dropout.cuh"
 #include "gemm_f32.cuh"
 #include "seq_train.cuh"
 
@@ -136,6 +137,7 @@ struct AttnBwdArgs {
   float* dqkv;             // [T, 3D]
   const int32_t* offsets;  // [B+1]
   int D, H, LP;
+  Dropout drop;            // the forward's attention-probability mask M: O_h = (P * M) V_h
 };
 
 constexpr int kAttnThreads = 256;
@@ -190,13 +192,20 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const __grid_con
       }
       const float inv = 1.0f / warp_sum(s);
       float pd = 0.f;
+      // with dropout: dS holds d(P*M); dP = d(P*M) * M, and the value path (dV) needs P*M
       for (int j = lane; j < L; j += 32) {
         const float p = P[r * lds + j] * inv;
+        const float dp = dS[r * lds + j] * a.drop.mult((uint32_t)(((b * H + h) * LP + r) * LP + j));
         P[r * lds + j] = p;
-        pd = fmaf(p, dS[r * lds + j], pd);
+        dS[r * lds + j] = dp;
+        pd = fmaf(p, dp, pd);
       }
       pd = warp_sum(pd);
-      for (int j = lane; j < L; j += 32) dS[r * lds + j] = P[r * lds + j] * (dS[r * lds + j] - pd) * scale;
+      for (int j = lane; j < L; j += 32) {
+        const float p = P[r * lds + j];
+        dS[r * lds + j] = p * (dS[r * lds + j] - pd) * scale;
+        P[r * lds + j] = p * a.drop.mult((uint32_t)(((b * H + h) * LP + r) * LP + j));
+      }
     }
     __syncthreads();
     for (int i = tid; i < L * dk; i += kAttnThreads) {
@@ -228,6 +237,7 @@ struct DecAttnBwdArgs {
   float* dkvd;             // [T, 2D]
   const int32_t* offsets;
   int D, H, LP;
+  Dropout drop;
 };
 
 constexpr int kDecThreads = 128;
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(kDecThreads) dec_attn_bwd_kernel(const __grid_
     const int h = i / L, j = i - h * L;
     float dp = 0.f;
     for (int c = 0; c < dk; ++c) dp = fmaf(dod[h * dk + c], KV[j * ld + D + h * dk + c], dp);
-    ds[h * LP + j] = dp;
+    ds[h * LP + j] = dp * a.drop.mult((uint32_t)((b * H + h) * LP + j));   // d(p*M) -> dp
   }
   __syncthreads();
   if (tid < H) {
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(kDecThreads) dec_attn_bwd_kernel(const __grid_
     const int j = i / D, c = i - j * D, h = c / dk;
     float* row = a.dkvd + (off + j) * 2 * D;
     row[c] = ds[h * LP + j] * q[c];
-    row[D + c] = p[h * LP + j] * dod[c];
+    row[D + c] = p[h * LP + j] * a.drop.mult((uint32_t)((b * H + h) * LP + j)) * dod[c];
   }
   for (int c = tid; c < D; c += kDecThreads) {
     const int h = c / dk;
@@ -333,6 +343,12 @@ __global__ void pos_grad_reduce_kernel(const __grid_constant__ PosGradArgs a) {
   float tot = 0.f;
   for (int s = 0; s < kPosSplits; ++s) tot += a.partial[(int64_t)s * a.LP * a.D + i];
   a.dpos[i] += tot * a.inv_scale;
+}
+
+// In-place backward of an input-dropout site: g[i] *= M[i] (rows x D, element index = r * D + c).
+__global__ void dropout_bwd_kernel(float* __restrict__ g, int64_t n, Dropout drop) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] *= drop.mult((uint32_t)i);
 }
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, int64_t lds_, float* __restrict__ dst, int64_t ldd,
@@ -502,7 +518,8 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
                        const_cast<float*>(ag.ln.gamma), const_cast<float*>(ag.ln.beta), st);
     if (rc) return rc;
     {
-      DecAttnBwdArgs a{sv.qd[blk], sv.kvd[blk], sv.pd[blk], ws.dz1d, ws.dqd, ws.dkvd, offsets, d, H, LP};
+      DecAttnBwdArgs a{sv.qd[blk], sv.kvd[blk], sv.pd[blk], ws.dz1d, ws.dqd, ws.dkvd, offsets, d, H, LP,
+                       Dropout(c.dropout_rate, c.dropout_seed, kSiteVanillaProbs + blk)};
       const size_t smem = ((size_t)LP * (2 * d + 1) + 2 * d + 2 * H * LP + H + 8) * sizeof(float);
       cudaError_t e = cudaFuncSetAttribute(dec_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec_attn_bwd_kernel)");
@@ -557,6 +574,11 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
                                                                                sqrt_d);
     DMT_CUDA_LAUNCH_CHECK("scale_copy_kernel");
   }
+  if (c.dropout_rate > 0.f) {
+    dropout_bwd_kernel<<<(unsigned)(((int64_t)B * d + 255) / 256), 256, 0, st>>>(
+        d_target, (int64_t)B * d, Dropout(c.dropout_rate, c.dropout_seed, kSiteDecIn));
+    DMT_CUDA_LAUNCH_CHECK("dropout_bwd_kernel");
+  }
   if (T == 0) return DMT_OK;
   if (!dmem_written) {
     cudaError_t e = cudaMemsetAsync(dmem, 0, (size_t)T * d * sizeof(float), st);
@@ -604,7 +626,8 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
                        const_cast<float*>(ag.ln.gamma), const_cast<float*>(ag.ln.beta), st);
     if (rc) return rc;
     {
-      AttnBwdArgs a{sv.qkv[blk], ws.dz1, ws.dqkv, offsets, d, H, LP};
+      AttnBwdArgs a{sv.qkv[blk], ws.dz1, ws.dqkv, offsets, d, H, LP,
+                    Dropout(c.dropout_rate, c.dropout_seed, kSiteSelfProbs + blk)};
       const size_t smem = ((size_t)4 * LP * (d + 1) + 2 * LP * (LP + 1)) * sizeof(float);
       DMT_REQUIRE(smem <= 227 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_bwd: attention tile needs %zu B", smem);
       cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -645,6 +668,11 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
   if (c.n_enc_blocks == 0) {   // memory = encoder input
     scale_copy_kernel<<<(unsigned)((T * d + 255) / 256), 256, 0, st>>>(dmem, d, d_tokens, d, T, d, sqrt_d);
     DMT_CUDA_LAUNCH_CHECK("scale_copy_kernel");
+  }
+  if (c.dropout_rate > 0.f) {   // H0 = dropout(X sqrt(d) + P), D0 = dropout(q sqrt(d)): gradients pick up the masks
+    dropout_bwd_kernel<<<(unsigned)((T * d + 255) / 256), 256, 0, st>>>(d_tokens, T * d,
+                                                                      Dropout(c.dropout_rate, c.dropout_seed, kSiteEncIn));
+    DMT_CUDA_LAUNCH_CHECK("dropout_bwd_kernel");
   }
   {
     PosGradArgs a{d_tokens, offsets, ws.pos_partial, const_cast<float*>(g->pos), 1.0f / sqrt_d, B, d, LP};

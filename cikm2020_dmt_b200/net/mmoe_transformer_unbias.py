@@ -259,11 +259,12 @@ class mmoe_transformer_unbias(object):
             self._prepared[seq_index] = (self.params_version, buf)
         return buf, nbytes
 
-    def _seq_cfg(self, inputs, seq, batch, precision):
+    def _seq_cfg(self, inputs, seq, batch, precision, dropout_rate=0.0, dropout_seed=0):
         plan = self.plan
         return abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
                           plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
-                          len(seq.user_features), precision, self._seq_len_hint(inputs, seq), 0)
+                          len(seq.user_features), precision, self._seq_len_hint(inputs, seq), 0,
+                          float(dropout_rate), int(dropout_seed) & 0xFFFFFFFF)
 
     def _seq_input(self, inputs, seq, batch):
         si = abi.SeqInput()
@@ -359,7 +360,8 @@ class mmoe_transformer_unbias(object):
             abi.check(self.lib.dmt_mmoe_fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),
                                             logits.data_ptr(), ws.data_ptr(), nbytes, prep_ptr, stream))
 
-    def _bias_cfg(self, batch, passthrough=False, loss_unbias_method=None, loss_ctr_rel_method=None):
+    def _bias_cfg(self, batch, passthrough=False, loss_unbias_method=None, loss_ctr_rel_method=None,
+                  dropout_rates=None, dropout_seed=0):
         plan = self.plan
         cfg = abi.BiasLossCfg()
         cfg.batch = batch
@@ -374,6 +376,10 @@ class mmoe_transformer_unbias(object):
             cfg.weight_ctr[i] = plan.weight_ctr[i]
             cfg.weight_ecvr[i] = plan.weight_ecvr[i]
         cfg.loss_weight[0], cfg.loss_weight[1] = plan.loss_weight[0], plan.loss_weight[1]
+        for i, r in enumerate(dropout_rates or []):
+            if i < abi.MAX_LAYERS:
+                cfg.dropout_rate[i] = float(r)
+        cfg.dropout_seed = int(dropout_seed) & 0xFFFFFFFF
         return cfg
 
     # ------------------------------------------------------------------ plugin protocol
@@ -449,7 +455,7 @@ class mmoe_transformer_unbias(object):
                                                  abi.ptr(probs), loss.data_ptr(), abi.ptr(dlog),
                                                  scratch.data_ptr(), stream))
         self._last_loss = {"mask": mask, "yb": yb_in}
-        out = loss[0]
+        out = loss[0].clone()       # the buffer is reused by the next call
         if want_probs or want_grads:
             return out, probs, dlog
         return out
@@ -465,16 +471,25 @@ class mmoe_transformer_unbias(object):
         self._seq_g, self._mmoe_g, self._bias_g = self._bind(gviews)
         self._grad_views = gviews
 
-    def compute_gradients(self, inputs, mask=None, loss_unbias_method=None, loss_ctr_rel_method=None):
-        """`optimizer.compute_gradients(loss)` of the reference's training graph (run_dnn.py:154-181): one
-        forward that saves activations + the backward, fp32.  Returns `(loss, Gradients)`; the loss is the
-        batch mean, so averaging `Gradients` over data-parallel ranks equals `average_gradients`
-        (run_dnn.py:45-80)."""
+    def compute_gradients(self, inputs, mask=None, loss_unbias_method=None, loss_ctr_rel_method=None,
+                          is_train=True, dropout_seed=None):
+        """`optimizer.compute_gradients(loss)` of the reference's training graph (run_dnn.py:154-181, built with
+        is_train=True): one forward that saves activations + the backward.  Returns `(loss, Gradients)`; the
+        loss is the batch mean, so averaging `Gradients` over data-parallel ranks equals `average_gradients`
+        (run_dnn.py:45-80).
+
+        is_train activates the dropout sites of the graph (transformer_dropout_rate at the encoder / decoder
+        inputs and the attention probabilities, dropout_rate_bias in the bias tower); the keep masks are a
+        counter-based hash of (dropout_seed, site, element), a fresh seed per call unless one is given."""
         from ..optim import Gradients, LookupGrad
+        from .. import dropout as DO
         plan, lib = self.plan, self.lib
-        if plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias):
-            raise NotImplementedError("training-mode dropout is not built yet; set transformer_dropout_rate and "
-                                      "dropout_rate_bias to 0")
+        rate = float(plan.dropout_rate) if is_train else 0.0
+        rates_bias = [float(r) for r in plan.dropout_rate_bias] if is_train else []
+        if dropout_seed is None:
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            dropout_seed = DO.step_seed(getattr(self, "dropout_base_seed", 20201019), self._train_calls)
+        self.last_dropout_seed = dropout_seed
         inputs = self.stage_inputs(inputs)
         mask = self._dev(inputs["mask"] if mask is None else mask)
         feats = inputs["features"] if plan.is_use_feature else None
@@ -505,7 +520,7 @@ class mmoe_transformer_unbias(object):
         keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
         seq_state = []
         for s, seq in enumerate(plan.sequences):
-            cfg = self._seq_cfg(inputs, seq, batch, F32)
+            cfg = self._seq_cfg(inputs, seq, batch, F32, rate, DO.step_seed(dropout_seed, 0, 1 + seq.index))
             si, kp = self._seq_input(inputs, seq, batch)
             keep += kp
             users = [self._sparse(inputs, uf, "seq%d" % seq.index) for uf in seq.user_features]
@@ -530,7 +545,8 @@ class mmoe_transformer_unbias(object):
         bias_in = self._buf("bias_in", (batch, plan.bias_width))
         keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
         y_bias = self._buf("y_bias", (batch,))
-        bcfg = self._bias_cfg(batch, loss_unbias_method=loss_unbias_method, loss_ctr_rel_method=loss_ctr_rel_method)
+        bcfg = self._bias_cfg(batch, loss_unbias_method=loss_unbias_method, loss_ctr_rel_method=loss_ctr_rel_method,
+                              dropout_rates=rates_bias, dropout_seed=DO.step_seed(dropout_seed, 0, 0))
         loss = self._buf("loss", (1,))
         dlog = self._buf("dlogits", (3, batch))
         scratch = self._buf("loss_scratch", (lib.dmt_loss_scratch_bytes(batch),), torch.uint8)
@@ -587,7 +603,7 @@ class mmoe_transformer_unbias(object):
                 it = self._sparse(inputs, seq.item_features[f], "seq%d" % seq.index)
                 add(scope, LookupGrad(it.values, d_tar, seq.col_offsets[f], id_off))
         self._keep_train = (keep, seq_state, inputs)
-        return loss[0], Gradients(g_dense, lookups, self._grad_views)
+        return loss[0].clone(), Gradients(g_dense, lookups, self._grad_views)   # (the loss buffer is reused)
 
     def l2_norm(self, inputs):
         raise NotImplementedError("l2_norm is gated off by wnd_wd = 0.0 in dmt.conf (run_dnn.py:174)")

@@ -55,6 +55,7 @@ class Trainer(object):
         self.model = mmoe_transformer_unbias(plan, device=self.device, params=store, precision=precision,
                                              train_gemm=train_gemm)
         self.store = store
+        self.model.dropout_base_seed = (seed * 0x9E3779B1 + 7919 * self.rank) & 0xFFFFFFFF   # ranks draw different masks
         self.opt = TFAdam(self.model, learning_rate)
         self.learning_rate = learning_rate
         self.lib = self.model.lib

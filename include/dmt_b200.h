@@ -38,7 +38,7 @@ extern "C" {
 #define DMT_API __attribute__((visibility("default")))
 #endif
 
-#define DMT_ABI_VERSION 5
+#define DMT_ABI_VERSION 6
 
 #define DMT_MAX_SEQ_FEATS 8   /* (user, item) feature pairs per behaviour sequence */
 #define DMT_MAX_BLOCKS 4      /* transformer_num_blocks_{encode,decode}            */
@@ -106,6 +106,12 @@ typedef struct dmt_seq_cfg {
                            the bf16 path packs 128/slot samples per tile (slot = 16/32/64)
                            and truncates longer sequences to it                        */
   int32_t _reserved;
+  /* training entry points only (dmt_seq_encode_fwd_train / _bwd): transformer_dropout_rate applied at the
+     encoder input, the decoder input and the attention probabilities (TransformerModel.py:101,151;
+     TransformerModel_util.py:51).  The keep mask is a counter-based hash of (dropout_seed, site, element),
+     recomputed by the backward; pass the same cfg to both.  0 = no dropout. */
+  float dropout_rate;
+  uint32_t dropout_seed;
 } dmt_seq_cfg;
 
 /* per-sequence inputs: generate_data(), mmoe_transformer_unbias.py:130-186 */
@@ -168,6 +174,10 @@ typedef struct dmt_bias_loss_cfg {
   float weight_ctr[5];                 /* [class_weight] weight_ctr by ascending label */
   float weight_ecvr[5];                /* [class_weight] weight_ecvr                   */
   float loss_weight[2];                /* [parameter] loss_weight                      */
+  /* training mode: dropout_rate_bias after each hidden layer (mmoe_transformer_unbias.py:272,280); same
+     hash mask as dmt_seq_cfg, pass the same cfg to dmt_bias_loss_fwd and dmt_bias_bwd.  0 = off. */
+  float dropout_rate[DMT_MAX_LAYERS];
+  uint32_t dropout_seed;
 } dmt_bias_loss_cfg;
 
 typedef struct dmt_bias_weights {

@@ -126,7 +126,7 @@ def _mask(inputs, query_masks, key_masks, kind):
     return torch.where(qm, inputs, paddings)
 
 
-def scaled_dot_product_attention(Q, K, V, query_masks, key_masks, dropout_rate, training):
+def scaled_dot_product_attention(Q, K, V, query_masks, key_masks, dropout_rate, training, site=None):
     """TransformerModel_util.py:11-56."""
     d_k = Q.shape[-1]
     outputs = torch.matmul(Q, K.transpose(1, 2))              # :30
@@ -134,8 +134,7 @@ def scaled_dot_product_attention(Q, K, V, query_masks, key_masks, dropout_rate, 
     outputs = _mask(outputs, query_masks, key_masks, "key")   # :36
     outputs = torch.softmax(outputs, dim=-1)                  # :43
     outputs = _mask(outputs, query_masks, key_masks, "query") # :48 (after the softmax)
-    if training and dropout_rate > 0:
-        outputs = torch.nn.functional.dropout(outputs, dropout_rate, True)   # :51
+    outputs = _dropout(outputs, dropout_rate, training, site)     # :51
     return torch.matmul(outputs, V)                           # :54
 
 
@@ -150,7 +149,8 @@ def multihead_attention(P, scope, queries, keys, values, queries_length, keys_le
     Q_ = torch.cat(torch.chunk(Q, num_heads, dim=2), dim=0)                           # :193-195
     K_ = torch.cat(torch.chunk(K, num_heads, dim=2), dim=0)
     V_ = torch.cat(torch.chunk(V, num_heads, dim=2), dim=0)
-    outputs = scaled_dot_product_attention(Q_, K_, V_, query_masks, key_masks, dropout_rate, training)
+    outputs = scaled_dot_product_attention(Q_, K_, V_, query_masks, key_masks, dropout_rate, training,
+                                           site=("probs", scope))
     outputs = torch.cat(torch.chunk(outputs, num_heads, dim=0), dim=2)                # :201
     outputs = outputs + queries                                                       # :204
     return ln(outputs, P[scope + "/ln/beta"], P[scope + "/ln/gamma"])                 # :207
@@ -164,8 +164,17 @@ def ff(P, scope, inputs):
     return ln(outputs, P[scope + "/ln/beta"], P[scope + "/ln/gamma"])
 
 
-def _dropout(x, rate, training):
+# TF's RNG stream cannot be reproduced.  Tests that compare TRAINING mode install a hook
+# `(site, x, rate) -> multiplier tensor (0 or 1/(1-rate))` so that the oracle drops exactly the elements the
+# CUDA path drops (tests/test_gpu_dropout.py); without a hook the sites draw from torch's generator.
+DROPOUT_HOOK = None
+
+
+def _dropout(x, rate, training, site=None):
+    """tf.layers.dropout(x, rate, training) -- inverted dropout, keep probability 1 - rate."""
     if training and rate > 0:
+        if DROPOUT_HOOK is not None:
+            return x * DROPOUT_HOOK(site, x, rate).to(x.dtype)
         return torch.nn.functional.dropout(x, rate, True)
     return x
 
@@ -176,7 +185,7 @@ def encode(plan, P, scope, seq_emb, seqlens, training):
     T = enc.shape[1]
     pos = P[scope + "/positional_encoding_k_position_learn/embedding_position_learn"]
     enc = enc + pos[torch.arange(T)][None, :, :]                                      # :67-69
-    enc = _dropout(enc, plan.dropout_rate, training)                                  # :101
+    enc = _dropout(enc, plan.dropout_rate, training, ("enc_in", scope))               # :101
     for i in range(plan.num_blocks_encode):
         blk = "%s/num_blocks_%d" % (scope, i)
         enc = multihead_attention(P, blk + "/self-attention", enc, enc, enc, seqlens, seqlens,
@@ -188,7 +197,7 @@ def encode(plan, P, scope, seq_emb, seqlens, training):
 def decode(plan, P, scope, query_emb, query_length, memory, key_length, training):
     """TransformerModel.py:125-171."""
     dec = query_emb * plan.d_model ** 0.5                                             # :147
-    dec = _dropout(dec, plan.dropout_rate, training)                                  # :151
+    dec = _dropout(dec, plan.dropout_rate, training, ("dec_in", scope))               # :151
     for i in range(plan.num_blocks_decode):
         blk = "%s/num_blocks_%d" % (scope, i)
         dec = multihead_attention(P, blk + "/vanilla_attention", dec, memory, memory,
@@ -272,7 +281,7 @@ def embedding_mlp_bias(plan, P, inputs, training):
     n_hidden = len(plan.hidden_units_bias)
     for l in range(n_hidden):
         y = torch.relu(y @ P["DnnModel/layer_bias%d/kernel" % l] + P["DnnModel/layer_bias%d/bias" % l])
-        y = _dropout(y, plan.dropout_rate_bias[l], training)
+        y = _dropout(y, plan.dropout_rate_bias[l], training, ("bias", l))
     return y @ P["DnnModel/layer_bias%d/kernel" % n_hidden] + P["DnnModel/layer_bias%d/bias" % n_hidden]
 
 
