@@ -1,0 +1,127 @@
+"""TFRecord -> CSR batch reader and string-id -> index lookup, against fixtures produced by an
+independent parser (google.protobuf) and the reference's own ID tables (tests/golden/make_golden_data.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CONF_DIR
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLD, "demo_records.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def payloads():
+    from cikm2020_dmt_b200 import tfrecord as T
+    return list(T.read_records(os.path.join(GOLD, "demo_records.tfrecord"), verify=True))   # both CRCs checked
+
+
+def test_framing_and_crc(payloads, tmp_path):
+    from cikm2020_dmt_b200 import tfrecord as T
+    assert len(payloads) == 10 and all(len(p) > 1000 for p in payloads)
+    assert T._crc32c(b"123456789") == 0xE3069283                        # CRC-32C check value
+    raw = open(os.path.join(GOLD, "demo_records.tfrecord"), "rb").read()
+    bad = bytearray(raw)
+    bad[40] ^= 0xFF                                                     # corrupt one payload byte
+    p = tmp_path / "bad.tfrecord"
+    p.write_bytes(bytes(bad))
+    with pytest.raises(IOError):
+        list(T.read_records(str(p), verify=True))
+    p.write_bytes(raw[:-3])                                             # truncated file
+    with pytest.raises(IOError):
+        list(T.read_records(str(p)))
+
+
+def test_example_parser_matches_protobuf(payloads, gold):
+    from cikm2020_dmt_b200 import tfrecord as T
+    for payload, want in zip(payloads, gold["records"]):
+        ex = T.parse_example(payload)
+        assert len(ex) == want["n_keys"]
+        assert float(ex["label"][0]) == want["label"]
+        assert [float(v) for v in ex["mask"]] == want["mask"]
+        assert len(ex["features"]) == want["features_len"] == 615
+        assert abs(float(np.sum(ex["features"].astype(np.float64))) - want["features_sum"]) < 1e-9
+        assert ex["header"][0].decode() == want["header"]
+        for k, ids in want["ids"].items():
+            assert [v.decode() for v in ex[k]] == ids, k
+        for k, s in want["wts_sum"].items():
+            assert abs(float(np.sum(ex[k + "Wts"])) - s) < 1e-6
+
+
+def test_batcher_builds_the_input_contract(payloads, gold):
+    """parse_single_line (tfrecord_mask.py:23-84): CSR ids, Wts, mask, em_position / em_page from the header."""
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200 import tfrecord as T
+    conf = Conf(CONF_DIR, "dmt_demo.conf")
+    vocab = {n: [] for n in ("Sku", "Brand", "Shopid", "TimeClick", "TimeOrder", "TimeCart")}   # hashed only (no 73 MB table)
+    idt = "/root/reference/DMT_code/conf/idtables"
+    have_ref = os.path.isdir(idt)
+    if not have_ref:
+        vocab.update({"Cid2": [], "Cid3": []})
+    tables = T.LookupTables(conf, idt, vocab_override=vocab)
+    batch = T.ExampleBatcher(conf, tables).batch(payloads)
+    B = len(payloads)
+    assert batch["features"].shape == (B, 615) and batch["mask"].shape == (B, 5)
+    assert torch.equal(batch["mask"].sum(1), torch.ones(B))
+    for b, want in enumerate(gold["records"]):
+        cols = want["header"].split("\t")
+        assert int(batch["em_position"][b]) == min(int(cols[4]), 400)
+        assert int(batch["em_page"][b]) == min(int(cols[11]), 100)
+        assert float(batch["label"][b]) == want["label"]
+    for f in ("clk_seq_sku_7d_50", "ord_seq_sku_12m_10", "cart_seq_sku_12m_10", "item_fea_sku", "near_expo_seq_c2"):
+        sp = batch[f]
+        lens = (sp.offsets[1:] - sp.offsets[:-1]).tolist()
+        assert lens == [len(r["ids"][f]) for r in gold["records"]], f
+        assert sp.values.dtype == torch.int32 and sp.offsets.dtype == torch.int32
+        assert torch.equal(sp.weights, torch.ones_like(sp.weights))                 # every Wts is 1.0 in the data
+        rows = next(int(e[1]) for e in list(conf.embedding_list) + list(conf.embedding_list_bias) if e[3] == f)
+        assert int(sp.values.min()) >= 0 and int(sp.values.max()) < rows
+    # the five features of one behaviour sequence have equal lengths (what generate_data assumes, :141-146)
+    assert torch.equal(batch["clk_seq_sku_7d_50"].offsets, batch["clk_seq_shop_7d_50"].offsets)
+    if have_ref:   # in-vocabulary indices are exact: list position in the reference's ID_TABLES
+        for f, tab in (("item_c2", "Cid2"), ("item_c3", "Cid3"), ("clk_seq_c2_7d_50", "Cid2"),
+                       ("clk_seq_c3_7d_50", "Cid3"), ("near_expo_seq_c2", "Cid2")):
+            got = batch[f].values.tolist()
+            want = [i for r in gold["records"] for i in r["index"][f]]
+            nv = gold["vocab_sizes"][tab]
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert (g == w) if w >= 0 else (g >= nv), (f, g, w)     # OOV -> a hash bucket behind the vocabulary
+
+
+def test_id_table_semantics():
+    from cikm2020_dmt_b200.tfrecord import IdTable, fingerprint64
+    t = IdTable("T", ["unknow", "a", "b"], 10)
+    assert t.lookup([b"unknow", b"a", b"b"]).tolist() == [0, 1, 2]
+    oov = t.lookup([b"zzz", b"zzz", b"another"])
+    assert oov[0] == oov[1] and all(3 <= v < 10 for v in oov)
+    assert oov[0] == 3 + fingerprint64(b"zzz") % 7
+    assert IdTable("T", ["unknow", "a"], 2).lookup([b"nope"]).tolist() == [0]       # no buckets: default_value=0
+    with pytest.raises(ValueError):
+        IdTable("T", ["a", "b", "c"], 2)
+    assert fingerprint64(b"") == 0x9AE16A3B2F90404F                                 # k2: the empty-string fingerprint
+    for n in (1, 3, 4, 7, 8, 16, 17, 32, 33, 64, 65, 200):                          # every length class runs
+        assert 0 <= fingerprint64(bytes(range(n % 251)) * 1 if n < 251 else b"x" * n) < 2 ** 64
+
+
+def test_batches_shard_by_rank(tmp_path):
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200 import tfrecord as T
+    conf = Conf(CONF_DIR, "dmt_demo.conf")
+    prefix = os.path.join(GOLD, "demo_records.tfrecord")
+    all_b = list(T.batches(conf, None, prefix, batch_size=3))
+    assert [b["features"].shape[0] for b in all_b] == [3, 3, 3, 1]
+    r0 = list(T.batches(conf, None, prefix, batch_size=3, world=2, rank=0))
+    r1 = list(T.batches(conf, None, prefix, batch_size=3, world=2, rank=1))
+    assert len(r0) == 2 and len(r1) == 2
+    assert torch.equal(r0[1]["features"], all_b[2]["features"]) and torch.equal(r1[0]["features"], all_b[1]["features"])
+    two_epochs = list(T.batches(conf, None, prefix, batch_size=5, epochs=2, shuffle_size=4, drop_remainder=True))
+    assert len(two_epochs) == 4
