@@ -111,12 +111,18 @@ def main():
         step(i)
     trainer.enable_stage_timing(True)
     launches0 = model.launches
+    from bench import ClockSampler
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
     ms_staged = timed(args.steps)
     launches = model.launches - launches0
     torch.cuda.synchronize()
     stage = trainer.stage_times_ms()
     trainer.enable_stage_timing(False)
     ms = min(ms_staged, timed(args.steps))
+    clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -139,7 +145,7 @@ def main():
                               % (plan.dropout_rate, list(plan.dropout_rate_bias))},
         "stage_ms_per_step": {k: round(t / args.steps, 4) for k, (t, _) in sorted(stage.items())},
         "stage_share": {k: round(t / total, 4) for k, (t, _) in sorted(stage.items())},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "clocks": clocks,
         "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
     }
     if args.cpu_seconds > 0:

@@ -183,28 +183,44 @@ __global__ void __launch_bounds__(256) adam_sorted_pass1_kernel(const __grid_con
       gr = g.grad + (ref & 0xFFFFFFFFFFll) * g.grad_ld + g.grad_col;
     }
     const int cnt = (int)min((int64_t)32, end - i0);
-    for (int j = 0; j < cnt; ++j) {
-      const int32_t kj = __shfl_sync(0xffffffffu, k, j);
-      const float scj = __shfl_sync(0xffffffffu, sc, j);
-      const float* grj = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gr, j));
-      if (kj != cur) {
-        if (cur != INT32_MAX) {
-          if (starts_here) {
-            finish_row(a, cur, acc, lane);      // the run began and ended inside this chunk
-          } else {
+    // four lookups per trip: their gradient-row loads are independent and issued together (the walk itself is
+    // sequential because the sums must be formed in sorted order)
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      int32_t kq[4];
+      float sq[4], gq[4][kMaxCols];
 #pragma unroll
-            for (int c = 0; c < kMaxCols; ++c)
-              if (lane + 32 * c < D) a.carry[(chunk * 2 + 0) * D + lane + 32 * c] = acc[c];
-          }
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, 31);
+        kq[u] = __shfl_sync(0xffffffffu, k, j);
+        sq[u] = __shfl_sync(0xffffffffu, sc, j);
+        const float* grj = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)gr, j));
+        const bool live = j0 + u < cnt && kq[u] != INT32_MAX;
 #pragma unroll
-        for (int c = 0; c < kMaxCols; ++c) acc[c] = 0.f;
-        cur = kj;
-        starts_here = true;
+        for (int c = 0; c < kMaxCols; ++c)
+          gq[u][c] = (live && lane + 32 * c < D) ? __ldg(grj + lane + 32 * c) : 0.f;
       }
 #pragma unroll
-      for (int c = 0; c < kMaxCols; ++c)
-        if (lane + 32 * c < D) acc[c] = fmaf(scj, __ldg(grj + lane + 32 * c), acc[c]);
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u >= cnt) break;
+        const int32_t kj = kq[u];
+        if (kj != cur) {
+          if (cur != INT32_MAX) {
+            if (starts_here) {
+              finish_row(a, cur, acc, lane);      // the run began and ended inside this chunk
+            } else {
+#pragma unroll
+              for (int c = 0; c < kMaxCols; ++c)
+                if (lane + 32 * c < D) a.carry[(chunk * 2 + 0) * D + lane + 32 * c] = acc[c];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < kMaxCols; ++c) acc[c] = 0.f;
+          cur = kj;
+          starts_here = true;
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) acc[c] = fmaf(sq[u], gq[u][c], acc[c]);
+      }
     }
   }
   if (cur == INT32_MAX) return;

@@ -153,11 +153,23 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
   const float scale = 1.0f / sqrtf((float)dk);
   for (int h = 0; h < H; ++h) {
     const int hc = h * dk;
-    for (int i = tid; i < L * L; i += 256) {
-      const int qi = i / L, kj = i - qi * L;
-      float s = 0.f;
-      for (int c = 0; c < dk; ++c) s = fmaf(Q[qi * ld + hc + c], K[kj * ld + hc + c], s);
-      S[qi * lds + kj] = s * scale;
+    // 2 x 2 register tile per thread (rows qa, qa+hl; keys kb, kb+hl): one shared-memory load per FMA
+    const int hl = (L + 1) >> 1;
+    for (int i = tid; i < hl * hl; i += 256) {
+      const int qa = i / hl, kb = i - qa * hl;
+      const int qb = min(qa + hl, L - 1), kc = min(kb + hl, L - 1);
+      const float *q0 = Q + qa * ld + hc, *q1 = Q + qb * ld + hc, *k0 = K + kb * ld + hc, *k1 = K + kc * ld + hc;
+      float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+      for (int c = 0; c < dk; ++c) {
+        const float a0 = q0[c], a1 = q1[c], b0 = k0[c], b1 = k1[c];
+        s00 = fmaf(a0, b0, s00); s01 = fmaf(a0, b1, s01); s10 = fmaf(a1, b0, s10); s11 = fmaf(a1, b1, s11);
+      }
+      S[qa * lds + kb] = s00 * scale;
+      if (kb + hl < L) S[qa * lds + kb + hl] = s01 * scale;
+      if (qa + hl < L) {
+        S[(qa + hl) * lds + kb] = s10 * scale;
+        if (kb + hl < L) S[(qa + hl) * lds + kb + hl] = s11 * scale;
+      }
     }
     __syncthreads();
     for (int r = warp; r < L; r += 8) {
@@ -175,11 +187,17 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const __grid_constant__ A
         S[r * lds + j] *= inv * a.drop.mult((uint32_t)(((b * H + h) * LP + r) * LP + j));
     }
     __syncthreads();
-    for (int i = tid; i < L * dk; i += 256) {
+    for (int i = tid; i < hl * dk; i += 256) {   // two query rows per thread share every V load
       const int qi = i / dk, c = i - qi * dk;
-      float acc = 0.f;
-      for (int j = 0; j < L; ++j) acc = fmaf(S[qi * lds + j], V[j * ld + hc + c], acc);
+      const int q2 = min(qi + hl, L - 1);
+      float acc = 0.f, acc2 = 0.f;
+      for (int j = 0; j < L; ++j) {
+        const float vx = V[j * ld + hc + c];
+        acc = fmaf(S[qi * lds + j], vx, acc);
+        acc2 = fmaf(S[q2 * lds + j], vx, acc2);
+      }
       Q[qi * ld + hc + c] = acc;     // this head's Q columns are dead after the scores
+      if (qi + hl < L) Q[(qi + hl) * ld + hc + c] = acc2;
     }
     __syncthreads();
   }

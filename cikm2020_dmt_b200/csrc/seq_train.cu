@@ -169,15 +169,27 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const __grid_con
   const float scale = 1.0f / sqrtf((float)dk);
   for (int h = 0; h < H; ++h) {
     const int hc = h * dk;
-    for (int i = tid; i < L * L; i += kAttnThreads) {
-      const int qi = i / L, kj = i - qi * L;
-      float s = 0.f, dp = 0.f;
+    // 2 x 2 register tile per thread (rows qa, qa+hl; keys kb, kb+hl): one shared-memory load per FMA instead of
+    // two; consecutive lanes take consecutive keys, so the K / V rows (odd stride) are conflict-free
+    const int hl = (L + 1) >> 1;
+    for (int i = tid; i < hl * hl; i += kAttnThreads) {
+      const int qa = i / hl, kb = i - qa * hl;
+      const int qb = min(qa + hl, L - 1), kc = min(kb + hl, L - 1);
+      const float *q0 = Q + qa * ld + hc, *q1 = Q + qb * ld + hc, *k0 = K + kb * ld + hc, *k1 = K + kc * ld + hc;
+      const float *o0 = dO + qa * ld + hc, *o1 = dO + qb * ld + hc, *v0 = V + kb * ld + hc, *v1 = V + kc * ld + hc;
+      float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f, p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
       for (int c = 0; c < dk; ++c) {
-        s = fmaf(Q[qi * ld + hc + c], K[kj * ld + hc + c], s);
-        dp = fmaf(dO[qi * ld + hc + c], V[kj * ld + hc + c], dp);
+        const float a0 = q0[c], a1 = q1[c], b0 = k0[c], b1 = k1[c];
+        s00 = fmaf(a0, b0, s00); s01 = fmaf(a0, b1, s01); s10 = fmaf(a1, b0, s10); s11 = fmaf(a1, b1, s11);
+        const float e0 = o0[c], e1 = o1[c], w0 = v0[c], w1 = v1[c];
+        p00 = fmaf(e0, w0, p00); p01 = fmaf(e0, w1, p01); p10 = fmaf(e1, w0, p10); p11 = fmaf(e1, w1, p11);
       }
-      P[qi * lds + kj] = s * scale;
-      dS[qi * lds + kj] = dp;
+      P[qa * lds + kb] = s00 * scale; dS[qa * lds + kb] = p00;
+      if (kb + hl < L) { P[qa * lds + kb + hl] = s01 * scale; dS[qa * lds + kb + hl] = p01; }
+      if (qa + hl < L) {
+        P[(qa + hl) * lds + kb] = s10 * scale; dS[(qa + hl) * lds + kb] = p10;
+        if (kb + hl < L) { P[(qa + hl) * lds + kb + hl] = s11 * scale; dS[(qa + hl) * lds + kb + hl] = p11; }
+      }
     }
     __syncthreads();
     for (int r = warp; r < L; r += kAttnThreads / 32) {
@@ -208,18 +220,30 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const __grid_con
       }
     }
     __syncthreads();
-    for (int i = tid; i < L * dk; i += kAttnThreads) {
+    // two rows (t, t+hl) per thread share the K / Q / dO loads of every j
+    for (int i = tid; i < hl * dk; i += kAttnThreads) {
       const int t = i / dk, c = i - t * dk;
-      float dq = 0.f, dkk = 0.f, dv = 0.f;
+      const int t2 = min(t + hl, L - 1);
+      float dq = 0.f, dkk = 0.f, dv = 0.f, dq2 = 0.f, dkk2 = 0.f, dv2 = 0.f;
       for (int j = 0; j < L; ++j) {
-        dq = fmaf(dS[t * lds + j], K[j * ld + hc + c], dq);      // t = query row
-        dkk = fmaf(dS[j * lds + t], Q[j * ld + hc + c], dkk);    // t = key row
-        dv = fmaf(P[j * lds + t], dO[j * ld + hc + c], dv);
+        const float kx = K[j * ld + hc + c], qx = Q[j * ld + hc + c], ox = dO[j * ld + hc + c];
+        dq = fmaf(dS[t * lds + j], kx, dq);        // t = query row
+        dkk = fmaf(dS[j * lds + t], qx, dkk);      // t = key row
+        dv = fmaf(P[j * lds + t], ox, dv);
+        dq2 = fmaf(dS[t2 * lds + j], kx, dq2);
+        dkk2 = fmaf(dS[j * lds + t2], qx, dkk2);
+        dv2 = fmaf(P[j * lds + t2], ox, dv2);
       }
       float* row = a.dqkv + (off + t) * 3 * D + hc + c;
       row[0] = dq;
       row[D] = dkk;
       row[2 * D] = dv;
+      if (t + hl < L) {
+        float* row2 = a.dqkv + (off + t + hl) * 3 * D + hc + c;
+        row2[0] = dq2;
+        row2[D] = dkk2;
+        row2[2 * D] = dv2;
+      }
     }
     __syncthreads();
   }
