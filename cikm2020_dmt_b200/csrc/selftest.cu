@@ -11,6 +11,10 @@ using namespace umma;
 // mode 0: A K-major (no swizzle), B K-major (no swizzle), B given as [N][K]
 // mode 1: A K-major (no swizzle), B MN-major (no swizzle), B given as [K][N]
 // mode 2: A, B K-major SWIZZLE_128B (64-element k-blocks), B given as [N][K]
+// mode 3: A in TENSOR MEMORY (row-owning threads pack bf16 pairs and tcgen05.st them), B K-major, [N][K]
+// mode 4: A in tensor memory, B MN-major, B given as [K][N]
+// mode 5: A K-major compact image of 16 rows (LBO = 256 B; rows >= 16 of the MMA read neighbouring bytes and
+//         only produce garbage in their own accumulator rows), B MN-major [K][N]; rows 0..15 of C are checked
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv_bfloat16* __restrict__ A,
                                                             const __nv_bfloat16* __restrict__ B,
                                                             float* __restrict__ C, int N, int K) {
@@ -33,11 +37,15 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
     const uint4 v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + c * 8);
     uint32_t off;
     if (mode == 2) off = (c / 8) * (128 * 128) + r * 128 + (((c % 8) ^ (r % 8)) * 16);
+    else if (mode == 5) off = c * 256 + r * 16;
     else off = c * (128 * 16) + r * 16;
+    if (mode == 5 && r >= 16) continue;
     *reinterpret_cast<uint4*>(sA + off) = v;
   }
   // ---- stage B ----
-  if (mode == 1) {            // B given [K][N]; image [n/8][k][8]
+  const bool b_mn = (mode == 1 || mode == 4 || mode == 5);
+  constexpr int kTmemA = 128;   // first column of the TMEM-resident A operand (modes 3, 4); C uses [0, N)
+  if (b_mn) {                 // B given [K][N]; image [n/8][k][8]
     for (int i = tid; i < K * (N / 8); i += 128) {
       const int k = i % K, g = i / K;
       const uint4 v = *reinterpret_cast<const uint4*>(B + (size_t)k * N + g * 8);
@@ -58,9 +66,22 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_base_s;
+  if (mode == 3 || mode == 4) {   // A row `tid` -> lane tid, columns kTmemA + k/2
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        r[j] = (c0 + j < K / 2) ? *reinterpret_cast<const uint32_t*>(A + (size_t)tid * K + 2 * (c0 + j)) : 0u;
+      tmem_st16(tmem_addr(tbase, kTmemA + c0), r);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
 
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, false, mode == 1);
+    const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn);
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t da, db;
@@ -69,11 +90,13 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
         da = make_smem_desc(a0 + blk * (128 * 128) + sub * 32, 16, 1024, kLayoutSW128);
         db = make_smem_desc(b0 + blk * (N * 128) + sub * 32, 16, 1024, kLayoutSW128);
       } else {
-        da = make_smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
-        if (mode == 0) db = make_smem_desc(b0 + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
+        if (mode == 5) da = make_smem_desc(a0 + ks * 2 * 256, 256, 128, kLayoutNone);
+        else da = make_smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
+        if (!b_mn) db = make_smem_desc(b0 + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
         else db = make_smem_desc(b0 + ks * 2 * 128, 128, K * 16, kLayoutNone);   // MN-major: LBO = next 8 k, SBO = next 8 n
       }
-      mma_bf16_ss(tbase, da, db, idesc, ks > 0 ? 1u : 0u);
+      if (mode == 3 || mode == 4) mma_bf16_ts(tbase, tbase + kTmemA + ks * 8, db, idesc, ks > 0 ? 1u : 0u);
+      else mma_bf16_ss(tbase, da, db, idesc, ks > 0 ? 1u : 0u);
     }
     commit(&bar);
   }
@@ -99,8 +122,9 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
 extern "C" int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float* C, int32_t N, int32_t K,
                                  void* stream) {
   DMT_REQUIRE(A && B && C, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: null pointer");
-  DMT_REQUIRE(mode >= 0 && mode <= 2, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: mode %d", mode);
-  DMT_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0 && (mode != 2 || K % 64 == 0),
+  DMT_REQUIRE(mode >= 0 && mode <= 5, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: mode %d", mode);
+  DMT_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0 && (mode != 2 || K % 64 == 0) &&
+                  ((mode != 3 && mode != 4) || (N <= 128 && K <= 256)),
               DMT_ERR_UNSUPPORTED_SHAPE, "dmt_selftest_umma: N=%d K=%d", N, K);
   const size_t bytes = ((128 * (size_t)K * 2 + 1023) & ~(size_t)1023) + (size_t)N * K * 2 + 1024;
   DMT_REQUIRE(bytes <= 200 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_selftest_umma: tile needs %zu B", bytes);

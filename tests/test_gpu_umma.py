@@ -26,3 +26,25 @@ def test_umma_selftest(mode, N, K):
     torch.cuda.synchronize()
     err = (C.cpu() - want).abs().max().item()
     assert err < 1e-3 * max(1.0, want.abs().max().item()), "mode %d N %d K %d: max err %g" % (mode, N, K, err)
+
+
+@pytest.mark.parametrize("mode", [3, 4, 5])
+@pytest.mark.parametrize("N,K", [(64, 64), (32, 128), (64, 256), (80, 128), (128, 32), (16, 64)])
+def test_umma_tmem_operand_selftest(mode, N, K):
+    """A operand read from tensor memory (modes 3, 4: P.V, H.W2 in the sequence kernel) and the compact
+    16-row A image of the decoder context MMA (mode 5)."""
+    from cikm2020_dmt_b200 import abi
+    lib = abi.load()
+    g = torch.Generator().manual_seed(N * 1000 + K + mode)
+    A = (torch.randn(128, K, generator=g)).to(torch.bfloat16)
+    Bt = (torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    want = A.float() @ Bt.float().t()
+    Ad = A.cuda()
+    Bd = (Bt if mode == 3 else Bt.t().contiguous()).cuda()
+    C = torch.full((128, N), float("nan"), device="cuda")
+    abi.check(lib.dmt_selftest_umma(mode, Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), N, K,
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    rows = 16 if mode == 5 else 128
+    err = (C.cpu()[:rows] - want[:rows]).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), "mode %d N %d K %d: max err %g" % (mode, N, K, err)
