@@ -16,7 +16,8 @@ bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const cha
 int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared, cudaStream_t st);
 void seq_tc_set_profile(unsigned long long* p);
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
-                         int64_t out_ld, const void* prepared, cudaStream_t st);
+                         int64_t out_ld, void* workspace, cudaStream_t st);
+size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg);
 }
 
 static int validate_seq(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w) {
@@ -48,7 +49,8 @@ extern "C" {
 size_t dmt_seq_encode_workspace_bytes(const dmt_seq_cfg* cfg, int64_t max_tokens) {
   (void)max_tokens;
   if (!cfg) return 0;
-  if (cfg->precision == DMT_PRECISION_BF16) return dmt::seq_tc_prepared_bytes(cfg);   // resident weight images
+  if (cfg->precision == DMT_PRECISION_BF16)   // weight images + per-sample decoder contexts (grows with batch)
+    return dmt::seq_tc_workspace_bytes(cfg);
   return 256;   // the fused fp32 path keeps every intermediate on chip
 }
 
@@ -75,8 +77,10 @@ int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
               cfg->precision);
   const char* why = nullptr;
   DMT_REQUIRE(dmt::seq_tc_supported(cfg, in, &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd: %s", why);
-  DMT_REQUIRE(workspace && workspace_bytes >= dmt::seq_tc_prepared_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
-              "dmt_seq_encode_fwd(bf16): workspace must hold the images written by dmt_seq_prepare_weights");
+  DMT_REQUIRE(workspace && workspace_bytes >= dmt::seq_tc_workspace_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_seq_encode_fwd(bf16): workspace %zu < %zu bytes (dmt_seq_encode_workspace_bytes: the images written "
+              "by dmt_seq_prepare_weights + batch-sized scratch)", workspace_bytes, dmt::seq_tc_workspace_bytes(cfg));
+  DMT_REQUIRE(((uintptr_t)workspace & 15) == 0, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd(bf16): unaligned workspace");
   return dmt::seq_encode_tc_launch(cfg, in, w, out, out_ld, workspace, (cudaStream_t)stream);
 }
 

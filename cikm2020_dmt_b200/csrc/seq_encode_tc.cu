@@ -16,41 +16,17 @@
 // interest vector out.  Weights live in shared memory for the lifetime of the CTA (bf16 images
 // produced once by dmt_seq_prepare_weights).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "dmt_common.cuh"
+#include "seq_tc.cuh"
 #include "umma.cuh"
 
 namespace dmt {
 
 using namespace umma;
 
-struct SeqTcArgs {
-  dmt_seq_cfg cfg;
-  dmt_seq_input in;
-  const float* pos;
-  // fp32 small vectors (global): biases + LayerNorm
-  const float *bq, *bk, *bv, *ln1_g, *ln1_b;          // encoder self-attention
-  const float *b1, *b2, *ln2_g, *ln2_b;               // feed-forward (shared enc/dec)
-  const float *dbq, *dbk, *dbv, *ln3_g, *ln3_b;       // decoder vanilla attention
-  const __nv_bfloat16* prepared;                      // bf16 weight images (see seq_prepare_kernel)
-  float* out;
-  int64_t out_ld;
-  int32_t n_tiles;
-  unsigned long long* dbg;                            // diagnostics: per-phase SM cycles (thread 0), or NULL
-  int32_t chunk_feat[32];                             // 16-byte chunk c of a token -> feature pair
-  int32_t chunk_off[32];                              //                          -> first column inside that row
-};
-
 constexpr int kTcThreads = 256;
-
-// element counts of the prepared images
-__host__ __device__ constexpr size_t prep_wqkv(int D) { return (size_t)3 * D * D; }
-__host__ __device__ constexpr size_t prep_w1(int D, int DFF) { return (size_t)D * DFF; }
-// decoder block (bf16 units): G image (H*D outputs x D) | Wv image (D x D) | g fp32 [H*D]
-__host__ __device__ constexpr size_t prep_dec(int D, int H) { return (size_t)H * D * D + (size_t)D * D + 2 * (size_t)H * D; }
-__host__ __device__ constexpr size_t prep_total(int D, int DFF, int H) {
-  return prep_wqkv(D) + 2 * prep_w1(D, DFF) + prep_dec(D, H);
-}
 
 // Weight images (all bf16), "image(N, K)" = [k/8][n][8] with element (n, k) = W_tf[k][n] unless noted:
 //   wqkv  image(3D, D)   columns n = [Q | K | V]            (tcgen05 B operand, K-major)
@@ -61,6 +37,7 @@ __host__ __device__ constexpr size_t prep_total(int D, int DFF, int H) {
 //                        (sample, head) that softmax ignores)
 //   dv    image(D, D)    decoder Wv                          (mat-vec  o = ctx Wv)
 //   g     fp32 [H*D]     g[(h,k)] = sum_{c in head h} bq[c] Wk[k][c]
+//   wvbd  image(D, H*D)  element (n = c, k = (h, j)) = Wv_dec[j][c] if column c belongs to head h, else 0 (v2 tail)
 __global__ void seq_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
                                    const float* __restrict__ wv, const float* __restrict__ w1,
                                    const float* __restrict__ w2, const float* __restrict__ dq,
@@ -70,10 +47,17 @@ __global__ void seq_prepare_kernel(const float* __restrict__ wq, const float* __
   const size_t n_qkv = prep_wqkv(D), n_w1 = prep_w1(D, DFF), n_dd = (size_t)D * D, n_g = (size_t)H * D * D;
   const size_t total_bf16 = n_qkv + 2 * n_w1 + n_g + n_dd;
   const int DK = D / H;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_bf16 + (size_t)H * D;
+  const size_t off_wvbd = prep_off_wvbd(D, DFF, H), n_wvbd = prep_wvbd(D, H);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_bf16 + (size_t)H * D + n_wvbd;
        i += (size_t)gridDim.x * blockDim.x) {
     float v;
     size_t j = i;
+    if (i >= total_bf16 + (size_t)H * D) {  // wvbd image(D, H*D): [k/8][n][8]
+      const size_t q = i - total_bf16 - (size_t)H * D;
+      const int e = q % 8, n = (q / 8) % D, kc = q / (8 * D), k = kc * 8 + e, h = k / D, jj = k % D;
+      out[off_wvbd + q] = __float2bfloat16((n / DK == h) ? dv[(size_t)jj * D + n] : 0.f);
+      continue;
+    }
     if (i >= total_bf16) {                 // g[(h,k)] fp32, stored right after the bf16 images
       const int hk = (int)(i - total_bf16), h = hk / D, k = hk % D;
       float acc = 0.f;
@@ -832,7 +816,27 @@ static unsigned long long* g_seq_profile = nullptr;   // diagnostics only (dmt_d
 void seq_tc_set_profile(unsigned long long* p) { g_seq_profile = p; }
 
 size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg) {
-  return prep_total(cfg->d_model, cfg->d_ff, cfg->num_heads) * 2 + 256;
+  return (prep_total(cfg->d_model, cfg->d_ff, cfg->num_heads) * 2 + 511) / 256 * 256;
+}
+
+// v2 (seq_encode_tc2.cu)
+bool seq_tc2_supported(const dmt_seq_cfg* cfg);
+size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg);
+int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st);
+
+// DMT_SEQ_TC_V1=1 selects the v1 kernel (one tile in flight per SM) -- kept for A/B measurements
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DMT_SEQ_TC_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// workspace = [prepared weight images | v2: decoder contexts [B][H*D] fp32]
+size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg) {
+  return seq_tc_prepared_bytes(cfg) + seq_tc2_ctx_bytes(cfg);
 }
 
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why) {
@@ -860,7 +864,8 @@ int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepa
 }
 
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
-                         int64_t out_ld, const void* prepared, cudaStream_t st) {
+                         int64_t out_ld, void* workspace, cudaStream_t st) {
+  const void* prepared = workspace;
   SeqTcArgs a;
   a.cfg = *cfg;
   a.in = *in;
@@ -881,6 +886,8 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
       a.chunk_off[c] = o;
     }
   for (; c < 32; ++c) a.chunk_feat[c] = a.chunk_off[c] = 0;
+  a.ctx = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg));
+  if (!use_v1() && seq_tc2_supported(cfg)) return seq_encode_tc2_launch(a, st);
   int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
   if (slot > cfg->maxlen) slot = cfg->maxlen;
   DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);

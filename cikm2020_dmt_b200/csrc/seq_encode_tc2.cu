@@ -1,0 +1,927 @@
+// dmt_seq_encode_fwd, DMT_PRECISION_BF16, v2: two tiles in flight per SM, tensor-memory A operands.
+//
+// Same math as seq_encode_tc.cu (gather -> X Wqkv -> masked softmax attention -> LN -> FF -> LN -> decoder), but
+// organised so that the tensor pipe, the shared-memory pipe and the SIMT pipes of one SM always have two
+// independent tiles to work on:
+//
+//   * one CTA per SM = 2 GROUPS of 128 threads; each group runs the whole per-tile program on its own 128-row
+//     tile (one thread = one token row = one TMEM lane), with its own mbarrier, named barrier, 256 TMEM columns
+//     and 64 KB of shared memory.  The bf16 weight images (88 KB) are shared by both groups.
+//   * the softmax probabilities P_h and the ReLU hidden H never touch shared memory: the row-owning thread packs
+//     them to bf16 and writes them back with tcgen05.st IN PLACE over the fp32 accumulator columns it just read;
+//     P_h V_h and H W2 are issued with the A operand in tensor memory.  That removes 96 KB of activation
+//     buffers per tile, which is what makes the second tile fit.
+//   * decoder (one query per sample): the key/query projections are folded into qt = dvec G_h + g_h (computed on
+//     CUDA cores while the P V MMAs run); every token thread takes its own score from the memory row it holds in
+//     registers; the softmax is a flash-style partial softmax per (warp segment, head) -- no cross-warp max; the
+//     context sum_t p_t M_t is ONE more MMA: A = the partial probabilities transposed into a compact 16-row
+//     image, B = the memory rows (bf16, MN-major) with a column of ones appended, so the same accumulator row
+//     carries the softmax denominator.  The per-sample tail (ctx_h Wv_h + residual -> LN -> FF -> LN) is row-batched
+//     over 128 SAMPLES per tile in seq_tail_kernel, on tensor cores, instead of mat-vec loops per sample.
+//
+// HBM traffic per (sample, sequence): ids + embedding rows in, 128 context floats out and in again (L2), one
+// interest vector out.
+#include <limits.h>
+
+#include "dmt_common.cuh"
+#include "seq_tc.cuh"
+#include "umma.cuh"
+
+namespace dmt {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kD = 64, kDFF = 256, kH = 2, kDK = 32, kKC = 8, kROWB = 128 * 16;
+constexpr int kInvalidId = INT_MIN;
+
+__device__ __forceinline__ void bf16x8_to_f(const uint4& v, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f8_to_bf16(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// Row-local LayerNorm over 64 values held in registers (TransformerModel_util.py:58-78); four independent
+// partial sums keep the dependent-add chains short.
+__device__ __forceinline__ void ln64(float* y, const float* __restrict__ g, const float* __restrict__ b) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kD; i += 4) {
+    s0 += y[i]; s1 += y[i + 1]; s2 += y[i + 2]; s3 += y[i + 3];
+  }
+  const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / kD);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kD; i += 4) {
+    const float d0 = y[i] - mean, d1 = y[i + 1] - mean, d2 = y[i + 2] - mean, d3 = y[i + 3] - mean;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+  }
+  const float rstd = 1.0f / sqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / kD) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < kD; i += 4) {
+    const float4 gg = *reinterpret_cast<const float4*>(g + i), bb = *reinterpret_cast<const float4*>(b + i);
+    y[i] = fmaf(gg.x, (y[i] - mean) * rstd, bb.x);
+    y[i + 1] = fmaf(gg.y, (y[i + 1] - mean) * rstd, bb.y);
+    y[i + 2] = fmaf(gg.z, (y[i + 2] - mean) * rstd, bb.z);
+    y[i + 3] = fmaf(gg.w, (y[i + 3] - mean) * rstd, bb.w);
+  }
+}
+
+template <int SLOT>
+struct Tc2Layout {
+  static constexpr int NS = 128 / SLOT;                 // samples per tile
+  static constexpr int W = SLOT < 32 ? SLOT : 32;       // rows of one decoder softmax segment (inside a warp)
+  static constexpr int NPARTS = 128 / W;                // partial softmaxes per tile
+  static constexpr int PPS = SLOT / W;                  // parts per sample (2 when a slot spans two warps)
+  static constexpr int NR = NPARTS * kH;                // rows of the transposed-probability image
+  static constexpr int CW = SLOT < 32 ? 32 : SLOT;      // score columns a warp loads (covers its rows' slots)
+  // ---- shared memory (bytes) ----
+  static constexpr int oWqkv = 0;
+  static constexpr int oW1 = oWqkv + 3 * kD * kD * 2;
+  static constexpr int oW2 = oW1 + kD * kDFF * 2;
+  static constexpr int oGrp = oW2 + kDFF * kD * 2;      // 90112
+  static constexpr int gXA = 0, gQ = 16384, gK = 32768, gV = 49152, szGrp = 65536;
+  // aliases inside a group's Q region, valid once the S MMAs have completed
+  static constexpr int gPd = gQ;                        // [k/8][16 rows][8] bf16: LBO 256, <= 6 KB touched
+  static constexpr int gQt = gQ + 8192;                 // fp32 [NS][H*D] folded decoder queries
+  static constexpr int gDvec = gQ + 12288;              // fp32 [NS][D] scaled target embeddings
+  static constexpr int gMx = gQ + 14336;                // fp32 [NR] partial-softmax maxima
+  // the memory image (MN-major B operand of the context MMA) takes the K region, its ones chunk the first 2 KB of V
+  static constexpr int oFV = oGrp + 2 * szGrp;          // 221184
+  static constexpr int vBQKV = 0, vB1 = 3 * kD, vB2 = vB1 + kDFF, vLN = vB2 + kD, nFV = vLN + 4 * kD;
+  static constexpr int oPos = oFV + nFV * 4;            // bf16 [maxlen][D] learned positions
+  static_assert(NS * kH * kD * 4 <= 4096 && NS * kD * 4 <= 2048 && NR <= 16, "decoder scratch aliases");
+  // ---- tensor memory columns (per group, relative to its 256-column half) ----
+  static constexpr int tQKV = 0;                        // [0,192)   X Wqkv
+  static constexpr int tS = 0;                          // head h: [h*128, h*128+128); P_h in place at [h*128, +64)
+  static constexpr int tO = 64;                         // head h: [h*128+64, +32)
+  static constexpr int tFF1 = 0;                        // [0,256); H in place at [0,128)
+  static constexpr int tFF2 = 128;                      // [128,192)
+  static constexpr int tCtx = 0;                        // [0,80)
+};
+
+#define T2_TICK(idx)                                                    \
+  do {                                                                  \
+    if (a.dbg && tid == 0) {                                            \
+      const long long _now = clock64();                                 \
+      atomicAdd(a.dbg + (idx), (unsigned long long)(_now - t_last));    \
+      t_last = _now;                                                    \
+    }                                                                   \
+  } while (0)
+
+template <int SLOT>
+__global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_constant__ SeqTcArgs a) {
+  using L = Tc2Layout<SLOT>;
+  constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
+  constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int slen_s[2][2][NS];                    // [group][tile parity][slot]
+
+  const int tid = threadIdx.x, grp = tid >> 7, row = tid & 127, wg = row >> 5, lane = tid & 31;
+  uint8_t* gbase = smem + L::oGrp + grp * L::szGrp;
+  uint8_t* sXA = gbase + L::gXA;
+  uint8_t* sQ = gbase + L::gQ;
+  uint8_t* sK = gbase + L::gK;
+  uint8_t* sV = gbase + L::gV;
+  float* fv = reinterpret_cast<float*>(smem + L::oFV);
+  const uint4* spos = reinterpret_cast<const uint4*>(smem + L::oPos);
+  uint64_t* bar = &bars[grp];
+  const int B = a.cfg.batch;
+  const uint32_t bar_id = 1 + grp;
+
+  // ---- one-time setup (all 256 threads): TMEM, barriers, resident weights, vectors, positions ----
+  if (tid < 32) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.prepared);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::oWqkv);
+    constexpr int n16 = L::oGrp / 16;
+    for (int i = tid; i < n16; i += 256) dst[i] = __ldg(src + i);
+    for (int i = tid; i < D; i += 256) {
+      fv[L::vBQKV + i] = a.bq[i];
+      fv[L::vBQKV + D + i] = a.bk[i];
+      fv[L::vBQKV + 2 * D + i] = a.bv[i];
+      fv[L::vB2 + i] = a.b2[i];
+      fv[L::vLN + 0 * D + i] = a.ln1_g[i];
+      fv[L::vLN + 1 * D + i] = a.ln1_b[i];
+      fv[L::vLN + 2 * D + i] = a.ln2_g[i];
+      fv[L::vLN + 3 * D + i] = a.ln2_b[i];
+    }
+    for (int i = tid; i < DFF; i += 256) fv[L::vB1 + i] = a.b1[i];
+    uint4* pdst = reinterpret_cast<uint4*>(smem + L::oPos);
+    for (int i = tid; i < a.cfg.maxlen * KC; i += 256) {
+      const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
+      const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      pdst[i] = f8_to_bf16(f);
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s + grp * 256;
+  const uint32_t aXA = smem_u32(sXA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
+  const uint32_t dXA = desc_lo(aXA, ROWB), dQ = desc_lo(aQ, ROWB), dK = desc_lo(aK, ROWB);
+  const uint32_t dWqkv = desc_lo(smem_u32(smem + L::oWqkv), 3 * D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
+                 dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
+  const __nv_bfloat16* gDec = a.prepared + prep_off_dec(D, DFF);          // G image | Wv image | g fp32
+  const uint4* gG = reinterpret_cast<const uint4*>(gDec);                 // image(H*D, D): chunk (jc, n) at jc*H*D + n
+  const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
+  const float sqrt_d = sqrtf((float)D);
+  const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;      // softmax(s/sqrt(dk)) through exp2
+  const int nf = a.cfg.n_feats;
+  const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
+  const int zp = a.cfg.zero_pad ? 1 : 0;
+  const int slot = row / SLOT, tpos = row % SLOT;
+  uint32_t phase = 0;
+
+  // ---- software-pipelined gather.  One thread = one token row: it loads the KC 32-byte chunks of ITS token
+  //      (chunk k of every lane belongs to the same table, so the index math is uniform).  Offsets, ids and rows
+  //      of the group's next tile are requested just before three of the current tile's MMA waits. ----
+  int pf_o0[KC], pf_cnt[KC], pf_id[KC];
+  int pf_len = 0;
+  bool pf_valid = false;
+  float4 pf_e[KC][2];
+  int pf_tid = kInvalidId;
+  float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
+
+  auto stage_offsets = [&](int nt) {
+    pf_len = 0;
+    pf_tid = kInvalidId;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) pf_o0[k] = pf_cnt[k] = 0;
+    if (nt >= a.n_tiles) return;
+    const int b = nt * NS + slot;
+    if (b < B) {
+      const int32_t* ol = a.in.offsets[nf - 1];
+      pf_len = min(__ldg(ol + b + 1) - __ldg(ol + b), lmax);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int f = a.chunk_feat[k];
+        if (k > 0 && f == a.chunk_feat[k - 1]) {
+          pf_o0[k] = pf_o0[k - 1];
+          pf_cnt[k] = pf_cnt[k - 1];
+        } else {
+          pf_o0[k] = __ldg(a.in.offsets[f] + b);
+          pf_cnt[k] = __ldg(a.in.offsets[f] + b + 1) - pf_o0[k];
+        }
+      }
+    }
+    if (row < NS * KC) {
+      const int bt = nt * NS + row / KC;
+      if (bt < B) pf_tid = __ldg(a.in.item_ids[a.chunk_feat[row % KC]] + bt);
+    }
+  };
+  auto stage_ids = [&](int nt, int par) {
+    pf_valid = tpos < pf_len;
+    if (tpos == 0) slen_s[grp][par][slot] = pf_len;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      pf_id[k] = kInvalidId;
+      if (pf_valid) {
+        const int f = a.chunk_feat[k];
+        if (k > 0 && f == a.chunk_feat[k - 1]) pf_id[k] = pf_id[k - 1];
+        else pf_id[k] = (tpos < pf_cnt[k]) ? __ldg(a.in.ids[f] + pf_o0[k] + tpos) : 0;
+      }
+    }
+  };
+  auto stage_rows = [&]() {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int f = a.chunk_feat[k];
+      pf_e[k][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_e[k][1] = pf_e[k][0];
+      const int64_t rw = (int64_t)pf_id[k] - zp;
+      if (pf_id[k] != kInvalidId && rw >= 0 && rw < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[k];
+        pf_e[k][0] = ld_stream4(src);
+        pf_e[k][1] = ld_stream4(src + 4);
+      }
+    }
+    pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    pf_t1 = pf_t0;
+    if (row < NS * KC) {
+      const int c = row % KC, f = a.chunk_feat[c];
+      const int64_t rw = (int64_t)pf_tid - zp;
+      if (pf_tid != kInvalidId && rw >= 0 && rw < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
+        pf_t0 = ld_stream4(src);
+        pf_t1 = ld_stream4(src + 4);
+      }
+    }
+  };
+  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
+  stage_offsets(tile0);
+  stage_ids(tile0, 0);
+  stage_rows();
+
+  long long t_last = clock64();
+  for (int it = 0;; ++it) {
+    const int tile = tile0 + it * tstride;
+    if (tile >= a.n_tiles) break;
+    const int par = it & 1;
+    const int b0 = tile * NS;
+    const int next_tile = tile + tstride;
+
+    // ---- P0: prefetched rows -> concat + sqrt(d) scale + learned position -> X image (bf16) ----
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = 0.f;
+      if (pf_valid) {
+        float p[8];
+        bf16x8_to_f(spos[tpos * KC + k], p);
+        x[0] = fmaf(pf_e[k][0].x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k][0].y, sqrt_d, p[1]);
+        x[2] = fmaf(pf_e[k][0].z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k][0].w, sqrt_d, p[3]);
+        x[4] = fmaf(pf_e[k][1].x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k][1].y, sqrt_d, p[5]);
+        x[6] = fmaf(pf_e[k][1].z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k][1].w, sqrt_d, p[7]);
+      }
+      *reinterpret_cast<uint4*>(sXA + k * ROWB + row * 16) = f8_to_bf16(x);
+    }
+    const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;        // target item chunk of (sample row/KC, chunk row%KC)
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(0);
+    stage_offsets(next_tile);
+
+    // ---- P1: [Q|K|V] = X Wqkv ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks)
+        mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
+      commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(1);
+
+    // ---- P2: + bias, bf16, Q / K / V images ([chunk][row][8] each) ----
+#pragma unroll
+    for (int blk = 0; blk < 3 * D / 32; ++blk) {
+      const int n0 = blk * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tQKV + n0), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + g * 8;
+        const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
+        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
+        float y[8];
+        y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
+        y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
+        y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
+        y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
+        const int m = n / D, ch = (n % D) / 8;
+        *reinterpret_cast<uint4*>(sQ + m * 16384 + ch * ROWB + row * 16) = f8_to_bf16(y);
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(2);
+    stage_ids(next_tile, par ^ 1);
+
+    // ---- P3: S_h = Q_h K_h^T for both heads ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ++ks) {
+          const uint32_t ch = (h * DK) / 8 + ks * 2;
+          mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dQ + ch * (ROWB / 16), dHi),
+                      desc_join(dK + ch * (ROWB / 16), dHi), idesc, ks > 0);
+        }
+      commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(3);
+
+    // ---- P4: masked softmax (one thread = one row, both heads); P_h packed to bf16 IN PLACE in tensor memory ----
+    const int len = slen_s[grp][par][slot];
+    {
+      const int col0 = (row / CW) * CW;               // warp-uniform: rows of a warp share the CW-key window
+      const int lo = slot * SLOT - col0;              // this row's keys are window columns [lo, lo + len)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        uint32_t r[CW];
+#pragma unroll
+        for (int blk = 0; blk < CW / 32; ++blk)
+          tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0 + blk * 32), r + blk * 32);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const bool ok = (unsigned)(j - lo) < (unsigned)len;
+          const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
+          r[j] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+        const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));       // exp2(-inf) == 0: masked keys
+          const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), sl2, -mxs));
+          r[j] = __float_as_uint(e0); r[j + 1] = __float_as_uint(e1);
+          r[j + 2] = __float_as_uint(e2); r[j + 3] = __float_as_uint(e3);
+          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+        }
+        const float sum = (s0 + s1) + (s2 + s3);
+        const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+        uint32_t pk[CW / 2];
+#pragma unroll
+        for (int j = 0; j < CW / 2; ++j)
+          pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+        uint32_t zz[CW / 2];
+#pragma unroll
+        for (int j = 0; j < CW / 2; ++j) zz[j] = 0u;
+        // A-operand image of P_h: key j of this row in column j/2 (64 columns); keys outside the window are zeros
+        const uint32_t pbase = tmem_addr(tbase, L::tS + h * 128);
+        if constexpr (CW == 64) {
+          tmem_st32(pbase + col0 / 2, pk);
+          tmem_st32(pbase + (32 - col0 / 2), zz);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 16 == col0 / 2) tmem_st16(pbase + q * 16, pk);
+            else tmem_st16(pbase + q * 16, zz);
+          }
+        }
+      }
+    }
+    if (row < NS * KC) {                                // target item rows -> decoder input (fp32), Q region is dead
+      float* dv = reinterpret_cast<float*>(gbase + L::gDvec) + (row / KC) * D + (row % KC) * 8;
+      *reinterpret_cast<float4*>(dv) = make_float4(cur_t0.x * sqrt_d, cur_t0.y * sqrt_d, cur_t0.z * sqrt_d, cur_t0.w * sqrt_d);
+      *reinterpret_cast<float4*>(dv + 4) = make_float4(cur_t1.x * sqrt_d, cur_t1.y * sqrt_d, cur_t1.z * sqrt_d, cur_t1.w * sqrt_d);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(4);
+
+    // ---- P5: O_h = P_h V_h  (A = P_h in tensor memory, B = V read MN-major straight from its image) ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const uint32_t dV = desc_lo(aV + ((h * DK) / 8) * ROWB, 128);   // MN-major: LBO = next 8 keys
+#pragma unroll
+        for (int ks = 0; ks < 128 / 16; ++ks)
+          mma_bf16_ts(tbase + L::tO + h * 128, tbase + L::tS + h * 128 + ks * 8,
+                      desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
+      }
+      commit(bar);
+    }
+    // while the tensor pipe works: folded decoder queries qt[s][n] = dvec[s] . G[n] + g[n], n = (head, k)
+    {
+      float acc[NS];
+      const float gb = __ldg(gGb + row);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = gb;
+      const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
+#pragma unroll
+      for (int jc = 0; jc < KC; ++jc) {
+        float w[8];
+        bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 d0 = *reinterpret_cast<const float4*>(dvs + s * D + jc * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(dvs + s * D + jc * 8 + 4);
+          acc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], acc[s]))));
+          acc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], acc[s]))));
+        }
+      }
+      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) qt[s * (H * D) + row] = acc[s];
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(5);
+
+    // ---- P6: A = LN(O + X) (self-attention LayerNorm), written over X ----
+    {
+      float y[D];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tbase, L::tO + h * 128), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) y[h * DK + e] = __uint_as_float(r[e]);
+      }
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        float x[8];
+        bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
+      }
+      ln64(y, fv + L::vLN + 0 * D, fv + L::vLN + 1 * D);
+#pragma unroll
+      for (int c = 0; c < KC; ++c) *reinterpret_cast<uint4*>(sXA + c * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(6);
+    stage_rows();
+
+    // ---- P7: hidden = A W1 ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks)
+        mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
+      commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(7);
+
+    // ---- P8: relu(+b1) -> H, packed to bf16 IN PLACE in tensor memory (A operand of the next MMA) ----
+#pragma unroll
+    for (int blk = 0; blk < DFF / 32; ++blk) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32), r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
+        pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+        pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+      }
+      tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(8);
+
+    // ---- P9: F = H W2 (A = H in tensor memory) ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+      for (int ks = 0; ks < DFF / 16; ++ks)
+        mma_bf16_ts(tbase + L::tFF2, tbase + L::tFF1 + ks * 8, desc_join(dW2 + ks * (2 * D), dHi), idesc, ks > 0);
+      commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(9);
+
+    // ---- P10: memory row = LN(F + b2 + A) in registers; decoder scores / partial softmax of this row; the memory
+    //      image (bf16, MN-major B operand, + ones chunk) and the transposed probabilities for the context MMA ----
+    {
+      float y[D];
+#pragma unroll
+      for (int blk = 0; blk < D / 32; ++blk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tbase, L::tFF2 + blk * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB2 + blk * 32 + e);
+          y[blk * 32 + e] = __uint_as_float(r[e]) + bb.x;
+          y[blk * 32 + e + 1] = __uint_as_float(r[e + 1]) + bb.y;
+          y[blk * 32 + e + 2] = __uint_as_float(r[e + 2]) + bb.z;
+          y[blk * 32 + e + 3] = __uint_as_float(r[e + 3]) + bb.w;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        float x[8];
+        bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
+      }
+      ln64(y, fv + L::vLN + 2 * D, fv + L::vLN + 3 * D);
+      // decoder scores of this token against its sample's folded queries (TransformerModel.py:157-166)
+      const float* qt = reinterpret_cast<const float*>(gbase + L::gQt) + slot * (H * D);
+      float u[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(qt + h * D + k);
+          a0 = fmaf(y[k], q.x, a0); a1 = fmaf(y[k + 1], q.y, a1);
+          a2 = fmaf(y[k + 2], q.z, a2); a3 = fmaf(y[k + 3], q.w, a3);
+        }
+        u[h] = (tpos < len) ? ((a0 + a1) + (a2 + a3)) * sl2 : -INFINITY;   // (the per-(sample, head) constant
+      }                                                                     //  bk_h . qd_h cancels in the softmax)
+      float e[H];
+      const int part = (SLOT >= 32) ? wg : (wg * (32 / W) + lane / W);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float m = u[h];
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((lane % W) == 0) reinterpret_cast<float*>(gbase + L::gMx)[part * H + h] = m;   // -inf: empty part
+        e[h] = (tpos < len) ? ex2_approx(u[h] - m) : 0.f;                  // tpos < len implies m is finite
+      }
+      // memory image: chunk c of token `row` at sK + c*ROWB + row*16; ones chunk (softmax denominator) in sV
+#pragma unroll
+      for (int c = 0; c < KC; ++c) *reinterpret_cast<uint4*>(sK + c * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+      *reinterpret_cast<uint4*>(sV + row * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      // transposed probabilities: image row (part, h), column = this token; zeros in every other part's row
+      const unsigned short eb[H] = {__bfloat16_as_ushort(__float2bfloat16(e[0])), __bfloat16_as_ushort(__float2bfloat16(e[1]))};
+      uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2;
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const unsigned short v = (rr == part * H) ? eb[0] : ((rr == part * H + 1) ? eb[1] : (unsigned short)0);
+        *reinterpret_cast<unsigned short*>(pd + rr * 16) = v;
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 128);
+    T2_TICK(10);
+
+    // ---- P11: ctx[(part,h)] = sum_t e_t M_t | sum_t e_t : one MMA, A = transposed probabilities (16-row image) ----
+    if (row == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, D + 16, false, true);
+      const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
+#pragma unroll
+      for (int ks = 0; ks < 128 / 16; ++ks)
+        mma_bf16_ss(tbase + L::tCtx, desc_join(dPd + ks * (2 * 256 / 16), dHi), desc_join(dM + ks * (256 / 16), dHiV),
+                    idesc, ks > 0);
+      commit(bar);
+    }
+    if (wg == 0) {
+      mbar_wait(bar, phase);
+      fence_after_sync();
+      uint32_t c0[32], c1[32], c2[16];
+      tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
+      tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
+      tmem_ld16(tmem_addr(tbase, L::tCtx + 64), c2);
+      tmem_ld_wait();
+      float den = __uint_as_float(c2[0]);
+      float wgt = 1.0f;
+      if constexpr (PPS == 2) {                          // a 64-row slot spans two warps: merge the two partials
+        const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
+        const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
+        const float m = fmaxf(ma, mb);
+        wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
+        den *= wgt;
+        den += __shfl_xor_sync(0xffffffffu, den, 2);
+      }
+      const float inv = den > 0.f ? 1.0f / den : 0.f;   // empty sequence: context 0
+      const int p = lane >> 1, h = lane & 1;
+      const int b = b0 + p / PPS;
+      const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
+      float* dst = a.ctx + ((int64_t)b * H + h) * D;
+#pragma unroll
+      for (int k = 0; k < D; k += 4) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kk = k + e;
+          v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
+          if constexpr (PPS == 2) {
+            v[e] *= wgt;
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
+          }
+          v[e] *= inv;
+        }
+        if (writer) *reinterpret_cast<float4*>(dst + k) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      fence_before_sync();
+    }
+    phase ^= 1;
+    T2_TICK(11);
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---- per-sample decoder tail, row-batched: 128 samples per CTA (one thread = one sample = one TMEM lane) ----
+//   o  = [ctx_0 | ctx_1] WvBD + bv (bv only for non-empty sequences) ; y = o + dvec ; av = LN3(y)
+//   u  = LN2(relu(av W1 + b1) W2 + b2 + av)                                   (TransformerModel.py:157-171)
+struct TailLayout {
+  static constexpr int oWv = 0;                         // image(D, H*D)   16 KB
+  static constexpr int oW1 = oWv + kH * kD * kD * 2;    // image(DFF, D)   32 KB
+  static constexpr int oW2 = oW1 + kD * kDFF * 2;       // image(D, DFF)   32 KB
+  static constexpr int oFV = oW2 + kDFF * kD * 2;
+  static constexpr int vBV = 0, vB1 = kD, vB2 = vB1 + kDFF, vLN2 = vB2 + kD, vLN3 = vLN2 + 2 * kD, nFV = vLN3 + 2 * kD;
+  static constexpr int oOut = oFV + nFV * 4;            // fp32 [128][D+1] output transpose
+  static constexpr int total = oOut + 128 * (kD + 1) * 4 + 64;
+  static constexpr int tA = 0, tO = 64, tFF1 = 128, tFF2 = 384;
+};
+
+__global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant__ SeqTcArgs a) {
+  using L = TailLayout;
+  constexpr int D = kD, DFF = kDFF, H = kH, KC = kKC;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int B = a.cfg.batch;
+  const int b = blockIdx.x * 128 + tid;
+  const bool live = b < B;
+  float* fv = reinterpret_cast<float*>(smem + L::oFV);
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  // issue this sample's loads first (ctx row, target item rows, length), then stage the weights
+  const int nf = a.cfg.n_feats;
+  const int zp = a.cfg.zero_pad ? 1 : 0;
+  bool has = false;
+  float dvec[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) dvec[i] = 0.f;
+  uint32_t cpk[H * D / 2];
+#pragma unroll
+  for (int i = 0; i < H * D / 2; ++i) cpk[i] = 0u;
+  if (live) {
+    const int32_t* ol = a.in.offsets[nf - 1];
+    has = (__ldg(ol + b + 1) - __ldg(ol + b)) > 0;
+    const float sqrt_d = sqrtf((float)D);
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      const int f = a.chunk_feat[c];
+      const int64_t rw = (int64_t)__ldg(a.in.item_ids[f] + b) - zp;
+      if (rw >= 0 && rw < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
+        const float4 t0 = ldg4(src), t1 = ldg4(src + 4);
+        dvec[c * 8 + 0] = t0.x * sqrt_d; dvec[c * 8 + 1] = t0.y * sqrt_d; dvec[c * 8 + 2] = t0.z * sqrt_d;
+        dvec[c * 8 + 3] = t0.w * sqrt_d; dvec[c * 8 + 4] = t1.x * sqrt_d; dvec[c * 8 + 5] = t1.y * sqrt_d;
+        dvec[c * 8 + 6] = t1.z * sqrt_d; dvec[c * 8 + 7] = t1.w * sqrt_d;
+      }
+    }
+    const float4* cs = reinterpret_cast<const float4*>(a.ctx + (int64_t)b * (H * D));
+#pragma unroll
+    for (int i = 0; i < H * D / 4; ++i) {
+      const float4 v = cs[i];
+      cpk[i * 2] = pack_bf16x2(v.x, v.y);
+      cpk[i * 2 + 1] = pack_bf16x2(v.z, v.w);
+    }
+  }
+  {
+    const __nv_bfloat16* p = a.prepared;
+    const uint4* s1 = reinterpret_cast<const uint4*>(p + prep_off_wvbd(D, DFF, H));
+    uint4* d1 = reinterpret_cast<uint4*>(smem + L::oWv);
+    for (int i = tid; i < (int)(prep_wvbd(D, H) * 2 / 16); i += 128) d1[i] = __ldg(s1 + i);
+    const uint4* s2 = reinterpret_cast<const uint4*>(p + prep_wqkv(D));          // w1 | w2 are contiguous
+    uint4* d2 = reinterpret_cast<uint4*>(smem + L::oW1);
+    for (int i = tid; i < (int)(2 * prep_w1(D, DFF) * 2 / 16); i += 128) d2[i] = __ldg(s2 + i);
+    for (int i = tid; i < D; i += 128) {
+      fv[L::vBV + i] = a.dbv[i];
+      fv[L::vB2 + i] = a.b2[i];
+      fv[L::vLN2 + i] = a.ln2_g[i];
+      fv[L::vLN2 + D + i] = a.ln2_b[i];
+      fv[L::vLN3 + i] = a.ln3_g[i];
+      fv[L::vLN3 + D + i] = a.ln3_b[i];
+    }
+    for (int i = tid; i < DFF; i += 128) fv[L::vB1 + i] = a.b1[i];
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t dHi = desc_hi(128, kLayoutNone);
+  const uint32_t dWv = desc_lo(smem_u32(smem + L::oWv), D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
+                 dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
+  uint32_t phase = 0;
+
+  // ---- o = ctx WvBD ----
+  tmem_st32(tmem_addr(tbase, L::tA), cpk);
+  tmem_st32(tmem_addr(tbase, L::tA + 32), cpk + 32);
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+    for (int ks = 0; ks < H * D / 16; ++ks)
+      mma_bf16_ts(tbase + L::tO, tbase + L::tA + ks * 8, desc_join(dWv + ks * (2 * D), dHi), idesc, ks > 0);
+    commit(&bar);
+  }
+  mbar_wait(&bar, phase);
+  phase ^= 1;
+  fence_after_sync();
+  float av[D];
+  {
+#pragma unroll
+    for (int blk = 0; blk < D / 32; ++blk) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tO + blk * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        av[blk * 32 + e] = __uint_as_float(r[e]) + (has ? fv[L::vBV + blk * 32 + e] : 0.f) + dvec[blk * 32 + e];
+    }
+    ln64(av, fv + L::vLN3, fv + L::vLN3 + D);
+    uint32_t pk[D / 2];
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) pk[i] = pack_bf16x2(av[2 * i], av[2 * i + 1]);
+    tmem_st32(tmem_addr(tbase, L::tA), pk);
+  }
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  // ---- hidden = relu(av W1 + b1), packed in place ----
+  if (tid == 0) {
+    fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks)
+      mma_bf16_ts(tbase + L::tFF1, tbase + L::tA + ks * 8, desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
+    commit(&bar);
+  }
+  mbar_wait(&bar, phase);
+  phase ^= 1;
+  fence_after_sync();
+#pragma unroll
+  for (int blk = 0; blk < DFF / 32; ++blk) {
+    uint32_t r[32];
+    tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32), r);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
+      pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+      pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+    }
+    tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);
+  }
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  // ---- f = hidden W2 ; u = LN2(f + b2 + av) ----
+  if (tid == 0) {
+    fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+    for (int ks = 0; ks < DFF / 16; ++ks)
+      mma_bf16_ts(tbase + L::tFF2, tbase + L::tFF1 + ks * 8, desc_join(dW2 + ks * (2 * D), dHi), idesc, ks > 0);
+    commit(&bar);
+  }
+  mbar_wait(&bar, phase);
+  phase ^= 1;
+  fence_after_sync();
+  {
+    float y[D];
+#pragma unroll
+    for (int blk = 0; blk < D / 32; ++blk) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tFF2 + blk * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) y[blk * 32 + e] = __uint_as_float(r[e]) + fv[L::vB2 + blk * 32 + e] + av[blk * 32 + e];
+    }
+    ln64(y, fv + L::vLN2, fv + L::vLN2 + D);
+    float* so = reinterpret_cast<float*>(smem + L::oOut) + tid * (D + 1);
+#pragma unroll
+    for (int i = 0; i < D; ++i) so[i] = y[i];
+  }
+  fence_before_sync();
+  __syncthreads();
+  // coalesced write: one warp per sample row
+  for (int r = warp; r < 128; r += 4) {
+    const int bb = blockIdx.x * 128 + r;
+    if (bb >= B) break;
+    const float* so = reinterpret_cast<const float*>(smem + L::oOut) + r * (D + 1);
+    a.out[(int64_t)bb * a.out_ld + lane] = so[lane];
+    a.out[(int64_t)bb * a.out_ld + 32 + lane] = so[32 + lane];
+  }
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+template <int SLOT>
+int launch_tc2(const SeqTcArgs& a, cudaStream_t st) {
+  using L = Tc2Layout<SLOT>;
+  const int total = L::oPos + a.cfg.maxlen * kD * 2 + 64;
+  auto kern = seq_encode_tc2_kernel<SLOT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc2_kernel)");
+  const int sms = sm_count_cached();
+  const int pairs = (a.n_tiles + 1) / 2;
+  const int grid = pairs < sms ? pairs : sms;
+  kern<<<grid, 256, total, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("seq_encode_tc2_kernel");
+  e = cudaFuncSetAttribute(seq_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailLayout::total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_tail_kernel)");
+  seq_tail_kernel<<<(a.cfg.batch + 127) / 128, 128, TailLayout::total, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("seq_tail_kernel");
+  return DMT_OK;
+}
+
+}  // namespace
+
+// shared-memory budget of the v2 kernel: the position table is the only size that depends on the configuration
+bool seq_tc2_supported(const dmt_seq_cfg* cfg) {
+  return Tc2Layout<64>::oPos + cfg->maxlen * kD * 2 + 64 + 1024 <= 227 * 1024 && cfg->n_feats <= kKC;   // + static smem
+}
+
+size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg) { return (size_t)cfg->batch * kH * kD * sizeof(float) + 256; }
+
+int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st) {
+  const dmt_seq_cfg* cfg = &a.cfg;
+  int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
+  if (slot > cfg->maxlen) slot = cfg->maxlen;
+  DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);
+  if (slot <= 16) {
+    a.n_tiles = (cfg->batch + 7) / 8;
+    return launch_tc2<16>(a, st);
+  }
+  if (slot <= 32) {
+    a.n_tiles = (cfg->batch + 3) / 4;
+    return launch_tc2<32>(a, st);
+  }
+  a.n_tiles = (cfg->batch + 1) / 2;
+  return launch_tc2<64>(a, st);
+}
+
+}  // namespace dmt

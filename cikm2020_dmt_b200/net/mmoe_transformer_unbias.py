@@ -249,8 +249,10 @@ class mmoe_transformer_unbias(object):
     def _prepared_for(self, seq_index, cfg):
         ver, buf = self._prepared.get(seq_index, (-1, None))
         nbytes = self.lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0)
-        if buf is None:
+        if buf is None or buf.numel() < nbytes:     # the workspace also holds batch-sized scratch: grow-only
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ver = -1
+        nbytes = buf.numel()
         if ver != self.params_version:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             with self._Stage(self, "prepare_weights", 1):

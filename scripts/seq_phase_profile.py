@@ -17,6 +17,11 @@ model = mmoe_transformer_unbias(plan, params=store, precision="bf16")
 B = 4096
 dev = batch_to(synthetic_batch(plan, B), "cuda")
 out = torch.zeros(B, 3 * plan.d_model, device="cuda")
+import os as _os
+V1 = _os.environ.get("DMT_SEQ_TC_V1") == "1"
+names2 = ["P0 convert+sync", "P1 QKV mma wait", "P2 QKV epilogue+sync", "P3 S mma wait", "P4 softmax->TMEM+sync",
+          "P5 PV mma wait (+qt)", "P6 LN1+sync", "P7 FF1 mma wait", "P8 relu->TMEM+sync", "P9 FF2 mma wait",
+          "P10 LN2+scores+images+sync", "P11 ctx mma + readout"]
 names = ["top sync", "P0 convert+sync", "P1 QKV mma wait", "P2 QKV epilogue+sync", "P3 S mma wait", "P4 softmax+sync",
          "P5 PV mma wait", "P6 LN1+sync", "P7 FF1 mma wait", "P8 relu epilogue+sync", "P9 FF2 mma wait", "P10 LN2+sync",
          "P11 decoder"]
@@ -31,6 +36,11 @@ for s in range(3):
     c = cnt.cpu().tolist()
     tot = sum(c[:13])
     ntiles = (B + 1) // 2 if s < 2 else (B + 7) // 8
-    print("sequence %d: %d tiles, %.0f cycles/tile (thread 0 view)" % (s, ntiles, tot / ntiles))
-    for n, v in zip(names, c):
+    if not V1:
+        ntiles = (ntiles + 1) // 2      # v2: thread 0 only sees the tiles of group 0
+        print("sequence %d: %d tiles of group 0, %.0f cycles/tile in the group = %.0f cycles/tile per SM"
+              % (s, ntiles, tot / ntiles, tot / ntiles / 2))
+    else:
+        print("sequence %d: %d tiles, %.0f cycles/tile (thread 0 view)" % (s, ntiles, tot / ntiles))
+    for n, v in zip(names if V1 else names2, c):
         print("   %-24s %7.0f cyc/tile  %5.1f%%" % (n, v / ntiles, 100.0 * v / tot))
