@@ -54,6 +54,16 @@ __device__ __forceinline__ uint4 f8_to_bf16(const float* f) {
   return v;
 }
 
+// streaming (read-once) 256-bit load: one 32-byte sector of an embedding row per lane, no L1 allocation
+struct f8 { float4 lo, hi; };
+__device__ __forceinline__ f8 ld_stream8(const float* p) {
+  f8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+
 // Row-local LayerNorm over 64 values held in registers (TransformerModel_util.py:58-78); four independent
 // partial sums keep the dependent-add chains short.
 __device__ __forceinline__ void ln64(float* y, const float* __restrict__ g, const float* __restrict__ b) {
@@ -98,7 +108,8 @@ struct Tc2Layout {
   static constexpr int gPd = gQ;                        // [k/8][16 rows][8] bf16: LBO 256, <= 6 KB touched
   static constexpr int gQt = gQ + 8192;                 // fp32 [NS][H*D] folded decoder queries
   static constexpr int gDvec = gQ + 12288;              // fp32 [NS][D] scaled target embeddings
-  static constexpr int gMx = gQ + 14336;                // fp32 [NR] partial-softmax maxima
+  static constexpr int gMx = gQ + 14336;                // fp32 [NR] partial-softmax maxima | [NR] denominators
+                                                        // (rows 0..7 of Q chunk 7: only warp 0 writes there)
   // the memory image (MN-major B operand of the context MMA) takes the K region, its ones chunk the first 2 KB of V
   static constexpr int oFV = oGrp + 2 * szGrp;          // 221184
   static constexpr int vBQKV = 0, vB1 = 3 * kD, vB2 = vB1 + kDFF, vLN = vB2 + kD, nFV = vLN + 4 * kD;
@@ -110,7 +121,7 @@ struct Tc2Layout {
   static constexpr int tO = 64;                         // head h: [h*128+64, +32)
   static constexpr int tFF1 = 0;                        // [0,256); H in place at [0,128)
   static constexpr int tFF2 = 128;                      // [128,192)
-  static constexpr int tCtx = 0;                        // [0,80)
+  static constexpr int tCtx = 192;                      // [192,256): untouched by the next tile's X Wqkv
 };
 
 #define T2_TICK(idx)                                                    \
@@ -122,14 +133,16 @@ struct Tc2Layout {
     }                                                                   \
   } while (0)
 
-template <int SLOT>
+// KW: key columns of the score window the softmax actually visits (>= the longest sequence; 64-row slots only)
+template <int SLOT, int KW>
 __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_constant__ SeqTcArgs a) {
   using L = Tc2Layout<SLOT>;
+  static_assert(KW % 8 == 0 && KW <= L::CW && (SLOT == 64 || KW == L::CW), "key window");
   constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
   constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[2];
+  __shared__ uint64_t bars[2], cbars[2];            // per group: phase MMAs | decoder-context MMA
   __shared__ uint32_t tmem_base_s;
   __shared__ int slen_s[2][2][NS];                    // [group][tile parity][slot]
 
@@ -142,6 +155,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   float* fv = reinterpret_cast<float*>(smem + L::oFV);
   const uint4* spos = reinterpret_cast<const uint4*>(smem + L::oPos);
   uint64_t* bar = &bars[grp];
+  uint64_t* cbar = &cbars[grp];
   const int B = a.cfg.batch;
   const uint32_t bar_id = 1 + grp;
 
@@ -150,6 +164,8 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&cbars[0], 1);
+    mbar_init(&cbars[1], 1);
     mbar_fence_init();
   }
   {
@@ -199,32 +215,34 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   // ---- software-pipelined gather.  One thread = one token row: it loads the KC 32-byte chunks of ITS token
   //      (chunk k of every lane belongs to the same table, so the index math is uniform).  Offsets, ids and rows
   //      of the group's next tile are requested just before three of the current tile's MMA waits. ----
-  int pf_o0[KC], pf_cnt[KC], pf_id[KC];
-  int pf_len = 0;
+  int pf_o0[KC], pf_o1[KC], pf_id[KC];
+  int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
   bool pf_valid = false;
-  float4 pf_e[KC][2];
+  f8 pf_e[KC];
   int pf_tid = kInvalidId;
   float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
 
   auto stage_offsets = [&](int nt) {
-    pf_len = 0;
+    // raw loads only: no arithmetic on the loaded values here, so nothing waits for them before stage_ids
+    pf_l0 = pf_l1 = 0;
     pf_tid = kInvalidId;
 #pragma unroll
-    for (int k = 0; k < KC; ++k) pf_o0[k] = pf_cnt[k] = 0;
+    for (int k = 0; k < KC; ++k) pf_o0[k] = pf_o1[k] = 0;
     if (nt >= a.n_tiles) return;
     const int b = nt * NS + slot;
     if (b < B) {
       const int32_t* ol = a.in.offsets[nf - 1];
-      pf_len = min(__ldg(ol + b + 1) - __ldg(ol + b), lmax);
+      pf_l0 = __ldg(ol + b);
+      pf_l1 = __ldg(ol + b + 1);
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         const int f = a.chunk_feat[k];
         if (k > 0 && f == a.chunk_feat[k - 1]) {
           pf_o0[k] = pf_o0[k - 1];
-          pf_cnt[k] = pf_cnt[k - 1];
+          pf_o1[k] = pf_o1[k - 1];
         } else {
           pf_o0[k] = __ldg(a.in.offsets[f] + b);
-          pf_cnt[k] = __ldg(a.in.offsets[f] + b + 1) - pf_o0[k];
+          pf_o1[k] = __ldg(a.in.offsets[f] + b + 1);
         }
       }
     }
@@ -234,6 +252,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     }
   };
   auto stage_ids = [&](int nt, int par) {
+    pf_len = min(pf_l1 - pf_l0, lmax);
     pf_valid = tpos < pf_len;
     if (tpos == 0) slen_s[grp][par][slot] = pf_len;
 #pragma unroll
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
       if (pf_valid) {
         const int f = a.chunk_feat[k];
         if (k > 0 && f == a.chunk_feat[k - 1]) pf_id[k] = pf_id[k - 1];
-        else pf_id[k] = (tpos < pf_cnt[k]) ? __ldg(a.in.ids[f] + pf_o0[k] + tpos) : 0;
+        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(a.in.ids[f] + pf_o0[k] + tpos) : 0;
       }
     }
   };
@@ -250,14 +269,11 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       const int f = a.chunk_feat[k];
-      pf_e[k][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      pf_e[k][1] = pf_e[k][0];
+      pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_e[k].hi = pf_e[k].lo;
       const int64_t rw = (int64_t)pf_id[k] - zp;
-      if (pf_id[k] != kInvalidId && rw >= 0 && rw < a.in.rows[f]) {
-        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[k];
-        pf_e[k][0] = ld_stream4(src);
-        pf_e[k][1] = ld_stream4(src + 4);
-      }
+      if (pf_id[k] != kInvalidId && rw >= 0 && rw < a.in.rows[f])
+        pf_e[k] = ld_stream8(a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[k]);
     }
     pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
     pf_t1 = pf_t0;
@@ -265,12 +281,57 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
       const int c = row % KC, f = a.chunk_feat[c];
       const int64_t rw = (int64_t)pf_tid - zp;
       if (pf_tid != kInvalidId && rw >= 0 && rw < a.in.rows[f]) {
-        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
-        pf_t0 = ld_stream4(src);
-        pf_t1 = ld_stream4(src + 4);
+        const f8 t = ld_stream8(a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c]);
+        pf_t0 = t.lo;
+        pf_t1 = t.hi;
       }
     }
   };
+  // decoder contexts of the tile whose first sample is rb0 (warp 0 of the group): merge the partial softmaxes of
+  // a 64-row slot, normalise, write [b][h][D] fp32 for the tail kernel
+  uint32_t cphase = 0;
+  auto ctx_readout = [&](int rb0) {
+    if (wg != 0) return;
+    mbar_wait(cbar, cphase);
+    cphase ^= 1;
+    fence_after_sync();
+    uint32_t c0[32], c1[32];
+    tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
+    tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
+    tmem_ld_wait();
+    const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
+    float den = mxs[NR + (lane & (NR - 1))];
+    float wgt = 1.0f;
+    if constexpr (PPS == 2) {                          // a 64-row slot spans two warps: merge the two partials
+      const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
+      const float m = fmaxf(ma, mb);
+      wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
+      den *= wgt;
+      den += __shfl_xor_sync(0xffffffffu, den, 2);
+    }
+    const float inv = den > 0.f ? 1.0f / den : 0.f;   // empty sequence: context 0
+    const int p = lane >> 1, h = lane & 1;
+    const int b = rb0 + p / PPS;
+    const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
+    float* dst = a.ctx + ((int64_t)b * H + h) * D;
+#pragma unroll
+    for (int k = 0; k < D; k += 4) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kk = k + e;
+        v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
+        if constexpr (PPS == 2) {
+          v[e] *= wgt;
+          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
+        }
+        v[e] *= inv;
+      }
+      if (writer) *reinterpret_cast<float4*>(dst + k) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    fence_before_sync();
+  };
+  int n_done = 0;
   const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
   stage_offsets(tile0);
   stage_ids(tile0, 0);
@@ -293,10 +354,10 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
       if (pf_valid) {
         float p[8];
         bf16x8_to_f(spos[tpos * KC + k], p);
-        x[0] = fmaf(pf_e[k][0].x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k][0].y, sqrt_d, p[1]);
-        x[2] = fmaf(pf_e[k][0].z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k][0].w, sqrt_d, p[3]);
-        x[4] = fmaf(pf_e[k][1].x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k][1].y, sqrt_d, p[5]);
-        x[6] = fmaf(pf_e[k][1].z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k][1].w, sqrt_d, p[7]);
+        x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
+        x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
+        x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
+        x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
       }
       *reinterpret_cast<uint4*>(sXA + k * ROWB + row * 16) = f8_to_bf16(x);
     }
@@ -305,7 +366,6 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     fence_before_sync();
     named_sync(bar_id, 128);
     T2_TICK(0);
-    stage_offsets(next_tile);
 
     // ---- P1: [Q|K|V] = X Wqkv ----
     if (row == 0) {
@@ -317,18 +377,24 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
                     desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
       commit(bar);
     }
+    // in the shadow of the MMA: the previous tile's decoder contexts (warp 0), the next tile's offsets
+    if (it > 0) ctx_readout(b0 - tstride * NS);
+    stage_offsets(next_tile);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     T2_TICK(1);
 
     // ---- P2: + bias, bf16, Q / K / V images ([chunk][row][8] each) ----
+    // (the load of block blk+1 is in flight while block blk is converted)
+    uint32_t rq[2][32];
+    tmem_ld32(tmem_addr(tbase, L::tQKV), rq[0]);
 #pragma unroll
     for (int blk = 0; blk < 3 * D / 32; ++blk) {
       const int n0 = blk * 32;
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, L::tQKV + n0), r);
       tmem_ld_wait();
+      if (blk + 1 < 3 * D / 32) tmem_ld32(tmem_addr(tbase, L::tQKV + n0 + 32), rq[(blk + 1) & 1]);
+      const uint32_t* r = rq[blk & 1];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n = n0 + g * 8;
@@ -347,7 +413,6 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     fence_before_sync();
     named_sync(bar_id, 128);
     T2_TICK(2);
-    stage_ids(next_tile, par ^ 1);
 
     // ---- P3: S_h = Q_h K_h^T for both heads ----
     if (row == 0) {
@@ -363,6 +428,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         }
       commit(bar);
     }
+    stage_ids(next_tile, par ^ 1);
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
@@ -375,14 +441,15 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
       const int lo = slot * SLOT - col0;              // this row's keys are window columns [lo, lo + len)
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        uint32_t r[CW];
-#pragma unroll
-        for (int blk = 0; blk < CW / 32; ++blk)
-          tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0 + blk * 32), r + blk * 32);
+        uint32_t r[KW];
+        tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0), r);
+        if constexpr (KW >= 48) tmem_ld16(tmem_addr(tbase, L::tS + h * 128 + col0 + 32), r + 32);
+        if constexpr (KW == 56) tmem_ld8(tmem_addr(tbase, L::tS + h * 128 + col0 + 48), r + 48);
+        if constexpr (KW == 64) tmem_ld16(tmem_addr(tbase, L::tS + h * 128 + col0 + 48), r + 48);
         tmem_ld_wait();
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
+        for (int j = 0; j < KW; ++j) {
           const bool ok = (unsigned)(j - lo) < (unsigned)len;
           const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
           r[j] = __float_as_uint(v);
@@ -391,7 +458,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW; j += 4) {
+        for (int j = 0; j < KW; j += 4) {
           const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));       // exp2(-inf) == 0: masked keys
           const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
           const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
@@ -405,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         uint32_t pk[CW / 2];
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j)
-          pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+          pk[j] = (j < KW / 2) ? pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv) : 0u;
         uint32_t zz[CW / 2];
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j) zz[j] = 0u;
@@ -501,7 +568,6 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     fence_before_sync();
     named_sync(bar_id, 128);
     T2_TICK(6);
-    stage_rows();
 
     // ---- P7: hidden = A W1 ----
     if (row == 0) {
@@ -513,25 +579,30 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
                     desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
       commit(bar);
     }
+    stage_rows();
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
     T2_TICK(7);
 
     // ---- P8: relu(+b1) -> H, packed to bf16 IN PLACE in tensor memory (A operand of the next MMA) ----
+    {
+      uint32_t rh[2][32];
+      tmem_ld32(tmem_addr(tbase, L::tFF1), rh[0]);
 #pragma unroll
-    for (int blk = 0; blk < DFF / 32; ++blk) {
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32), r);
-      tmem_ld_wait();
-      uint32_t pk[16];
+      for (int blk = 0; blk < DFF / 32; ++blk) {
+        tmem_ld_wait();
+        if (blk + 1 < DFF / 32) tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32 + 32), rh[(blk + 1) & 1]);
+        const uint32_t* r = rh[blk & 1];
+        uint32_t pk[16];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
-        pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
-        pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+        for (int g = 0; g < 8; ++g) {
+          const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
+          pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+          pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+        }
+        tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);   // columns [16 blk, +16): already consumed
       }
-      tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);
     }
     tmem_st_wait();
     fence_before_sync();
@@ -599,13 +670,19 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         float m = u[h];
 #pragma unroll
         for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((lane % W) == 0) reinterpret_cast<float*>(gbase + L::gMx)[part * H + h] = m;   // -inf: empty part
         e[h] = (tpos < len) ? ex2_approx(u[h] - m) : 0.f;                  // tpos < len implies m is finite
+        e[h] = __bfloat162float(__float2bfloat16(e[h]));                   // the MMA sums exactly these values
+        float dsum = e[h];
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        if ((lane % W) == 0) {
+          reinterpret_cast<float*>(gbase + L::gMx)[part * H + h] = m;      // -inf: empty part
+          reinterpret_cast<float*>(gbase + L::gMx)[NR + part * H + h] = dsum;
+        }
       }
-      // memory image: chunk c of token `row` at sK + c*ROWB + row*16; ones chunk (softmax denominator) in sV
+      // memory image: chunk c of token `row` at sK + c*ROWB + row*16
 #pragma unroll
       for (int c = 0; c < KC; ++c) *reinterpret_cast<uint4*>(sK + c * ROWB + row * 16) = f8_to_bf16(y + c * 8);
-      *reinterpret_cast<uint4*>(sV + row * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
       // transposed probabilities: image row (part, h), column = this token; zeros in every other part's row
       const unsigned short eb[H] = {__bfloat16_as_ushort(__float2bfloat16(e[0])), __bfloat16_as_ushort(__float2bfloat16(e[1]))};
       uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2;
@@ -620,61 +697,23 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     named_sync(bar_id, 128);
     T2_TICK(10);
 
-    // ---- P11: ctx[(part,h)] = sum_t e_t M_t | sum_t e_t : one MMA, A = transposed probabilities (16-row image) ----
+    // ---- P11: ctx[(part,h)] = sum_t e_t M_t : one MMA, A = transposed probabilities (16-row image).  Nobody waits
+    //      for it here: warp 0 reads it out in the shadow of the next tile's X Wqkv (or after the loop). ----
     if (row == 0) {
       fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, D + 16, false, true);
+      constexpr uint32_t idesc = make_idesc_bf16(128, D, false, true);
       const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
 #pragma unroll
       for (int ks = 0; ks < 128 / 16; ++ks)
         mma_bf16_ss(tbase + L::tCtx, desc_join(dPd + ks * (2 * 256 / 16), dHi), desc_join(dM + ks * (256 / 16), dHiV),
                     idesc, ks > 0);
-      commit(bar);
+      commit(cbar);
     }
-    if (wg == 0) {
-      mbar_wait(bar, phase);
-      fence_after_sync();
-      uint32_t c0[32], c1[32], c2[16];
-      tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
-      tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
-      tmem_ld16(tmem_addr(tbase, L::tCtx + 64), c2);
-      tmem_ld_wait();
-      float den = __uint_as_float(c2[0]);
-      float wgt = 1.0f;
-      if constexpr (PPS == 2) {                          // a 64-row slot spans two warps: merge the two partials
-        const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
-        const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
-        const float m = fmaxf(ma, mb);
-        wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
-        den *= wgt;
-        den += __shfl_xor_sync(0xffffffffu, den, 2);
-      }
-      const float inv = den > 0.f ? 1.0f / den : 0.f;   // empty sequence: context 0
-      const int p = lane >> 1, h = lane & 1;
-      const int b = b0 + p / PPS;
-      const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
-      float* dst = a.ctx + ((int64_t)b * H + h) * D;
-#pragma unroll
-      for (int k = 0; k < D; k += 4) {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kk = k + e;
-          v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
-          if constexpr (PPS == 2) {
-            v[e] *= wgt;
-            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
-          }
-          v[e] *= inv;
-        }
-        if (writer) *reinterpret_cast<float4*>(dst + k) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-      fence_before_sync();
-    }
-    phase ^= 1;
+    n_done = it + 1;
     T2_TICK(11);
   }
 
+  if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
   fence_before_sync();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_base_s, 512);
@@ -879,11 +918,11 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-template <int SLOT>
+template <int SLOT, int KW>
 int launch_tc2(const SeqTcArgs& a, cudaStream_t st) {
   using L = Tc2Layout<SLOT>;
   const int total = L::oPos + a.cfg.maxlen * kD * 2 + 64;
-  auto kern = seq_encode_tc2_kernel<SLOT>;
+  auto kern = seq_encode_tc2_kernel<SLOT, KW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc2_kernel)");
   const int sms = sm_count_cached();
@@ -914,14 +953,17 @@ int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st) {
   DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);
   if (slot <= 16) {
     a.n_tiles = (cfg->batch + 7) / 8;
-    return launch_tc2<16>(a, st);
+    return launch_tc2<16, 32>(a, st);
   }
   if (slot <= 32) {
     a.n_tiles = (cfg->batch + 3) / 4;
-    return launch_tc2<32>(a, st);
+    return launch_tc2<32, 32>(a, st);
   }
   a.n_tiles = (cfg->batch + 1) / 2;
-  return launch_tc2<64>(a, st);
+  const int lmax = cfg->maxlen < 64 ? cfg->maxlen : 64;   // no key beyond the longest possible sequence
+  if (lmax <= 48) return launch_tc2<64, 48>(a, st);
+  if (lmax <= 56) return launch_tc2<64, 56>(a, st);
+  return launch_tc2<64, 64>(a, st);
 }
 
 }  // namespace dmt
