@@ -38,6 +38,11 @@ __device__ __forceinline__ void xent_clip(float p, int y, float& xe, float& dxe_
   dxe_dp = (d0 + d1) / s - dy / cy;
 }
 
+// kLanes lanes per sample: lane j of a sample computes the units n = j, j + kLanes, ... of every layer, the
+// activations of the sample live in a private shared-memory row (stride kMaxBiasWidth + 1: conflict-free across the
+// samples of a warp).  Lane 0 of the sample then evaluates the loss terms.
+constexpr int kLanes = 4;
+constexpr int kActLd = kMaxBiasWidth + 1;
 __global__ void __launch_bounds__(128) bias_loss_kernel(const __grid_constant__ BiasLossArgs a) {
   extern __shared__ float wsm[];
   // stage all layer weights: [in,out] kernels then biases, in layer order
@@ -51,31 +56,40 @@ __global__ void __launch_bounds__(128) bias_loss_kernel(const __grid_constant__ 
     total += nw + units;
     in_dim = units;
   }
-  __syncthreads();
   const int B = a.cfg.batch;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-
-  float cur[kMaxBiasWidth], nxt[kMaxBiasWidth];
+  const int sl = threadIdx.x / kLanes, sub = threadIdx.x % kLanes;       // sample slot in the CTA, lane in the sample
+  const int b = blockIdx.x * (blockDim.x / kLanes) + sl;
+  const int bc = b < B ? b : B - 1;                                       // out-of-range slots redo the last sample
+  float* cur = wsm + ((total + 3) & ~3) + sl * 2 * kActLd;
+  float* nxt = cur + kActLd;
   in_dim = a.cfg.n_hidden < 0 ? 1 : a.cfg.in_dim;   // n_hidden < 0: bias_in already holds y_bias
-  for (int k = 0; k < in_dim; ++k) cur[k] = __ldg(a.bias_in + (int64_t)b * a.bias_ld + k);
+  for (int k = sub; k < in_dim; k += kLanes) cur[k] = __ldg(a.bias_in + (int64_t)bc * a.bias_ld + k);
+  __syncthreads();
   int base = 0;
   for (int l = 0; l < nl; ++l) {
     const int units = l < a.cfg.n_hidden ? a.cfg.units[l] : 1;
     const float* W = wsm + base;
     const float* bb = W + in_dim * units;
-    for (int n = 0; n < units; ++n) {
-      float acc = 0.f;
-      for (int k = 0; k < in_dim; ++k) acc = fmaf(cur[k], W[k * units + n], acc);
-      acc += bb[n];
-      nxt[n] = (l < a.cfg.n_hidden) ? fmaxf(acc, 0.f) : acc;   // relu hidden, identity output (:263-287)
+    for (int n = sub; n < units; n += kLanes) {
+      float a0 = 0.f, a1 = 0.f;
+      int k = 0;
+      for (; k + 2 <= in_dim; k += 2) {
+        a0 = fmaf(cur[k], W[k * units + n], a0);
+        a1 = fmaf(cur[k + 1], W[(k + 1) * units + n], a1);
+      }
+      if (k < in_dim) a0 = fmaf(cur[k], W[k * units + n], a0);
+      float acc = (a0 + a1) + bb[n];
+      acc = (l < a.cfg.n_hidden) ? fmaxf(acc, 0.f) : acc;      // relu hidden, identity output (:263-287)
       if (l < a.cfg.n_hidden && a.cfg.dropout_rate[l] > 0.f)   // training mode (:272,280)
-        nxt[n] *= Dropout(a.cfg.dropout_rate[l], a.cfg.dropout_seed, kSiteBias + l).mult((uint32_t)(b * units + n));
+        acc *= Dropout(a.cfg.dropout_rate[l], a.cfg.dropout_seed, kSiteBias + l).mult((uint32_t)(bc * units + n));
+      nxt[n] = acc;
     }
-    for (int n = 0; n < units; ++n) cur[n] = nxt[n];
+    __syncwarp();
+    float* tmp = cur; cur = nxt; nxt = tmp;
     base += in_dim * units + units;
     in_dim = units;
   }
+  if (sub != 0 || b >= B) return;
   const float yb = cur[0];
   a.y_bias[b] = yb;
 
@@ -184,7 +198,9 @@ int dmt_bias_loss_fwd(const dmt_bias_loss_cfg* cfg, const dmt_bias_weights* w, c
   a.dlogits = dlogits;
   a.per_sample = loss ? (float*)loss_scratch : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  dmt::bias_loss_kernel<<<(cfg->batch + 127) / 128, 128, wfloats * sizeof(float), st>>>(a);
+  constexpr int kSamplesPerCta = 128 / dmt::kLanes;
+  const size_t smem = (((wfloats + 3) & ~(size_t)3) + (size_t)kSamplesPerCta * 2 * dmt::kActLd) * sizeof(float);
+  dmt::bias_loss_kernel<<<(cfg->batch + kSamplesPerCta - 1) / kSamplesPerCta, 128, smem, st>>>(a);
   DMT_CUDA_LAUNCH_CHECK("bias_loss_kernel");
   if (loss) {
     dmt::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)loss_scratch, cfg->batch, loss);

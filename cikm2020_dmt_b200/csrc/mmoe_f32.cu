@@ -178,6 +178,102 @@ __global__ void __launch_bounds__(kHeadWarps * 32) mmoe_head_kernel(const __grid
   }
 }
 
+
+// Same computation with precomputed gates (bf16 path), restructured for throughput: the tower weights of every
+// task are staged in shared memory once per CTA (layer by layer: kernel [in, units], bias; then the output
+// kernel + bias), warps stride over the samples, and every lane keeps four independent accumulators.
+constexpr int kHeadFastWarps = 4;
+constexpr int kHeadSamples = 4;
+__global__ void __launch_bounds__(kHeadFastWarps * 32) mmoe_head_fast_kernel(const __grid_constant__ HeadArgs a,
+                                                                             int w_floats) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int E = a.cfg.n_experts, Hd = a.hdim, B = a.cfg.batch, T = a.cfg.n_tasks, NL = a.cfg.n_tower_layers;
+  (void)w_floats;   // the tower weights (a few KB per task) are read through L1: every CTA of an SM shares them
+  // every warp works on kHeadSamples samples at a time: one weight read serves all of them and the lanes carry
+  // kHeadSamples x 2 independent accumulators (the per-sample chains were latency-bound)
+  float* ybase = sm + warp * (kHeadSamples * a.vec_floats);
+  const int n_groups = (B + kHeadSamples - 1) / kHeadSamples;
+  for (int grp = blockIdx.x * kHeadFastWarps + warp; grp < n_groups; grp += gridDim.x * kHeadFastWarps) {
+    const int b0 = grp * kHeadSamples;
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int s = 0; s < kHeadSamples; ++s) {
+        const int b = min(b0 + s, B - 1);
+        float* y0 = ybase + s * a.vec_floats;
+        float gl[DMT_MAX_EXPERTS];
+#pragma unroll
+        for (int e = 0; e < DMT_MAX_EXPERTS; ++e) gl[e] = (e < E) ? __ldg(a.gates + ((int64_t)t * B + b) * E + e) : 0.f;
+        for (int c = lane * 2; c < Hd; c += 64) {              // Hd is even (checked by the launcher)
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+            if (e < E) {
+              const int64_t idx = ((int64_t)e * B + b) * Hd + c;
+              float h0, h1;
+              if (a.h_is_bf16) {
+                const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                    reinterpret_cast<const __nv_bfloat16*>(a.h_last) + idx));
+                h0 = hv.x; h1 = hv.y;
+              } else {
+                const float2 hv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.h_last) + idx);
+                h0 = hv.x; h1 = hv.y;
+              }
+              a0 = fmaf(gl[e], h0, a0);
+              a1 = fmaf(gl[e], h1, a1);
+            }
+          y0[c] = a0;
+          y0[c + 1] = a1;
+        }
+      }
+      __syncwarp();
+      int in_dim = Hd;
+      int cur_o = 0, nxt_o = a.vec_floats / 2;
+      for (int l = 0; l < NL; ++l) {
+        const int units = a.cfg.tower_units[l];
+        const float* __restrict__ Wt = a.tower[t][l].w;
+        const float* __restrict__ bt = a.tower[t][l].b;
+        for (int n = lane; n < units; n += 32) {
+          float c0[kHeadSamples], c1[kHeadSamples];
+#pragma unroll
+          for (int s = 0; s < kHeadSamples; ++s) c0[s] = c1[s] = 0.f;
+          int k = 0;
+          for (; k + 4 <= in_dim; k += 4) {
+            const float w0 = __ldg(Wt + k * units + n), w1 = __ldg(Wt + (k + 1) * units + n),
+                        w2 = __ldg(Wt + (k + 2) * units + n), w3 = __ldg(Wt + (k + 3) * units + n);
+#pragma unroll
+            for (int s = 0; s < kHeadSamples; ++s) {
+              const float4 xv = *reinterpret_cast<const float4*>(ybase + s * a.vec_floats + cur_o + k);
+              c0[s] = fmaf(xv.x, w0, c0[s]);
+              c1[s] = fmaf(xv.y, w1, c1[s]);
+              c0[s] = fmaf(xv.z, w2, c0[s]);
+              c1[s] = fmaf(xv.w, w3, c1[s]);
+            }
+          }
+          for (; k < in_dim; ++k) {
+            const float w0 = __ldg(Wt + k * units + n);
+#pragma unroll
+            for (int s = 0; s < kHeadSamples; ++s) c0[s] = fmaf(ybase[s * a.vec_floats + cur_o + k], w0, c0[s]);
+          }
+#pragma unroll
+          for (int s = 0; s < kHeadSamples; ++s) ybase[s * a.vec_floats + nxt_o + n] = fmaxf((c0[s] + c1[s]) + __ldg(bt + n), 0.f);
+        }
+        __syncwarp();
+        const int tmp = cur_o; cur_o = nxt_o; nxt_o = tmp;
+        in_dim = units;
+      }
+#pragma unroll
+      for (int s = 0; s < kHeadSamples; ++s) {
+        float acc = 0.f;
+        for (int k = lane; k < in_dim; k += 32) acc = fmaf(ybase[s * a.vec_floats + cur_o + k], __ldg(a.tower_out[t].w + k), acc);
+        acc = warp_sum(acc);
+        if (lane == 0 && b0 + s < B) a.logits[(int64_t)t * B + b0 + s] = acc + __ldg(a.tower_out[t].b);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
                      const void* h_last, int h_is_bf16, const float* gates, float* logits, cudaStream_t st) {
   const int B = cfg->batch;
@@ -199,6 +295,20 @@ int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const f
   int mx = in_dim;
   for (int l = 0; l < cfg->n_tower_layers; ++l) mx = cfg->tower_units[l] > mx ? cfg->tower_units[l] : mx;
   h.vec_floats = 2 * ((mx + 31) / 32 * 32);
+  if (gates && in_dim % 2 == 0) {   // bf16 path: gates come from the cast kernel
+    const int w_floats = 0;
+    const size_t fsmem = (size_t)kHeadFastWarps * kHeadSamples * h.vec_floats * sizeof(float);
+    if (fsmem <= 160 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(mmoe_head_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_head_fast_kernel)");
+      int grid = (B + kHeadFastWarps * kHeadSamples - 1) / (kHeadFastWarps * kHeadSamples);
+      const int cap = 8 * sm_count_cached();
+      if (grid > cap) grid = cap;
+      mmoe_head_fast_kernel<<<grid, kHeadFastWarps * 32, fsmem, st>>>(h, w_floats);
+      DMT_CUDA_LAUNCH_CHECK("mmoe_head_fast_kernel");
+      return DMT_OK;
+    }
+  }
   const size_t smem = (size_t)kHeadWarps * h.vec_floats * sizeof(float);
   DMT_REQUIRE(smem <= 48 * 1024, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_fwd: tower width %d too large", mx);
   mmoe_head_kernel<<<(B + kHeadWarps - 1) / kHeadWarps, kHeadWarps * 32, smem, st>>>(h);

@@ -189,6 +189,86 @@ __global__ void __launch_bounds__(256) mmoe_cast_gate_kernel(const float* __rest
     }
 }
 
+
+// Fast path for 4 experts (dmt.conf): the gate kernels [K, 4] of every task are staged in shared memory once per
+// CTA, warps stride over the samples, every lane converts 4 consecutive inputs per trip (float4 in, 4 x bf16 out,
+// one float4 of gate weights per (task, input)).
+constexpr int kCastWarps = 16;
+__global__ void __launch_bounds__(kCastWarps * 32) mmoe_cast_gate4_kernel(const float* __restrict__ x, int64_t x_ld, int B,
+                                                                          int K, __nv_bfloat16* __restrict__ xb, int ldxb,
+                                                                          dmt_dense g0, dmt_dense g1, dmt_dense g2,
+                                                                          dmt_dense g3, int n_tasks,
+                                                                          float* __restrict__ gates) {
+  // [task][K128] float4 = the 4 expert weights of input k, permuted inside every block of 128 inputs so that the
+  // lanes of a warp (lane owns inputs 4*lane .. 4*lane+3) read consecutive float4s: slot(k) = (k & ~127) |
+  // ((k & 3) << 5) | ((k & 127) >> 2)
+  extern __shared__ float4 sg[];
+  const dmt_dense gate[DMT_MAX_TASKS] = {g0, g1, g2, g3};
+  const int K128 = (K + 127) & ~127;
+  for (int t = 0; t < n_tasks; ++t)
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+      sg[t * K128 + ((i & ~127) | ((i & 3) << 5) | ((i & 127) >> 2))] = __ldg(reinterpret_cast<const float4*>(gate[t].w) + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * kCastWarps + warp; b < B; b += gridDim.x * kCastWarps) {
+    const float* __restrict__ xr = x + (int64_t)b * x_ld;
+    float acc[DMT_MAX_TASKS][4];
+#pragma unroll
+    for (int t = 0; t < DMT_MAX_TASKS; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll 3
+    for (int k0 = lane * 4; k0 < ldxb; k0 += 128) {
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k0 + 4 <= K) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k0));
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k0 + u < K) xv[u] = __ldg(xr + k0 + u);
+      }
+      uint2 pk;
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(xv[0], xv[1]), p23 = __floats2bfloat162_rn(xv[2], xv[3]);
+      pk.x = *reinterpret_cast<uint32_t*>(&p01);
+      pk.y = *reinterpret_cast<uint32_t*>(&p23);
+      *reinterpret_cast<uint2*>(xb + (int64_t)b * ldxb + k0) = pk;
+#pragma unroll
+      for (int t = 0; t < DMT_MAX_TASKS; ++t)
+        if (t < n_tasks) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (k0 + u < K) {
+              const float4 w = sg[t * K128 + (k0 & ~127) + (u << 5) + lane];
+              acc[t][0] = fmaf(xv[u], w.x, acc[t][0]);
+              acc[t][1] = fmaf(xv[u], w.y, acc[t][1]);
+              acc[t][2] = fmaf(xv[u], w.z, acc[t][2]);
+              acc[t][3] = fmaf(xv[u], w.w, acc[t][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < DMT_MAX_TASKS; ++t)
+      if (t < n_tasks) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[t][e] = warp_sum(acc[t][e]) + __ldg(gate[t].b + e);
+          mx = fmaxf(mx, acc[t][e]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[t][e] = expf(acc[t][e] - mx);
+          den += acc[t][e];
+        }
+        if (lane == 0)
+          *reinterpret_cast<float4*>(gates + ((int64_t)t * B + b) * 4) =
+              make_float4(acc[t][0] / den, acc[t][1] / den, acc[t][2] / den, acc[t][3] / den);
+      }
+  }
+}
+
 // Bt[z][n][k] = W_z[k][n] (bf16, K padded to ldk with zeros): the K-major B operand of layer l.
 __global__ void mmoe_prepare_kernel(dmt_mmoe_weights w, int layer, int E, int K, int N, int ldk,
                                     __nv_bfloat16* __restrict__ out) {
@@ -307,9 +387,23 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
   __nv_bfloat16* xb = (__nv_bfloat16*)ws;
   float* gates = (float*)(ws + gate_off);
   const int ldx = pad8(cfg->in_dim);
-  mmoe_cast_gate_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, x_ld, B, cfg->in_dim, xb, ldx, w->gate[0], w->gate[1],
-                                                     w->gate[2], w->gate[3], cfg->n_tasks, E, gates);
-  DMT_CUDA_LAUNCH_CHECK("mmoe_cast_gate_kernel");
+  const size_t gsm = (size_t)cfg->n_tasks * ((cfg->in_dim + 127) & ~127) * sizeof(float4);
+  bool gate_al = true;
+  for (int t = 0; t < cfg->n_tasks; ++t) gate_al = gate_al && ((uintptr_t)w->gate[t].w & 15) == 0;
+  if (E == 4 && gate_al && x_ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gates & 15) == 0 && gsm <= 160 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mmoe_cast_gate4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_cast_gate4_kernel)");
+    int grid = (B + kCastWarps - 1) / kCastWarps;
+    const int cap = 2 * sm_count_cached();
+    if (grid > cap) grid = cap;
+    mmoe_cast_gate4_kernel<<<grid, kCastWarps * 32, gsm, st>>>(x, x_ld, B, cfg->in_dim, xb, ldx, w->gate[0], w->gate[1],
+                                                                w->gate[2], w->gate[3], cfg->n_tasks, gates);
+    DMT_CUDA_LAUNCH_CHECK("mmoe_cast_gate4_kernel");
+  } else {
+    mmoe_cast_gate_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, x_ld, B, cfg->in_dim, xb, ldx, w->gate[0], w->gate[1],
+                                                       w->gate[2], w->gate[3], cfg->n_tasks, E, gates);
+    DMT_CUDA_LAUNCH_CHECK("mmoe_cast_gate_kernel");
+  }
 
   const int smem_bytes = GSTAGES * kStageBytes + 1024;
   {

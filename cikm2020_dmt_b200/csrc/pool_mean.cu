@@ -18,7 +18,7 @@ struct PoolArgs {
   int64_t out_ld;
 };
 
-__global__ void __launch_bounds__(256) pool_mean_kernel(const __grid_constant__ PoolArgs a) {
+__global__ void __launch_bounds__(1024) pool_mean_kernel(const __grid_constant__ PoolArgs a) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < a.width; c += blockDim.x) {
     int f = 0;
@@ -28,8 +28,25 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const __grid_constant__ 
     const int beg = __ldg(pf.offsets + b), end = __ldg(pf.offsets + b + 1);
     float num = 0.f, den = 0.f;
     int t = beg;
-    // four tokens per trip: the id -> row dependent loads of different tokens overlap (the kernel is
-    // latency-bound otherwise); accumulation order stays token order
+    // eight (then four) tokens per trip: the id -> row dependent loads of different tokens overlap (the kernel
+    // is latency-bound otherwise); accumulation order stays token order
+    for (; t + 8 <= end; t += 8) {
+      int64_t row[8];
+      float w[8], e[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        row[u] = __ldg(pf.ids + t + u);
+        w[u] = pf.weights ? __ldg(pf.weights + t + u) : 1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        e[u] = (row[u] >= 0 && row[u] < pf.rows) ? __ldg(pf.table + row[u] * pf.dim + j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        num = fmaf(w[u], e[u], num);
+        den += w[u];
+      }
+    }
     for (; t + 4 <= end; t += 4) {
       int64_t row[4];
       float w[4], e[4];
@@ -60,13 +77,85 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const __grid_constant__ 
   }
 }
 
+
+// Throughput version (every dim a power of two in [4, 128]): one WARP per (sample, feature) job.  A row is read as
+// dim/4 float4 lanes, so a warp covers 32/(dim/4) tokens per step and keeps up to 8 steps in flight: the ids of a
+// whole round are requested first, then all of its rows -- one dependent load pair per round instead of one per
+// few tokens -- and every lane has work no matter how long the sample's other features are.  The token lanes are
+// reduced in a fixed xor-shuffle order (deterministic).
+constexpr int kPoolSteps = 8;
+__global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_constant__ PoolArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_jobs = (int64_t)a.batch * a.n_feats;
+  for (int64_t job = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); job < n_jobs; job += (int64_t)gridDim.x * 8) {
+    const int b = (int)(job / a.n_feats), f = (int)(job - (int64_t)b * a.n_feats);
+    const dmt_pool_feat& pf = a.f[f];
+    const int V = pf.dim >> 2;                        // float4 lanes per row
+    const int TPI = 32 / V;                           // tokens per step
+    const int tl = lane / V, v = lane - tl * V;
+    const int beg = __ldg(pf.offsets + b), end = __ldg(pf.offsets + b + 1);
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+    float den = 0.f;
+    for (int t0 = beg; t0 < end; t0 += TPI * kPoolSteps) {
+      int64_t row[kPoolSteps];
+      float w[kPoolSteps];
+#pragma unroll
+      for (int u = 0; u < kPoolSteps; ++u) {
+        const int t = t0 + u * TPI + tl;
+        row[u] = -1;
+        w[u] = 0.f;
+        if (t < end) {
+          row[u] = __ldg(pf.ids + t);
+          w[u] = pf.weights ? __ldg(pf.weights + t) : 1.0f;
+        }
+      }
+      float4 e[kPoolSteps];
+#pragma unroll
+      for (int u = 0; u < kPoolSteps; ++u) {
+        e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row[u] >= 0 && row[u] < pf.rows) e[u] = ldg4(pf.table + row[u] * pf.dim + v * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < kPoolSteps; ++u) {
+        num.x = fmaf(w[u], e[u].x, num.x);
+        num.y = fmaf(w[u], e[u].y, num.y);
+        num.z = fmaf(w[u], e[u].z, num.z);
+        num.w = fmaf(w[u], e[u].w, num.w);
+        den += w[u];
+      }
+    }
+    for (int o = 16; o >= V; o >>= 1) {               // token lanes: lane bits above the float4 index
+      num.x += __shfl_xor_sync(0xffffffffu, num.x, o);
+      num.y += __shfl_xor_sync(0xffffffffu, num.y, o);
+      num.z += __shfl_xor_sync(0xffffffffu, num.z, o);
+      num.w += __shfl_xor_sync(0xffffffffu, num.w, o);
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
+    if (tl == 0) {
+      // tf.nn.embedding_lookup_sparse(combiner='mean'): sum(w*row)/sum(w); an absent row comes out as 0
+      const float inv = (end > beg) ? 1.0f / den : 0.f;
+      float* o = a.out + (int64_t)b * a.out_ld + pf.out_col + v * 4;
+      o[0] = (end > beg) ? num.x * inv : 0.f;
+      o[1] = (end > beg) ? num.y * inv : 0.f;
+      o[2] = (end > beg) ? num.z * inv : 0.f;
+      o[3] = (end > beg) ? num.w * inv : 0.f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 copy_dense_kernel(const float* __restrict__ src, int batch, int dim, float* __restrict__ dst, int64_t ld) {
-  const int64_t total = (int64_t)batch * dim;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / dim;
-    const int c = (int)(i - b * dim);
-    dst[b * ld + c] = __ldcs(src + i);
+  // one warp per row, lanes stride the columns (no per-element division); rows are independent
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < batch; b += gridDim.x * 8) {
+    const float* __restrict__ s = src + (int64_t)b * dim;
+    float* __restrict__ d = dst + (int64_t)b * ld;
+    int c = lane;
+    for (; c + 96 < dim; c += 128) {
+      const float v0 = __ldcs(s + c), v1 = __ldcs(s + c + 32), v2 = __ldcs(s + c + 64), v3 = __ldcs(s + c + 96);
+      d[c] = v0; d[c + 32] = v1; d[c + 64] = v2; d[c + 96] = v3;
+    }
+    for (; c < dim; c += 32) d[c] = __ldcs(s + c);
   }
 }
 
@@ -95,7 +184,22 @@ int dmt_pool_mean_fwd(int32_t batch, int32_t n_feats, const dmt_pool_feat* feats
   a.batch = batch;
   a.out = out;
   a.out_ld = out_ld;
-  const int threads = col >= 256 ? 256 : ((col + 31) / 32) * 32;
+  // one thread per output column (a second pass over the columns would double the dependent-load chain)
+  bool vec = true;                                    // float4 rows: dim a power of two in [4, 128], aligned tables
+  for (int f = 0; f < n_feats; ++f) {
+    const int d = feats[f].dim;
+    vec = vec && d >= 4 && d <= 128 && (d & (d - 1)) == 0 && ((uintptr_t)feats[f].table & 15) == 0;
+  }
+  if (vec) {
+    const int64_t jobs = (int64_t)batch * n_feats;
+    int64_t grid = (jobs + 7) / 8;
+    const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
+    if (grid > cap) grid = cap;
+    dmt::pool_mean_warp_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("pool_mean_warp_kernel");
+    return DMT_OK;
+  }
+  const int threads = col >= 1024 ? 1024 : ((col + 31) / 32) * 32;
   dmt::pool_mean_kernel<<<batch, threads, 0, (cudaStream_t)stream>>>(a);
   DMT_CUDA_LAUNCH_CHECK("pool_mean_kernel");
   return DMT_OK;
@@ -106,8 +210,7 @@ int dmt_copy_dense_features(const float* features, int32_t batch, int32_t dim, f
   DMT_REQUIRE(features && out && batch >= 0 && dim > 0, DMT_ERR_INVALID_ARGUMENT,
               "dmt_copy_dense_features: bad arguments");
   if (batch == 0) return DMT_OK;
-  const int64_t total = (int64_t)batch * dim;
-  int64_t blocks = (total + 255) / 256;
+  int64_t blocks = ((int64_t)batch + 7) / 8;           // one warp per row
   const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
   if (blocks > cap) blocks = cap;
   dmt::copy_dense_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(features, batch, dim, out, out_ld);

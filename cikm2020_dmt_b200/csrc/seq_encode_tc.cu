@@ -886,7 +886,7 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
       a.chunk_off[c] = o;
     }
   for (; c < 32; ++c) a.chunk_feat[c] = a.chunk_off[c] = 0;
-  a.ctx = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg));
+  a.ctx = static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg);
   if (!use_v1() && seq_tc2_supported(cfg)) return seq_encode_tc2_launch(a, st);
   int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
   if (slot > cfg->maxlen) slot = cfg->maxlen;

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     }
   };
   // decoder contexts of the tile whose first sample is rb0 (warp 0 of the group): merge the partial softmaxes of
-  // a 64-row slot, normalise, write [b][h][D] fp32 for the tail kernel
+  // a 64-row slot, normalise, write bf16 into the tail kernel's A-operand image
   uint32_t cphase = 0;
   auto ctx_readout = [&](int rb0) {
     if (wg != 0) return;
@@ -313,13 +313,15 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     const int p = lane >> 1, h = lane & 1;
     const int b = rb0 + p / PPS;
     const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
-    float* dst = a.ctx + ((int64_t)b * H + h) * D;
+    // destination: the K-major A-operand image of the tail kernel's 128-sample tile, [k/8][sample][8] bf16 with
+    // k = h*D + j  ->  16-byte chunk (h*8 + c, b % 128)
+    uint8_t* dst = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(b & 127) * 16;
 #pragma unroll
-    for (int k = 0; k < D; k += 4) {
-      float v[4];
+    for (int c = 0; c < KC; ++c) {
+      float v[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kk = k + e;
+      for (int e = 0; e < 8; ++e) {
+        const int kk = c * 8 + e;
         v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
         if constexpr (PPS == 2) {
           v[e] *= wgt;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         }
         v[e] *= inv;
       }
-      if (writer) *reinterpret_cast<float4*>(dst + k) = make_float4(v[0], v[1], v[2], v[3]);
+      if (writer) *reinterpret_cast<uint4*>(dst + (size_t)(h * KC + c) * (128 * 16)) = f8_to_bf16(v);
     }
     fence_before_sync();
   };
@@ -723,7 +725,8 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
 //   o  = [ctx_0 | ctx_1] WvBD + bv (bv only for non-empty sequences) ; y = o + dvec ; av = LN3(y)
 //   u  = LN2(relu(av W1 + b1) W2 + b2 + av)                                   (TransformerModel.py:157-171)
 struct TailLayout {
-  static constexpr int oWv = 0;                         // image(D, H*D)   16 KB
+  static constexpr int oA = 0;                          // ctx image(128 samples, H*D)  32 KB  (written by the main kernel)
+  static constexpr int oWv = oA + 128 * kH * kD * 2;    // image(D, H*D)   16 KB
   static constexpr int oW1 = oWv + kH * kD * kD * 2;    // image(DFF, D)   32 KB
   static constexpr int oW2 = oW1 + kD * kDFF * 2;       // image(D, DFF)   32 KB
   static constexpr int oFV = oW2 + kDFF * kD * 2;
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   using L = TailLayout;
   constexpr int D = kD, DFF = kDFF, H = kH, KC = kKC;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int B = a.cfg.batch;
@@ -748,82 +751,69 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
     mbar_fence_init();
+    // operands by bulk async copies: this tile's context image and the three weight images
+    constexpr uint32_t nA = 128 * H * D * 2, nWv = H * D * D * 2, nW = 2 * D * DFF * 2;
+    mbar_expect_tx(&wbar, nA + nWv + nW);
+    bulk_g2s(smem + L::oA, reinterpret_cast<const uint8_t*>(a.ctx) + (size_t)blockIdx.x * nA, nA, &wbar);
+    bulk_g2s(smem + L::oWv, a.prepared + prep_off_wvbd(D, DFF, H), nWv, &wbar);
+    bulk_g2s(smem + L::oW1, a.prepared + prep_wqkv(D), nW, &wbar);          // w1 | w2 are contiguous
   }
-  // issue this sample's loads first (ctx row, target item rows, length), then stage the weights
+  // meanwhile: this sample's target item rows and length, the small vectors
   const int nf = a.cfg.n_feats;
   const int zp = a.cfg.zero_pad ? 1 : 0;
   bool has = false;
   float dvec[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) dvec[i] = 0.f;
-  uint32_t cpk[H * D / 2];
-#pragma unroll
-  for (int i = 0; i < H * D / 2; ++i) cpk[i] = 0u;
   if (live) {
     const int32_t* ol = a.in.offsets[nf - 1];
+    int64_t rws[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) rws[c] = (int64_t)__ldg(a.in.item_ids[a.chunk_feat[c]] + b) - zp;
     has = (__ldg(ol + b + 1) - __ldg(ol + b)) > 0;
     const float sqrt_d = sqrtf((float)D);
 #pragma unroll
     for (int c = 0; c < KC; ++c) {
       const int f = a.chunk_feat[c];
-      const int64_t rw = (int64_t)__ldg(a.in.item_ids[f] + b) - zp;
-      if (rw >= 0 && rw < a.in.rows[f]) {
-        const float* src = a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c];
+      if (rws[c] >= 0 && rws[c] < a.in.rows[f]) {
+        const float* src = a.in.table[f] + rws[c] * a.in.dim[f] + a.chunk_off[c];
         const float4 t0 = ldg4(src), t1 = ldg4(src + 4);
         dvec[c * 8 + 0] = t0.x * sqrt_d; dvec[c * 8 + 1] = t0.y * sqrt_d; dvec[c * 8 + 2] = t0.z * sqrt_d;
         dvec[c * 8 + 3] = t0.w * sqrt_d; dvec[c * 8 + 4] = t1.x * sqrt_d; dvec[c * 8 + 5] = t1.y * sqrt_d;
         dvec[c * 8 + 6] = t1.z * sqrt_d; dvec[c * 8 + 7] = t1.w * sqrt_d;
       }
     }
-    const float4* cs = reinterpret_cast<const float4*>(a.ctx + (int64_t)b * (H * D));
-#pragma unroll
-    for (int i = 0; i < H * D / 4; ++i) {
-      const float4 v = cs[i];
-      cpk[i * 2] = pack_bf16x2(v.x, v.y);
-      cpk[i * 2 + 1] = pack_bf16x2(v.z, v.w);
-    }
   }
-  {
-    const __nv_bfloat16* p = a.prepared;
-    const uint4* s1 = reinterpret_cast<const uint4*>(p + prep_off_wvbd(D, DFF, H));
-    uint4* d1 = reinterpret_cast<uint4*>(smem + L::oWv);
-    for (int i = tid; i < (int)(prep_wvbd(D, H) * 2 / 16); i += 128) d1[i] = __ldg(s1 + i);
-    const uint4* s2 = reinterpret_cast<const uint4*>(p + prep_wqkv(D));          // w1 | w2 are contiguous
-    uint4* d2 = reinterpret_cast<uint4*>(smem + L::oW1);
-    for (int i = tid; i < (int)(2 * prep_w1(D, DFF) * 2 / 16); i += 128) d2[i] = __ldg(s2 + i);
-    for (int i = tid; i < D; i += 128) {
-      fv[L::vBV + i] = a.dbv[i];
-      fv[L::vB2 + i] = a.b2[i];
-      fv[L::vLN2 + i] = a.ln2_g[i];
-      fv[L::vLN2 + D + i] = a.ln2_b[i];
-      fv[L::vLN3 + i] = a.ln3_g[i];
-      fv[L::vLN3 + D + i] = a.ln3_b[i];
-    }
-    for (int i = tid; i < DFF; i += 128) fv[L::vB1 + i] = a.b1[i];
+  for (int i = tid; i < D; i += 128) {
+    fv[L::vBV + i] = a.dbv[i];
+    fv[L::vB2 + i] = a.b2[i];
+    fv[L::vLN2 + i] = a.ln2_g[i];
+    fv[L::vLN2 + D + i] = a.ln2_b[i];
+    fv[L::vLN3 + i] = a.ln3_g[i];
+    fv[L::vLN3 + D + i] = a.ln3_b[i];
   }
-  fence_proxy_async();
+  for (int i = tid; i < DFF; i += 128) fv[L::vB1 + i] = a.b1[i];
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   const uint32_t dHi = desc_hi(128, kLayoutNone);
+  const uint32_t dA = desc_lo(smem_u32(smem + L::oA), kROWB);
   const uint32_t dWv = desc_lo(smem_u32(smem + L::oWv), D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
                  dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
   uint32_t phase = 0;
 
   // ---- o = ctx WvBD ----
-  tmem_st32(tmem_addr(tbase, L::tA), cpk);
-  tmem_st32(tmem_addr(tbase, L::tA + 32), cpk + 32);
-  tmem_st_wait();
-  fence_before_sync();
-  __syncthreads();
   if (tid == 0) {
+    mbar_wait(&wbar, 0);
     fence_after_sync();
     constexpr uint32_t idesc = make_idesc_bf16(128, D);
 #pragma unroll
     for (int ks = 0; ks < H * D / 16; ++ks)
-      mma_bf16_ts(tbase + L::tO, tbase + L::tA + ks * 8, desc_join(dWv + ks * (2 * D), dHi), idesc, ks > 0);
+      mma_bf16_ss(tbase + L::tO, desc_join(dA + ks * (2 * kROWB / 16), dHi), desc_join(dWv + ks * (2 * D), dHi), idesc,
+                  ks > 0);
     commit(&bar);
   }
   mbar_wait(&bar, phase);
@@ -839,6 +829,10 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 32; ++e)
         av[blk * 32 + e] = __uint_as_float(r[e]) + (has ? fv[L::vBV + blk * 32 + e] : 0.f) + dvec[blk * 32 + e];
+    }
+    if (!live) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) av[i] = 0.f;          // rows past the batch hold whatever the image held
     }
     ln64(av, fv + L::vLN3, fv + L::vLN3 + D);
     uint32_t pk[D / 2];
@@ -861,19 +855,23 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   mbar_wait(&bar, phase);
   phase ^= 1;
   fence_after_sync();
+  {
+    uint32_t rh[2][32];
+    tmem_ld32(tmem_addr(tbase, L::tFF1), rh[0]);
 #pragma unroll
-  for (int blk = 0; blk < DFF / 32; ++blk) {
-    uint32_t r[32];
-    tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32), r);
-    tmem_ld_wait();
-    uint32_t pk[16];
+    for (int blk = 0; blk < DFF / 32; ++blk) {
+      tmem_ld_wait();
+      if (blk + 1 < DFF / 32) tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32 + 32), rh[(blk + 1) & 1]);
+      const uint32_t* r = rh[blk & 1];
+      uint32_t pk[16];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
-      pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
-      pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
+        pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+        pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+      }
+      tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);
     }
-    tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);
   }
   tmem_st_wait();
   fence_before_sync();
@@ -944,7 +942,8 @@ bool seq_tc2_supported(const dmt_seq_cfg* cfg) {
   return Tc2Layout<64>::oPos + cfg->maxlen * kD * 2 + 64 + 1024 <= 227 * 1024 && cfg->n_feats <= kKC;   // + static smem
 }
 
-size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg) { return (size_t)cfg->batch * kH * kD * sizeof(float) + 256; }
+// decoder contexts: one bf16 A-operand image (128 samples x H*D) per tail tile
+size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg) { return (size_t)((cfg->batch + 127) / 128) * (128 * kH * kD * 2) + 256; }
 
 int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st) {
   const dmt_seq_cfg* cfg = &a.cfg;

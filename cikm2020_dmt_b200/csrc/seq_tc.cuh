@@ -20,7 +20,8 @@ struct SeqTcArgs {
   int64_t out_ld;
   int32_t n_tiles;
   unsigned long long* dbg;                            // diagnostics: per-phase SM cycles (thread 0), or NULL
-  float* ctx;                                         // v2: [B][H*D] fp32 decoder attention contexts (workspace)
+  void* ctx;                                          // v2: decoder attention contexts, one bf16 [k/8][128 samples][8]
+                                                      //     A-operand image per 128 samples (workspace)
   int32_t chunk_feat[32];                             // 16-byte chunk c of a token -> feature pair
   int32_t chunk_off[32];                              //                          -> first column inside that row
 };
