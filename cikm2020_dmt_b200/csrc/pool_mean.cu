@@ -83,7 +83,38 @@ __global__ void __launch_bounds__(1024) pool_mean_kernel(const __grid_constant__
 // whole round are requested first, then all of its rows -- one dependent load pair per round instead of one per
 // few tokens -- and every lane has work no matter how long the sample's other features are.  The token lanes are
 // reduced in a fixed xor-shuffle order (deterministic).
-constexpr int kPoolSteps = 8;
+// one round of STEPS steps: ids (and weights) of the whole round first, then all rows, then the accumulation
+template <int STEPS, bool WTS>
+__device__ __forceinline__ void pool_round(const dmt_pool_feat& pf, int t0, int end, int TPI, int tl, int v4,
+                                           float4& num, float& den) {
+  int row[STEPS];
+  float w[STEPS];
+#pragma unroll
+  for (int u = 0; u < STEPS; ++u) {
+    const int t = t0 + u * TPI + tl;
+    row[u] = -1;
+    w[u] = 0.f;
+    if (t < end) {
+      row[u] = __ldg(pf.ids + t);
+      w[u] = WTS ? __ldg(pf.weights + t) : 1.0f;
+    }
+  }
+  float4 e[STEPS];
+#pragma unroll
+  for (int u = 0; u < STEPS; ++u) {
+    e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row[u] >= 0 && row[u] < pf.rows) e[u] = ldg4(pf.table + (int64_t)row[u] * pf.dim + v4);
+  }
+#pragma unroll
+  for (int u = 0; u < STEPS; ++u) {
+    num.x = fmaf(w[u], e[u].x, num.x);
+    num.y = fmaf(w[u], e[u].y, num.y);
+    num.z = fmaf(w[u], e[u].z, num.z);
+    num.w = fmaf(w[u], e[u].w, num.w);
+    den += w[u];
+  }
+}
+
 __global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_constant__ PoolArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t n_jobs = (int64_t)a.batch * a.n_feats;
@@ -96,33 +127,16 @@ __global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_consta
     const int beg = __ldg(pf.offsets + b), end = __ldg(pf.offsets + b + 1);
     float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
     float den = 0.f;
-    for (int t0 = beg; t0 < end; t0 += TPI * kPoolSteps) {
-      int64_t row[kPoolSteps];
-      float w[kPoolSteps];
-#pragma unroll
-      for (int u = 0; u < kPoolSteps; ++u) {
-        const int t = t0 + u * TPI + tl;
-        row[u] = -1;
-        w[u] = 0.f;
-        if (t < end) {
-          row[u] = __ldg(pf.ids + t);
-          w[u] = pf.weights ? __ldg(pf.weights + t) : 1.0f;
-        }
-      }
-      float4 e[kPoolSteps];
-#pragma unroll
-      for (int u = 0; u < kPoolSteps; ++u) {
-        e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row[u] >= 0 && row[u] < pf.rows) e[u] = ldg4(pf.table + row[u] * pf.dim + v * 4);
-      }
-#pragma unroll
-      for (int u = 0; u < kPoolSteps; ++u) {
-        num.x = fmaf(w[u], e[u].x, num.x);
-        num.y = fmaf(w[u], e[u].y, num.y);
-        num.z = fmaf(w[u], e[u].z, num.z);
-        num.w = fmaf(w[u], e[u].w, num.w);
-        den += w[u];
-      }
+    int t0 = beg;
+    // (warp-uniform branches: the issue slots of steps that have no tokens are not spent)
+    if (pf.weights) {
+      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, true>(pf, t0, end, TPI, tl, v * 4, num, den);
+      if (end - t0 > TPI) pool_round<2, true>(pf, t0, end, TPI, tl, v * 4, num, den);
+      else if (end > t0) pool_round<1, true>(pf, t0, end, TPI, tl, v * 4, num, den);
+    } else {
+      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, false>(pf, t0, end, TPI, tl, v * 4, num, den);
+      if (end - t0 > TPI) pool_round<2, false>(pf, t0, end, TPI, tl, v * 4, num, den);
+      else if (end > t0) pool_round<1, false>(pf, t0, end, TPI, tl, v * 4, num, den);
     }
     for (int o = 16; o >= V; o >>= 1) {               // token lanes: lane bits above the float4 index
       num.x += __shfl_xor_sync(0xffffffffu, num.x, o);
@@ -135,10 +149,10 @@ __global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_consta
       // tf.nn.embedding_lookup_sparse(combiner='mean'): sum(w*row)/sum(w); an absent row comes out as 0
       const float inv = (end > beg) ? 1.0f / den : 0.f;
       float* o = a.out + (int64_t)b * a.out_ld + pf.out_col + v * 4;
-      o[0] = (end > beg) ? num.x * inv : 0.f;
-      o[1] = (end > beg) ? num.y * inv : 0.f;
-      o[2] = (end > beg) ? num.z * inv : 0.f;
-      o[3] = (end > beg) ? num.w * inv : 0.f;
+      o[0] = num.x * inv;
+      o[1] = num.y * inv;
+      o[2] = num.z * inv;
+      o[3] = num.w * inv;
     }
   }
 }

@@ -388,27 +388,34 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     T2_TICK(1);
 
     // ---- P2: + bias, bf16, Q / K / V images ([chunk][row][8] each) ----
-    // (the load of block blk+1 is in flight while block blk is converted)
-    uint32_t rq[2][32];
-    tmem_ld32(tmem_addr(tbase, L::tQKV), rq[0]);
+    // (the load of block blk+1 is in flight while block blk is converted; pairs of blocks, outer loop rolled)
+    {
+      uint32_t rq[2][32];
+      tmem_ld32(tmem_addr(tbase, L::tQKV), rq[0]);
+#pragma unroll 1
+      for (int bp = 0; bp < 3 * D / 64; ++bp) {
 #pragma unroll
-    for (int blk = 0; blk < 3 * D / 32; ++blk) {
-      const int n0 = blk * 32;
-      tmem_ld_wait();
-      if (blk + 1 < 3 * D / 32) tmem_ld32(tmem_addr(tbase, L::tQKV + n0 + 32), rq[(blk + 1) & 1]);
-      const uint32_t* r = rq[blk & 1];
+        for (int half = 0; half < 2; ++half) {
+          const int n0 = (bp * 2 + half) * 32;
+          tmem_ld_wait();
+          if (half == 0 || bp + 1 < 3 * D / 64) tmem_ld32(tmem_addr(tbase, L::tQKV + n0 + 32), rq[half ^ 1]);
+          const uint32_t* r = rq[half];
+          const int m = n0 / D;                         // 0: Q, 1: K, 2: V image
+          uint8_t* dstm = sQ + m * 16384 + row * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n0 + g * 8;
-        const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
-        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
-        float y[8];
-        y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
-        y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
-        y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
-        y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
-        const int m = n / D, ch = (n % D) / 8;
-        *reinterpret_cast<uint4*>(sQ + m * 16384 + ch * ROWB + row * 16) = f8_to_bf16(y);
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
+            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
+            float y[8];
+            y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
+            y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
+            y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
+            y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
+            const int ch = ((n0 % D) >> 3) + g;
+            *reinterpret_cast<uint4*>(dstm + ch * ROWB) = f8_to_bf16(y);
+          }
+        }
       }
     }
     fence_proxy_async();
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     {
       const int col0 = (row / CW) * CW;               // warp-uniform: rows of a warp share the CW-key window
       const int lo = slot * SLOT - col0;              // this row's keys are window columns [lo, lo + len)
-#pragma unroll
+#pragma unroll 1                                      // (code size: the unrolled kernel overflowed the instruction cache)
       for (int h = 0; h < H; ++h) {
         uint32_t r[KW];
         tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0), r);
@@ -591,19 +598,23 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     {
       uint32_t rh[2][32];
       tmem_ld32(tmem_addr(tbase, L::tFF1), rh[0]);
+#pragma unroll 1
+      for (int bp = 0; bp < DFF / 64; ++bp) {
 #pragma unroll
-      for (int blk = 0; blk < DFF / 32; ++blk) {
-        tmem_ld_wait();
-        if (blk + 1 < DFF / 32) tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32 + 32), rh[(blk + 1) & 1]);
-        const uint32_t* r = rh[blk & 1];
-        uint32_t pk[16];
+        for (int half = 0; half < 2; ++half) {
+          const int blk = bp * 2 + half;
+          tmem_ld_wait();
+          if (half == 0 || bp + 1 < DFF / 64) tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32 + 32), rh[half ^ 1]);
+          const uint32_t* r = rh[half];
+          uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
-          pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
-          pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
+            pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+            pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+          }
+          tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);   // columns [16 blk, +16): already consumed
         }
-        tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);   // columns [16 blk, +16): already consumed
       }
     }
     tmem_st_wait();
