@@ -48,6 +48,8 @@ class mmoe_transformer_unbias(object):
         self.params_version = 0      # bump (invalidate_prepared) whenever the parameters change
         self._events = None          # bench hook: {stage: [(start, stop), ...]} CUDA events
         self.launches = 0            # kernels of this library enqueued so far
+        self._stream_h = None        # set for the duration of inference() / compute_gradients()
+        self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
         self._bind_weights()
 
     # ------------------------------------------------------------------ per-stage device timing
@@ -145,6 +147,14 @@ class mmoe_transformer_unbias(object):
             self._buffers[("scratch", name)] = t
         return t
 
+    def _stream(self):
+        """Raw handle of the current CUDA stream; looked up once per public entry point (the torch call costs
+        ~5 us and every stage needs it)."""
+        h = self._stream_h
+        if h is None:
+            h = torch.cuda.current_stream(self.device).cuda_stream
+        return h
+
     def _dev(self, t):
         if t is None:
             return None
@@ -215,9 +225,16 @@ class mmoe_transformer_unbias(object):
         (generate_data of sequence i, row = id-1).  A row-sharded table re-maps them to different compact rows
         (`inputs['__remap__'][(role, name)]`, see shard.py / train.py); otherwise all read `inputs[name]`."""
         remap = inputs.get("__remap__")
+        cache = inputs.get("__sparse__")
+        if cache is None:
+            cache = inputs["__sparse__"] = {}
+        ckey = (role, name) if remap else name
         sp = remap.get((role, name)) if remap else None
         if sp is None:
             sp = inputs[name]
+        hit = cache.get(ckey)
+        if hit is not None and hit[0] is sp and hit[1] is inputs.get(name + "Wts"):
+            return hit[2]
         if not isinstance(sp, SparseIds):
             raise TypeError("feature %r must be a SparseIds (CSR) value" % name)
         w = sp.weights
@@ -229,6 +246,7 @@ class mmoe_transformer_unbias(object):
         out = SparseIds(self._dev(sp.values), self._dev(sp.offsets), self._dev(w))
         if out.values.dtype != torch.int32 or out.offsets.dtype != torch.int32:
             raise TypeError("feature %r: ids/offsets must be int32" % name)
+        cache[ckey] = (sp, wts, out)
         return out
 
     # ------------------------------------------------------------------ forward pieces
@@ -254,7 +272,7 @@ class mmoe_transformer_unbias(object):
             ver = -1
         nbytes = buf.numel()
         if ver != self.params_version:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = self._stream()
             with self._Stage(self, "prepare_weights", 1):
                 abi.check(self.lib.dmt_seq_prepare_weights(C.byref(cfg), C.byref(self._seq_w[seq_index]),
                                                            buf.data_ptr(), nbytes, stream))
@@ -299,7 +317,7 @@ class mmoe_transformer_unbias(object):
             ws, ws_bytes = self._prepared_for(seq_index, cfg)
             ws_ptr = ws.data_ptr()
         si, keep = self._seq_input(inputs, seq, batch)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._stream()
         with self._Stage(self, "seq_encode", 1):
             abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
                                                   out, out_ld, ws_ptr, ws_bytes, stream))
@@ -307,7 +325,10 @@ class mmoe_transformer_unbias(object):
 
     def pool_mean(self, inputs, specs, tables_bias, out, batch):
         plan = self.plan
-        arr = (abi.PoolFeat * len(specs))()
+        key = (id(specs), tables_bias, len(specs))
+        arr = self._pool_static.get(key)
+        if arr is None:                      # descriptor array reused across calls (every field is rewritten)
+            arr = self._pool_static[key] = (abi.PoolFeat * len(specs))()
         keep = []
         for i, p in enumerate(specs):
             table = self.params.table(p.table, bias=tables_bias)
@@ -315,9 +336,11 @@ class mmoe_transformer_unbias(object):
             if sp.offsets.numel() != batch + 1:
                 raise ValueError("feature %r: offsets has %d entries, batch is %d" % (p.feature, sp.offsets.numel(), batch))
             keep.append(sp)
-            arr[i] = abi.PoolFeat(abi.ptr(table), table.shape[0], abi.ptr(sp.values), abi.ptr(sp.offsets),
-                                  abi.ptr(sp.weights), table.shape[1], p.col)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+            e = arr[i]
+            e.table, e.rows, e.dim, e.out_col = table.data_ptr(), table.shape[0], table.shape[1], p.col
+            e.ids, e.offsets = sp.values.data_ptr(), sp.offsets.data_ptr()
+            e.weights = None if sp.weights is None else sp.weights.data_ptr()
+        stream = self._stream()
         for s in range(0, len(specs), abi.MAX_POOL_FEATS):
             n = min(abi.MAX_POOL_FEATS, len(specs) - s)
             sub = C.cast(C.byref(arr, s * C.sizeof(abi.PoolFeat)), C.POINTER(abi.PoolFeat))
@@ -343,7 +366,7 @@ class mmoe_transformer_unbias(object):
         cfg = self._mmoe_cfg(batch, self.precision)
         nbytes = self.lib.dmt_mmoe_workspace_bytes(C.byref(cfg))
         ws = self._buf("mmoe_ws", ((nbytes + 255) // 256 * 256,), torch.uint8)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._stream()
         prep_ptr = None
         launches = cfg.n_layers + 1
         if self.precision == abi.PRECISION_BF16:
@@ -388,6 +411,13 @@ class mmoe_transformer_unbias(object):
     def inference(self, inputs, is_train=True, is_predict=False):
         """mmoe_transformer_unbias.py:293-316.  Returns ((click_logit [B,1], order_logit [B,1]),
         y_bias [B,1]) or, with is_predict, just the logit pair."""
+        self._stream_h = torch.cuda.current_stream(self.device).cuda_stream
+        try:
+            return self._inference(inputs, is_train, is_predict)
+        finally:
+            self._stream_h = None
+
+    def _inference(self, inputs, is_train, is_predict):
         plan = self.plan
         if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
             raise NotImplementedError("training-mode dropout is not built yet; call with is_train=False "
@@ -396,7 +426,7 @@ class mmoe_transformer_unbias(object):
         feats = inputs["features"] if plan.is_use_feature else None
         first = inputs[plan.pooled[0].feature]
         batch = first.offsets.numel() - 1
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._stream()
         x_ld = (plan.mmoe_in + 3) // 4 * 4
         x = self._buf("x", (batch, x_ld))
         keep = []
@@ -450,7 +480,7 @@ class mmoe_transformer_unbias(object):
         probs = self._buf("probs", (2, batch)) if want_probs else None
         dlog = self._buf("dlogits", (3, batch)) if want_grads else None
         scratch = self._buf("loss_scratch", (self.lib.dmt_loss_scratch_bytes(batch),), torch.uint8)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._stream()
         with self._Stage(self, "loss", 2):
             abi.check(self.lib.dmt_bias_loss_fwd(C.byref(cfg), C.byref(self._bias_w), yb_in.data_ptr(), 1,
                                                  lg.data_ptr(), mask.data_ptr(), yb_out.data_ptr(),
@@ -499,7 +529,7 @@ class mmoe_transformer_unbias(object):
         if mask.dtype != torch.float32 or tuple(mask.shape) != (batch, 5):
             raise ValueError("mask must be fp32 [%d, 5]" % batch)
         mask = mask.contiguous()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._stream()
         F32 = self.train_precision   # engine of the training-path GEMMs (activations / gradients stay fp32)
 
         if getattr(self, "_grad_dense", None) is None:
