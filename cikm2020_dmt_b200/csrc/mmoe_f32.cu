@@ -179,98 +179,101 @@ __global__ void __launch_bounds__(kHeadWarps * 32) mmoe_head_kernel(const __grid
 }
 
 
-// Same computation with precomputed gates (bf16 path), restructured for throughput: the tower weights of every
-// task are staged in shared memory once per CTA (layer by layer: kernel [in, units], bias; then the output
-// kernel + bias), warps stride over the samples, and every lane keeps four independent accumulators.
-constexpr int kHeadFastWarps = 4;
-constexpr int kHeadSamples = 4;
-__global__ void __launch_bounds__(kHeadFastWarps * 32) mmoe_head_fast_kernel(const __grid_constant__ HeadArgs a,
-                                                                             int w_floats) {
+// Same computation with precomputed gates (bf16 path) for ONE tower layer (dmt.conf: 128 -> 32 -> 1), organised as a
+// small batched GEMM per CTA: 32 samples x all tasks.  The tower kernels of every task are staged in shared memory
+// once, the gate mixtures z[s][t][:] are built with coalesced 8-byte loads of the bf16 expert outputs, then
+// thread (s, t, q) computes units/4 tower outputs from shared memory and the 4 threads of (s, t) reduce
+// relu(out + b) . w_out by shuffles.
+constexpr int kHeadTileS = 32;
+__global__ void __launch_bounds__(256) mmoe_head_tile_kernel(const __grid_constant__ HeadArgs a) {
   extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int E = a.cfg.n_experts, Hd = a.hdim, B = a.cfg.batch, T = a.cfg.n_tasks, NL = a.cfg.n_tower_layers;
-  (void)w_floats;   // the tower weights (a few KB per task) are read through L1: every CTA of an SM shares them
-  // every warp works on kHeadSamples samples at a time: one weight read serves all of them and the lanes carry
-  // kHeadSamples x 2 independent accumulators (the per-sample chains were latency-bound)
-  float* ybase = sm + warp * (kHeadSamples * a.vec_floats);
-  const int n_groups = (B + kHeadSamples - 1) / kHeadSamples;
-  for (int grp = blockIdx.x * kHeadFastWarps + warp; grp < n_groups; grp += gridDim.x * kHeadFastWarps) {
-    const int b0 = grp * kHeadSamples;
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-      for (int s = 0; s < kHeadSamples; ++s) {
-        const int b = min(b0 + s, B - 1);
-        float* y0 = ybase + s * a.vec_floats;
-        float gl[DMT_MAX_EXPERTS];
-#pragma unroll
-        for (int e = 0; e < DMT_MAX_EXPERTS; ++e) gl[e] = (e < E) ? __ldg(a.gates + ((int64_t)t * B + b) * E + e) : 0.f;
-        for (int c = lane * 2; c < Hd; c += 64) {              // Hd is even (checked by the launcher)
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
-            if (e < E) {
-              const int64_t idx = ((int64_t)e * B + b) * Hd + c;
-              float h0, h1;
-              if (a.h_is_bf16) {
-                const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
-                    reinterpret_cast<const __nv_bfloat16*>(a.h_last) + idx));
-                h0 = hv.x; h1 = hv.y;
-              } else {
-                const float2 hv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.h_last) + idx);
-                h0 = hv.x; h1 = hv.y;
-              }
-              a0 = fmaf(gl[e], h0, a0);
-              a1 = fmaf(gl[e], h1, a1);
-            }
-          y0[c] = a0;
-          y0[c + 1] = a1;
-        }
-      }
-      __syncwarp();
-      int in_dim = Hd;
-      int cur_o = 0, nxt_o = a.vec_floats / 2;
-      for (int l = 0; l < NL; ++l) {
-        const int units = a.cfg.tower_units[l];
-        const float* __restrict__ Wt = a.tower[t][l].w;
-        const float* __restrict__ bt = a.tower[t][l].b;
-        for (int n = lane; n < units; n += 32) {
-          float c0[kHeadSamples], c1[kHeadSamples];
-#pragma unroll
-          for (int s = 0; s < kHeadSamples; ++s) c0[s] = c1[s] = 0.f;
-          int k = 0;
-          for (; k + 4 <= in_dim; k += 4) {
-            const float w0 = __ldg(Wt + k * units + n), w1 = __ldg(Wt + (k + 1) * units + n),
-                        w2 = __ldg(Wt + (k + 2) * units + n), w3 = __ldg(Wt + (k + 3) * units + n);
-#pragma unroll
-            for (int s = 0; s < kHeadSamples; ++s) {
-              const float4 xv = *reinterpret_cast<const float4*>(ybase + s * a.vec_floats + cur_o + k);
-              c0[s] = fmaf(xv.x, w0, c0[s]);
-              c1[s] = fmaf(xv.y, w1, c1[s]);
-              c0[s] = fmaf(xv.z, w2, c0[s]);
-              c1[s] = fmaf(xv.w, w3, c1[s]);
-            }
-          }
-          for (; k < in_dim; ++k) {
-            const float w0 = __ldg(Wt + k * units + n);
-#pragma unroll
-            for (int s = 0; s < kHeadSamples; ++s) c0[s] = fmaf(ybase[s * a.vec_floats + cur_o + k], w0, c0[s]);
-          }
-#pragma unroll
-          for (int s = 0; s < kHeadSamples; ++s) ybase[s * a.vec_floats + nxt_o + n] = fmaxf((c0[s] + c1[s]) + __ldg(bt + n), 0.f);
-        }
-        __syncwarp();
-        const int tmp = cur_o; cur_o = nxt_o; nxt_o = tmp;
-        in_dim = units;
-      }
-#pragma unroll
-      for (int s = 0; s < kHeadSamples; ++s) {
-        float acc = 0.f;
-        for (int k = lane; k < in_dim; k += 32) acc = fmaf(ybase[s * a.vec_floats + cur_o + k], __ldg(a.tower_out[t].w + k), acc);
-        acc = warp_sum(acc);
-        if (lane == 0 && b0 + s < B) a.logits[(int64_t)t * B + b0 + s] = acc + __ldg(a.tower_out[t].b);
-      }
-      __syncwarp();
+  const int E = a.cfg.n_experts, Hd = a.hdim, B = a.cfg.batch, T = a.cfg.n_tasks, U = a.cfg.tower_units[0];
+  float* sW = sm;                                   // [T][Hd][U]
+  float* sB = sW + T * Hd * U;                      // [T][U] tower bias | [T][U] output kernel
+  float* sZ = sB + 2 * T * U;                       // [kHeadTileS][T][Hd + 4]
+  const int zld = Hd + 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int t = 0; t < T; ++t) {
+    for (int i = tid; i < Hd * U; i += 256) sW[t * Hd * U + i] = __ldg(a.tower[t][0].w + i);
+    for (int i = tid; i < U; i += 256) {
+      sB[t * U + i] = __ldg(a.tower[t][0].b + i);
+      sB[(T + t) * U + i] = __ldg(a.tower_out[t].w + i);
     }
+  }
+  const int b0 = blockIdx.x * kHeadTileS;
+  // mixtures: warp w handles samples w, w + 8, ...; a lane covers 4 consecutive columns per trip
+  for (int s = warp; s < kHeadTileS; s += 8) {
+    const int b = min(b0 + s, B - 1);
+    float g[DMT_MAX_TASKS][DMT_MAX_EXPERTS];
+#pragma unroll
+    for (int t = 0; t < DMT_MAX_TASKS; ++t)
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        g[t][e] = (t < T && e < E) ? __ldg(a.gates + ((int64_t)t * B + b) * E + e) : 0.f;
+    for (int c = lane * 4; c < Hd; c += 128) {
+      float z[DMT_MAX_TASKS][4];
+#pragma unroll
+      for (int t = 0; t < DMT_MAX_TASKS; ++t) z[t][0] = z[t][1] = z[t][2] = z[t][3] = 0.f;
+#pragma unroll
+      for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+        if (e < E) {
+          const int64_t idx = ((int64_t)e * B + b) * Hd + c;
+          float h[4];
+          if (a.h_is_bf16) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.h_last) + idx));
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            h[0] = lo.x; h[1] = lo.y; h[2] = hi.x; h[3] = hi.y;
+          } else {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.h_last) + idx));
+            h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
+          }
+#pragma unroll
+          for (int t = 0; t < DMT_MAX_TASKS; ++t)
+            if (t < T) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) z[t][j] = fmaf(g[t][e], h[j], z[t][j]);
+            }
+        }
+#pragma unroll
+      for (int t = 0; t < DMT_MAX_TASKS; ++t)
+        if (t < T) *reinterpret_cast<float4*>(sZ + (s * T + t) * zld + c) = make_float4(z[t][0], z[t][1], z[t][2], z[t][3]);
+    }
+  }
+  __syncthreads();
+  // tower: item = (s, t, q); q-th quarter of the units.  4 consecutive lanes share (s, t).
+  const int UQ = U / 4;                              // units per thread (<= 16, checked by the launcher)
+  for (int item = tid; item < kHeadTileS * T * 4; item += 256) {
+    const int q = item & 3, st = item >> 2, t = st % T, s = st / T;
+    const float* zr = sZ + (s * T + t) * zld;
+    const float* W = sW + t * Hd * U + q * UQ;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int k = 0; k < Hd; k += 4) {
+      const float4 zv = *reinterpret_cast<const float4*>(zr + k);
+      const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float* wr = W + (k + kk) * U;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          if (j < UQ) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + j);
+            acc[j] = fmaf(zz[kk], w.x, acc[j]);
+            acc[j + 1] = fmaf(zz[kk], w.y, acc[j + 1]);
+            acc[j + 2] = fmaf(zz[kk], w.z, acc[j + 2]);
+            acc[j + 3] = fmaf(zz[kk], w.w, acc[j + 3]);
+          }
+      }
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < UQ) part = fmaf(fmaxf(acc[j] + sB[t * U + q * UQ + j], 0.f), sB[(T + t) * U + q * UQ + j], part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q == 0 && b0 + s < B) a.logits[(int64_t)t * B + b0 + s] = part + __ldg(a.tower_out[t].b);
   }
 }
 
@@ -295,17 +298,16 @@ int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const f
   int mx = in_dim;
   for (int l = 0; l < cfg->n_tower_layers; ++l) mx = cfg->tower_units[l] > mx ? cfg->tower_units[l] : mx;
   h.vec_floats = 2 * ((mx + 31) / 32 * 32);
-  if (gates && in_dim % 2 == 0) {   // bf16 path: gates come from the cast kernel
-    const int w_floats = 0;
-    const size_t fsmem = (size_t)kHeadFastWarps * kHeadSamples * h.vec_floats * sizeof(float);
-    if (fsmem <= 160 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(mmoe_head_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_head_fast_kernel)");
-      int grid = (B + kHeadFastWarps * kHeadSamples - 1) / (kHeadFastWarps * kHeadSamples);
-      const int cap = 8 * sm_count_cached();
-      if (grid > cap) grid = cap;
-      mmoe_head_fast_kernel<<<grid, kHeadFastWarps * 32, fsmem, st>>>(h, w_floats);
-      DMT_CUDA_LAUNCH_CHECK("mmoe_head_fast_kernel");
+  const int U0 = cfg->tower_units[0];
+  if (gates && cfg->n_tower_layers == 1 && in_dim % 4 == 0 && U0 % 16 == 0 && U0 <= 64 &&
+      (kHeadTileS * cfg->n_tasks * 4) % 256 == 0 && ((uintptr_t)h_last & 15) == 0) {   // bf16 path (gates precomputed)
+    const size_t fsmem = ((size_t)cfg->n_tasks * in_dim * U0 + 2 * (size_t)cfg->n_tasks * U0 +
+                          (size_t)kHeadTileS * cfg->n_tasks * (in_dim + 4)) * sizeof(float);
+    if (fsmem <= 200 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(mmoe_head_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_head_tile_kernel)");
+      mmoe_head_tile_kernel<<<(B + kHeadTileS - 1) / kHeadTileS, 256, fsmem, st>>>(h);
+      DMT_CUDA_LAUNCH_CHECK("mmoe_head_tile_kernel");
       return DMT_OK;
     }
   }
