@@ -337,15 +337,18 @@ def main():
         t_ms, n = stage["seq_encode"]
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
         achieved = alg / (t_ms / 1e3) / 1e9
-        roofline = {"kernel": ("seq_encode_tc_kernel (bf16 tcgen05" if args.precision == "bf16" else
-                               "seq_encode_f32_kernel (fp32 CUDA cores") + ", fused gather->encoder->decoder, per sequence)",
+        roofline = {"kernel": ("seq_encode_tc2_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM"
+                               if args.precision == "bf16" else "seq_encode_f32_kernel (fp32 CUDA cores") +
+                              ", fused gather->encoder->decoder, per sequence)",
                     "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                     "launches": n, "avg_launch_ms": t_ms / n, "algorithmic_bytes_per_launch": alg / n,
                     "flops_per_launch": mean_b(flops_seq) / n,
                     "achieved_tflops": mean_b(flops_seq) / (t_ms / 1e3) / 1e12,
-                    "note": "fully fused kernel: 432 FLOP/B vs a 209 FLOP/B ridge, latency-bound at L<=50 "
-                            "(DESIGN.md 4.1); the HBM-bound gather is reported under embed_gather"}
+                    "note": "fully fused kernel: 432 FLOP/B vs a 209 FLOP/B ridge -> not HBM-bound; at L<=50 it is "
+                            "bound by the SIMT epilogues between its six dependent MMA round trips (issue slots 30 % busy, "
+                            "DESIGN.md 4.1); achieved_tflops is the tensor-side reading, the HBM-bound gather is reported "
+                            "under embed_gather"}
     else:
         t_ms, n = stage[dom]
         fl = flops_mmoe(plan, B) * steps_used

@@ -318,7 +318,8 @@ class mmoe_transformer_unbias(object):
             ws_ptr = ws.data_ptr()
         si, keep = self._seq_input(inputs, seq, batch)
         stream = self._stream()
-        with self._Stage(self, "seq_encode", 1):
+        # bf16: the fused tile kernel + the row-batched decoder tail kernel
+        with self._Stage(self, "seq_encode", 2 if self.precision == abi.PRECISION_BF16 else 1):
             abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
                                                   out, out_ld, ws_ptr, ws_bytes, stream))
         return keep

@@ -205,11 +205,14 @@ DMT_API int dmt_embed_gather(const float* table, int64_t rows, int32_t dim, cons
  * (dropout sites inactive).  Writes the interest vector of sample b to
  * out[b*out_ld + 0 .. d_model).  Samples are independent; padded positions are never
  * computed (they are inert in the reference). */
+/* DMT_PRECISION_BF16: bytes of the per-sequence workspace = [bf16 weight images | batch-sized scratch: one
+ * bf16 decoder-context image per 128 samples].  Grows with cfg->batch; 16-byte aligned; one buffer per
+ * sequence (the images are that sequence's weights).  DMT_PRECISION_F32: 256 (nothing is spilled). */
 DMT_API size_t dmt_seq_encode_workspace_bytes(const dmt_seq_cfg* cfg, int64_t max_tokens);
 /* DMT_PRECISION_BF16 only: convert this sequence's transformer weights to the bf16 shared-memory
- * images the tensor-core kernel keeps resident (call again whenever the weights change).  The
- * `prepared` buffer (dmt_seq_encode_workspace_bytes bytes) is then passed as `workspace` to
- * dmt_seq_encode_fwd. */
+ * images the tensor-core kernels keep resident, at the front of the workspace (call again whenever
+ * the weights change or the workspace is re-allocated).  The same buffer is then passed as
+ * `workspace` to dmt_seq_encode_fwd. */
 DMT_API int dmt_seq_prepare_weights(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepared,
                                     size_t prepared_bytes, void* stream);
 DMT_API int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in,
