@@ -315,6 +315,40 @@ def test_seq_encode_bf16_edge_lengths_and_batch_tail():
     assert err.max().item() < ATOL_BF16 and err.mean().item() < MEAN_BF16, (err.max().item(), err.mean().item())
 
 
+@pytest.mark.parametrize("maxlen", [40, 50, 55])
+def test_seq_encode_bf16_many_tiles_per_group(maxlen):
+    """2400 samples = 1200 (64-row slots) / 300 (16-row slots) tiles: every CTA group of the persistent kernel loops
+    over several tiles (software-pipelined gather, deferred decoder-context read-out, mbarrier phase tracking), and
+    the three softmax key windows (maxlen 40 -> 48 keys, 50 -> 56, 55 -> 64) are compiled."""
+    from cikm2020_dmt_b200.params import ParamStore
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    from conftest import SMALL_ROWS
+    from oracle import dmt_oracle as O
+    from cikm2020_dmt_b200 import keys as K
+    conf, plan = make_plan("dmt_d64.conf", overrides={(K.MODEL, "transformer_maxlen_k"): str(maxlen)})
+    assert plan.maxlen_k == maxlen
+    store = ParamStore(plan, device="cuda", seed=5).randomize_(6)
+    B = 2400
+    host = synthetic_batch(plan, B, seed=77, table_rows=SMALL_ROWS)
+    dev = batch_to(host, "cuda")
+    tc = mmoe_transformer_unbias(plan, params=store, precision="bf16")
+    P = O.params_from_store(store, torch.float32)
+    want = O.trans_core(plan, P, O.generate_data(plan, P, host), training=False)
+    out = torch.zeros(B, len(plan.sequences) * plan.d_model, device="cuda")
+    for s in range(len(plan.sequences)):
+        tc.seq_encode(dev, s, out.data_ptr() + 4 * s * plan.d_model, out.stride(0), B)
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - want.double()).abs()
+    assert err.max().item() < ATOL_BF16 and err.mean().item() < MEAN_BF16, (err.max().item(), err.mean().item())
+    # run-to-run determinism of the whole path (no atomics anywhere)
+    out2 = torch.zeros_like(out)
+    for s in range(len(plan.sequences)):
+        tc.seq_encode(dev, s, out2.data_ptr() + 4 * s * plan.d_model, out2.stride(0), B)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 def test_inference_bf16_matches_oracle():
     plan, model, host, dev, P, O = _setup("dmt_d64.conf", 300, seed=41)
     tc = _bf16_model(plan, model.params)
