@@ -445,9 +445,11 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
 
     // ---- P4: masked softmax (one thread = one row, both heads); P_h packed to bf16 IN PLACE in tensor memory ----
     const int len = slen_s[grp][par][slot];
+    float inv0 = 0.f, inv1 = 0.f;                     // 1 / softmax denominators: applied to O_h in P6
     {
       const int col0 = (row / CW) * CW;               // warp-uniform: rows of a warp share the CW-key window
-      const int lo = slot * SLOT - col0;              // this row's keys are window columns [lo, lo + len)
+      // this row's keys are window columns [lo, lo + len); a 64-row slot is its own window
+      const int lo = (SLOT == CW) ? 0 : slot * SLOT - col0;
 #pragma unroll 1                                      // (code size: the unrolled kernel overflowed the instruction cache)
       for (int h = 0; h < H; ++h) {
         uint32_t r[KW];
@@ -478,10 +480,14 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
         }
         const float sum = (s0 + s1) + (s2 + s3);
         const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+        if (h == 0) inv0 = inv;
+        else inv1 = inv;
+        // P_h is stored UNNORMALISED (e in (0, 1], same relative precision in bf16); the row scale 1/sum is applied
+        // to the 32 outputs of P_h V_h instead of to the KW probabilities
         uint32_t pk[CW / 2];
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j)
-          pk[j] = (j < KW / 2) ? pack_bf16x2(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv) : 0u;
+          pk[j] = (j < KW / 2) ? pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])) : 0u;
         uint32_t zz[CW / 2];
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j) zz[j] = 0u;
@@ -554,20 +560,16 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     // ---- P6: A = LN(O + X) (self-attention LayerNorm), written over X ----
     {
       float y[D];
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tmem_addr(tbase, L::tO), r0);
+      tmem_ld32(tmem_addr(tbase, L::tO + 128), r1);
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tbase, L::tO + h * 128), r);
-        tmem_ld_wait();
+      for (int c = 0; c < KC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), y + c * 8);
+      tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) y[h * DK + e] = __uint_as_float(r[e]);
-      }
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        float x[8];
-        bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), x);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
+      for (int e = 0; e < 32; ++e) {                     // y = O_h / sum_h + X
+        y[e] = fmaf(__uint_as_float(r0[e]), inv0, y[e]);
+        y[DK + e] = fmaf(__uint_as_float(r1[e]), inv1, y[DK + e]);
       }
       ln64(y, fv + L::vLN + 0 * D, fv + L::vLN + 1 * D);
 #pragma unroll
