@@ -33,11 +33,15 @@ class FFWeights(C.Structure):
     _fields_ = [("w1", Dense), ("w2", Dense), ("ln", LayerNorm)]
 
 
+SEQ_DEFER_TAIL = 1
+MAX_TAIL_SEQS = 4
+
+
 class SeqCfg(C.Structure):
     _fields_ = [("batch", C.c_int32), ("d_model", C.c_int32), ("d_ff", C.c_int32), ("num_heads", C.c_int32),
                 ("n_enc_blocks", C.c_int32), ("n_dec_blocks", C.c_int32), ("maxlen", C.c_int32),
                 ("zero_pad", C.c_int32), ("n_feats", C.c_int32), ("precision", C.c_int32),
-                ("slot_len", C.c_int32), ("_reserved", C.c_int32), ("dropout_rate", C.c_float),
+                ("slot_len", C.c_int32), ("flags", C.c_int32), ("dropout_rate", C.c_float),
                 ("dropout_seed", C.c_uint32)]
 
 
@@ -103,6 +107,7 @@ PROTOTYPES = {
     "dmt_seq_prepare_weights": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqWeights), _fp, C.c_size_t, _fp]),
     "dmt_seq_encode_fwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), _fp,
                                      C.c_int64, _fp, C.c_size_t, _fp]),
+    "dmt_seq_tail_fwd": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
     "dmt_copy_dense_features": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_mmoe_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),

@@ -18,6 +18,8 @@ void seq_tc_set_profile(unsigned long long* p);
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                          int64_t out_ld, void* workspace, cudaStream_t st);
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg);
+int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
 }
 
 static int validate_seq(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w) {
@@ -82,6 +84,25 @@ int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
               "by dmt_seq_prepare_weights + batch-sized scratch)", workspace_bytes, dmt::seq_tc_workspace_bytes(cfg));
   DMT_REQUIRE(((uintptr_t)workspace & 15) == 0, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_fwd(bf16): unaligned workspace");
   return dmt::seq_encode_tc_launch(cfg, in, w, out, out_ld, workspace, (cudaStream_t)stream);
+}
+
+int dmt_seq_tail_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                     const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                     void* const* workspaces, void* stream) {
+  DMT_REQUIRE(n_seq >= 0 && n_seq <= DMT_MAX_TAIL_SEQS, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_tail_fwd: n_seq=%d (max %d)",
+              n_seq, DMT_MAX_TAIL_SEQS);
+  if (n_seq == 0) return DMT_OK;
+  DMT_REQUIRE(cfgs && ins && ws && outs && out_lds && workspaces, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_tail_fwd: null pointer");
+  for (int i = 0; i < n_seq; ++i) {
+    int rc = validate_seq(cfgs[i], ins[i], ws[i]);
+    if (rc != DMT_OK) return rc;
+    DMT_REQUIRE(cfgs[i]->precision == DMT_PRECISION_BF16 && outs[i] && workspaces[i] && out_lds[i] >= cfgs[i]->d_model,
+                DMT_ERR_INVALID_ARGUMENT, "dmt_seq_tail_fwd: sequence %d: bf16 path, output and workspace required", i);
+    const char* why = nullptr;
+    DMT_REQUIRE(dmt::seq_tc_supported(cfgs[i], ins[i], &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_tail_fwd: %s", why);
+  }
+  return dmt::seq_tc_tails(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, (cudaStream_t)stream);
 }
 
 size_t dmt_seq_saved_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens) {

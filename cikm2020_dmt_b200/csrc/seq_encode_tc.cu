@@ -863,10 +863,9 @@ int seq_tc_prepare(const dmt_seq_cfg* cfg, const dmt_seq_weights* w, void* prepa
   return DMT_OK;
 }
 
-int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
-                         int64_t out_ld, void* workspace, cudaStream_t st) {
+static void fill_args(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
+                      int64_t out_ld, void* workspace, SeqTcArgs& a) {
   const void* prepared = workspace;
-  SeqTcArgs a;
   a.cfg = *cfg;
   a.in = *in;
   a.pos = w->pos;
@@ -879,6 +878,7 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
   a.dbg = g_seq_profile;
   a.out = out;
   a.out_ld = out_ld;
+  a.n_tiles = 0;
   int c = 0;
   for (int f = 0; f < cfg->n_feats; ++f)
     for (int o = 0; o < in->dim[f]; o += 8, ++c) {
@@ -887,7 +887,28 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
     }
   for (; c < 32; ++c) a.chunk_feat[c] = a.chunk_off[c] = 0;
   a.ctx = static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg);
+}
+
+int seq_tails_launch(int n, const SeqTcArgs* args, cudaStream_t st);
+
+int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st) {
+  SeqTcArgs args[DMT_MAX_TAIL_SEQS];
+  for (int i = 0; i < n; ++i) {
+    DMT_REQUIRE(!use_v1() && seq_tc2_supported(cfgs[i]), DMT_ERR_UNSUPPORTED_SHAPE,
+                "dmt_seq_tail_fwd: sequence %d was not run by the deferred-tail kernel", i);
+    fill_args(cfgs[i], ins[i], ws[i], outs[i], out_lds[i], workspaces[i], args[i]);
+  }
+  return seq_tails_launch(n, args, st);
+}
+
+int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
+                         int64_t out_ld, void* workspace, cudaStream_t st) {
+  SeqTcArgs a;
+  fill_args(cfg, in, w, out, out_ld, workspace, a);
   if (!use_v1() && seq_tc2_supported(cfg)) return seq_encode_tc2_launch(a, st);
+  DMT_REQUIRE(!(cfg->flags & DMT_SEQ_DEFER_TAIL), DMT_ERR_UNSUPPORTED_SHAPE,
+              "dmt_seq_encode_fwd: DMT_SEQ_DEFER_TAIL needs the v2 kernel (maxlen <= 55)");
   int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
   if (slot > cfg->maxlen) slot = cfg->maxlen;
   DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);

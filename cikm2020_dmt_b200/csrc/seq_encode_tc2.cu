@@ -749,15 +749,25 @@ struct TailLayout {
   static constexpr int tA = 0, tO = 64, tFF1 = 128, tFF2 = 384;
 };
 
-__global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant__ SeqTcArgs a) {
+struct TailBatch {                                    // the tails of up to DMT_MAX_TAIL_SEQS sequences in one launch
+  SeqTcArgs a[DMT_MAX_TAIL_SEQS];
+  int32_t first_tile[DMT_MAX_TAIL_SEQS + 1];          // CTA range of each sequence
+  int32_t n_seq;
+};
+
+__global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant__ TailBatch tb) {
   using L = TailLayout;
   constexpr int D = kD, DFF = kDFF, H = kH, KC = kKC;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int sq = 0;
+  while (sq + 1 < tb.n_seq && (int)blockIdx.x >= tb.first_tile[sq + 1]) ++sq;
+  const SeqTcArgs& a = tb.a[sq];
+  const int tile = blockIdx.x - tb.first_tile[sq];
   const int B = a.cfg.batch;
-  const int b = blockIdx.x * 128 + tid;
+  const int b = tile * 128 + tid;
   const bool live = b < B;
   float* fv = reinterpret_cast<float*>(smem + L::oFV);
 
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
     // operands by bulk async copies: this tile's context image and the three weight images
     constexpr uint32_t nA = 128 * H * D * 2, nWv = H * D * D * 2, nW = 2 * D * DFF * 2;
     mbar_expect_tx(&wbar, nA + nWv + nW);
-    bulk_g2s(smem + L::oA, reinterpret_cast<const uint8_t*>(a.ctx) + (size_t)blockIdx.x * nA, nA, &wbar);
+    bulk_g2s(smem + L::oA, reinterpret_cast<const uint8_t*>(a.ctx) + (size_t)tile * nA, nA, &wbar);
     bulk_g2s(smem + L::oWv, a.prepared + prep_off_wvbd(D, DFF, H), nWv, &wbar);
     bulk_g2s(smem + L::oW1, a.prepared + prep_wqkv(D), nW, &wbar);          // w1 | w2 are contiguous
   }
@@ -920,7 +930,7 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   __syncthreads();
   // coalesced write: one warp per sample row
   for (int r = warp; r < 128; r += 4) {
-    const int bb = blockIdx.x * 128 + r;
+    const int bb = tile * 128 + r;
     if (bb >= B) break;
     const float* so = reinterpret_cast<const float*>(smem + L::oOut) + r * (D + 1);
     a.out[(int64_t)bb * a.out_ld + lane] = so[lane];
@@ -929,8 +939,16 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+int launch_tails(const TailBatch& tb, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(seq_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailLayout::total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_tail_kernel)");
+  seq_tail_kernel<<<tb.first_tile[tb.n_seq], 128, TailLayout::total, st>>>(tb);
+  DMT_CUDA_LAUNCH_CHECK("seq_tail_kernel");
+  return DMT_OK;
+}
+
 template <int SLOT, int KW>
-int launch_tc2(const SeqTcArgs& a, cudaStream_t st) {
+int launch_tc2(const SeqTcArgs& a, bool defer_tail, cudaStream_t st) {
   using L = Tc2Layout<SLOT>;
   const int total = L::oPos + a.cfg.maxlen * kD * 2 + 64;
   auto kern = seq_encode_tc2_kernel<SLOT, KW>;
@@ -941,11 +959,13 @@ int launch_tc2(const SeqTcArgs& a, cudaStream_t st) {
   const int grid = pairs < sms ? pairs : sms;
   kern<<<grid, 256, total, st>>>(a);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_tc2_kernel");
-  e = cudaFuncSetAttribute(seq_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailLayout::total);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_tail_kernel)");
-  seq_tail_kernel<<<(a.cfg.batch + 127) / 128, 128, TailLayout::total, st>>>(a);
-  DMT_CUDA_LAUNCH_CHECK("seq_tail_kernel");
-  return DMT_OK;
+  if (defer_tail) return DMT_OK;
+  TailBatch tb;
+  tb.a[0] = a;
+  tb.n_seq = 1;
+  tb.first_tile[0] = 0;
+  tb.first_tile[1] = (a.cfg.batch + 127) / 128;
+  return launch_tails(tb, st);
 }
 
 }  // namespace
@@ -960,22 +980,38 @@ size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg) { return (size_t)((cfg->batch +
 
 int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st) {
   const dmt_seq_cfg* cfg = &a.cfg;
+  const bool defer = (cfg->flags & DMT_SEQ_DEFER_TAIL) != 0;
   int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
   if (slot > cfg->maxlen) slot = cfg->maxlen;
   DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);
   if (slot <= 16) {
     a.n_tiles = (cfg->batch + 7) / 8;
-    return launch_tc2<16, 32>(a, st);
+    return launch_tc2<16, 32>(a, defer, st);
   }
   if (slot <= 32) {
     a.n_tiles = (cfg->batch + 3) / 4;
-    return launch_tc2<32, 32>(a, st);
+    return launch_tc2<32, 32>(a, defer, st);
   }
   a.n_tiles = (cfg->batch + 1) / 2;
   const int lmax = cfg->maxlen < 64 ? cfg->maxlen : 64;   // no key beyond the longest possible sequence
-  if (lmax <= 48) return launch_tc2<64, 48>(a, st);
-  if (lmax <= 56) return launch_tc2<64, 56>(a, st);
-  return launch_tc2<64, 64>(a, st);
+  if (lmax <= 48) return launch_tc2<64, 48>(a, defer, st);
+  if (lmax <= 56) return launch_tc2<64, 56>(a, defer, st);
+  return launch_tc2<64, 64>(a, defer, st);
+}
+
+// dmt_seq_tail_fwd: the deferred tails of several sequences, one launch
+int seq_tails_launch(int n, const SeqTcArgs* args, cudaStream_t st) {
+  TailBatch tb;
+  tb.n_seq = n;
+  int t = 0;
+  for (int i = 0; i < n; ++i) {
+    tb.a[i] = args[i];
+    tb.first_tile[i] = t;
+    t += (args[i].cfg.batch + 127) / 128;
+  }
+  for (int i = n; i <= DMT_MAX_TAIL_SEQS; ++i) tb.first_tile[i] = t;
+  if (t == 0) return DMT_OK;
+  return launch_tails(tb, st);
 }
 
 }  // namespace dmt

@@ -8,6 +8,7 @@ allocator), fills the POD descriptors and enqueues the C-ABI calls on the curren
 stream.  There is no PyTorch math on the path and no CPU fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -50,6 +51,8 @@ class mmoe_transformer_unbias(object):
         self.launches = 0            # kernels of this library enqueued so far
         self._stream_h = None        # set for the duration of inference() / compute_gradients()
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
+        # deferred decoder tails need the v2 sequence kernel (position table must fit its shared-memory plan)
+        self._v2_ok = self.plan.maxlen_k <= 55 and os.environ.get("DMT_SEQ_TC_V1") != "1"
         self._bind_weights()
 
     # ------------------------------------------------------------------ per-stage device timing
@@ -307,8 +310,10 @@ class mmoe_transformer_unbias(object):
             si.item_ids[f] = abi.ptr(it.values)
         return si, keep
 
-    def seq_encode(self, inputs, seq_index, out, out_ld, batch):
-        """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld)."""
+    def seq_encode(self, inputs, seq_index, out, out_ld, batch, deferred=None):
+        """A2-A8 for one behaviour sequence; writes [B, d_model] at `out` (row stride out_ld).
+        deferred: a list -> bf16 path only: the decoder tail of this sequence is left to `seq_tails(deferred)`,
+        which runs the tails of all sequences as one launch."""
         plan = self.plan
         seq = plan.sequences[seq_index]
         cfg = self._seq_cfg(inputs, seq, batch, self.precision)
@@ -316,13 +321,32 @@ class mmoe_transformer_unbias(object):
         if self.precision == abi.PRECISION_BF16:
             ws, ws_bytes = self._prepared_for(seq_index, cfg)
             ws_ptr = ws.data_ptr()
+        defer = deferred is not None and self.precision == abi.PRECISION_BF16 and self._v2_ok
+        if defer:
+            cfg.flags = abi.SEQ_DEFER_TAIL
         si, keep = self._seq_input(inputs, seq, batch)
         stream = self._stream()
-        # bf16: the fused tile kernel + the row-batched decoder tail kernel
-        with self._Stage(self, "seq_encode", 2 if self.precision == abi.PRECISION_BF16 else 1):
+        # bf16: the fused tile kernel (+ the row-batched decoder tail kernel unless deferred)
+        with self._Stage(self, "seq_encode", 2 if self.precision == abi.PRECISION_BF16 and not defer else 1):
             abi.check(self.lib.dmt_seq_encode_fwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
                                                   out, out_ld, ws_ptr, ws_bytes, stream))
+        if defer:
+            deferred.append((cfg, si, self._seq_w[seq_index], out, out_ld, ws_ptr))
         return keep
+
+    def seq_tails(self, deferred):
+        """dmt_seq_tail_fwd over the sequences collected by `seq_encode(..., deferred=list)`."""
+        n = len(deferred)
+        if n == 0:
+            return
+        cfgs = (C.c_void_p * n)(*[C.addressof(d[0]) for d in deferred])
+        ins = (C.c_void_p * n)(*[C.addressof(d[1]) for d in deferred])
+        wts = (C.c_void_p * n)(*[C.addressof(d[2]) for d in deferred])
+        outs = (C.c_void_p * n)(*[d[3] for d in deferred])
+        lds = (C.c_int64 * n)(*[d[4] for d in deferred])
+        wss = (C.c_void_p * n)(*[d[5] for d in deferred])
+        with self._Stage(self, "seq_encode", 1):
+            abi.check(self.lib.dmt_seq_tail_fwd(n, cfgs, ins, wts, outs, lds, wss, self._stream()))
 
     def pool_mean(self, inputs, specs, tables_bias, out, batch):
         plan = self.plan
@@ -440,9 +464,12 @@ class mmoe_transformer_unbias(object):
                                                            x.data_ptr(), x_ld, stream))
             keep.append(feats)
         keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
+        deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
         for s in range(len(plan.sequences)):
             col = plan.interest_col + s * plan.d_model
-            keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch)
+            keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
+        if deferred:
+            self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
         logits = self._buf("logits", (plan.num_tasks, batch))
         self.mmoe(x, batch, logits)
         self._last = {"x": x, "batch": batch, "keep": keep}

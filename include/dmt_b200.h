@@ -90,6 +90,11 @@ typedef struct dmt_ff_weights {
   dmt_layernorm ln;
 } dmt_ff_weights;
 
+/* dmt_seq_cfg.flags (bf16 path): leave the decoder tail (ctx Wv + residual -> LN -> FF -> LN) of this call to a
+ * later dmt_seq_tail_fwd, which runs the tails of several sequences as ONE launch.  Without the bit,
+ * dmt_seq_encode_fwd is self-contained. */
+#define DMT_SEQ_DEFER_TAIL 1
+
 typedef struct dmt_seq_cfg {
   int32_t batch;        /* B                                                          */
   int32_t d_model;      /* transformer_d_model == sum of the pair dims                */
@@ -105,7 +110,7 @@ typedef struct dmt_seq_cfg {
   int32_t slot_len;     /* upper bound on the sequence lengths in THIS batch (0 = maxlen);
                            the bf16 path packs 128/slot samples per tile (slot = 16/32/64)
                            and truncates longer sequences to it                        */
-  int32_t _reserved;
+  int32_t flags;        /* DMT_SEQ_* bits (0 = none)                                 */
   /* training entry points only (dmt_seq_encode_fwd_train / _bwd): transformer_dropout_rate applied at the
      encoder input, the decoder input and the attention probabilities (TransformerModel.py:101,151;
      TransformerModel_util.py:51).  The keep mask is a counter-based hash of (dropout_seed, site, element),
@@ -218,6 +223,13 @@ DMT_API int dmt_seq_prepare_weights(const dmt_seq_cfg* cfg, const dmt_seq_weight
 DMT_API int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in,
                                const dmt_seq_weights* w, float* out, int64_t out_ld,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* DMT_PRECISION_BF16: the decoder tails of n_seq (<= DMT_MAX_TAIL_SEQS) sequences whose dmt_seq_encode_fwd ran with
+ * DMT_SEQ_DEFER_TAIL, one launch (TransformerModel.py:157-171 for every sample of every sequence).  Element i of
+ * each array is the argument the deferred call of sequence i was given. */
+#define DMT_MAX_TAIL_SEQS 4
+DMT_API int dmt_seq_tail_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                             const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                             void* const* workspaces, void* stream);
 
 /* ---- A9/A11: pooled embeddings ----------------------------------------------------
  * Replaces embedding_combiner (model/net/base.py:93-124) and embedding_combiner_bias
