@@ -115,28 +115,30 @@ __device__ __forceinline__ void pool_round(const dmt_pool_feat& pf, int t0, int 
   }
 }
 
+// grid = (sample groups, features): the feature -- table, dim, lane split -- is uniform per CTA, so its descriptor
+// is read once and the only per-job index math is shifts; warps stride over the samples.
 __global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_constant__ PoolArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t n_jobs = (int64_t)a.batch * a.n_feats;
-  for (int64_t job = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); job < n_jobs; job += (int64_t)gridDim.x * 8) {
-    const int b = (int)(job / a.n_feats), f = (int)(job - (int64_t)b * a.n_feats);
-    const dmt_pool_feat& pf = a.f[f];
-    const int V = pf.dim >> 2;                        // float4 lanes per row
-    const int TPI = 32 / V;                           // tokens per step
-    const int tl = lane / V, v = lane - tl * V;
+  const dmt_pool_feat pf = a.f[blockIdx.y];
+  const int V = pf.dim >> 2;                          // float4 lanes per row (power of two)
+  const int lgV = 31 - __clz(V);
+  const int TPI = 32 >> lgV;                          // tokens per step
+  const int tl = lane >> lgV, v4 = (lane & (V - 1)) * 4;
+  float* const out = a.out + pf.out_col + v4;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < a.batch; b += gridDim.x * 8) {
     const int beg = __ldg(pf.offsets + b), end = __ldg(pf.offsets + b + 1);
     float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
     float den = 0.f;
     int t0 = beg;
     // (warp-uniform branches: the issue slots of steps that have no tokens are not spent)
     if (pf.weights) {
-      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, true>(pf, t0, end, TPI, tl, v * 4, num, den);
-      if (end - t0 > TPI) pool_round<2, true>(pf, t0, end, TPI, tl, v * 4, num, den);
-      else if (end > t0) pool_round<1, true>(pf, t0, end, TPI, tl, v * 4, num, den);
+      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, true>(pf, t0, end, TPI, tl, v4, num, den);
+      if (end - t0 > TPI) pool_round<2, true>(pf, t0, end, TPI, tl, v4, num, den);
+      else if (end > t0) pool_round<1, true>(pf, t0, end, TPI, tl, v4, num, den);
     } else {
-      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, false>(pf, t0, end, TPI, tl, v * 4, num, den);
-      if (end - t0 > TPI) pool_round<2, false>(pf, t0, end, TPI, tl, v * 4, num, den);
-      else if (end > t0) pool_round<1, false>(pf, t0, end, TPI, tl, v * 4, num, den);
+      for (; end - t0 > 2 * TPI; t0 += 8 * TPI) pool_round<8, false>(pf, t0, end, TPI, tl, v4, num, den);
+      if (end - t0 > TPI) pool_round<2, false>(pf, t0, end, TPI, tl, v4, num, den);
+      else if (end > t0) pool_round<1, false>(pf, t0, end, TPI, tl, v4, num, den);
     }
     for (int o = 16; o >= V; o >>= 1) {               // token lanes: lane bits above the float4 index
       num.x += __shfl_xor_sync(0xffffffffu, num.x, o);
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) pool_mean_warp_kernel(const __grid_consta
     if (tl == 0) {
       // tf.nn.embedding_lookup_sparse(combiner='mean'): sum(w*row)/sum(w); an absent row comes out as 0
       const float inv = (end > beg) ? 1.0f / den : 0.f;
-      float* o = a.out + (int64_t)b * a.out_ld + pf.out_col + v * 4;
+      float* o = out + (int64_t)b * a.out_ld;
       o[0] = num.x * inv;
       o[1] = num.y * inv;
       o[2] = num.z * inv;
@@ -205,11 +207,10 @@ int dmt_pool_mean_fwd(int32_t batch, int32_t n_feats, const dmt_pool_feat* feats
     vec = vec && d >= 4 && d <= 128 && (d & (d - 1)) == 0 && ((uintptr_t)feats[f].table & 15) == 0;
   }
   if (vec) {
-    const int64_t jobs = (int64_t)batch * n_feats;
-    int64_t grid = (jobs + 7) / 8;
-    const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
-    if (grid > cap) grid = cap;
-    dmt::pool_mean_warp_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
+    int gx = (batch + 7) / 8;                          // 8 warps per CTA, one sample per warp and trip
+    const int cap = (dmt::sm_count_cached() * 16 + n_feats - 1) / n_feats;
+    if (gx > cap) gx = cap < 1 ? 1 : cap;
+    dmt::pool_mean_warp_kernel<<<dim3(gx, n_feats), 256, 0, (cudaStream_t)stream>>>(a);
     DMT_CUDA_LAUNCH_CHECK("pool_mean_warp_kernel");
     return DMT_OK;
   }
