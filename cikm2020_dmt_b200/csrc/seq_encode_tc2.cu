@@ -90,6 +90,18 @@ __device__ __forceinline__ void ln64(float* y, const float* __restrict__ g, cons
   }
 }
 
+// per-chunk gather descriptor (chunk k = 32 bytes of a token row), staged once per CTA in shared memory so the
+// software-pipelined stages read plain words instead of walking the kernel-parameter tables
+struct ChunkDesc {
+  const int32_t* ids;       // CSR values of the chunk's feature
+  const int32_t* offs;      // CSR offsets
+  const int32_t* item_ids;  // target item ids
+  const float* tab;         // table + first column of the chunk
+  int64_t rows;
+  int32_t dim;
+  int32_t dup;              // same feature as chunk k-1 (same id, same offsets)
+};
+
 template <int SLOT>
 struct Tc2Layout {
   static constexpr int NS = 128 / SLOT;                 // samples per tile
@@ -145,6 +157,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   __shared__ uint64_t bars[2], cbars[2];            // per group: phase MMAs | decoder-context MMA
   __shared__ uint32_t tmem_base_s;
   __shared__ int slen_s[2][2][NS];                    // [group][tile parity][slot]
+  __shared__ ChunkDesc sd[KC];
 
   const int tid = threadIdx.x, grp = tid >> 7, row = tid & 127, wg = row >> 5, lane = tid & 31;
   uint8_t* gbase = smem + L::oGrp + grp * L::szGrp;
@@ -161,6 +174,16 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
 
   // ---- one-time setup (all 256 threads): TMEM, barriers, resident weights, vectors, positions ----
   if (tid < 32) tmem_alloc(&tmem_base_s, 512);
+  if (tid < KC) {
+    const int f = a.chunk_feat[tid];
+    sd[tid].ids = a.in.ids[f];
+    sd[tid].offs = a.in.offsets[f];
+    sd[tid].item_ids = a.in.item_ids[f];
+    sd[tid].tab = a.in.table[f] + a.chunk_off[tid];
+    sd[tid].rows = a.in.rows[f];
+    sd[tid].dim = a.in.dim[f];
+    sd[tid].dup = (tid > 0 && f == a.chunk_feat[tid - 1]) ? 1 : 0;
+  }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -206,7 +229,7 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
   const float sqrt_d = sqrtf((float)D);
   const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;      // softmax(s/sqrt(dk)) through exp2
-  const int nf = a.cfg.n_feats;
+  const int32_t* const len_offs = a.in.offsets[a.cfg.n_feats - 1];   // the LAST pair's lengths are the sequence lengths
   const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
   const int zp = a.cfg.zero_pad ? 1 : 0;
   const int slot = row / SLOT, tpos = row % SLOT;
@@ -231,24 +254,23 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     if (nt >= a.n_tiles) return;
     const int b = nt * NS + slot;
     if (b < B) {
-      const int32_t* ol = a.in.offsets[nf - 1];
-      pf_l0 = __ldg(ol + b);
-      pf_l1 = __ldg(ol + b + 1);
+      pf_l0 = __ldg(len_offs + b);
+      pf_l1 = __ldg(len_offs + b + 1);
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
-        const int f = a.chunk_feat[k];
-        if (k > 0 && f == a.chunk_feat[k - 1]) {
+        if (k > 0 && sd[k].dup) {
           pf_o0[k] = pf_o0[k - 1];
           pf_o1[k] = pf_o1[k - 1];
         } else {
-          pf_o0[k] = __ldg(a.in.offsets[f] + b);
-          pf_o1[k] = __ldg(a.in.offsets[f] + b + 1);
+          const int32_t* of = sd[k].offs;
+          pf_o0[k] = __ldg(of + b);
+          pf_o1[k] = __ldg(of + b + 1);
         }
       }
     }
     if (row < NS * KC) {
       const int bt = nt * NS + row / KC;
-      if (bt < B) pf_tid = __ldg(a.in.item_ids[a.chunk_feat[row % KC]] + bt);
+      if (bt < B) pf_tid = __ldg(sd[row % KC].item_ids + bt);
     }
   };
   auto stage_ids = [&](int nt, int par) {
@@ -259,29 +281,26 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
     for (int k = 0; k < KC; ++k) {
       pf_id[k] = kInvalidId;
       if (pf_valid) {
-        const int f = a.chunk_feat[k];
-        if (k > 0 && f == a.chunk_feat[k - 1]) pf_id[k] = pf_id[k - 1];
-        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(a.in.ids[f] + pf_o0[k] + tpos) : 0;
+        if (k > 0 && sd[k].dup) pf_id[k] = pf_id[k - 1];
+        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(sd[k].ids + pf_o0[k] + tpos) : 0;
       }
     }
   };
   auto stage_rows = [&]() {
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-      const int f = a.chunk_feat[k];
       pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
       pf_e[k].hi = pf_e[k].lo;
       const int64_t rw = (int64_t)pf_id[k] - zp;
-      if (pf_id[k] != kInvalidId && rw >= 0 && rw < a.in.rows[f])
-        pf_e[k] = ld_stream8(a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[k]);
+      if (pf_id[k] != kInvalidId && rw >= 0 && rw < sd[k].rows) pf_e[k] = ld_stream8(sd[k].tab + rw * sd[k].dim);
     }
     pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
     pf_t1 = pf_t0;
     if (row < NS * KC) {
-      const int c = row % KC, f = a.chunk_feat[c];
+      const int c = row % KC;
       const int64_t rw = (int64_t)pf_tid - zp;
-      if (pf_tid != kInvalidId && rw >= 0 && rw < a.in.rows[f]) {
-        const f8 t = ld_stream8(a.in.table[f] + rw * a.in.dim[f] + a.chunk_off[c]);
+      if (pf_tid != kInvalidId && rw >= 0 && rw < sd[c].rows) {
+        const f8 t = ld_stream8(sd[c].tab + rw * sd[c].dim);
         pf_t0 = t.lo;
         pf_t1 = t.hi;
       }
