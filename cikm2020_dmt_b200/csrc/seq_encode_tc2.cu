@@ -22,6 +22,7 @@
 // HBM traffic per (sample, sequence): ids + embedding rows in, 128 context floats out and in again (L2), one
 // interest vector out.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "dmt_common.cuh"
 #include "seq_tc.cuh"
@@ -753,6 +754,622 @@ __global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_con
   if (tid < 32) tmem_dealloc(tmem_base_s, 512);
 }
 
+// =====================================================================================================================
+// v3: the same per-tile program with every token row split across TWO threads (warps w and w + 4 of a group share
+// TMEM lane quarter w): 2 groups x 256 threads = 16 warps per SM at 128 registers.  v2 is limited by the dependent-
+// issue rate of 2 warps per scheduler (issue slots 30 % busy, no pipe above 40 %); v3 halves every thread's share
+// of the epilogues (half hf owns head hf / feature columns [32 hf, 32 hf + 32) / 4 of the 8 gather chunks) and
+// doubles the warps the schedulers can pick from.  LayerNorm and the decoder scores need the whole row: the two
+// halves exchange partial sums through 2 KB of (otherwise unused) shared memory inside the Q region.
+// TMEM plan per group (256 columns):  X Wqkv [0,192) -> S_0 [0,128) | S_1 [128,256) -> P_h in place [128h, +64),
+// O_h [128h+64, +32) -> A W1 [0,256) -> H packed by half hf IN PLACE inside ITS OWN 128 accumulator columns:
+// [128hf, 128hf+64) (so the K = 256 A operand of H W2 is two 64-column pieces) -> H W2 [64,128) -> context [192,256).
+// =====================================================================================================================
+constexpr int kT3Threads = 512;
+
+template <int SLOT, int KW>
+__global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __grid_constant__ SeqTcArgs a) {
+  using L = Tc2Layout<SLOT>;
+  static_assert(KW % 8 == 0 && KW <= L::CW && (SLOT == 64 || KW == L::CW), "key window");
+  constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
+  constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
+  constexpr int HC = KC / 2;                          // gather chunks per half
+  constexpr int tFF2 = 64;                            // H W2 accumulator (v3 plan)
+  constexpr int oExLN = 6144, oExSc = 4096;           // exchange scratch inside the Q region (see Tc2Layout aliases)
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2], cbars[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int slen_s[2][2][NS];
+  __shared__ ChunkDesc sd[KC];
+
+  const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, row = gt & 127, hf = gt >> 7;
+  const int wq = (gt >> 5) & 3, lane = tid & 31;      // wq: warp inside the half = TMEM lane quarter
+  uint8_t* gbase = smem + L::oGrp + grp * L::szGrp;
+  uint8_t* sXA = gbase + L::gXA;
+  uint8_t* sQ = gbase + L::gQ;
+  uint8_t* sK = gbase + L::gK;
+  float* fv = reinterpret_cast<float*>(smem + L::oFV);
+  const uint4* spos = reinterpret_cast<const uint4*>(smem + L::oPos);
+  uint64_t* bar = &bars[grp];
+  uint64_t* cbar = &cbars[grp];
+  const int B = a.cfg.batch;
+  const uint32_t bar_id = 1 + grp;
+
+  if (tid < 32) tmem_alloc(&tmem_base_s, 512);
+  if (tid < KC) {
+    const int f = a.chunk_feat[tid];
+    sd[tid].ids = a.in.ids[f];
+    sd[tid].offs = a.in.offsets[f];
+    sd[tid].item_ids = a.in.item_ids[f];
+    sd[tid].tab = a.in.table[f] + a.chunk_off[tid];
+    sd[tid].rows = a.in.rows[f];
+    sd[tid].dim = a.in.dim[f];
+    sd[tid].dup = (tid > 0 && (tid % HC) != 0 && f == a.chunk_feat[tid - 1]) ? 1 : 0;   // dup only inside a half
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&cbars[0], 1);
+    mbar_init(&cbars[1], 1);
+    mbar_fence_init();
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.prepared);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L::oWqkv);
+    constexpr int n16 = L::oGrp / 16;
+    for (int i = tid; i < n16; i += kT3Threads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < D; i += kT3Threads) {
+      fv[L::vBQKV + i] = a.bq[i];
+      fv[L::vBQKV + D + i] = a.bk[i];
+      fv[L::vBQKV + 2 * D + i] = a.bv[i];
+      fv[L::vB2 + i] = a.b2[i];
+      fv[L::vLN + 0 * D + i] = a.ln1_g[i];
+      fv[L::vLN + 1 * D + i] = a.ln1_b[i];
+      fv[L::vLN + 2 * D + i] = a.ln2_g[i];
+      fv[L::vLN + 3 * D + i] = a.ln2_b[i];
+    }
+    for (int i = tid; i < DFF; i += kT3Threads) fv[L::vB1 + i] = a.b1[i];
+    uint4* pdst = reinterpret_cast<uint4*>(smem + L::oPos);
+    for (int i = tid; i < a.cfg.maxlen * KC; i += kT3Threads) {
+      const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
+      const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      pdst[i] = f8_to_bf16(f);
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s + grp * 256;
+  const uint32_t aXA = smem_u32(sXA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(gbase + L::gV);
+  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
+  const uint32_t dXA = desc_lo(aXA, ROWB), dQ = desc_lo(aQ, ROWB), dK = desc_lo(aK, ROWB);
+  const uint32_t dWqkv = desc_lo(smem_u32(smem + L::oWqkv), 3 * D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
+                 dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
+  const __nv_bfloat16* gDec = a.prepared + prep_off_dec(D, DFF);
+  const uint4* gG = reinterpret_cast<const uint4*>(gDec);
+  const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
+  const float sqrt_d = sqrtf((float)D);
+  const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;
+  const int32_t* const len_offs = a.in.offsets[a.cfg.n_feats - 1];
+  const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
+  const int zp = a.cfg.zero_pad ? 1 : 0;
+  const int slot = row / SLOT, tpos = row % SLOT;
+  const int c0h = hf * HC;                             // first gather chunk / 8-column group of this half
+  uint32_t phase = 0;
+  // exchange slots: [row][half] pairs of floats
+  float2* exLN = reinterpret_cast<float2*>(sQ + oExLN);
+  float2* exSc = reinterpret_cast<float2*>(sQ + oExSc);
+
+  // ---- software-pipelined gather: this thread loads chunks c0h .. c0h+HC-1 of its token row ----
+  int pf_o0[HC], pf_o1[HC], pf_id[HC];
+  int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
+  bool pf_valid = false;
+  f8 pf_e[HC];
+  int pf_tid = kInvalidId;
+  float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
+
+  auto stage_offsets = [&](int nt) {
+    pf_l0 = pf_l1 = 0;
+    pf_tid = kInvalidId;
+#pragma unroll
+    for (int k = 0; k < HC; ++k) pf_o0[k] = pf_o1[k] = 0;
+    if (nt >= a.n_tiles) return;
+    const int b = nt * NS + slot;
+    if (b < B) {
+      pf_l0 = __ldg(len_offs + b);
+      pf_l1 = __ldg(len_offs + b + 1);
+#pragma unroll
+      for (int k = 0; k < HC; ++k) {
+        if (k > 0 && sd[c0h + k].dup) {
+          pf_o0[k] = pf_o0[k - 1];
+          pf_o1[k] = pf_o1[k - 1];
+        } else {
+          const int32_t* of = sd[c0h + k].offs;
+          pf_o0[k] = __ldg(of + b);
+          pf_o1[k] = __ldg(of + b + 1);
+        }
+      }
+    }
+    if (gt < NS * KC) {
+      const int bt = nt * NS + gt / KC;
+      if (bt < B) pf_tid = __ldg(sd[gt % KC].item_ids + bt);
+    }
+  };
+  auto stage_ids = [&](int nt, int par) {
+    pf_len = min(pf_l1 - pf_l0, lmax);
+    pf_valid = tpos < pf_len;
+    if (tpos == 0 && hf == 0) slen_s[grp][par][slot] = pf_len;
+#pragma unroll
+    for (int k = 0; k < HC; ++k) {
+      pf_id[k] = kInvalidId;
+      if (pf_valid) {
+        if (k > 0 && sd[c0h + k].dup) pf_id[k] = pf_id[k - 1];
+        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(sd[c0h + k].ids + pf_o0[k] + tpos) : 0;
+      }
+    }
+  };
+  auto stage_rows = [&]() {
+#pragma unroll
+    for (int k = 0; k < HC; ++k) {
+      pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_e[k].hi = pf_e[k].lo;
+      const int64_t rw = (int64_t)pf_id[k] - zp;
+      if (pf_id[k] != kInvalidId && rw >= 0 && rw < sd[c0h + k].rows)
+        pf_e[k] = ld_stream8(sd[c0h + k].tab + rw * sd[c0h + k].dim);
+    }
+    pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    pf_t1 = pf_t0;
+    if (gt < NS * KC) {
+      const int c = gt % KC;
+      const int64_t rw = (int64_t)pf_tid - zp;
+      if (pf_tid != kInvalidId && rw >= 0 && rw < sd[c].rows) {
+        const f8 t = ld_stream8(sd[c].tab + rw * sd[c].dim);
+        pf_t0 = t.lo;
+        pf_t1 = t.hi;
+      }
+    }
+  };
+  // decoder contexts of the tile whose first sample is rb0: warp 0 of the group
+  uint32_t cphase = 0;
+  auto ctx_readout = [&](int rb0) {
+    if (gt >= 32) return;
+    mbar_wait(cbar, cphase);
+    cphase ^= 1;
+    fence_after_sync();
+    uint32_t c0[32], c1[32];
+    tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
+    tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
+    tmem_ld_wait();
+    const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
+    float den = mxs[NR + (lane & (NR - 1))];
+    float wgt = 1.0f;
+    if constexpr (PPS == 2) {
+      const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
+      const float m = fmaxf(ma, mb);
+      wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
+      den *= wgt;
+      den += __shfl_xor_sync(0xffffffffu, den, 2);
+    }
+    const float inv = den > 0.f ? 1.0f / den : 0.f;
+    const int p = lane >> 1, h = lane & 1;
+    const int b = rb0 + p / PPS;
+    const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(b & 127) * 16;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int kk = c * 8 + e;
+        v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
+        if constexpr (PPS == 2) {
+          v[e] *= wgt;
+          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
+        }
+        v[e] *= inv;
+      }
+      if (writer) *reinterpret_cast<uint4*>(dst + (size_t)(h * KC + c) * (128 * 16)) = f8_to_bf16(v);
+    }
+    fence_before_sync();
+  };
+  int n_done = 0;
+  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
+  stage_offsets(tile0);
+  stage_ids(tile0, 0);
+  stage_rows();
+
+  long long t_last = clock64();
+  for (int it = 0;; ++it) {
+    const int tile = tile0 + it * tstride;
+    if (tile >= a.n_tiles) break;
+    const int par = it & 1;
+    const int b0 = tile * NS;
+    const int next_tile = tile + tstride;
+
+    // ---- P0: this half's four chunks -> X image ----
+#pragma unroll
+    for (int k = 0; k < HC; ++k) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = 0.f;
+      if (pf_valid) {
+        float p[8];
+        bf16x8_to_f(spos[tpos * KC + c0h + k], p);
+        x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
+        x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
+        x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
+        x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
+      }
+      *reinterpret_cast<uint4*>(sXA + (c0h + k) * ROWB + row * 16) = f8_to_bf16(x);
+    }
+    const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(0);
+
+    // ---- P1: [Q|K|V] = X Wqkv ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks)
+        mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
+      commit(bar);
+    }
+    if (it > 0) ctx_readout(b0 - tstride * NS);
+    stage_offsets(next_tile);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(1);
+
+    // ---- P2: + bias, bf16 -> Q / K / V images; half hf converts columns [96 hf, 96 hf + 96) ----
+#pragma unroll 1
+    for (int blk = 0; blk < 3; ++blk) {
+      const int n0 = hf * 96 + blk * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tQKV + n0), r);
+      tmem_ld_wait();
+      const int m = n0 >> 6;                           // 0: Q, 1: K, 2: V image
+      uint8_t* dstm = sQ + m * 16384 + row * 16;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + g * 8;
+        const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
+        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
+        float y[8];
+        y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
+        y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
+        y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
+        y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
+        const int ch = ((n0 & 63) >> 3) + g;
+        *reinterpret_cast<uint4*>(dstm + ch * ROWB) = f8_to_bf16(y);
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(2);
+
+    // ---- P3: S_h = Q_h K_h^T ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ++ks) {
+          const uint32_t ch = (h * DK) / 8 + ks * 2;
+          mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dQ + ch * (ROWB / 16), dHi),
+                      desc_join(dK + ch * (ROWB / 16), dHi), idesc, ks > 0);
+        }
+      commit(bar);
+    }
+    stage_ids(next_tile, par ^ 1);
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(3);
+
+    // ---- P4: masked softmax of head hf; unnormalised P_hf packed IN PLACE ----
+    const int len = slen_s[grp][par][slot];
+    float inv_h = 0.f;
+    {
+      const int col0 = (row / CW) * CW;
+      const int lo = (SLOT == CW) ? 0 : slot * SLOT - col0;
+      const uint32_t sbase = tmem_addr(tbase, L::tS + hf * 128);
+      uint32_t r[CW];
+      tmem_ld32(sbase + col0, r);
+      if constexpr (KW >= 48) tmem_ld16(sbase + col0 + 32, r + 32);
+      if constexpr (KW == 56) tmem_ld8(sbase + col0 + 48, r + 48);
+      if constexpr (KW == 64) tmem_ld16(sbase + col0 + 48, r + 48);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        const bool ok = (unsigned)(j - lo) < (unsigned)len;
+        const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
+        r[j] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KW; j += 4) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
+        const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
+        const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), sl2, -mxs));
+        s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+        r[j / 2] = pack_bf16x2(e0, e1);                 // (j/2 <= j: the packed words trail the reads)
+        r[j / 2 + 1] = pack_bf16x2(e2, e3);
+      }
+      const float sum = (s0 + s1) + (s2 + s3);
+      inv_h = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+      for (int j = KW / 2; j < CW; ++j) r[j] = 0u;
+      if constexpr (CW == 64) {
+        tmem_st32(sbase + col0 / 2, r);
+        tmem_st32(sbase + (32 - col0 / 2), r + 32);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q * 16 == col0 / 2) tmem_st16(sbase + q * 16, r);
+          else tmem_st16(sbase + q * 16, r + 16);
+        }
+      }
+    }
+    if (gt < NS * KC) {
+      float* dv = reinterpret_cast<float*>(gbase + L::gDvec) + (gt / KC) * D + (gt % KC) * 8;
+      *reinterpret_cast<float4*>(dv) = make_float4(cur_t0.x * sqrt_d, cur_t0.y * sqrt_d, cur_t0.z * sqrt_d, cur_t0.w * sqrt_d);
+      *reinterpret_cast<float4*>(dv + 4) = make_float4(cur_t1.x * sqrt_d, cur_t1.y * sqrt_d, cur_t1.z * sqrt_d, cur_t1.w * sqrt_d);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(4);
+
+    // ---- P5: O_h = P_h V_h ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const uint32_t dV = desc_lo(aV + ((h * DK) / 8) * ROWB, 128);
+#pragma unroll
+        for (int ks = 0; ks < 128 / 16; ++ks)
+          mma_bf16_ts(tbase + L::tO + h * 128, tbase + L::tS + h * 128 + ks * 8,
+                      desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
+      }
+      commit(bar);
+    }
+    // folded decoder queries: thread (n = row, hf) computes the samples s = hf, hf + 2, ...
+    {
+      constexpr int NSH = NS / 2;
+      float acc[NSH];
+      const float gb = __ldg(gGb + row);
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) acc[s] = gb;
+      const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
+#pragma unroll
+      for (int jc = 0; jc < KC; ++jc) {
+        float w[8];
+        bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
+#pragma unroll
+        for (int s = 0; s < NSH; ++s) {
+          const float4 d0 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8 + 4);
+          acc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], acc[s]))));
+          acc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], acc[s]))));
+        }
+      }
+      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) qt[(2 * s + hf) * (H * D) + row] = acc[s];
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(5);
+
+    // ---- P6: A = LN(O + X): half hf owns columns [32 hf, 32 hf + 32) = head hf ----
+    {
+      float y[DK];
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tO + hf * 128), r);
+#pragma unroll
+      for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
+      tmem_ld_wait();
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < DK; e += 2) {
+        y[e] = fmaf(__uint_as_float(r[e]), inv_h, y[e]);
+        y[e + 1] = fmaf(__uint_as_float(r[e + 1]), inv_h, y[e + 1]);
+        s0 += y[e]; s1 += y[e + 1];
+        q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
+      }
+      exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+      named_sync(bar_id, 256);
+      const float2 o = exLN[row * 2 + (hf ^ 1)];
+      const float mean = ((s0 + s1) + o.x) * (1.0f / D);
+      const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + kLnEps);
+      const float* g = fv + L::vLN + 0 * D + hf * DK;
+      const float* bt = fv + L::vLN + 1 * D + hf * DK;
+#pragma unroll
+      for (int e = 0; e < DK; e += 4) {
+        const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
+        y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
+        y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
+        y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
+        y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
+      }
+#pragma unroll
+      for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sXA + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(6);
+
+    // ---- P7: hidden = A W1 ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks)
+        mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                    desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
+      commit(bar);
+    }
+    stage_rows();
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(7);
+
+    // ---- P8: relu(+b1): half hf packs accumulator columns [128 hf, 128 hf + 128) into [128 hf, 128 hf + 64) ----
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 32), r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + hf * 128 + blk * 32 + g * 4);
+        pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+        pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+      }
+      tmem_st16(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 16), pk);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(8);
+
+    // ---- P9: F = H W2; the K = 256 A operand is two 64-column pieces of tensor memory ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+      for (int ks = 0; ks < DFF / 16; ++ks)
+        mma_bf16_ts(tbase + tFF2, tbase + L::tFF1 + (ks / 8) * 128 + (ks % 8) * 8, desc_join(dW2 + ks * (2 * D), dHi),
+                    idesc, ks > 0);
+      commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    T2_TICK(9);
+
+    // ---- P10: memory = LN(F + b2 + A); decoder scores; partial softmax of head hf; images for the context MMA ----
+    {
+      float y[DK];
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, tFF2 + hf * DK), r);
+#pragma unroll
+      for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
+      tmem_ld_wait();
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < DK; e += 2) {
+        y[e] += __uint_as_float(r[e]) + fv[L::vB2 + hf * DK + e];
+        y[e + 1] += __uint_as_float(r[e + 1]) + fv[L::vB2 + hf * DK + e + 1];
+        s0 += y[e]; s1 += y[e + 1];
+        q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
+      }
+      exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+      named_sync(bar_id, 256);
+      {
+        const float2 o = exLN[row * 2 + (hf ^ 1)];
+        const float mean = ((s0 + s1) + o.x) * (1.0f / D);
+        const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + kLnEps);
+        const float* g = fv + L::vLN + 2 * D + hf * DK;
+        const float* bt = fv + L::vLN + 3 * D + hf * DK;
+#pragma unroll
+        for (int e = 0; e < DK; e += 4) {
+          const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
+          y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
+          y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
+          y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
+          y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
+        }
+      }
+      // memory image: this half's four chunks
+#pragma unroll
+      for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sK + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+      // partial decoder scores over this half's 32 columns, both heads; exchanged with the other half
+      const float* qt = reinterpret_cast<const float*>(gbase + L::gQt) + slot * (H * D) + hf * DK;
+      float pu[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < DK; k += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(qt + h * D + k);
+          a0 = fmaf(y[k], q.x, a0); a1 = fmaf(y[k + 1], q.y, a1);
+          a0 = fmaf(y[k + 2], q.z, a0); a1 = fmaf(y[k + 3], q.w, a1);
+        }
+        pu[h] = a0 + a1;
+      }
+      exSc[row * 2 + hf] = make_float2(pu[0], pu[1]);
+      named_sync(bar_id, 256);
+      const float2 os = exSc[row * 2 + (hf ^ 1)];
+      // this half finishes head hf
+      const float dot = (hf == 0 ? pu[0] + os.x : pu[1] + os.y);
+      const float u = (tpos < len) ? dot * sl2 : -INFINITY;
+      const int part = (SLOT >= 32) ? wq : (wq * (32 / W) + lane / W);
+      float m = u;
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float e = (tpos < len) ? ex2_approx(u - m) : 0.f;
+      e = __bfloat162float(__float2bfloat16(e));
+      float dsum = e;
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      if ((lane % W) == 0) {
+        reinterpret_cast<float*>(gbase + L::gMx)[part * H + hf] = m;
+        reinterpret_cast<float*>(gbase + L::gMx)[NR + part * H + hf] = dsum;
+      }
+      // transposed probabilities: rows (p, hf) for every part p, column = this token
+      const unsigned short eb = __bfloat16_as_ushort(__float2bfloat16(e));
+      uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2 + hf * 16;
+#pragma unroll
+      for (int p = 0; p < NR / H; ++p)
+        *reinterpret_cast<unsigned short*>(pd + p * (H * 16)) = (p == part) ? eb : (unsigned short)0;
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    named_sync(bar_id, 256);
+    T2_TICK(10);
+
+    // ---- P11: context MMA (read out by warp 0 in the shadow of the next tile's X Wqkv) ----
+    if (gt == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, D, false, true);
+      const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
+#pragma unroll
+      for (int ks = 0; ks < 128 / 16; ++ks)
+        mma_bf16_ss(tbase + L::tCtx, desc_join(dPd + ks * (2 * 256 / 16), dHi), desc_join(dM + ks * (256 / 16), dHiV),
+                    idesc, ks > 0);
+      commit(cbar);
+    }
+    n_done = it + 1;
+    T2_TICK(11);
+  }
+
+  if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base_s, 512);
+}
+
 // ---- per-sample decoder tail, row-batched: 128 samples per CTA (one thread = one sample = one TMEM lane) ----
 //   o  = [ctx_0 | ctx_1] WvBD + bv (bv only for non-empty sequences) ; y = o + dvec ; av = LN3(y)
 //   u  = LN2(relu(av W1 + b1) W2 + b2 + av)                                   (TransformerModel.py:157-171)
@@ -966,18 +1583,36 @@ int launch_tails(const TailBatch& tb, cudaStream_t st) {
   return DMT_OK;
 }
 
+// DMT_SEQ_TC=2 selects the v2 kernel (one thread per row, 8 warps) for A/B measurements; default: v3
+int tc_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("DMT_SEQ_TC");
+    v = (e && e[0] == '2') ? 2 : 3;
+  }
+  return v;
+}
+
 template <int SLOT, int KW>
 int launch_tc2(const SeqTcArgs& a, bool defer_tail, cudaStream_t st) {
   using L = Tc2Layout<SLOT>;
   const int total = L::oPos + a.cfg.maxlen * kD * 2 + 64;
-  auto kern = seq_encode_tc2_kernel<SLOT, KW>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc2_kernel)");
   const int sms = sm_count_cached();
   const int pairs = (a.n_tiles + 1) / 2;
   const int grid = pairs < sms ? pairs : sms;
-  kern<<<grid, 256, total, st>>>(a);
-  DMT_CUDA_LAUNCH_CHECK("seq_encode_tc2_kernel");
+  if (tc_version() == 3) {
+    auto kern = seq_encode_tc3_kernel<SLOT, KW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc3_kernel)");
+    kern<<<grid, kT3Threads, total, st>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("seq_encode_tc3_kernel");
+  } else {
+    auto kern = seq_encode_tc2_kernel<SLOT, KW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc2_kernel)");
+    kern<<<grid, 256, total, st>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("seq_encode_tc2_kernel");
+  }
   if (defer_tail) return DMT_OK;
   TailBatch tb;
   tb.a[0] = a;
