@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
   constexpr int oExLN = 6144, oExSc = 4096;           // exchange scratch inside the Q region (see Tc2Layout aliases)
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[2], cbars[2];
+  __shared__ uint64_t bars[2], cbars[2], wbar;        // per group: phase MMAs | context MMA; weights landed
   __shared__ uint32_t tmem_base_s;
   __shared__ int slen_s[2][2][NS];
   __shared__ ChunkDesc sd[KC];
@@ -812,13 +812,14 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
     mbar_init(&bars[1], 1);
     mbar_init(&cbars[0], 1);
     mbar_init(&cbars[1], 1);
+    mbar_init(&wbar, 1);
     mbar_fence_init();
+    // the 88 KB of weight images: one bulk async copy; only the MMA-issuing threads ever wait for it, so it
+    // overlaps the first tile's gather
+    mbar_expect_tx(&wbar, L::oGrp);
+    bulk_g2s(smem + L::oWqkv, a.prepared, L::oGrp, &wbar);
   }
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.prepared);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L::oWqkv);
-    constexpr int n16 = L::oGrp / 16;
-    for (int i = tid; i < n16; i += kT3Threads) dst[i] = __ldg(src + i);
     for (int i = tid; i < D; i += kT3Threads) {
       fv[L::vBQKV + i] = a.bq[i];
       fv[L::vBQKV + D + i] = a.bk[i];
@@ -1012,6 +1013,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
 
     // ---- P1: [Q|K|V] = X Wqkv ----
     if (gt == 0) {
+      if (it == 0) mbar_wait(&wbar, 0);              // weight images landed (bulk copy issued in the prologue)
       fence_after_sync();
       constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
 #pragma unroll
