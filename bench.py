@@ -281,8 +281,8 @@ def main():
     def step_e2e(i):
         # every step copies ONE batch host->device (the next step's, on the copy stream, overlapping this step's
         # kernels -- a data-loader prefetch) and reads this step's scores back
-        cur = staged_next[0] if staged_next[0] is not None else model.prefetch(packed[i % len(packed)])
-        staged_next[0] = model.prefetch(packed[(i + 1) % len(packed)])
+        cur = staged_next[0] if staged_next[0] is not None else model.prefetch(packed[i % len(packed)], views=False)
+        staged_next[0] = model.prefetch(packed[(i + 1) % len(packed)], views=False)
         (yr, yb) = infer(cur, is_train=False)
         oh = out_host[i & 1]
         oh[0].copy_(yr[0].view(-1), non_blocking=True)

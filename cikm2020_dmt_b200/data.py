@@ -21,6 +21,23 @@ LABEL_VALUES = (0, 1, 2, 4, 5)
 LABEL_PRIOR = (0.9322, 0.0088, 0.0569, 0.0015, 0.00065)   # jd_recsys_demo/stat/stat/part-00000
 
 
+class DevArray:
+    """A 1-D device array known only by address: what the C ABI needs of an id / offset / weight array
+    (`data_ptr()`, `numel()`, `dtype`, `device`).  `PackedBatch.to(..., views=False)` hands these out instead of
+    torch views: staging a batch for inference then costs two small objects per feature instead of ~100 tensor
+    views.  Not a tensor -- the training path (which sorts and indexes ids with torch) asks for real views."""
+    __slots__ = ("_p", "_n", "dtype", "device")
+
+    def __init__(self, ptr, numel, dtype, device):
+        self._p, self._n, self.dtype, self.device = ptr, numel, dtype, device
+
+    def data_ptr(self):
+        return self._p
+
+    def numel(self):
+        return self._n
+
+
 @dataclass
 class SparseIds:
     values: torch.Tensor             # int32 [nnz], post-lookup index in [0, V)
@@ -299,8 +316,34 @@ class PackedBatch:
             out[key] = SparseIds(p["v"], p["o"], p.get("w"))
         return out
 
-    def to(self, device, out: Optional[torch.Tensor] = None) -> Dict:
+    def unpack_ptrs(self, buf: torch.Tensor) -> Dict:
+        """Like `unpack`, but the id / offset / weight arrays come back as `DevArray`s (address + length) and only
+        the dense tensors ('features', 'mask', ...) as torch views."""
+        if not hasattr(self, "_ptr_plan"):
+            dense, sparse = [], {}
+            for key, kind, dtype, shape, o in self.layout:
+                n = 1
+                for d in shape:
+                    n *= d
+                if kind == "t":
+                    dense.append((key, dtype, shape, o, n * (4 if dtype in (torch.int32, torch.float32) else
+                                                            torch.empty((), dtype=dtype).element_size())))
+                else:
+                    sparse.setdefault(key, {})[kind] = (o, n, dtype)
+            self._ptr_plan = (dense, [(k, p["v"], p["o"], p.get("w")) for k, p in sparse.items()])
+        dense, sparse = self._ptr_plan
+        base, dev = buf.data_ptr(), buf.device
+        out = {}
+        for key, dtype, shape, o, nb in dense:
+            out[key] = buf[o:o + nb].view(dtype).view(shape)
+        for key, v, off, w in sparse:
+            out[key] = SparseIds(DevArray(base + v[0], v[1], v[2], dev), DevArray(base + off[0], off[1], off[2], dev),
+                                 None if w is None else DevArray(base + w[0], w[1], w[2], dev))
+        out["__buffer__"] = buf          # keeps the storage alive as long as the descriptors
+        return out
+
+    def to(self, device, out: Optional[torch.Tensor] = None, views: bool = True) -> Dict:
         if out is None:
             out = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         out[:self.nbytes].copy_(self.host, non_blocking=True)
-        return self.unpack(out)
+        return self.unpack(out) if views else self.unpack_ptrs(out)

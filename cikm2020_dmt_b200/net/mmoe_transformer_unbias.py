@@ -196,9 +196,10 @@ class mmoe_transformer_unbias(object):
                 out[k] = v
         return out
 
-    def prefetch(self, packed):
+    def prefetch(self, packed, views=True):
         """Start the host->device copy of a `PackedBatch` on a side stream and return the staged batch; pass
-        it to `inference` / `compute_gradients` later.  The copy overlaps whatever the compute stream is doing
+        it to `inference` / `compute_gradients` later.  views=False (inference only): the id arrays are handed
+        over as raw `DevArray` descriptors instead of torch views -- the cheapest way to stage a batch.  The copy overlaps whatever the compute stream is doing
         (what a data-loader prefetch thread does for the reference's tf.data pipeline,
         tfrecord_mask.py:140-157).  Three rotating device buffers: a buffer is rewritten only after the
         compute enqueued before this call -- which includes its previous consumer -- has finished."""
@@ -215,7 +216,7 @@ class mmoe_transformer_unbias(object):
         done.record(cur)
         self._copy_stream.wait_event(done)
         with torch.cuda.stream(self._copy_stream):
-            out = packed.to(self.device, out=buf)
+            out = packed.to(self.device, out=buf, views=views)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         out["__max_len__"] = packed.max_len(self.plan)

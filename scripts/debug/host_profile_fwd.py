@@ -17,7 +17,7 @@ packed = [PackedBatch(synthetic_batch(plan, B, seed=SEED + i)) for i in range(4)
 out_host = torch.empty(3, B).pin_memory()
 
 def step(i):
-    cur = model.prefetch(packed[i % 4])
+    cur = model.prefetch(packed[i % 4], views=False)
     (yr, yb) = model.inference(cur, is_train=False)
     out_host[0].copy_(yr[0].view(-1), non_blocking=True)
     out_host[1].copy_(yr[1].view(-1), non_blocking=True)

@@ -391,3 +391,18 @@ def test_mmoe_bf16_matches_oracle(batch):
     torch.cuda.synchronize()
     _close(logits, want, atol=5e-2, rtol=2e-2)
     assert (logits - ref).abs().mean().item() < 1e-2
+
+
+def test_prefetch_pointer_staging_matches_views():
+    """`prefetch(packed, views=False)` (raw DevArray descriptors) must give bit-identical scores to the torch-view
+    staging of the same packed batch, on both kernel paths."""
+    from cikm2020_dmt_b200.data import PackedBatch
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 260, seed=61)
+    tc = _bf16_model(plan, model.params)
+    packed = PackedBatch(host)
+    for m in (model, tc):
+        (a_r, a_b) = m.inference(m.prefetch(packed, views=True), is_train=False)
+        a = [a_r[0].clone(), a_r[1].clone(), a_b.clone()]
+        (b_r, b_b) = m.inference(m.prefetch(packed, views=False), is_train=False)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], b_r[0]) and torch.equal(a[1], b_r[1]) and torch.equal(a[2], b_b)
