@@ -15,6 +15,8 @@ using namespace umma;
 // mode 4: A in tensor memory, B MN-major, B given as [K][N]
 // mode 5: A K-major compact image of 16 rows (LBO = 256 B; rows >= 16 of the MMA read neighbouring bytes and
 //         only produce garbage in their own accumulator rows), B MN-major [K][N]; rows 0..15 of C are checked
+// mode 6: A MN-major (given as [K][128]: the image [m/8][k][8] of the memory rows, read with M contiguous), B K-major
+//         compact image of N <= 16 rows given as [N][K] (the transposed decoder-context MMA of the sequence kernel)
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv_bfloat16* __restrict__ A,
                                                             const __nv_bfloat16* __restrict__ B,
                                                             float* __restrict__ C, int N, int K) {
@@ -31,7 +33,13 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
     mbar_fence_init();
   }
 
-  // ---- stage A [128][K] ----
+  // ---- stage A [128][K] (mode 6: A^T given as [K][128], image [m/8][k][8]) ----
+  if (mode == 6) {
+    for (int i = tid; i < K * 16; i += 128) {
+      const int k = i % K, g = i / K;                   // 8 rows m = 8g..8g+7 of column k
+      *reinterpret_cast<uint4*>(sA + g * (K * 16) + k * 16) = *reinterpret_cast<const uint4*>(A + (size_t)k * 128 + g * 8);
+    }
+  } else
   for (int i = tid; i < 128 * (K / 8); i += 128) {
     const int r = i % 128, c = i / 128;                 // 16-byte chunk c of row r
     const uint4 v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + c * 8);
@@ -81,7 +89,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
   }
 
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn);
+    const uint32_t idesc = make_idesc_bf16(128, N, mode == 6, b_mn);
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t da, db;
@@ -91,6 +99,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
         db = make_smem_desc(b0 + blk * (N * 128) + sub * 32, 16, 1024, kLayoutSW128);
       } else {
         if (mode == 5) da = make_smem_desc(a0 + ks * 2 * 256, 256, 128, kLayoutNone);
+        else if (mode == 6) da = make_smem_desc(a0 + ks * 2 * 128, 128, K * 16, kLayoutNone);   // MN-major A
         else da = make_smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128, kLayoutNone);
         if (!b_mn) db = make_smem_desc(b0 + ks * 2 * (N * 16), N * 16, 128, kLayoutNone);
         else db = make_smem_desc(b0 + ks * 2 * 128, 128, K * 16, kLayoutNone);   // MN-major: LBO = next 8 k, SBO = next 8 n
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const __nv
 extern "C" int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float* C, int32_t N, int32_t K,
                                  void* stream) {
   DMT_REQUIRE(A && B && C, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: null pointer");
-  DMT_REQUIRE(mode >= 0 && mode <= 5, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: mode %d", mode);
+  DMT_REQUIRE(mode >= 0 && mode <= 6, DMT_ERR_INVALID_ARGUMENT, "dmt_selftest_umma: mode %d", mode);
   DMT_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0 && (mode != 2 || K % 64 == 0) &&
                   ((mode != 3 && mode != 4) || (N <= 128 && K <= 256)),
               DMT_ERR_UNSUPPORTED_SHAPE, "dmt_selftest_umma: N=%d K=%d", N, K);

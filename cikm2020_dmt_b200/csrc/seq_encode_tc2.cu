@@ -932,46 +932,44 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
       }
     }
   };
-  // decoder contexts of the tile whose first sample is rb0: warp 0 of the group
+  // decoder contexts of the tile whose first sample is rb0.  The context MMA is issued TRANSPOSED (A = the memory
+  // image read MN-major, B = the 16-row probability image): accumulator row k = feature k, column (part, head), so
+  // the read-out is 16 values in each of 64 lanes (two warps) instead of 64 values in each of 8-16 lanes of one
+  // warp, and the two partial softmaxes of a 64-row slot sit in the same lane (no shuffles).
   uint32_t cphase = 0;
   auto ctx_readout = [&](int rb0) {
-    if (gt >= 32) return;
+    if (gt >= D) return;
     mbar_wait(cbar, cphase);
     cphase ^= 1;
     fence_after_sync();
-    uint32_t c0[32], c1[32];
-    tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
-    tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
+    uint32_t c[16];
+    tmem_ld16(tmem_addr(tbase, L::tCtx), c);
     tmem_ld_wait();
     const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
-    float den = mxs[NR + (lane & (NR - 1))];
-    float wgt = 1.0f;
-    if constexpr (PPS == 2) {
-      const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
-      const float m = fmaxf(ma, mb);
-      wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
-      den *= wgt;
-      den += __shfl_xor_sync(0xffffffffu, den, 2);
-    }
-    const float inv = den > 0.f ? 1.0f / den : 0.f;
-    const int p = lane >> 1, h = lane & 1;
-    const int b = rb0 + p / PPS;
-    const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(b & 127) * 16;
+    const int kf = gt;                                 // feature column = TMEM lane
+    uint8_t* dst0 = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(kf >> 3) * (128 * 16) + (kf & 7) * 2;
 #pragma unroll
-    for (int c = 0; c < KC; ++c) {
-      float v[8];
+    for (int s = 0; s < NS; ++s) {
+      const int b = rb0 + s;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int kk = c * 8 + e;
-        v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
+      for (int h = 0; h < H; ++h) {
+        float num, den;
         if constexpr (PPS == 2) {
-          v[e] *= wgt;
-          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
+          const int ia = (2 * s) * H + h, ib = (2 * s + 1) * H + h;
+          const float ma = mxs[ia], mb = mxs[ib];
+          const float m = fmaxf(ma, mb);
+          const float wa = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m), wb = (mb == -INFINITY) ? 0.f : ex2_approx(mb - m);
+          num = __uint_as_float(c[ia]) * wa + __uint_as_float(c[ib]) * wb;
+          den = mxs[NR + ia] * wa + mxs[NR + ib] * wb;
+        } else {
+          num = __uint_as_float(c[s * H + h]);
+          den = mxs[NR + s * H + h];
         }
-        v[e] *= inv;
+        const float v = den > 0.f ? num / den : 0.f;    // empty sequence: context 0
+        if (b < B)
+          *reinterpret_cast<unsigned short*>(dst0 + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(h * KC) * (128 * 16) +
+                                             (size_t)(b & 127) * 16) = __bfloat16_as_ushort(__float2bfloat16(v));
       }
-      if (writer) *reinterpret_cast<uint4*>(dst + (size_t)(h * KC + c) * (128 * 16)) = f8_to_bf16(v);
     }
     fence_before_sync();
   };
@@ -1351,14 +1349,15 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
     named_sync(bar_id, 256);
     T2_TICK(10);
 
-    // ---- P11: context MMA (read out by warp 0 in the shadow of the next tile's X Wqkv) ----
+    // ---- P11: context MMA, transposed: D[feature][(part, head)] = sum_t M_t[feature] e_t  (A = memory image read
+    //      MN-major, B = the compact probability image); read out in the shadow of the next tile's X Wqkv ----
     if (gt == 0) {
       fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, D, false, true);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 16, true, false);
       const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
 #pragma unroll
       for (int ks = 0; ks < 128 / 16; ++ks)
-        mma_bf16_ss(tbase + L::tCtx, desc_join(dPd + ks * (2 * 256 / 16), dHi), desc_join(dM + ks * (256 / 16), dHiV),
+        mma_bf16_ss(tbase + L::tCtx, desc_join(dM + ks * (256 / 16), dHiV), desc_join(dPd + ks * (2 * 256 / 16), dHi),
                     idesc, ks > 0);
       commit(cbar);
     }

@@ -48,3 +48,22 @@ def test_umma_tmem_operand_selftest(mode, N, K):
     rows = 16 if mode == 5 else 128
     err = (C.cpu()[:rows] - want[:rows]).abs().max().item()
     assert err < 1e-3 * max(1.0, want.abs().max().item()), "mode %d N %d K %d: max err %g" % (mode, N, K, err)
+
+
+@pytest.mark.parametrize("N,K", [(16, 128), (16, 64), (32, 128), (64, 32)])
+def test_umma_mn_major_a_selftest(N, K):
+    """A operand read MN-major from shared memory (the memory rows of the transposed decoder-context MMA)."""
+    from cikm2020_dmt_b200 import abi
+    lib = abi.load()
+    g = torch.Generator().manual_seed(N * 1000 + K + 6)
+    A = (torch.randn(128, K, generator=g)).to(torch.bfloat16)
+    Bt = (torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    want = A.float() @ Bt.float().t()
+    Ad = A.t().contiguous().cuda()            # [K][128]
+    Bd = Bt.cuda()
+    C = torch.full((128, N), float("nan"), device="cuda")
+    abi.check(lib.dmt_selftest_umma(6, Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), N, K,
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (C.cpu() - want).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), "N %d K %d: max err %g" % (N, K, err)
