@@ -27,7 +27,7 @@ def _digest():
     paths.append(os.path.join(HERE, "..", "include", "dmt_b200.h"))
     for p in paths:
         with open(p, "rb") as fh:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())    # not the absolute path: the tree is copied to other boxes
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -40,12 +40,32 @@ def nvcc_path():
     return None
 
 
-def build(force=False, verbose=False):
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _up_to_date(digest):
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
-            if fh.read().strip() == digest:
+            return fh.read().strip() == digest
+    return False
+
+
+def build(force=False, verbose=False):
+    """Build if the sources changed.  Safe under `torchrun`: the ranks of one box serialise on a lock file and
+    all but the first find the library up to date."""
+    digest = _digest()
+    if not force and _up_to_date(digest):
+        return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "csrc", "_obj"), exist_ok=True)
+    with open(os.path.join(HERE, "csrc", "_obj", ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(digest):
                 return LIB
+            return _build_locked(digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest, verbose):
     nvcc = nvcc_path()
     if nvcc is None:
         if os.path.exists(LIB):
@@ -71,9 +91,11 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see %s" % os.path.join(objdir, "build.log"))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                  "-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)                      # atomic: a concurrent loader never sees a half-written library
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB
