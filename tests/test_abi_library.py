@@ -47,7 +47,7 @@ def test_struct_layouts_match_header(tmp_path):
                "dmt_pool_feat": abi.PoolFeat, "dmt_mmoe_cfg": abi.MmoeCfg, "dmt_mmoe_weights": abi.MmoeWeights,
                "dmt_bias_loss_cfg": abi.BiasLossCfg, "dmt_bias_weights": abi.BiasWeights,
                "dmt_dense": abi.Dense, "dmt_attn_weights": abi.AttnWeights, "dmt_ff_weights": abi.FFWeights}
-    probes = {"dmt_seq_cfg": ["precision", "n_feats"], "dmt_seq_input": ["ids", "item_ids", "dim"],
+    probes = {"dmt_seq_cfg": ["precision", "n_feats", "flags", "dropout_seed"], "dmt_seq_input": ["ids", "item_ids", "dim"],
               "dmt_seq_weights": ["dec_attn", "ff"], "dmt_pool_feat": ["weights", "out_col"],
               "dmt_mmoe_cfg": ["n_tasks", "tower_units", "precision"], "dmt_mmoe_weights": ["gate", "tower_out"],
               "dmt_bias_loss_cfg": ["ctr_rel", "weight_ecvr", "loss_weight"]}
@@ -86,3 +86,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_build_digest_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch):
+    """The source digest decides whether a box rebuilds the library: it must be the same for a copy of the tree
+    under another path (gpurun boxes, CI checkouts), or every rank of a torchrun launch would recompile."""
+    import shutil
+    from cikm2020_dmt_b200 import build as B
+    want = B._digest()
+    pkg = tmp_path / "elsewhere" / "cikm2020_dmt_b200"
+    (pkg / "csrc").mkdir(parents=True)
+    (tmp_path / "elsewhere" / "include").mkdir()
+    for f in os.listdir(B.CSRC):
+        if f.endswith((".cu", ".cuh", ".h")):
+            shutil.copy(os.path.join(B.CSRC, f), pkg / "csrc" / f)
+    shutil.copy(HEADER, tmp_path / "elsewhere" / "include" / "dmt_b200.h")
+    monkeypatch.setattr(B, "HERE", str(pkg))
+    monkeypatch.setattr(B, "CSRC", str(pkg / "csrc"))
+    assert B._digest() == want

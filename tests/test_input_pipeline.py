@@ -125,3 +125,34 @@ def test_batches_shard_by_rank(tmp_path):
     assert torch.equal(r0[1]["features"], all_b[2]["features"]) and torch.equal(r1[0]["features"], all_b[1]["features"])
     two_epochs = list(T.batches(conf, None, prefix, batch_size=5, epochs=2, shuffle_size=4, drop_remainder=True))
     assert len(two_epochs) == 4
+
+
+def test_packed_batch_pointer_staging_matches_views():
+    """`PackedBatch.unpack_ptrs` (DevArray descriptors: address + length) must describe exactly the arrays that
+    `unpack` returns as torch views -- checked on a host copy by reading the memory behind the addresses."""
+    import ctypes
+    import torch
+    from conftest import make_plan
+    from cikm2020_dmt_b200.data import DevArray, PackedBatch, SparseIds, synthetic_batch
+    conf, plan = make_plan("dmt_d64.conf")
+    host = synthetic_batch(plan, 37, seed=5)
+    packed = PackedBatch(host, pin=False)
+    buf = packed.host.clone()
+    views, ptrs = packed.unpack(buf), packed.unpack_ptrs(buf)
+    assert set(views) == set(k for k in ptrs if not k.startswith("__"))
+    n_sparse = 0
+    for k, v in views.items():
+        p = ptrs[k]
+        if isinstance(v, SparseIds):
+            n_sparse += 1
+            for a, b in ((v.values, p.values), (v.offsets, p.offsets), (v.weights, p.weights)):
+                assert (a is None) == (b is None)
+                if a is None:
+                    continue
+                assert isinstance(b, DevArray) and b.numel() == a.numel() and b.dtype == a.dtype
+                assert b.data_ptr() == a.data_ptr()
+                raw = (ctypes.c_char * (a.numel() * 4)).from_address(b.data_ptr())
+                assert bytes(raw) == a.contiguous().view(torch.uint8).numpy().tobytes()
+        else:
+            assert torch.equal(v, p) and v.data_ptr() == p.data_ptr()
+    assert n_sparse >= 20
