@@ -1147,29 +1147,30 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
       }
       commit(bar);
     }
-    // folded decoder queries: thread (n = row, hf) computes the samples s = hf, hf + 2, ...
-    {
-      constexpr int NSH = NS / 2;
-      float acc[NSH];
-      const float gb = __ldg(gGb + row);
-#pragma unroll
-      for (int s = 0; s < NSH; ++s) acc[s] = gb;
+    // folded decoder queries qt[s][n] = dvec[s] . G[n] + g[n]: thread (n = row, hf) computes the samples s = hf,
+    // hf + 2, ...; the contraction is split between the shadows of the P.V and the H.W2 MMAs
+    constexpr int NSH = NS / 2;
+    float qacc[NSH];
+    auto qt_part = [&](int jc0) {
       const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
 #pragma unroll
-      for (int jc = 0; jc < KC; ++jc) {
+      for (int jc = jc0; jc < jc0 + KC / 2; ++jc) {
         float w[8];
         bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
 #pragma unroll
         for (int s = 0; s < NSH; ++s) {
           const float4 d0 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8);
           const float4 d1 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8 + 4);
-          acc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], acc[s]))));
-          acc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], acc[s]))));
+          qacc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], qacc[s]))));
+          qacc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], qacc[s]))));
         }
       }
-      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
+    };
+    {
+      const float gb = __ldg(gGb + row);
 #pragma unroll
-      for (int s = 0; s < NSH; ++s) qt[(2 * s + hf) * (H * D) + row] = acc[s];
+      for (int s = 0; s < NSH; ++s) qacc[s] = gb;
+      qt_part(0);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -1262,10 +1263,16 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
                     idesc, ks > 0);
       commit(bar);
     }
+    {
+      qt_part(KC / 2);
+      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
+#pragma unroll
+      for (int s = 0; s < NSH; ++s) qt[(2 * s + hf) * (H * D) + row] = qacc[s];
+    }
     mbar_wait(bar, phase);
     phase ^= 1;
     fence_after_sync();
-    T2_TICK(9);
+    T2_TICK(9);                                          // (qt is read after P10's LayerNorm-exchange barrier)
 
     // ---- P10: memory = LN(F + b2 + A); decoder scores; partial softmax of head hf; images for the context MMA ----
     {
