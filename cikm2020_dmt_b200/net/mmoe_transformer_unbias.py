@@ -471,7 +471,13 @@ class mmoe_transformer_unbias(object):
             keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
         if deferred:
             self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
-        logits = self._buf("logits", (plan.num_tasks, batch))
+        # scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can
+        # read them back with a single copy; two buffers alternate, so the result of call i stays valid while
+        # call i + 1 runs
+        self._score_flip = getattr(self, "_score_flip", 0) ^ 1
+        scores = self._buf("scores%d" % self._score_flip, (plan.num_tasks + 1, batch))
+        self.last_scores = scores
+        logits = scores[:plan.num_tasks]
         self.mmoe(x, batch, logits)
         self._last = {"x": x, "batch": batch, "keep": keep}
         y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
@@ -479,7 +485,7 @@ class mmoe_transformer_unbias(object):
             return y_rel
         bias_in = self._buf("bias_in", (batch, plan.bias_width))
         keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
-        y_bias = self._buf("y_bias", (batch,))
+        y_bias = scores[plan.num_tasks]
         cfg = self._bias_cfg(batch)
         with self._Stage(self, "bias_tower", 1):
             abi.check(self.lib.dmt_bias_loss_fwd(C.byref(cfg), C.byref(self._bias_w), bias_in.data_ptr(),
@@ -492,7 +498,9 @@ class mmoe_transformer_unbias(object):
         """A12 on the outputs of `inference` (inference_mlp.py:173-223)."""
         (click, order), y_bias = logits
         batch = click.shape[0]
-        lg = self._buf("logits", (self.plan.num_tasks, batch))
+        last = getattr(self, "last_scores", None)
+        lg = last[:self.plan.num_tasks] if last is not None and last.shape[1] == batch else \
+            self._buf("logits", (self.plan.num_tasks, batch))
         if click.data_ptr() != lg[0].data_ptr() or order.data_ptr() != lg[1].data_ptr():
             lg = self._buf("logits_in", (2, batch))
             lg[0].copy_(click.reshape(-1))
