@@ -104,3 +104,20 @@ def test_build_digest_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch
     monkeypatch.setattr(B, "HERE", str(pkg))
     monkeypatch.setattr(B, "CSRC", str(pkg / "csrc"))
     assert B._digest() == want
+
+
+def test_argument_errors_need_no_gpu():
+    """Argument validation happens before any CUDA call: error codes and messages without a device."""
+    import ctypes as C
+    from cikm2020_dmt_b200 import abi
+    lib = abi.load()
+    rc = lib.dmt_seq_tail_fwd(abi.MAX_TAIL_SEQS + 1, None, None, None, None, None, None, None)
+    assert rc < 0 and b"n_seq" in lib.dmt_last_error()
+    assert lib.dmt_seq_tail_fwd(0, None, None, None, None, None, None, None) == 0
+    rc = lib.dmt_seq_tail_fwd(1, None, None, None, None, None, None, None)
+    assert rc < 0 and b"null" in lib.dmt_last_error()
+    cfg = abi.SeqCfg(4, 64, 256, 2, 1, 1, 50, 1, 5, abi.PRECISION_BF16, 0, 0, 0.0, 0)
+    assert lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0) > 128 * 1024       # weight images + context image
+    big = abi.SeqCfg(4096, 64, 256, 2, 1, 1, 50, 1, 5, abi.PRECISION_BF16, 0, 0, 0.0, 0)
+    grow = lib.dmt_seq_encode_workspace_bytes(C.byref(big), 0) - lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0)
+    assert grow == (4096 // 128 - 1) * 128 * 128 * 2                             # one 32 KB image per 128 samples
