@@ -973,21 +973,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
     }
     fence_before_sync();
   };
-  int n_done = 0;
-  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
-  stage_offsets(tile0);
-  stage_ids(tile0, 0);
-  stage_rows();
-
-  long long t_last = clock64();
-  for (int it = 0;; ++it) {
-    const int tile = tile0 + it * tstride;
-    if (tile >= a.n_tiles) break;
-    const int par = it & 1;
-    const int b0 = tile * NS;
-    const int next_tile = tile + tstride;
-
-    // ---- P0: this half's four chunks -> X image ----
+  // concat + sqrt(d) scale + learned position -> bf16, in registers: done early (in an MMA shadow) so that P0 is
+  // four stores
+  uint4 px[HC];
+  auto convert_rows = [&]() {
 #pragma unroll
     for (int k = 0; k < HC; ++k) {
       float x[8];
@@ -1001,8 +990,27 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
         x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
         x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
       }
-      *reinterpret_cast<uint4*>(sXA + (c0h + k) * ROWB + row * 16) = f8_to_bf16(x);
+      px[k] = f8_to_bf16(x);
     }
+  };
+  int n_done = 0;
+  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
+  stage_offsets(tile0);
+  stage_ids(tile0, 0);
+  stage_rows();
+  convert_rows();
+
+  long long t_last = clock64();
+  for (int it = 0;; ++it) {
+    const int tile = tile0 + it * tstride;
+    if (tile >= a.n_tiles) break;
+    const int par = it & 1;
+    const int b0 = tile * NS;
+    const int next_tile = tile + tstride;
+
+    // ---- P0: this half's four (already converted) chunks -> X image ----
+#pragma unroll
+    for (int k = 0; k < HC; ++k) *reinterpret_cast<uint4*>(sXA + (c0h + k) * ROWB + row * 16) = px[k];
     const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;
     fence_proxy_async();
     fence_before_sync();
@@ -1263,6 +1271,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
                     idesc, ks > 0);
       commit(bar);
     }
+    convert_rows();                                      // next tile's rows (requested in P7) -> bf16 registers
     {
       qt_part(KC / 2);
       float* qt = reinterpret_cast<float*>(gbase + L::gQt);
