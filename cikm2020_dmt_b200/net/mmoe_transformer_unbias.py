@@ -446,8 +446,9 @@ class mmoe_transformer_unbias(object):
     def _inference(self, inputs, is_train, is_predict):
         plan = self.plan
         if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
-            raise NotImplementedError("training-mode dropout is not built yet; call with is_train=False "
-                                      "or set the dropout rates to 0")
+            raise NotImplementedError("inference() is the eval-mode graph; the training graph with its dropout sites "
+                                      "(run_dnn.py:154-181) is compute_gradients().  Call with is_train=False, or set "
+                                      "the dropout rates to 0")
         inputs = self.stage_inputs(inputs)
         feats = inputs["features"] if plan.is_use_feature else None
         first = inputs[plan.pooled[0].feature]
