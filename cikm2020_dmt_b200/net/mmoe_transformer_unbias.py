@@ -434,21 +434,86 @@ class mmoe_transformer_unbias(object):
         return cfg
 
     # ------------------------------------------------------------------ plugin protocol
-    def inference(self, inputs, is_train=True, is_predict=False):
+    def inference(self, inputs, is_train=True, is_predict=False, dropout_seed=None):
         """mmoe_transformer_unbias.py:293-316.  Returns ((click_logit [B,1], order_logit [B,1]),
-        y_bias [B,1]) or, with is_predict, just the logit pair."""
+        y_bias [B,1]) or, with is_predict, just the logit pair.  With is_train and non-zero dropout rates the
+        forward of the TRAINING graph runs (the dropout sites of TransformerModel.py:101,151 /
+        TransformerModel_util.py:51 / mmoe_transformer_unbias.py:272,280 active, masks = the counter-based hash of
+        `dropout_seed`, a fresh seed per call unless given) -- the same forward `compute_gradients` differentiates."""
         self._stream_h = torch.cuda.current_stream(self.device).cuda_stream
         try:
+            plan = self.plan
+            if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
+                return self._inference_train(inputs, is_predict, dropout_seed)
             return self._inference(inputs, is_train, is_predict)
         finally:
             self._stream_h = None
 
+    def _inference_train(self, inputs, is_predict, dropout_seed):
+        """Forward of the training graph (dropout active); no activations are kept for a backward."""
+        from .. import dropout as DO
+        plan, lib = self.plan, self.lib
+        rate = float(plan.dropout_rate)
+        rates_bias = [float(r) for r in plan.dropout_rate_bias]
+        if dropout_seed is None:
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            dropout_seed = DO.step_seed(getattr(self, "dropout_base_seed", 20201019), self._train_calls)
+        self.last_dropout_seed = dropout_seed
+        inputs = self.stage_inputs(inputs)
+        feats = inputs["features"] if plan.is_use_feature else None
+        batch = inputs[plan.pooled[0].feature].offsets.numel() - 1
+        stream = self._stream()
+        F32 = self.train_precision
+        x_ld = (plan.mmoe_in + 3) // 4 * 4
+        x = self._buf("x", (batch, x_ld))
+        keep = []
+        if feats is not None:
+            if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
+                raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
+            feats = feats.contiguous()
+            with self._Stage(self, "copy_dense", 1):
+                abi.check(lib.dmt_copy_dense_features(feats.data_ptr(), batch, plan.feature_dim,
+                                                      x.data_ptr(), x_ld, stream))
+            keep.append(feats)
+        keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
+        for s, seq in enumerate(plan.sequences):
+            cfg = self._seq_cfg(inputs, seq, batch, F32, rate, DO.step_seed(dropout_seed, 0, 1 + seq.index))
+            si, kp = self._seq_input(inputs, seq, batch)
+            keep += kp
+            n_tok = self._sparse(inputs, seq.user_features[-1], "seq%d" % seq.index).values.numel()
+            nbytes = lib.dmt_seq_saved_bytes(C.byref(cfg), n_tok)
+            saved = self._scratch("seq_saved_%d" % s, nbytes)
+            col = plan.interest_col + s * plan.d_model
+            with self._Stage(self, "seq_encode_train", 1):
+                abi.check(lib.dmt_seq_encode_fwd_train(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]),
+                                                       x.data_ptr() + 4 * col, x_ld, n_tok, saved.data_ptr(),
+                                                       saved.numel(), stream))
+        mcfg = self._mmoe_cfg(batch, F32)
+        mws_bytes = lib.dmt_mmoe_train_workspace_bytes(C.byref(mcfg))
+        mws = self._buf("mmoe_ws_f32", ((mws_bytes + 255) // 256 * 256,), torch.uint8)
+        self._score_flip = getattr(self, "_score_flip", 0) ^ 1
+        scores = self._buf("scores%d" % self._score_flip, (plan.num_tasks + 1, batch))
+        self.last_scores = scores
+        logits = scores[:plan.num_tasks]
+        with self._Stage(self, "mmoe", mcfg.n_layers + 1):
+            abi.check(lib.dmt_mmoe_fwd_train(C.byref(mcfg), C.byref(self._mmoe_w), x.data_ptr(), x_ld,
+                                             logits.data_ptr(), mws.data_ptr(), mws_bytes, stream))
+        self._last = {"x": x, "batch": batch, "keep": keep}
+        y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
+        if is_predict:
+            return y_rel
+        bias_in = self._buf("bias_in", (batch, plan.bias_width))
+        keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
+        y_bias = scores[plan.num_tasks]
+        bcfg = self._bias_cfg(batch, dropout_rates=rates_bias, dropout_seed=DO.step_seed(dropout_seed, 0, 0))
+        with self._Stage(self, "bias_tower", 1):
+            abi.check(lib.dmt_bias_loss_fwd(C.byref(bcfg), C.byref(self._bias_w), bias_in.data_ptr(),
+                                            bias_in.stride(0), logits.data_ptr(), None, y_bias.data_ptr(),
+                                            None, None, None, None, stream))
+        return (y_rel, y_bias.view(batch, 1))
+
     def _inference(self, inputs, is_train, is_predict):
         plan = self.plan
-        if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
-            raise NotImplementedError("inference() is the eval-mode graph; the training graph with its dropout sites "
-                                      "(run_dnn.py:154-181) is compute_gradients().  Call with is_train=False, or set "
-                                      "the dropout rates to 0")
         inputs = self.stage_inputs(inputs)
         feats = inputs["features"] if plan.is_use_feature else None
         first = inputs[plan.pooled[0].feature]

@@ -124,3 +124,19 @@ def test_dropout_seed_semantics():
     # eval mode equals the inference path's loss
     out = model.inference(dev, is_train=False)
     assert abs(model.loss(out, dev["mask"]).item() - l_eval) <= 1e-5 * abs(l_eval)
+
+
+def test_inference_in_training_mode_is_the_forward_of_compute_gradients():
+    """`inference(inputs, is_train=True)` (run_dnn.py:154) runs the dropout sites: with the seed of a
+    `compute_gradients` call its scores give the same loss, with another seed a different one."""
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 48, seed=21)
+    l_ref, _ = model.compute_gradients(dev, is_train=True, dropout_seed=4242)
+    l_ref = l_ref.item()
+    out = model.inference(dev, is_train=True, dropout_seed=4242)
+    l_inf = model.loss(out, dev["mask"]).item()
+    assert abs(l_inf - l_ref) <= 1e-5 * abs(l_ref), (l_inf, l_ref)
+    out2 = model.inference(dev, is_train=True, dropout_seed=4243)
+    assert abs(model.loss(out2, dev["mask"]).item() - l_ref) > 1e-6 * abs(l_ref)
+    (click, order) = model.inference(dev, is_train=True, is_predict=True, dropout_seed=4242)
+    torch.cuda.synchronize()
+    assert click.shape == (48, 1) and order.shape == (48, 1)
