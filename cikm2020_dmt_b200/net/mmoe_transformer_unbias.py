@@ -626,6 +626,9 @@ class mmoe_transformer_unbias(object):
             dropout_seed = DO.step_seed(getattr(self, "dropout_base_seed", 20201019), self._train_calls)
         self.last_dropout_seed = dropout_seed
         inputs = self.stage_inputs(inputs)
+        if "__buffer__" in inputs:
+            raise TypeError("compute_gradients sorts and indexes the id arrays with torch: stage the batch with "
+                            "tensor views (prefetch(packed) / PackedBatch.to(device)), not views=False")
         mask = self._dev(inputs["mask"] if mask is None else mask)
         feats = inputs["features"] if plan.is_use_feature else None
         batch = inputs[plan.pooled[0].feature].offsets.numel() - 1
