@@ -338,7 +338,9 @@ def main():
     steps_used = args.steps
     mean_b = lambda fn: sum(fn(plan, batches[i % len(batches)]) for i in range(steps_used))
     if dom == "seq_encode":
-        t_ms, n = stage["seq_encode"]
+        t_ms, _ = stage["seq_encode"]
+        n = steps_used * len(plan.sequences)                     # one fused tile-kernel launch per sequence and step
+        #                                                          (its share of the batched tail launch is in t_ms)
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
         fl = mean_b(flops_seq)                                   # algorithmic FLOPs (valid tokens only)
         hbm = alg / (t_ms / 1e3) / 1e9
