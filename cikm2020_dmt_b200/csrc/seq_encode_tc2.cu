@@ -782,6 +782,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
   __shared__ uint32_t tmem_base_s;
   __shared__ int slen_s[2][2][NS];
   __shared__ ChunkDesc sd[KC];
+  // partial-softmax maxima | denominators of the group's last tile.  NOT inside the Q image like the other decoder
+  // scratch: the two read-out warps read them in the shadow of the next tile's X Wqkv, and the first of them to
+  // finish goes on to rewrite the Q image
+  __shared__ float mxs_s[2][32];
 
   const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, row = gt & 127, hf = gt >> 7;
   const int wq = (gt >> 5) & 3, lane = tid & 31;      // wq: warp inside the half = TMEM lane quarter
@@ -945,7 +949,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
     uint32_t c[16];
     tmem_ld16(tmem_addr(tbase, L::tCtx), c);
     tmem_ld_wait();
-    const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
+    const float* mxs = mxs_s[grp];
     const int kf = gt;                                 // feature column = TMEM lane
     uint8_t* dst0 = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(kf >> 3) * (128 * 16) + (kf & 7) * 2;
 #pragma unroll
@@ -1350,8 +1354,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
 #pragma unroll
       for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
       if ((lane % W) == 0) {
-        reinterpret_cast<float*>(gbase + L::gMx)[part * H + hf] = m;
-        reinterpret_cast<float*>(gbase + L::gMx)[NR + part * H + hf] = dsum;
+        mxs_s[grp][part * H + hf] = m;
+        mxs_s[grp][NR + part * H + hf] = dsum;
       }
       // transposed probabilities: rows (p, hf) for every part p, column = this token
       const unsigned short eb = __bfloat16_as_ushort(__float2bfloat16(e));
