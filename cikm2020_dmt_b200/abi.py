@@ -145,6 +145,7 @@ PROTOTYPES = {
     "dmt_embed_grad_scatter_rows": (C.c_int, [C.c_int32, C.POINTER(GradSource), _fp, _fp, _fp, C.c_int64, C.c_int32,
                                               _fp, _fp]),
     "dmt_adam_rows_untouched": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp]),
+    "dmt_build_digest": (C.c_char_p, []),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),
 }
@@ -180,6 +181,15 @@ def load(rebuild=True):
     got = lib.dmt_abi_version()
     if got != ABI_VERSION:
         raise RuntimeError("libdmt_b200.so ABI %d != binding ABI %d" % (got, ABI_VERSION))
+    built = lib.dmt_build_digest()
+    built = built.decode() if built else ""
+    want = _build.source_digest()
+    if built != want and os.environ.get("DMT_ALLOW_STALE_LIB") != "1":
+        # the ctypes structures above mirror the header the library was compiled from: a stale library means
+        # mismatched layouts, i.e. memory corruption instead of an error
+        raise RuntimeError("libdmt_b200.so was built from other sources (digest %s..., tree %s...) and nvcc is not "
+                           "available to rebuild it; run `python -m cikm2020_dmt_b200.build` where nvcc exists"
+                           % (built[:12], want[:12]))
     _LIB = lib
     return lib
 

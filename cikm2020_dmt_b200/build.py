@@ -33,6 +33,11 @@ def _digest():
     return h.hexdigest()
 
 
+def source_digest():
+    """Digest of the sources next to this file (what `dmt_build_digest()` of a current library returns)."""
+    return _digest()
+
+
 def nvcc_path():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -69,7 +74,7 @@ def _build_locked(digest, verbose):
     nvcc = nvcc_path()
     if nvcc is None:
         if os.path.exists(LIB):
-            return LIB   # GPU box without a changed source tree: use the shipped build
+            return LIB   # no compiler: abi.load() compares the library's own digest and refuses a stale one
         raise RuntimeError("nvcc not found and %s is missing" % LIB)
     objdir = os.path.join(HERE, "csrc", "_obj")
     os.makedirs(objdir, exist_ok=True)
@@ -78,6 +83,8 @@ def _build_locked(digest, verbose):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
+        if os.path.basename(src) == "abi.cu":       # dmt_build_digest(): checked by abi.load()
+            cmd += ['-DDMT_BUILD_DIGEST="%s"' % digest]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -42,6 +42,8 @@ def save(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
             arrays[name] = t.detach().cpu().numpy()
     if optimizer is not None:
         arrays["global_step"] = np.asarray(optimizer.t, dtype=np.int64)
+        if hasattr(optimizer, "global_step"):      # the learning-rate schedule's clock (run_dnn.py:122-126)
+            arrays["lr_global_step"] = np.asarray(optimizer.global_step, dtype=np.int64)
         if rank == 0:
             for spec in store.specs:
                 sl = slice(spec.offset, spec.offset + spec.numel)
@@ -75,9 +77,12 @@ def latest(directory: str) -> Optional[int]:
 
 
 def load(directory: str, step: int, store, optimizer=None, shards: Optional[Dict[str, tuple]] = None,
-         rank: int = 0, strict: bool = True) -> Dict[str, np.ndarray]:
+         rank: int = 0, strict: bool = True, model=None) -> Dict[str, np.ndarray]:
     """Restore `store` (and the Adam slots when `optimizer` is given and they were saved).  A sharded table is
-    cut out of a full table or assembled from the per-rank shard files, whichever the checkpoint holds."""
+    cut out of a full table or assembled from the per-rank shard files, whichever the checkpoint holds; its Adam
+    slots (`<var>/Adam`, `<var>/Adam_1`) are sharded by the SAME row range as the variable.
+    `model` (or `optimizer.model`): its cached bf16 weight images are invalidated, so the next forward re-derives
+    them from the restored parameters."""
     files = [_ckpt_path(directory, step)] + sorted(glob.glob(_ckpt_path(directory, step)[:-4] + ".rank*.npz"))
     data = {}
     for f in files:
@@ -86,21 +91,25 @@ def load(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
                 data[k] = z[k]
     shards = shards or {}
 
-    def fetch(name, rows_total=None):
-        if name in shards or any(k.startswith(name + "@rows") for k in data):
-            lo, hi = shards.get(name, (0, rows_total))
+    def fetch(name, shard_of=None):
+        """`name`: array to restore; `shard_of`: the variable whose row range cuts it (the variable itself, or
+        the variable an Adam slot belongs to)."""
+        key = name if shard_of is None else shard_of
+        pieces = [k for k in data if k.startswith(name + "@rows")]
+        if key in shards or pieces:
+            lo, hi = shards.get(key, (0, None))
             if name in data:
                 return data[name][lo:hi]
-            parts = sorted((int(re.search(r"@rows(\d+)-", k).group(1)), data[k])
-                           for k in data if k.startswith(name + "@rows"))
+            if not pieces:
+                return None
+            parts = sorted((int(re.search(r"@rows(\d+)-", k).group(1)), data[k]) for k in pieces)
             full = np.concatenate([p for _, p in parts], 0)
             return full[lo:hi]
         return data.get(name)
 
     missing = []
     for name, t in store.named_parameters():
-        rows_total = None
-        arr = fetch(name, rows_total)
+        arr = fetch(name)
         if arr is None:
             missing.append(name)
             continue
@@ -109,17 +118,23 @@ def load(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
         raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (files[0], len(missing), missing[0]))
     if optimizer is not None and "global_step" in data:
         optimizer.t = int(data["global_step"])
+        if hasattr(optimizer, "global_step"):
+            optimizer.global_step = int(data.get("lr_global_step", data["global_step"]))
         for spec in store.specs:
             sl = slice(spec.offset, spec.offset + spec.numel)
             if spec.name + "/Adam" in data:
                 optimizer.m_dense[sl].copy_(torch.from_numpy(data[spec.name + "/Adam"]).reshape(-1))
                 optimizer.v_dense[sl].copy_(torch.from_numpy(data[spec.name + "/Adam_1"]).reshape(-1))
         for name in store.tables:
-            m = fetch(name + "/Adam")
-            v = fetch(name + "/Adam_1")
+            m = fetch(name + "/Adam", shard_of=name)
+            v = fetch(name + "/Adam_1", shard_of=name)
             if m is not None and v is not None:
                 optimizer.m_tab[name].copy_(torch.from_numpy(np.ascontiguousarray(m)))
                 optimizer.v_tab[name].copy_(torch.from_numpy(np.ascontiguousarray(v)))
+    if model is None and optimizer is not None:
+        model = getattr(optimizer, "model", None)
+    if model is not None and hasattr(model, "invalidate_prepared"):
+        model.invalidate_prepared()
     return {k[6:]: v for k, v in data.items() if k.startswith("extra/")}
 
 

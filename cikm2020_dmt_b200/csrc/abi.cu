@@ -100,6 +100,11 @@ int dmt_abi_version(void) { return DMT_ABI_VERSION; }
 
 const char* dmt_last_error(void) { return dmt::g_err; }
 
+#ifndef DMT_BUILD_DIGEST
+#define DMT_BUILD_DIGEST "unknown"
+#endif
+const char* dmt_build_digest(void) { return DMT_BUILD_DIGEST; }
+
 int dmt_device_sm_count(void) {
   int dev = 0, n = 0;
   cudaError_t e = cudaGetDevice(&dev);

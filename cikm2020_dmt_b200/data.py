@@ -79,9 +79,18 @@ class SparseIds:
 
 
 def batch_to(batch: Dict, device, non_blocking=False) -> Dict:
+    """Move a batch; the longest row of every CSR feature whose offsets are still on the host is recorded under
+    `__max_len__` (feature name -> length) so the model never needs a device->host read to size its row slots."""
     out = {}
+    max_len = dict(batch.get("__max_len__") or {})
     for k, v in batch.items():
+        if k == "__max_len__":
+            continue
+        if isinstance(v, SparseIds) and v.offsets.device.type == "cpu" and k not in max_len:
+            off = v.offsets
+            max_len[k] = int((off[1:] - off[:-1]).max()) if off.numel() > 1 else 0
         out[k] = v.to(device, non_blocking=non_blocking) if hasattr(v, "to") else v
+    out["__max_len__"] = max_len
     return out
 
 

@@ -176,6 +176,7 @@ class mmoe_transformer_unbias(object):
             ready = inputs.get("__ready__")
             if ready is not None:     # produced by prefetch(): order the consumer after the copy
                 torch.cuda.current_stream(self.device).wait_event(ready)
+                self._pf_busy[inputs["__slot__"]] = False      # its consumer is enqueued: the slot may rotate
             return inputs
         cache, out = {}, {"__staged__": self}
 
@@ -202,14 +203,21 @@ class mmoe_transformer_unbias(object):
         over as raw `DevArray` descriptors instead of torch views -- the cheapest way to stage a batch.  The copy overlaps whatever the compute stream is doing
         (what a data-loader prefetch thread does for the reference's tf.data pipeline,
         tfrecord_mask.py:140-157).  Three rotating device buffers: a buffer is rewritten only after the
-        compute enqueued before this call -- which includes its previous consumer -- has finished."""
+        compute enqueued before this call -- which includes its previous consumer -- has finished; prefetching
+        a third batch while two are still unconsumed would overwrite one of them and raises instead."""
         if not isinstance(packed, PackedBatch):
             raise TypeError("prefetch takes a PackedBatch (one pinned host buffer)")
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
             self._pf_slot = 0
+            self._pf_busy = [False, False, False]
         cur = torch.cuda.current_stream(self.device)
-        self._pf_slot = (self._pf_slot + 1) % 3
+        nxt = (self._pf_slot + 1) % 3
+        if self._pf_busy[nxt]:
+            raise RuntimeError("prefetch: the batch staged 3 calls ago has not been consumed yet (pass it to "
+                               "inference / compute_gradients first); only 3 device buffers rotate")
+        self._pf_slot = nxt
+        self._pf_busy[nxt] = True
         buf = self._scratch("prefetch_%d" % self._pf_slot, packed.nbytes)
         buf.record_stream(self._copy_stream)
         done = torch.cuda.Event()
@@ -222,6 +230,7 @@ class mmoe_transformer_unbias(object):
         out["__max_len__"] = packed.max_len(self.plan)
         out["__staged__"] = self
         out["__ready__"] = ready
+        out["__slot__"] = self._pf_slot
         return out
 
     def _sparse(self, inputs, name, role="pool"):
@@ -259,13 +268,24 @@ class mmoe_transformer_unbias(object):
         self.params_version += 1
 
     def _seq_len_hint(self, inputs, seq):
-        """Upper bound on this sequence's lengths: exact when the offsets are host tensors (a data loader
-        knows them for free), otherwise the `_<N>` suffix of the reference's feature names
-        (clk_seq_*_7d_50, cart_seq_*_12m_10 -- dmt.conf:121) capped at transformer_maxlen_k."""
-        hint = inputs.get("__max_len__", {}).get(seq.index) if isinstance(inputs.get("__max_len__"), dict) else None
+        """Upper bound on this sequence's lengths (selects the row-slot size of the bf16 tile kernels, which clamp
+        every sequence to it).  Exact when known: `inputs['__max_len__']` ({sequence index | feature name: longest
+        sequence}, filled by `PackedBatch` / `batch_to` from the host copy), or computed here when the offsets
+        are still host tensors.  Otherwise transformer_maxlen_k -- the feature-name suffix (`..._12m_10`) is NOT
+        a bound: the reference sizes the sequence by the batch's own longest row
+        (mmoe_transformer_unbias.py:141-146)."""
+        name = seq.user_features[-1]
+        hints = inputs.get("__max_len__")
+        hint = None
+        if isinstance(hints, dict):
+            hint = hints.get(seq.index, hints.get(name))
         if hint is None:
-            tail = seq.user_features[-1].rsplit("_", 1)[-1]
-            hint = int(tail) if tail.isdigit() else seq.maxlen
+            sp = inputs.get(name)
+            off = getattr(sp, "offsets", None)
+            if torch.is_tensor(off) and _is_host(off) and off.numel() > 1:
+                hint = int((off[1:] - off[:-1]).max())
+        if hint is None:
+            hint = seq.maxlen
         return max(1, min(int(hint), seq.maxlen))
 
     def _prepared_for(self, seq_index, cfg):

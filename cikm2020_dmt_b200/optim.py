@@ -73,12 +73,44 @@ class Gradients(object):
         return out * grad_scale
 
 
+def piecewise_constant(step, boundaries, values):
+    """`tf.train.piecewise_constant(global_step, step_boundary, learning_rate)` (run_dnn.py:125-126):
+    values[0] while step <= boundaries[0], values[i] while boundaries[i-1] < step <= boundaries[i],
+    values[-1] beyond the last boundary.  TF requires len(values) == len(boundaries) + 1."""
+    boundaries, values = list(boundaries), list(values)
+    if len(values) != len(boundaries) + 1:
+        raise ValueError("piecewise_constant: %d learning rates need %d step boundaries, got %d"
+                         % (len(values), len(values) - 1, len(boundaries)))
+    for b, v in zip(boundaries, values):
+        if step <= b:
+            return float(v)
+    return float(values[-1])
+
+
 class TFAdam(object):
-    def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, step_boundary=None,
+                 global_step=0):
+        """learning_rate: a float, or the conf's comma list (`[model] learning_rate = 0.001,0.0001`) together
+        with `step_boundary` (`[model] step_boundary`, default: the model's conf): the rate of a step is
+        `piecewise_constant(global_step, step_boundary, learning_rate)` evaluated BEFORE the step increments
+        `global_step` (run_dnn.py:119-126; `global_step` starts at the resumed checkpoint's step while the Adam
+        beta powers `t` restart, run_dnn.py:296-306)."""
         self.model = model
         self.store = model.params
         self.lib = model.lib
         self.learning_rate = learning_rate
+        if step_boundary is None and isinstance(learning_rate, (list, tuple)) and len(learning_rate) > 1:
+            plan = getattr(model, "plan", None)
+            step_boundary = getattr(plan, "step_boundary", None)
+        if isinstance(learning_rate, (list, tuple)):
+            if len(learning_rate) == 1 and not step_boundary:
+                step_boundary = []
+            if step_boundary is None:
+                raise ValueError("a list of learning rates needs step_boundary (run_dnn.py:125-126)")
+            piecewise_constant(0, step_boundary, learning_rate)      # validates the lengths
+        self.step_boundary = list(step_boundary) if step_boundary is not None else None
+        self.global_step = int(global_step)
+        self._lr_now = None
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.t = 0
         dev = self.store.dense.device
@@ -88,13 +120,23 @@ class TFAdam(object):
         self.v_tab = {k: torch.zeros_like(t) for k, t in self.store.tables.items()}
         self.touched = {k: torch.zeros(t.shape[0], dtype=torch.uint8, device=dev) for k, t in self.store.tables.items()}
 
-    def _cfg(self, lr):
-        lr = self.learning_rate if lr is None else lr
+    def current_lr(self, step=None):
+        """Learning rate of the step that starts at `global_step` (default: the next one)."""
+        lr = self.learning_rate
         if isinstance(lr, (list, tuple)):
-            lr = lr[0]
+            return piecewise_constant(self.global_step if step is None else step, self.step_boundary, lr)
+        return float(lr)
+
+    def _cfg(self, lr):
+        if lr is None:
+            lr = self._lr_now if self._lr_now is not None else self.current_lr()
+        elif isinstance(lr, (list, tuple)):
+            raise TypeError("pass a scalar learning rate per step; schedules belong to the constructor")
         return abi.AdamCfg(float(lr), self.beta1, self.beta2, self.epsilon, int(self.t), 0)
 
     def begin_step(self):
+        self._lr_now = self.current_lr()       # evaluated at the pre-increment global_step, like the TF graph
+        self.global_step += 1
         self.t += 1
 
     def apply_gradients(self, grads, lr=None, grad_scale=1.0):

@@ -84,6 +84,8 @@ class ModelPlan:
     loss_weight: List[float] = field(default_factory=list)
     loss_unbias_method: str = "two_head_add"
     loss_ctr_rel_method: str = "ctr"
+    learning_rate: List[float] = field(default_factory=lambda: [1e-3])   # [model] learning_rate (comma list)
+    step_boundary: List[int] = field(default_factory=list)               # [model] step_boundary
 
     @property
     def d_k(self):
@@ -132,6 +134,8 @@ def build_plan(conf) -> ModelPlan:
         loss_weight=list(conf[K.PARAMETER][K.LOSS_WEIGHT]),
         loss_unbias_method=conf.loss_unbias_method,
         loss_ctr_rel_method=conf.loss_ctr_rel_method,
+        learning_rate=list(model.get(K.LEARNING_RATE) or [1e-3]),
+        step_boundary=list(model.get(K.STEP_BOUNDARY) or []),
     )
     if plan.d_model % plan.num_heads:
         raise PlanError("transformer_d_model must be divisible by transformer_num_heads")

@@ -402,7 +402,8 @@ def list_files(prefix: str) -> List[str]:
 def batches(wnd_conf, tables, file_prefix: str, batch_size: int, epochs: int = 1, shuffle_size: int = 0,
             seed: int = 131, world: int = 1, rank: int = 0, drop_remainder: bool = False) -> Iterator[Dict]:
     """get_multi_towers_batch (tfrecord_mask.py:120-158): repeat -> shuffle buffer -> batch; data-parallel rank
-    `rank` of `world` takes every world-th batch (each tower calls iterator.get_next() in turn, :152-157)."""
+    `rank` of `world` takes every world-th batch (each tower calls iterator.get_next() in turn, :152-157).
+    With world > 1 all ranks yield the same number of (full) batches."""
     batcher = ExampleBatcher(wnd_conf, tables)
     rng = np.random.Generator(np.random.PCG64(seed))
 
@@ -427,13 +428,23 @@ def batches(wnd_conf, tables, file_prefix: str, batch_size: int, epochs: int = 1
         rng.shuffle(buf)
         yield from buf
 
-    cur, n = [], 0
+    # world > 1: every step of synchronous data-parallel training runs collectives on all ranks, so all ranks must
+    # see the SAME number of steps: only complete groups of `world` FULL batches are handed out; the trailing
+    # partial group and the remainder batch are dropped (the reference pulls all towers' batches of a step from
+    # one iterator and abandons the whole step on OutOfRangeError, run_dnn.py:148-156,330-341).
+    cur, n, mine = [], 0, None
     for rec in shuffled():
         cur.append(rec)
         if len(cur) == batch_size:
-            if n % world == rank:
+            if world == 1:
                 yield batcher.batch(cur)
+            else:
+                if n % world == rank:
+                    mine = cur
+                if n % world == world - 1:          # the group is complete: every rank has its batch
+                    yield batcher.batch(mine)
+                    mine = None
             n += 1
             cur = []
-    if cur and not drop_remainder and n % world == rank:
+    if cur and not drop_remainder and world == 1:
         yield batcher.batch(cur)

@@ -30,10 +30,17 @@ from .shard import RowExchange, RowShard, remap_ids
 
 
 class Trainer(object):
-    def __init__(self, plan, device, learning_rate=1e-3, world=1, rank=0, seed=20201019, sharded_tables=("Sku",),
-                 group=None, randomize=None, force_dp_path=False, precision="f32", train_gemm=None):
-        """force_dp_path: run the data-parallel code path (compact tables, densified replicas, bucket) even
+    def __init__(self, plan, device, learning_rate=None, world=1, rank=0, seed=20201019, sharded_tables=("Sku",),
+                 group=None, randomize=None, force_dp_path=False, precision="f32", train_gemm=None,
+                 step_boundary=None, global_step=0):
+        """learning_rate / step_boundary: default to the conf's `[model] learning_rate` / `step_boundary` lists
+        (piecewise-constant schedule over `global_step`, run_dnn.py:119-126); a float = constant rate.
+        force_dp_path: run the data-parallel code path (compact tables, densified replicas, bucket) even
         with world == 1 -- the single-GPU test of that path."""
+        if learning_rate is None:
+            learning_rate = list(getattr(plan, "learning_rate", [1e-3]))
+            if step_boundary is None:
+                step_boundary = list(getattr(plan, "step_boundary", []))
         self.plan, self.device = plan, torch.device(device)
         self.world, self.rank, self.group = int(world), int(rank), group
         self.dp = self.world > 1 or force_dp_path
@@ -56,7 +63,7 @@ class Trainer(object):
                                              train_gemm=train_gemm)
         self.store = store
         self.model.dropout_base_seed = (seed * 0x9E3779B1 + 7919 * self.rank) & 0xFFFFFFFF   # ranks draw different masks
-        self.opt = TFAdam(self.model, learning_rate)
+        self.opt = TFAdam(self.model, learning_rate, step_boundary=step_boundary, global_step=global_step)
         self.learning_rate = learning_rate
         self.lib = self.model.lib
         self.replicated = [k for k in store.tables if k not in self.sharded]

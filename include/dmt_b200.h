@@ -192,6 +192,10 @@ typedef struct dmt_bias_weights {
 /* ---- library ------------------------------------------------------------------- */
 DMT_API int dmt_abi_version(void);
 DMT_API const char* dmt_last_error(void);
+/* sha256 (hex) of the sources this library was built from (the .cu / .cuh files of csrc, this header, the nvcc flags): the
+ * binding compares it with the digest of the sources it sits next to and refuses a stale library -- struct
+ * layouts are part of those sources */
+DMT_API const char* dmt_build_digest(void);
 /* number of SMs of the current device (grid sizing); < 0 on error */
 DMT_API int dmt_device_sm_count(void);
 

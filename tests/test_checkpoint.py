@@ -66,6 +66,50 @@ def test_sharded_tables_reassemble(tmp_path):
     assert torch.equal(part1.tables[name], full.tables[name][half:])
 
 
+def test_sharded_tables_resume_with_adam_slots(tmp_path):
+    """Data-parallel exact resume: the Adam slots of a row-sharded table are cut by the variable's row range
+    (2 ranks save with optimizer; each rank, and a single-GPU reader, gets its own rows of m / v back), and the
+    model's cached weight images are invalidated by `load`."""
+    from cikm2020_dmt_b200 import checkpoint as CK
+    from cikm2020_dmt_b200.params import ParamStore
+    conf, plan = make_plan("dmt_d64.conf")
+    name = plan.tables["Sku"].scope
+    full = ParamStore(plan, device="cpu", seed=3)
+    rows = full.tables[name].shape[0]
+    half = (rows + 1) // 2
+    d = str(tmp_path / "ck")
+    opts = []
+    for rank, (lo, hi) in enumerate([(0, half), (half, rows)]):
+        part = ParamStore(plan, device="cpu", seed=3, row_shards={name: (lo, hi)})
+        torch.manual_seed(100 + rank)
+        opt = _Opt(part)
+        opts.append(opt)
+        CK.save(d, 9, part, optimizer=opt, shards={name: (lo, hi)}, rank=rank)
+
+    class _Model(object):
+        invalidated = 0
+
+        def invalidate_prepared(self):
+            self.invalidated += 1
+
+    for rank, (lo, hi) in enumerate([(0, half), (half, rows)]):
+        part = ParamStore(plan, device="cpu", seed=8, row_shards={name: (lo, hi)})
+        opt = _Opt(part)
+        opt.model = _Model()
+        CK.load(d, 9, part, optimizer=opt, shards={name: (lo, hi)}, rank=rank)
+        assert opt.t == 7 and opt.model.invalidated == 1
+        assert torch.equal(part.tables[name], full.tables[name][lo:hi])
+        assert torch.equal(opt.m_tab[name], opts[rank].m_tab[name])
+        assert torch.equal(opt.v_tab[name], opts[rank].v_tab[name])
+    one = ParamStore(plan, device="cpu", seed=8)
+    opt = _Opt(one)
+    m = _Model()
+    CK.load(d, 9, one, optimizer=opt, model=m)
+    assert m.invalidated == 1
+    assert torch.equal(opt.m_tab[name], torch.cat([opts[0].m_tab[name], opts[1].m_tab[name]], 0))
+    assert torch.equal(opt.v_tab[name], torch.cat([opts[0].v_tab[name], opts[1].v_tab[name]], 0))
+
+
 def test_serving_feature_normalisation_formula():
     """export_model.py:88-96 / preprocess.py:17-43 restated in numpy fp64."""
     from cikm2020_dmt_b200 import checkpoint as CK

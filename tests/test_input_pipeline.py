@@ -121,8 +121,16 @@ def test_batches_shard_by_rank(tmp_path):
     assert [b["features"].shape[0] for b in all_b] == [3, 3, 3, 1]
     r0 = list(T.batches(conf, None, prefix, batch_size=3, world=2, rank=0))
     r1 = list(T.batches(conf, None, prefix, batch_size=3, world=2, rank=1))
-    assert len(r0) == 2 and len(r1) == 2
-    assert torch.equal(r0[1]["features"], all_b[2]["features"]) and torch.equal(r1[0]["features"], all_b[1]["features"])
+    # 10 records -> batches 3,3,3,1: only the complete group (b0, b1) is handed out -- every rank sees the same
+    # number of steps (a partial step would hang the collectives of the last step), the remainder is dropped
+    assert len(r0) == 1 and len(r1) == 1
+    assert torch.equal(r0[0]["features"], all_b[0]["features"]) and torch.equal(r1[0]["features"], all_b[1]["features"])
+    for world in (2, 3, 4):
+        for bs in (1, 2, 3):
+            per_rank = [list(T.batches(conf, None, prefix, batch_size=bs, world=world, rank=r)) for r in range(world)]
+            assert len({len(x) for x in per_rank}) == 1, (world, bs)
+            assert len(per_rank[0]) == (10 // bs) // world
+            assert all(b["features"].shape[0] == bs for x in per_rank for b in x)
     two_epochs = list(T.batches(conf, None, prefix, batch_size=5, epochs=2, shuffle_size=4, drop_remainder=True))
     assert len(two_epochs) == 4
 
