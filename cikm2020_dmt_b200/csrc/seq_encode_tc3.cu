@@ -1,6 +1,7 @@
-// dmt_seq_encode_fwd, DMT_PRECISION_BF16, v2: two tiles in flight per SM, tensor-memory A operands.
+// dmt_seq_encode_fwd, DMT_PRECISION_BF16 (v3 tile kernel + decoder tail kernel): two tiles in flight per SM,
+// tensor-memory A operands, two threads per token row.
 //
-// Same math as seq_encode_tc.cu (gather -> X Wqkv -> masked softmax attention -> LN -> FF -> LN -> decoder), but
+// Same math as seq_tc_host.cu (gather -> X Wqkv -> masked softmax attention -> LN -> FF -> LN -> decoder), but
 // organised so that the tensor pipe, the shared-memory pipe and the SIMT pipes of one SM always have two
 // independent tiles to work on:
 //
@@ -147,612 +148,6 @@ struct Tc2Layout {
   } while (0)
 
 // KW: key columns of the score window the softmax actually visits (>= the longest sequence; 64-row slots only)
-template <int SLOT, int KW>
-__global__ void __launch_bounds__(256, 1) seq_encode_tc2_kernel(const __grid_constant__ SeqTcArgs a) {
-  using L = Tc2Layout<SLOT>;
-  static_assert(KW % 8 == 0 && KW <= L::CW && (SLOT == 64 || KW == L::CW), "key window");
-  constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
-  constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[2], cbars[2];            // per group: phase MMAs | decoder-context MMA
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int slen_s[2][2][NS];                    // [group][tile parity][slot]
-  __shared__ ChunkDesc sd[KC];
-
-  const int tid = threadIdx.x, grp = tid >> 7, row = tid & 127, wg = row >> 5, lane = tid & 31;
-  uint8_t* gbase = smem + L::oGrp + grp * L::szGrp;
-  uint8_t* sXA = gbase + L::gXA;
-  uint8_t* sQ = gbase + L::gQ;
-  uint8_t* sK = gbase + L::gK;
-  uint8_t* sV = gbase + L::gV;
-  float* fv = reinterpret_cast<float*>(smem + L::oFV);
-  const uint4* spos = reinterpret_cast<const uint4*>(smem + L::oPos);
-  uint64_t* bar = &bars[grp];
-  uint64_t* cbar = &cbars[grp];
-  const int B = a.cfg.batch;
-  const uint32_t bar_id = 1 + grp;
-
-  // ---- one-time setup (all 256 threads): TMEM, barriers, resident weights, vectors, positions ----
-  if (tid < 32) tmem_alloc(&tmem_base_s, 512);
-  if (tid < KC) {
-    const int f = a.chunk_feat[tid];
-    sd[tid].ids = a.in.ids[f];
-    sd[tid].offs = a.in.offsets[f];
-    sd[tid].item_ids = a.in.item_ids[f];
-    sd[tid].tab = a.in.table[f] + a.chunk_off[tid];
-    sd[tid].rows = a.in.rows[f];
-    sd[tid].dim = a.in.dim[f];
-    sd[tid].dup = (tid > 0 && f == a.chunk_feat[tid - 1]) ? 1 : 0;
-  }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&cbars[0], 1);
-    mbar_init(&cbars[1], 1);
-    mbar_fence_init();
-  }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.prepared);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L::oWqkv);
-    constexpr int n16 = L::oGrp / 16;
-    for (int i = tid; i < n16; i += 256) dst[i] = __ldg(src + i);
-    for (int i = tid; i < D; i += 256) {
-      fv[L::vBQKV + i] = a.bq[i];
-      fv[L::vBQKV + D + i] = a.bk[i];
-      fv[L::vBQKV + 2 * D + i] = a.bv[i];
-      fv[L::vB2 + i] = a.b2[i];
-      fv[L::vLN + 0 * D + i] = a.ln1_g[i];
-      fv[L::vLN + 1 * D + i] = a.ln1_b[i];
-      fv[L::vLN + 2 * D + i] = a.ln2_g[i];
-      fv[L::vLN + 3 * D + i] = a.ln2_b[i];
-    }
-    for (int i = tid; i < DFF; i += 256) fv[L::vB1 + i] = a.b1[i];
-    uint4* pdst = reinterpret_cast<uint4*>(smem + L::oPos);
-    for (int i = tid; i < a.cfg.maxlen * KC; i += 256) {
-      const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
-      const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-      pdst[i] = f8_to_bf16(f);
-    }
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = tmem_base_s + grp * 256;
-  const uint32_t aXA = smem_u32(sXA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
-  const uint32_t dXA = desc_lo(aXA, ROWB), dQ = desc_lo(aQ, ROWB), dK = desc_lo(aK, ROWB);
-  const uint32_t dWqkv = desc_lo(smem_u32(smem + L::oWqkv), 3 * D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
-                 dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
-  const __nv_bfloat16* gDec = a.prepared + prep_off_dec(D, DFF);          // G image | Wv image | g fp32
-  const uint4* gG = reinterpret_cast<const uint4*>(gDec);                 // image(H*D, D): chunk (jc, n) at jc*H*D + n
-  const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
-  const float sqrt_d = sqrtf((float)D);
-  const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;      // softmax(s/sqrt(dk)) through exp2
-  const int32_t* const len_offs = a.in.offsets[a.cfg.n_feats - 1];   // the LAST pair's lengths are the sequence lengths
-  const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
-  const int zp = a.cfg.zero_pad ? 1 : 0;
-  const int slot = row / SLOT, tpos = row % SLOT;
-  uint32_t phase = 0;
-
-  // ---- software-pipelined gather.  One thread = one token row: it loads the KC 32-byte chunks of ITS token
-  //      (chunk k of every lane belongs to the same table, so the index math is uniform).  Offsets, ids and rows
-  //      of the group's next tile are requested just before three of the current tile's MMA waits. ----
-  int pf_o0[KC], pf_o1[KC], pf_id[KC];
-  int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
-  bool pf_valid = false;
-  f8 pf_e[KC];
-  int pf_tid = kInvalidId;
-  float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
-
-  auto stage_offsets = [&](int nt) {
-    // raw loads only: no arithmetic on the loaded values here, so nothing waits for them before stage_ids
-    pf_l0 = pf_l1 = 0;
-    pf_tid = kInvalidId;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) pf_o0[k] = pf_o1[k] = 0;
-    if (nt >= a.n_tiles) return;
-    const int b = nt * NS + slot;
-    if (b < B) {
-      pf_l0 = __ldg(len_offs + b);
-      pf_l1 = __ldg(len_offs + b + 1);
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        if (k > 0 && sd[k].dup) {
-          pf_o0[k] = pf_o0[k - 1];
-          pf_o1[k] = pf_o1[k - 1];
-        } else {
-          const int32_t* of = sd[k].offs;
-          pf_o0[k] = __ldg(of + b);
-          pf_o1[k] = __ldg(of + b + 1);
-        }
-      }
-    }
-    if (row < NS * KC) {
-      const int bt = nt * NS + row / KC;
-      if (bt < B) pf_tid = __ldg(sd[row % KC].item_ids + bt);
-    }
-  };
-  auto stage_ids = [&](int nt, int par) {
-    pf_len = min(pf_l1 - pf_l0, lmax);
-    pf_valid = tpos < pf_len;
-    if (tpos == 0) slen_s[grp][par][slot] = pf_len;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      pf_id[k] = kInvalidId;
-      if (pf_valid) {
-        if (k > 0 && sd[k].dup) pf_id[k] = pf_id[k - 1];
-        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(sd[k].ids + pf_o0[k] + tpos) : 0;
-      }
-    }
-  };
-  auto stage_rows = [&]() {
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
-      pf_e[k].hi = pf_e[k].lo;
-      const int64_t rw = (int64_t)pf_id[k] - zp;
-      if (pf_id[k] != kInvalidId && rw >= 0 && rw < sd[k].rows) pf_e[k] = ld_stream8(sd[k].tab + rw * sd[k].dim);
-    }
-    pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    pf_t1 = pf_t0;
-    if (row < NS * KC) {
-      const int c = row % KC;
-      const int64_t rw = (int64_t)pf_tid - zp;
-      if (pf_tid != kInvalidId && rw >= 0 && rw < sd[c].rows) {
-        const f8 t = ld_stream8(sd[c].tab + rw * sd[c].dim);
-        pf_t0 = t.lo;
-        pf_t1 = t.hi;
-      }
-    }
-  };
-  // decoder contexts of the tile whose first sample is rb0 (warp 0 of the group): merge the partial softmaxes of
-  // a 64-row slot, normalise, write bf16 into the tail kernel's A-operand image
-  uint32_t cphase = 0;
-  auto ctx_readout = [&](int rb0) {
-    if (wg != 0) return;
-    mbar_wait(cbar, cphase);
-    cphase ^= 1;
-    fence_after_sync();
-    uint32_t c0[32], c1[32];
-    tmem_ld32(tmem_addr(tbase, L::tCtx), c0);
-    tmem_ld32(tmem_addr(tbase, L::tCtx + 32), c1);
-    tmem_ld_wait();
-    const float* mxs = reinterpret_cast<const float*>(gbase + L::gMx);
-    float den = mxs[NR + (lane & (NR - 1))];
-    float wgt = 1.0f;
-    if constexpr (PPS == 2) {                          // a 64-row slot spans two warps: merge the two partials
-      const float ma = mxs[lane & (NR - 1)], mb = mxs[(lane ^ 2) & (NR - 1)];
-      const float m = fmaxf(ma, mb);
-      wgt = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m);
-      den *= wgt;
-      den += __shfl_xor_sync(0xffffffffu, den, 2);
-    }
-    const float inv = den > 0.f ? 1.0f / den : 0.f;   // empty sequence: context 0
-    const int p = lane >> 1, h = lane & 1;
-    const int b = rb0 + p / PPS;
-    const bool writer = lane < NR && (PPS == 1 || (p & 1) == 0) && b < B;
-    // destination: the K-major A-operand image of the tail kernel's 128-sample tile, [k/8][sample][8] bf16 with
-    // k = h*D + j  ->  16-byte chunk (h*8 + c, b % 128)
-    uint8_t* dst = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(b & 127) * 16;
-#pragma unroll
-    for (int c = 0; c < KC; ++c) {
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int kk = c * 8 + e;
-        v[e] = __uint_as_float(kk < 32 ? c0[kk] : c1[kk - 32]);
-        if constexpr (PPS == 2) {
-          v[e] *= wgt;
-          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
-        }
-        v[e] *= inv;
-      }
-      if (writer) *reinterpret_cast<uint4*>(dst + (size_t)(h * KC + c) * (128 * 16)) = f8_to_bf16(v);
-    }
-    fence_before_sync();
-  };
-  int n_done = 0;
-  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
-  stage_offsets(tile0);
-  stage_ids(tile0, 0);
-  stage_rows();
-
-  long long t_last = clock64();
-  for (int it = 0;; ++it) {
-    const int tile = tile0 + it * tstride;
-    if (tile >= a.n_tiles) break;
-    const int par = it & 1;
-    const int b0 = tile * NS;
-    const int next_tile = tile + tstride;
-
-    // ---- P0: prefetched rows -> concat + sqrt(d) scale + learned position -> X image (bf16) ----
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = 0.f;
-      if (pf_valid) {
-        float p[8];
-        bf16x8_to_f(spos[tpos * KC + k], p);
-        x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
-        x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
-        x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
-        x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
-      }
-      *reinterpret_cast<uint4*>(sXA + k * ROWB + row * 16) = f8_to_bf16(x);
-    }
-    const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;        // target item chunk of (sample row/KC, chunk row%KC)
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(0);
-
-    // ---- P1: [Q|K|V] = X Wqkv ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
-                    desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
-      commit(bar);
-    }
-    // in the shadow of the MMA: the previous tile's decoder contexts (warp 0), the next tile's offsets
-    if (it > 0) ctx_readout(b0 - tstride * NS);
-    stage_offsets(next_tile);
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(1);
-
-    // ---- P2: + bias, bf16, Q / K / V images ([chunk][row][8] each) ----
-    // (the load of block blk+1 is in flight while block blk is converted; pairs of blocks, outer loop rolled)
-    {
-      uint32_t rq[2][32];
-      tmem_ld32(tmem_addr(tbase, L::tQKV), rq[0]);
-#pragma unroll 1
-      for (int bp = 0; bp < 3 * D / 64; ++bp) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int n0 = (bp * 2 + half) * 32;
-          tmem_ld_wait();
-          if (half == 0 || bp + 1 < 3 * D / 64) tmem_ld32(tmem_addr(tbase, L::tQKV + n0 + 32), rq[half ^ 1]);
-          const uint32_t* r = rq[half];
-          const int m = n0 / D;                         // 0: Q, 1: K, 2: V image
-          uint8_t* dstm = sQ + m * 16384 + row * 16;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
-            const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
-            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
-            float y[8];
-            y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
-            y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
-            y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
-            y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
-            const int ch = ((n0 % D) >> 3) + g;
-            *reinterpret_cast<uint4*>(dstm + ch * ROWB) = f8_to_bf16(y);
-          }
-        }
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(2);
-
-    // ---- P3: S_h = Q_h K_h^T for both heads ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int ks = 0; ks < DK / 16; ++ks) {
-          const uint32_t ch = (h * DK) / 8 + ks * 2;
-          mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dQ + ch * (ROWB / 16), dHi),
-                      desc_join(dK + ch * (ROWB / 16), dHi), idesc, ks > 0);
-        }
-      commit(bar);
-    }
-    stage_ids(next_tile, par ^ 1);
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(3);
-
-    // ---- P4: masked softmax (one thread = one row, both heads); P_h packed to bf16 IN PLACE in tensor memory ----
-    const int len = slen_s[grp][par][slot];
-    float inv0 = 0.f, inv1 = 0.f;                     // 1 / softmax denominators: applied to O_h in P6
-    {
-      const int col0 = (row / CW) * CW;               // warp-uniform: rows of a warp share the CW-key window
-      // this row's keys are window columns [lo, lo + len); a 64-row slot is its own window
-      const int lo = (SLOT == CW) ? 0 : slot * SLOT - col0;
-#pragma unroll 1                                      // (code size: the unrolled kernel overflowed the instruction cache)
-      for (int h = 0; h < H; ++h) {
-        uint32_t r[KW];
-        tmem_ld32(tmem_addr(tbase, L::tS + h * 128 + col0), r);
-        if constexpr (KW >= 48) tmem_ld16(tmem_addr(tbase, L::tS + h * 128 + col0 + 32), r + 32);
-        if constexpr (KW == 56) tmem_ld8(tmem_addr(tbase, L::tS + h * 128 + col0 + 48), r + 48);
-        if constexpr (KW == 64) tmem_ld16(tmem_addr(tbase, L::tS + h * 128 + col0 + 48), r + 48);
-        tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < KW; ++j) {
-          const bool ok = (unsigned)(j - lo) < (unsigned)len;
-          const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
-          r[j] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
-        const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < KW; j += 4) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));       // exp2(-inf) == 0: masked keys
-          const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
-          const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
-          const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), sl2, -mxs));
-          r[j] = __float_as_uint(e0); r[j + 1] = __float_as_uint(e1);
-          r[j + 2] = __float_as_uint(e2); r[j + 3] = __float_as_uint(e3);
-          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-        }
-        const float sum = (s0 + s1) + (s2 + s3);
-        const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-        if (h == 0) inv0 = inv;
-        else inv1 = inv;
-        // P_h is stored UNNORMALISED (e in (0, 1], same relative precision in bf16); the row scale 1/sum is applied
-        // to the 32 outputs of P_h V_h instead of to the KW probabilities
-        uint32_t pk[CW / 2];
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j)
-          pk[j] = (j < KW / 2) ? pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])) : 0u;
-        uint32_t zz[CW / 2];
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) zz[j] = 0u;
-        // A-operand image of P_h: key j of this row in column j/2 (64 columns); keys outside the window are zeros
-        const uint32_t pbase = tmem_addr(tbase, L::tS + h * 128);
-        if constexpr (CW == 64) {
-          tmem_st32(pbase + col0 / 2, pk);
-          tmem_st32(pbase + (32 - col0 / 2), zz);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q * 16 == col0 / 2) tmem_st16(pbase + q * 16, pk);
-            else tmem_st16(pbase + q * 16, zz);
-          }
-        }
-      }
-    }
-    if (row < NS * KC) {                                // target item rows -> decoder input (fp32), Q region is dead
-      float* dv = reinterpret_cast<float*>(gbase + L::gDvec) + (row / KC) * D + (row % KC) * 8;
-      *reinterpret_cast<float4*>(dv) = make_float4(cur_t0.x * sqrt_d, cur_t0.y * sqrt_d, cur_t0.z * sqrt_d, cur_t0.w * sqrt_d);
-      *reinterpret_cast<float4*>(dv + 4) = make_float4(cur_t1.x * sqrt_d, cur_t1.y * sqrt_d, cur_t1.z * sqrt_d, cur_t1.w * sqrt_d);
-    }
-    tmem_st_wait();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(4);
-
-    // ---- P5: O_h = P_h V_h  (A = P_h in tensor memory, B = V read MN-major straight from its image) ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const uint32_t dV = desc_lo(aV + ((h * DK) / 8) * ROWB, 128);   // MN-major: LBO = next 8 keys
-#pragma unroll
-        for (int ks = 0; ks < 128 / 16; ++ks)
-          mma_bf16_ts(tbase + L::tO + h * 128, tbase + L::tS + h * 128 + ks * 8,
-                      desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
-      }
-      commit(bar);
-    }
-    // while the tensor pipe works: folded decoder queries qt[s][n] = dvec[s] . G[n] + g[n], n = (head, k)
-    {
-      float acc[NS];
-      const float gb = __ldg(gGb + row);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) acc[s] = gb;
-      const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
-#pragma unroll
-      for (int jc = 0; jc < KC; ++jc) {
-        float w[8];
-        bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const float4 d0 = *reinterpret_cast<const float4*>(dvs + s * D + jc * 8);
-          const float4 d1 = *reinterpret_cast<const float4*>(dvs + s * D + jc * 8 + 4);
-          acc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], acc[s]))));
-          acc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], acc[s]))));
-        }
-      }
-      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) qt[s * (H * D) + row] = acc[s];
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(5);
-
-    // ---- P6: A = LN(O + X) (self-attention LayerNorm), written over X ----
-    {
-      float y[D];
-      uint32_t r0[32], r1[32];
-      tmem_ld32(tmem_addr(tbase, L::tO), r0);
-      tmem_ld32(tmem_addr(tbase, L::tO + 128), r1);
-#pragma unroll
-      for (int c = 0; c < KC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), y + c * 8);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {                     // y = O_h / sum_h + X
-        y[e] = fmaf(__uint_as_float(r0[e]), inv0, y[e]);
-        y[DK + e] = fmaf(__uint_as_float(r1[e]), inv1, y[DK + e]);
-      }
-      ln64(y, fv + L::vLN + 0 * D, fv + L::vLN + 1 * D);
-#pragma unroll
-      for (int c = 0; c < KC; ++c) *reinterpret_cast<uint4*>(sXA + c * ROWB + row * 16) = f8_to_bf16(y + c * 8);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(6);
-
-    // ---- P7: hidden = A W1 ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
-                    desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
-      commit(bar);
-    }
-    stage_rows();
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(7);
-
-    // ---- P8: relu(+b1) -> H, packed to bf16 IN PLACE in tensor memory (A operand of the next MMA) ----
-    {
-      uint32_t rh[2][32];
-      tmem_ld32(tmem_addr(tbase, L::tFF1), rh[0]);
-#pragma unroll 1
-      for (int bp = 0; bp < DFF / 64; ++bp) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int blk = bp * 2 + half;
-          tmem_ld_wait();
-          if (half == 0 || bp + 1 < DFF / 64) tmem_ld32(tmem_addr(tbase, L::tFF1 + blk * 32 + 32), rh[half ^ 1]);
-          const uint32_t* r = rh[half];
-          uint32_t pk[16];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + blk * 32 + g * 4);
-            pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
-            pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
-          }
-          tmem_st16(tmem_addr(tbase, L::tFF1 + blk * 16), pk);   // columns [16 blk, +16): already consumed
-        }
-      }
-    }
-    tmem_st_wait();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(8);
-
-    // ---- P9: F = H W2 (A = H in tensor memory) ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, D);
-#pragma unroll
-      for (int ks = 0; ks < DFF / 16; ++ks)
-        mma_bf16_ts(tbase + L::tFF2, tbase + L::tFF1 + ks * 8, desc_join(dW2 + ks * (2 * D), dHi), idesc, ks > 0);
-      commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(9);
-
-    // ---- P10: memory row = LN(F + b2 + A) in registers; decoder scores / partial softmax of this row; the memory
-    //      image (bf16, MN-major B operand, + ones chunk) and the transposed probabilities for the context MMA ----
-    {
-      float y[D];
-#pragma unroll
-      for (int blk = 0; blk < D / 32; ++blk) {
-        uint32_t r[32];
-        tmem_ld32(tmem_addr(tbase, L::tFF2 + blk * 32), r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB2 + blk * 32 + e);
-          y[blk * 32 + e] = __uint_as_float(r[e]) + bb.x;
-          y[blk * 32 + e + 1] = __uint_as_float(r[e + 1]) + bb.y;
-          y[blk * 32 + e + 2] = __uint_as_float(r[e + 2]) + bb.z;
-          y[blk * 32 + e + 3] = __uint_as_float(r[e + 3]) + bb.w;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        float x[8];
-        bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + c * ROWB + row * 16), x);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
-      }
-      ln64(y, fv + L::vLN + 2 * D, fv + L::vLN + 3 * D);
-      // decoder scores of this token against its sample's folded queries (TransformerModel.py:157-166)
-      const float* qt = reinterpret_cast<const float*>(gbase + L::gQt) + slot * (H * D);
-      float u[H];
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < D; k += 4) {
-          const float4 q = *reinterpret_cast<const float4*>(qt + h * D + k);
-          a0 = fmaf(y[k], q.x, a0); a1 = fmaf(y[k + 1], q.y, a1);
-          a2 = fmaf(y[k + 2], q.z, a2); a3 = fmaf(y[k + 3], q.w, a3);
-        }
-        u[h] = (tpos < len) ? ((a0 + a1) + (a2 + a3)) * sl2 : -INFINITY;   // (the per-(sample, head) constant
-      }                                                                     //  bk_h . qd_h cancels in the softmax)
-      float e[H];
-      const int part = (SLOT >= 32) ? wg : (wg * (32 / W) + lane / W);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float m = u[h];
-#pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        e[h] = (tpos < len) ? ex2_approx(u[h] - m) : 0.f;                  // tpos < len implies m is finite
-        e[h] = __bfloat162float(__float2bfloat16(e[h]));                   // the MMA sums exactly these values
-        float dsum = e[h];
-#pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-        if ((lane % W) == 0) {
-          reinterpret_cast<float*>(gbase + L::gMx)[part * H + h] = m;      // -inf: empty part
-          reinterpret_cast<float*>(gbase + L::gMx)[NR + part * H + h] = dsum;
-        }
-      }
-      // memory image: chunk c of token `row` at sK + c*ROWB + row*16
-#pragma unroll
-      for (int c = 0; c < KC; ++c) *reinterpret_cast<uint4*>(sK + c * ROWB + row * 16) = f8_to_bf16(y + c * 8);
-      // transposed probabilities: image row (part, h), column = this token; zeros in every other part's row
-      const unsigned short eb[H] = {__bfloat16_as_ushort(__float2bfloat16(e[0])), __bfloat16_as_ushort(__float2bfloat16(e[1]))};
-      uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2;
-#pragma unroll
-      for (int rr = 0; rr < NR; ++rr) {
-        const unsigned short v = (rr == part * H) ? eb[0] : ((rr == part * H + 1) ? eb[1] : (unsigned short)0);
-        *reinterpret_cast<unsigned short*>(pd + rr * 16) = v;
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 128);
-    T2_TICK(10);
-
-    // ---- P11: ctx[(part,h)] = sum_t e_t M_t : one MMA, A = transposed probabilities (16-row image).  Nobody waits
-    //      for it here: warp 0 reads it out in the shadow of the next tile's X Wqkv (or after the loop). ----
-    if (row == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, D, false, true);
-      const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
-#pragma unroll
-      for (int ks = 0; ks < 128 / 16; ++ks)
-        mma_bf16_ss(tbase + L::tCtx, desc_join(dPd + ks * (2 * 256 / 16), dHi), desc_join(dM + ks * (256 / 16), dHiV),
-                    idesc, ks > 0);
-      commit(cbar);
-    }
-    n_done = it + 1;
-    T2_TICK(11);
-  }
-
-  if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
-  fence_before_sync();
-  __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem_base_s, 512);
-}
 
 // =====================================================================================================================
 // v3: the same per-tile program with every token row split across TWO threads (warps w and w + 4 of a group share
@@ -1604,16 +999,6 @@ int launch_tails(const TailBatch& tb, cudaStream_t st) {
   return DMT_OK;
 }
 
-// DMT_SEQ_TC=2 selects the v2 kernel (one thread per row, 8 warps) for A/B measurements; default: v3
-int tc_version() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("DMT_SEQ_TC");
-    v = (e && e[0] == '2') ? 2 : 3;
-  }
-  return v;
-}
-
 template <int SLOT, int KW>
 int launch_tc2(const SeqTcArgs& a, bool defer_tail, cudaStream_t st) {
   using L = Tc2Layout<SLOT>;
@@ -1621,18 +1006,12 @@ int launch_tc2(const SeqTcArgs& a, bool defer_tail, cudaStream_t st) {
   const int sms = sm_count_cached();
   const int pairs = (a.n_tiles + 1) / 2;
   const int grid = pairs < sms ? pairs : sms;
-  if (tc_version() == 3) {
+  {
     auto kern = seq_encode_tc3_kernel<SLOT, KW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc3_kernel)");
     kern<<<grid, kT3Threads, total, st>>>(a);
     DMT_CUDA_LAUNCH_CHECK("seq_encode_tc3_kernel");
-  } else {
-    auto kern = seq_encode_tc2_kernel<SLOT, KW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc2_kernel)");
-    kern<<<grid, 256, total, st>>>(a);
-    DMT_CUDA_LAUNCH_CHECK("seq_encode_tc2_kernel");
   }
   if (defer_tail) return DMT_OK;
   TailBatch tb;

@@ -1,6 +1,5 @@
-// Shared between the bf16 tensor-core sequence kernels (seq_encode_tc.cu: v1, one tile in flight per SM;
-// seq_encode_tc2.cu: v2, two tiles in flight + tensor-memory operands): kernel arguments and the layout of the
-// bf16 weight images written by dmt_seq_prepare_weights.
+// Shared between the host side (seq_tc_host.cu) and the kernels (seq_encode_tc3.cu) of the bf16 tensor-core sequence
+// path: kernel arguments and the layout of the bf16 weight images written by dmt_seq_prepare_weights.
 #pragma once
 #include "dmt_common.cuh"
 #include <cuda_bf16.h>

@@ -51,8 +51,7 @@ class mmoe_transformer_unbias(object):
         self.launches = 0            # kernels of this library enqueued so far
         self._stream_h = None        # set for the duration of inference() / compute_gradients()
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
-        # deferred decoder tails need the v2 sequence kernel (position table must fit its shared-memory plan)
-        self._v2_ok = self.plan.maxlen_k <= 55 and os.environ.get("DMT_SEQ_TC_V1") != "1"
+        self._v2_ok = True           # bf16 path: the decoder tails of all sequences run as one deferred launch
         self._bind_weights()
 
     # ------------------------------------------------------------------ per-stage device timing

@@ -17,8 +17,7 @@ model = mmoe_transformer_unbias(plan, params=store, precision="bf16")
 B = 4096
 dev = batch_to(synthetic_batch(plan, B), "cuda")
 out = torch.zeros(B, 3 * plan.d_model, device="cuda")
-import os as _os
-V1 = _os.environ.get("DMT_SEQ_TC_V1") == "1"
+V1 = False      # the first-generation kernel (one tile in flight per SM) was removed in round 2
 names2 = ["P0 convert+sync", "P1 QKV mma wait", "P2 QKV epilogue+sync", "P3 S mma wait", "P4 softmax->TMEM+sync",
           "P5 PV mma wait (+qt)", "P6 LN1+sync", "P7 FF1 mma wait", "P8 relu->TMEM+sync", "P9 FF2 mma wait",
           "P10 LN2+scores+images+sync", "P11 ctx mma + readout"]

@@ -108,6 +108,13 @@ def test_id_table_semantics():
     with pytest.raises(ValueError):
         IdTable("T", ["a", "b", "c"], 2)
     assert fingerprint64(b"") == 0x9AE16A3B2F90404F                                 # k2: the empty-string fingerprint
+    # known-answer vector from the TensorFlow documentation of tf.strings.to_hash_bucket_fast (the op behind the
+    # OOV buckets of index_table_from_tensor, index_tables.py:18-28):
+    #   tf.strings.to_hash_bucket_fast(["Hello", "TensorFlow", "2.x"], 3) -> [0, 2, 2]
+    # It pins the three sub-branches of FarmHash's 0..16-byte class (1-3, 4-7, 8-16 bytes) -- the class every id
+    # string of the reference's vocabularies falls in (longest entry of conf/idtables: 10 bytes).  The 17-32 /
+    # 33-64 / > 64 byte classes have no published vector available offline and stay unpinned (they only run).
+    assert [fingerprint64(s) % 3 for s in (b"Hello", b"TensorFlow", b"2.x")] == [0, 2, 2]
     for n in (1, 3, 4, 7, 8, 16, 17, 32, 33, 64, 65, 200):                          # every length class runs
         assert 0 <= fingerprint64(bytes(range(n % 251)) * 1 if n < 251 else b"x" * n) < 2 ** 64
 
