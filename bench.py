@@ -48,6 +48,13 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small-tables", action="store_true", help="debug: tiny vocabularies")
+    ap.add_argument("--train-batch", type=int, default=8192, help="per-GPU training batch (BASELINE configs 3/4: 8192)")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps of the `train` block")
+    ap.add_argument("--train-gemm", default="bf16", choices=["f32", "bf16", "bf16x3"],
+                    help="GEMM engine of the training step (BASELINE config 3 names bf16)")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs 3/4)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the `f32` forward block")
+    ap.add_argument("--f32-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -197,7 +204,10 @@ def run_reference(args):
         "impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, plan),
+        "config": dict(workload_config(args, plan), precision="f32", cpu_batch=args.cpu_batch,
+                       sample="each step = one forward pass over a %d-sample slice of the %d-sample batch"
+                              % (args.cpu_batch, args.batch),
+                       l2="n/a (CPU arm)"),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,6 +225,186 @@ def workload_config(args, plan):
             "conf": args.conf, "per_gpu_batch": args.batch, "precision": args.precision,
             "l2": "inputs larger than L2: random rows of a %.0f MB Sku table + %d rotating batches"
                   % (plan.tables["Sku"].rows * plan.tables["Sku"].dim * 4 / 1e6, args.n_batches)}
+
+
+NO_DROPOUT = {("model", "transformer_dropout_rate"): "0.0", ("model", "dropout_rate_bias"): "0.0,0.0"}
+SMALL_ROWS = {"Sku": 20000, "Brand": 2000, "Shopid": 2000, "Cid3": 1000, "Cid2": 100}
+
+
+def make_timer(world, device):
+    """timed(step_fn, steps) -> ms: CUDA events on the current stream between barriers, MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    return timed
+
+
+def slice_batch(batch, lo, hi):
+    """Samples [lo, hi) of a host batch (CSR features re-based)."""
+    from cikm2020_dmt_b200.data import SparseIds
+    sub = {}
+    for k, v in batch.items():
+        if isinstance(v, SparseIds):
+            a, b = int(v.offsets[lo]), int(v.offsets[hi])
+            sub[k] = SparseIds(v.values[a:b].clone(), (v.offsets[lo:hi + 1] - a).clone(),
+                               None if v.weights is None else v.weights[a:b].clone())
+        elif hasattr(v, "shape"):
+            sub[k] = v[lo:hi].clone()
+    return sub
+
+
+def run_f32_forward(args, plan, store, dev_batches, timed, world):
+    """The `f32` block: the same forward workload in the reference's own arithmetic (fp32 end to end, CUDA-core
+    kernels; logits within 2e-4 of the fp64 oracle -- tests/test_gpu_parity.py).  The headline `value` is the bf16
+    tensor-core path (logits atol 5e-2); this is the number to hold against the fp32 reference arm."""
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    model = mmoe_transformer_unbias(plan, params=store, precision="f32")
+    step = lambda i: model.inference(dev_batches[i % len(dev_batches)], is_train=False)
+    for i in range(3):
+        step(i)
+    l0 = model.launches
+    ms = timed(step, args.f32_steps)
+    B = args.batch
+    return {"value": world * B * args.f32_steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / args.f32_steps,
+            "steps": args.f32_steps, "warmup": 3, "dtype": "f32", "gpu_launches": int(model.launches - l0),
+            "kernels": "seq_encode_f32_kernel + fp32 SIMT MMoE (CUDA cores)",
+            "tolerance": "logits atol 2e-4 vs the fp64 oracle (tests/test_gpu_parity.py)",
+            "note": "same workload and batches as `value`, inputs resident in HBM"}
+
+
+def run_dp_parity(args, world, rank, device):
+    """N ranks on 1/N of a global batch each (row-sharded Sku, one allreduce bucket) vs ONE rank on the whole batch,
+    2 optimizer steps, dropout off, small vocabularies: max / mean |delta parameter| over every variable (the
+    attention key biases excluded: their exact gradient is 0 and Adam amplifies fp32 noise -- same rule as
+    tests/test_gpu_dist_train.py).  With N == 1 the data-parallel code path (compact tables, densified replicas,
+    bucket) runs with world 1 against the plain step."""
+    import torch
+    import torch.distributed as dist
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    from cikm2020_dmt_b200.plan import build_plan
+    from cikm2020_dmt_b200.train import Trainer
+    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", args.conf, overrides=NO_DROPOUT)
+    plan = build_plan(conf)
+    for t in list(plan.tables.values()) + list(plan.bias_tables.values()):
+        if t.name in SMALL_ROWS:
+            t.rows = SMALL_ROWS[t.name]
+    per = 32
+    G = per * world
+    engine = dict(precision="f32", train_gemm="f32")          # exact engines: the comparison is about the routing
+    dp = Trainer(plan, device, seed=3, randomize=4, world=world, rank=rank, force_dp_path=(world == 1),
+                 learning_rate=1e-3, **engine)
+    ref = Trainer(plan, device, seed=3, randomize=4, learning_rate=1e-3, **engine)
+    loss_err = 0.0
+    for s in range(2):
+        h = synthetic_batch(plan, G, seed=500 + s, table_rows=SMALL_ROWS)
+        h["mask"] = torch.nn.functional.one_hot((torch.arange(G) + s) % 5, 5).float()
+        dp.train_step(batch_to(slice_batch(h, rank * per, (rank + 1) * per), device))
+        lr_ = ref.train_step(batch_to(h, device)).item()
+        loss_err = max(loss_err, abs(dp.global_loss().item() - lr_) / max(abs(lr_), 1e-12))
+    torch.cuda.synchronize()
+    mx, mean_mx = 0.0, 0.0
+    for name, v in ref.store.named_parameters():
+        if name.endswith("attention/dense_1/bias"):
+            continue
+        got = dp.store.views[name]
+        if name in dp.sharded:
+            sh = dp.sharded[name]
+            v = v[sh.lo:sh.hi]
+        err = (v - got).abs()
+        if err.numel():
+            mx = max(mx, float(err.max()))
+            mean_mx = max(mean_mx, float(err.mean()))
+    stats = torch.tensor([mx, mean_mx, loss_err], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    mx, mean_mx, loss_err = [float(x) for x in stats]
+    del dp, ref
+    torch.cuda.empty_cache()
+    return {"max_abs_dparam": mx, "max_mean_abs_dparam": mean_mx, "loss_rel_err": loss_err, "steps": 2,
+            "ranks": world, "global_batch": G, "tol": {"max": 2e-4, "mean": 2e-6, "loss_rel": 5e-5},
+            "ok": bool(mx <= 2e-4 and mean_mx <= 2e-6 and loss_err <= 5e-5),
+            "what": "%d rank(s) on split batches (Sku row-sharded, allreduce bucket) vs 1 rank on the whole batch"
+                    % world}
+
+
+def run_train(args, world, rank, local_rank, device, timed):
+    """The `train` block: BASELINE config 3 (N = 1) / config 4 (N > 1: global batch N x 8192, dense + small-table
+    gradients in ONE NCCL allreduce, Sku row-sharded with all-to-all row / gradient exchange): forward with saved
+    activations + backward + TF-1 Adam (dense semantics), the conf's training-mode dropout, batches resident."""
+    import torch
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to, batch_tokens, SEED
+    from cikm2020_dmt_b200.plan import build_plan
+    from cikm2020_dmt_b200.train import Trainer
+    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", args.conf)
+    plan = build_plan(conf)
+    rows = None
+    if args.small_tables:
+        rows = SMALL_ROWS
+        for t in list(plan.tables.values()) + list(plan.bias_tables.values()):
+            if t.name in rows:
+                t.rows = rows[t.name]
+    B = args.train_batch
+    batches = [synthetic_batch(plan, B, seed=SEED + 50000 + 1000 * rank + i, id_mode=args.id_mode, table_rows=rows)
+               for i in range(3)]
+    trainer = Trainer(plan, device, world=world, rank=rank, seed=SEED,
+                      precision="f32" if args.train_gemm == "f32" else "bf16", train_gemm=args.train_gemm)
+    dev_batches = [batch_to(b, device) for b in batches]
+    step = lambda i: trainer.train_step(dev_batches[i % len(dev_batches)])
+    for i in range(3):
+        step(i)
+    trainer.enable_stage_timing(True)
+    l0 = trainer.model.launches
+    ms_staged = timed(step, args.train_steps)
+    launches = trainer.model.launches - l0
+    torch.cuda.synchronize()
+    stage = trainer.stage_times_ms()
+    trainer.enable_stage_timing(False)
+    ms = min(ms_staged, timed(step, args.train_steps))
+    a2a = trainer.last_a2a_bytes
+    out = {
+        "workload": "BASELINE config %d: DMT training step (fwd + bwd + TF-1 Adam, dense over every row), 615 dense + "
+                    "all id sequences, MMoE 2 tasks, per-GPU batch %d (global %d), d_model=%d, %d heads, Sku vocabulary "
+                    "%d%s, training-mode dropout (transformer %.2g, bias tower %s)"
+                    % (4 if world > 1 else 3, B, B * world, plan.d_model, plan.num_heads, plan.tables["Sku"].rows,
+                       " row-sharded over %d ranks" % world if world > 1 else "", plan.dropout_rate,
+                       list(plan.dropout_rate_bias)),
+        "value": world * B * args.train_steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / args.train_steps,
+        "steps": args.train_steps, "warmup": 3, "scaling": "weak",
+        "dtype": {"f32": "f32", "bf16": "bf16 GEMM operands on tcgen05 / fp32 accumulate + storage",
+                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate + storage"}[args.train_gemm],
+        "stage_ms": {k: round(t / args.train_steps, 4) for k, (t, _) in sorted(stage.items())},
+        "gpu_launches": int(launches),
+        "allreduce_bytes": trainer.allreduce_bytes if world > 1 else 0,
+        "a2a_bytes": int(a2a),
+        "collectives": ("per step and rank: 1 NCCL allreduce of the flat [dense | replicated small tables] gradient "
+                        "bucket; Sku: all_gather of split points + 3 all_to_all_single (row ids, rows, gradient rows)")
+                       if world > 1 else "none (1 GPU)",
+        "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
+        "loss": float(trainer.global_loss()),
+    }
+    del trainer, dev_batches
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -256,23 +446,7 @@ def main():
     out_done = [None, None]
     d2h_stream = torch.cuda.Stream(device)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            step_fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    timed = make_timer(world, device)
 
     def step_resident(i):
         infer(dev_batches[i % len(dev_batches)], is_train=False)
@@ -322,6 +496,23 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
+    # ---- every rank: the fp32 forward block and the training / data-parallel blocks (collectives inside)
+    def guarded(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as exc:      # a failing side block must not lose the headline line; it is reported
+            import traceback
+            return {"error": "%s: %s" % (type(exc).__name__, exc), "trace": traceback.format_exc()[-800:]}
+
+    f32_block = None if args.no_f32 else guarded(run_f32_forward, args, plan, store, dev_batches, timed, world)
+    train_block = None
+    if not args.no_train:
+        dev_batches = None
+        torch.cuda.empty_cache()
+        train_block = guarded(run_train, args, world, rank, local_rank, device, timed)
+        if isinstance(train_block, dict) and "error" not in train_block:
+            train_block["dp_parity"] = guarded(run_dp_parity, args, world, rank, device)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,7 +536,7 @@ def main():
         fl = mean_b(flops_seq)                                   # algorithmic FLOPs (valid tokens only)
         hbm = alg / (t_ms / 1e3) / 1e9
         tfl = fl / (t_ms / 1e3) / 1e12
-        name = ("seq_encode_tc2_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM"
+        name = ("seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM"
                 if args.precision == "bf16" else "seq_encode_f32_kernel (fp32 CUDA cores") + \
                ", fused gather->encoder->decoder, per sequence)"
         if args.precision == "bf16":
@@ -445,6 +636,7 @@ def main():
                             "step i computes; one H2D copy and one D2H read (side stream) per step inside the timed region; the host "
                             "waits for step i-1's scores after launching step i"},
         "embed_gather": embed_gather,
+        "f32": f32_block, "train": train_block,
         "gpu_launches": int(gpu_launches), "clocks": clocks,
         "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
     }

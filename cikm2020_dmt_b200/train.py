@@ -79,6 +79,12 @@ class Trainer(object):
                 self.table_grad[k] = self.bucket[off:off + n].view(store.tables[k].shape)
                 off += pad4(n)
         self.last_loss = None
+        self.last_a2a_bytes = 0           # all-to-all payload of the last step (this rank's sends)
+
+    @property
+    def allreduce_bytes(self):
+        """Payload of the one gradient allreduce per step (dense variables + replicated small tables)."""
+        return int(self.bucket.numel() * 4) if self.dp else 0
 
     # ------------------------------------------------------------------ stage timing (bench hook)
     def enable_stage_timing(self, on=True):
@@ -117,6 +123,10 @@ class Trainer(object):
             need = torch.cat([sp.values.to(torch.int64) + off for _, _, sp, off in lookups])
             with self._stage("sku_route"):
                 ex = RowExchange(shard, need, group=self.group)
+            # bytes this rank puts on the wire for the table this step: row ids out (int64) + rows back + gradient
+            # rows out again (fp32 [n, dim] each way); rows it owns itself never leave the GPU
+            remote = ex.n_valid - ex.send_counts[shard.rank]
+            self.last_a2a_bytes += remote * 8 + 2 * remote * self.store.tables[scope].shape[1] * 4
             full = self.store.tables[scope]
             dim = full.shape[1]
 
@@ -151,6 +161,7 @@ class Trainer(object):
             self.last_loss = loss
             return loss
         staged = dict(model.stage_inputs(inputs))
+        self.last_a2a_bytes = 0
         remap, state = self._exchange(staged)
         staged["__remap__"] = remap
         try:
