@@ -54,6 +54,8 @@ def parse_args():
                     help="GEMM engine of the training step (BASELINE config 3 names bf16)")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs 3/4)")
     ap.add_argument("--no-f32", action="store_true", help="skip the `f32` forward block")
+    ap.add_argument("--wide-batch", action="store_true",
+                    help="e2e: ship int32 ids + fp32 features (the round-1 packed format) instead of the compact one")
     ap.add_argument("--f32-steps", type=int, default=10)
     return ap.parse_args()
 
@@ -440,7 +442,13 @@ def main():
         model = inf.model
         infer = inf.inference
     dev_batches = [batch_to(b, device) for b in batches]
-    packed = [PackedBatch(b) for b in batches]
+    # the data loader's product: ONE pinned buffer per batch, allocated on the NUMA node of this rank's GPU.  For the
+    # bf16 path it is the compact format (uint16 ids of the small vocabularies, bf16 features, inference keys only)
+    from cikm2020_dmt_b200.numa import numa_local
+    compact = args.precision == "bf16" and not args.wide_batch
+    infer_keys = set(plan.all_id_features()) | {"features"}
+    with numa_local(local_rank) as numa_node:
+        packed = [PackedBatch(b, compact=compact, keys=infer_keys if compact else None) for b in batches]
     B = args.batch
     out_host = torch.empty(2, 3, B, dtype=torch.float32).pin_memory()   # double-buffered D2H landing zone
     out_done = [None, None]
@@ -632,6 +640,10 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(out_host[0].numel() * 4), "ms_per_step": ms_e2e / args.steps,
+                "format": ("compact pinned batch: uint16 ids for vocabularies < 65536, bf16 features, inference keys "
+                           "only; widened on the device by dmt_widen_u16 (1 launch, copy stream)") if compact else
+                          "int32 ids + fp32 features, one pinned buffer",
+                "pinned_numa_node": numa_node,
                 "pipeline": "double-buffered prefetch: step i+1's packed batch is copied on a side stream while "
                             "step i computes; one H2D copy and one D2H read (side stream) per step inside the timed region; the host "
                             "waits for step i-1's scores after launching step i"},

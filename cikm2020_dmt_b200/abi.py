@@ -84,6 +84,13 @@ class BiasWeights(C.Structure):
     _fields_ = [("layer", Dense * (MAX_LAYERS + 1))]
 
 
+MAX_WIDEN = 64
+
+
+class WidenDesc(C.Structure):
+    _fields_ = [("src", _fp), ("dst", _fp), ("n", C.c_int64)]
+
+
 class AdamCfg(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
                 ("step", C.c_int32), ("_pad", C.c_int32)]
@@ -146,6 +153,8 @@ PROTOTYPES = {
                                               _fp, _fp]),
     "dmt_adam_rows_untouched": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp]),
     "dmt_build_digest": (C.c_char_p, []),
+    "dmt_widen_u16": (C.c_int, [C.c_int32, C.POINTER(WidenDesc), _fp]),
+    "dmt_copy_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),
 }

@@ -215,8 +215,16 @@ class PackedBatch:
 
     ALIGN = 256
 
-    def __init__(self, batch: Dict, pin=True):
+    def __init__(self, batch: Dict, pin=True, compact=False, keys=None):
+        """compact: ship id arrays whose ids all fit 16 bits (category / time-bucket vocabularies) as uint16 and
+        fp32 `features` as bf16 -- for the bf16 tensor-core path, which rounds the features to bf16 before its
+        first GEMM anyway.  `to()` widens the ids back to int32 on the device (dmt_widen_u16, one launch per
+        batch) and hands `features` over as a bf16 tensor.  keys: only these entries are packed (an inference
+        batch needs neither `label` nor the propensity arrays)."""
         self.layout = []          # (key, kind, dtype, shape, byte offset); kind in {t, v, o, w}
+        self.narrow = {}          # byte offset of a uint16-stored id array -> (byte offset in the wide buffer, n)
+        self.wide_bytes = 0
+        self.compact = bool(compact)
         blobs, seen, off = [], {}, 0
 
         def add(key, kind, t):
@@ -224,14 +232,25 @@ class PackedBatch:
             t = t.contiguous()
             ident = (t.data_ptr(), t.dtype, tuple(t.shape))
             if ident in seen and t.numel() > 0:
-                self.layout.append((key, kind, t.dtype, tuple(t.shape), seen[ident]))
+                self.layout.append((key, kind, seen[ident][1], tuple(t.shape), seen[ident][0]))
                 return
-            seen[ident] = off
-            self.layout.append((key, kind, t.dtype, tuple(t.shape), off))
-            blobs.append((off, t))
-            off += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            stored, logical = t, t.dtype
+            if compact and kind == "v" and t.dtype == torch.int32 and t.numel() > 0 and \
+                    int(t.min()) >= 0 and int(t.max()) < 65536:
+                stored = torch.from_numpy(t.numpy().astype(np.uint16))
+                self.narrow[off] = (self.wide_bytes, t.numel())
+                self.wide_bytes += (t.numel() * 4 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            elif compact and kind == "t" and key == "features" and t.dtype == torch.float32:
+                stored = t.to(torch.bfloat16)
+                logical = torch.bfloat16
+            seen[ident] = (off, logical)
+            self.layout.append((key, kind, logical, tuple(t.shape), off))
+            blobs.append((off, stored))
+            off += (stored.numel() * stored.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
 
         for k, v in batch.items():
+            if keys is not None and k not in keys:
+                continue
             if isinstance(v, SparseIds):
                 add(k, "v", v.values)
                 add(k, "o", v.offsets)
@@ -245,6 +264,7 @@ class PackedBatch:
             n = t.numel() * t.element_size()
             if n:
                 self.host[o:o + n].copy_(t.view(-1).view(torch.uint8))
+        self._widen_cache = {}
 
     def max_len(self, plan) -> Dict:
         """{sequence index: longest sequence in this batch}, computed once from the host copy."""
@@ -260,7 +280,7 @@ class PackedBatch:
         """All entries are 4-byte types: view the buffer once as int32 and once as float32 and cut both with ONE
         split_with_sizes each (entry, padding, entry, padding, ...): two tensor ops instead of three per entry."""
         if not hasattr(self, "_fast"):
-            ok = all(dt in (torch.int32, torch.float32) for _, _, dt, _, _ in self.layout)
+            ok = all(dt in (torch.int32, torch.float32) for _, _, dt, _, _ in self.layout) and not self.narrow
             uniq = sorted({o for _, _, _, _, o in self.layout})
             sizes, index, pos = [], {}, 0
             if ok:
@@ -288,8 +308,10 @@ class PackedBatch:
             self._fast = (sizes, index) if ok else None
         return self._fast
 
-    def unpack(self, buf: torch.Tensor) -> Dict:
-        """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device)."""
+    def unpack(self, buf: torch.Tensor, wide: Optional[torch.Tensor] = None) -> Dict:
+        """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device).  uint16-stored id arrays
+        of a compact batch are views of `wide` (the buffer `to()` widened them into) or, without it (host side),
+        converted copies."""
         out, parts = {}, {}
         fast = self._fast_plan()
         if fast is not None and buf.numel() >= self.nbytes:
@@ -315,8 +337,15 @@ class PackedBatch:
                 n = 1
                 for d in shape:
                     n *= d
-                nb = n * torch.empty((), dtype=dtype).element_size()
-                t = buf[o:o + nb].view(dtype).view(shape)
+                if o in self.narrow and kind == "v":
+                    wo, _ = self.narrow[o]
+                    if wide is not None:
+                        t = wide[wo:wo + 4 * n].view(torch.int32).view(shape)
+                    else:
+                        t = buf[o:o + 2 * n].view(torch.uint16).to(torch.int32).view(shape)
+                else:
+                    nb = n * torch.empty((), dtype=dtype).element_size()
+                    t = buf[o:o + nb].view(dtype).view(shape)
                 if kind == "t":
                     out[key] = t
                 else:
@@ -325,7 +354,7 @@ class PackedBatch:
             out[key] = SparseIds(p["v"], p["o"], p.get("w"))
         return out
 
-    def unpack_ptrs(self, buf: torch.Tensor) -> Dict:
+    def unpack_ptrs(self, buf: torch.Tensor, wide: Optional[torch.Tensor] = None) -> Dict:
         """Like `unpack`, but the id / offset / weight arrays come back as `DevArray`s (address + length) and only
         the dense tensors ('features', 'mask', ...) as torch views."""
         if not hasattr(self, "_ptr_plan"):
@@ -337,22 +366,53 @@ class PackedBatch:
                 if kind == "t":
                     dense.append((key, dtype, shape, o, n * (4 if dtype in (torch.int32, torch.float32) else
                                                             torch.empty((), dtype=dtype).element_size())))
+                elif kind == "v" and o in self.narrow:
+                    sparse.setdefault(key, {})[kind] = (self.narrow[o][0], n, dtype, True)
                 else:
-                    sparse.setdefault(key, {})[kind] = (o, n, dtype)
+                    sparse.setdefault(key, {})[kind] = (o, n, dtype, False)
             self._ptr_plan = (dense, [(k, p["v"], p["o"], p.get("w")) for k, p in sparse.items()])
         dense, sparse = self._ptr_plan
         base, dev = buf.data_ptr(), buf.device
+        wbase = wide.data_ptr() if wide is not None else 0
         out = {}
         for key, dtype, shape, o, nb in dense:
             out[key] = buf[o:o + nb].view(dtype).view(shape)
         for key, v, off, w in sparse:
-            out[key] = SparseIds(DevArray(base + v[0], v[1], v[2], dev), DevArray(base + off[0], off[1], off[2], dev),
+            out[key] = SparseIds(DevArray((wbase if v[3] else base) + v[0], v[1], v[2], dev),
+                                 DevArray(base + off[0], off[1], off[2], dev),
                                  None if w is None else DevArray(base + w[0], w[1], w[2], dev))
-        out["__buffer__"] = buf          # keeps the storage alive as long as the descriptors
+        out["__buffer__"] = (buf, wide)  # keeps the storage alive as long as the descriptors
         return out
 
-    def to(self, device, out: Optional[torch.Tensor] = None, views: bool = True) -> Dict:
+    def to(self, device, out: Optional[torch.Tensor] = None, views: bool = True,
+           wide: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> Dict:
+        """One async copy of the pinned buffer into `out` (+, for a compact batch, ONE dmt_widen_u16 launch that
+        restores the int32 id arrays into `wide`); both are enqueued on the current stream (`stream` = its raw
+        handle, looked up when omitted)."""
         if out is None:
             out = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         out[:self.nbytes].copy_(self.host, non_blocking=True)
-        return self.unpack(out) if views else self.unpack_ptrs(out)
+        if self.narrow:
+            if wide is None:
+                wide = torch.empty(self.wide_bytes, dtype=torch.uint8, device=device)
+            self.widen(out, wide, stream)
+        return self.unpack(out, wide) if views else self.unpack_ptrs(out, wide)
+
+    def widen(self, buf: torch.Tensor, wide: torch.Tensor, stream: Optional[int] = None):
+        """uint16 id arrays of `buf` -> int32 arrays in `wide` (C-ABI kernel; there is no host fallback)."""
+        from . import abi
+        if wide.numel() < self.wide_bytes:
+            raise ValueError("wide buffer holds %d bytes, the batch needs %d" % (wide.numel(), self.wide_bytes))
+        key = (buf.data_ptr(), wide.data_ptr())
+        descs = self._widen_cache.get(key)
+        if descs is None:
+            items = sorted(self.narrow.items())
+            descs = (abi.WidenDesc * len(items))()
+            for i, (o, (wo, n)) in enumerate(items):
+                descs[i].src, descs[i].dst, descs[i].n = key[0] + o, key[1] + wo, n
+            if len(self._widen_cache) > 8:
+                self._widen_cache.clear()
+            self._widen_cache[key] = descs
+        if stream is None:
+            stream = torch.cuda.current_stream(buf.device).cuda_stream
+        abi.check(abi.load().dmt_widen_u16(len(descs), descs, stream))

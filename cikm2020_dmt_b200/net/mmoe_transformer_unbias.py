@@ -168,7 +168,9 @@ class mmoe_transformer_unbias(object):
         the offsets of one sequence, are copied once)."""
         if isinstance(inputs, PackedBatch):
             buf = self._scratch("packed_in", inputs.nbytes)
-            out = inputs.to(self.device, out=buf)
+            wide = self._scratch("packed_wide", inputs.wide_bytes) if inputs.narrow else None
+            out = inputs.to(self.device, out=buf, wide=wide)
+            self.launches += 1 if inputs.narrow else 0          # dmt_widen_u16
             out["__max_len__"] = inputs.max_len(self.plan)
             return out
         if inputs.get("__staged__") is self:
@@ -219,11 +221,16 @@ class mmoe_transformer_unbias(object):
         self._pf_busy[nxt] = True
         buf = self._scratch("prefetch_%d" % self._pf_slot, packed.nbytes)
         buf.record_stream(self._copy_stream)
+        wide = None
+        if packed.narrow:       # compact batch: the uint16 id arrays are widened on the copy stream as well
+            wide = self._scratch("prefetch_wide_%d" % self._pf_slot, packed.wide_bytes)
+            wide.record_stream(self._copy_stream)
+            self.launches += 1
         done = torch.cuda.Event()
         done.record(cur)
         self._copy_stream.wait_event(done)
         with torch.cuda.stream(self._copy_stream):
-            out = packed.to(self.device, out=buf, views=views)
+            out = packed.to(self.device, out=buf, views=views, wide=wide)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
         out["__max_len__"] = packed.max_len(self.plan)
@@ -265,6 +272,21 @@ class mmoe_transformer_unbias(object):
     def invalidate_prepared(self):
         """Call after the parameters changed (optimizer step, checkpoint load)."""
         self.params_version += 1
+
+    def _copy_dense(self, feats, batch, x, x_ld, keep, precision):
+        """base.py:95-96: the dense `features` block into the first columns of the MMoE input.  fp32 [B, F], or --
+        bf16 tensor-core path only -- the bf16 block of a compact PackedBatch (that path rounds the features to
+        bf16 before its first GEMM anyway)."""
+        plan, lib = self.plan, self.lib
+        if tuple(feats.shape) != (batch, plan.feature_dim) or feats.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("'features' must be fp32 (or bf16) [%d, %d]" % (batch, plan.feature_dim))
+        if feats.dtype == torch.bfloat16 and precision != abi.PRECISION_BF16:
+            raise ValueError("bf16 'features' (compact batch) are only accepted by the bf16 inference path")
+        feats = feats.contiguous()
+        fn = lib.dmt_copy_dense_features if feats.dtype == torch.float32 else lib.dmt_copy_dense_features_bf16
+        with self._Stage(self, "copy_dense", 1):
+            abi.check(fn(feats.data_ptr(), batch, plan.feature_dim, x.data_ptr(), x_ld, self._stream()))
+        keep.append(feats)
 
     def _seq_len_hint(self, inputs, seq):
         """Upper bound on this sequence's lengths (selects the row-slot size of the bf16 tile kernels, which clamp
@@ -542,13 +564,7 @@ class mmoe_transformer_unbias(object):
         x = self._buf("x", (batch, x_ld))
         keep = []
         if feats is not None:
-            if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
-                raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
-            feats = feats.contiguous()
-            with self._Stage(self, "copy_dense", 1):
-                abi.check(self.lib.dmt_copy_dense_features(feats.data_ptr(), batch, plan.feature_dim,
-                                                           x.data_ptr(), x_ld, stream))
-            keep.append(feats)
+            self._copy_dense(feats, batch, x, x_ld, keep, self.precision)
         keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
         deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
         for s in range(len(plan.sequences)):

@@ -246,6 +246,23 @@ DMT_API int dmt_pool_mean_fwd(int32_t batch, int32_t n_feats, const dmt_pool_fea
 DMT_API int dmt_copy_dense_features(const float* features, int32_t batch, int32_t dim,
                                     float* out, int64_t out_ld, void* stream);
 
+/* ---- A0: compact host->device batch format ------------------------------------------
+ * The reference feeds int64 ids and fp32 features (data_feed/tfrecord_mask.py:23-84,140-157).  The data loader of
+ * this library may ship id arrays of small vocabularies (< 65536: Cid2, Cid3, Time*) as uint16 and the dense
+ * `features` block as bf16; these two calls restore the int32 id arrays / fp32 feature columns the kernels read.
+ * `arrays` is a HOST array; src/dst are device pointers, 16-byte aligned. */
+#define DMT_MAX_WIDEN 64
+typedef struct dmt_widen_desc {
+  const uint16_t* src;
+  int32_t* dst;
+  int64_t n;
+} dmt_widen_desc;
+DMT_API int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* stream);
+/* bf16 [batch, dim] (dense) -> fp32 columns [0, dim) of out (row stride out_ld); same role as
+ * dmt_copy_dense_features (base.py:95-96) */
+DMT_API int dmt_copy_dense_features_bf16(const void* features_bf16, int32_t batch, int32_t dim,
+                                         float* out, int64_t out_ld, void* stream);
+
 /* ---- A10: MMoE experts + gates + task towers --------------------------------------
  * Replaces expert_gate + build_tower (mmoe_transformer_unbias.py:63-126,293-310).
  * logits is [n_tasks][batch] (task-major): logits[0] = click_logit, logits[1] = order_logit. */

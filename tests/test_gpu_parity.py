@@ -406,3 +406,41 @@ def test_prefetch_pointer_staging_matches_views():
         (b_r, b_b) = m.inference(m.prefetch(packed, views=False), is_train=False)
         torch.cuda.synchronize()
         assert torch.equal(a[0], b_r[0]) and torch.equal(a[1], b_r[1]) and torch.equal(a[2], b_b)
+
+
+def test_compact_packed_batch_widen_and_bf16_features():
+    """Compact host->device format (data.py / stage_batch.cu): uint16 id arrays are restored bit-exactly by
+    dmt_widen_u16, the bf16 feature block lands in the MMoE input as the RNE-rounded fp32 values, and the bf16
+    path's scores from a compact batch stay within the bf16 tolerance of the oracle (and within 2e-2 of the scores
+    from the wide batch: only the gate inputs see bf16-rounded instead of fp32 features)."""
+    from cikm2020_dmt_b200.data import PackedBatch, SparseIds
+    plan, model, host, dev, P, O = _setup("dmt_d64.conf", 333, seed=71)       # ragged: 333 % 8 != 0 tails
+    tc = _bf16_model(plan, model.params)
+    keys = set(plan.all_id_features()) | {"features"}
+    packed = PackedBatch(host, compact=True, keys=keys)
+    assert packed.narrow and packed.nbytes < PackedBatch(host).nbytes
+    staged = packed.to("cuda")
+    torch.cuda.synchronize()
+    for k in keys:
+        v = host[k]
+        if isinstance(v, SparseIds):
+            assert staged[k].values.dtype == torch.int32
+            assert torch.equal(staged[k].values.cpu(), v.values), k
+            assert torch.equal(staged[k].offsets.cpu(), v.offsets), k
+    assert staged["features"].dtype == torch.bfloat16
+    assert torch.equal(staged["features"].cpu(), host["features"].to(torch.bfloat16))
+    (wr, wb) = O.inference(plan, P, host, is_train=False)
+    for views in (True, False):
+        (yr, yb) = tc.inference(tc.prefetch(packed, views=views), is_train=False)
+        torch.cuda.synchronize()
+        _close(yr[0], wr[0], atol=5e-2, rtol=2e-2)
+        _close(yr[1], wr[1], atol=5e-2, rtol=2e-2)
+        _close(yb, wb, atol=1e-5)
+        x = tc._last["x"][:, :plan.feature_dim].cpu()
+        assert torch.equal(x, host["features"].to(torch.bfloat16).float())
+    (zr, zb) = tc.inference(PackedBatch(host), is_train=False)
+    torch.cuda.synchronize()
+    assert (zr[0] - yr[0]).abs().max().item() < 2e-2 and (zr[1] - yr[1]).abs().max().item() < 2e-2
+    # the fp32 path refuses bf16 features instead of silently widening them
+    with pytest.raises(ValueError):
+        model.inference(packed, is_train=False)

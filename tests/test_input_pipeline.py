@@ -171,3 +171,30 @@ def test_packed_batch_pointer_staging_matches_views():
         else:
             assert torch.equal(v, p) and v.data_ptr() == p.data_ptr()
     assert n_sparse >= 20
+
+
+def test_compact_packed_batch_host_roundtrip():
+    """PackedBatch(compact=True): small-vocabulary id arrays are stored as uint16, `features` as bf16, only the
+    requested keys are packed; the host-side unpack returns the original ids / offsets and the RNE-rounded features,
+    and `max_len` (the row-slot bound handed to the kernels) is unchanged."""
+    import torch
+    from conftest import make_plan
+    from cikm2020_dmt_b200.data import PackedBatch, SparseIds, synthetic_batch
+    conf, plan = make_plan("dmt_d64.conf", rows={"Sku": 200000, "Brand": 70000, "Shopid": 900, "Cid3": 300, "Cid2": 60})
+    host = synthetic_batch(plan, 37, seed=5, table_rows={"Sku": 200000, "Brand": 70000, "Shopid": 900, "Cid3": 300,
+                                                         "Cid2": 60})
+    keys = set(plan.all_id_features()) | {"features"}
+    wide = PackedBatch(host, pin=False)
+    packed = PackedBatch(host, pin=False, compact=True, keys=keys)
+    assert packed.nbytes < wide.nbytes and packed.wide_bytes > 0
+    out = packed.unpack(packed.host)
+    assert set(out) == keys                                    # label / mask were not packed
+    narrow_keys = {k for k, kind, dt, shape, o in packed.layout if kind == "v" and o in packed.narrow}
+    assert "clk_seq_c2_7d_50" in narrow_keys and "clk_seq_sku_7d_50" not in narrow_keys    # Sku ids need > 16 bits
+    for k in keys:
+        v = host[k]
+        if isinstance(v, SparseIds):
+            assert torch.equal(out[k].values, v.values) and torch.equal(out[k].offsets, v.offsets), k
+        else:
+            assert torch.equal(out[k], v.to(torch.bfloat16))
+    assert packed.max_len(plan) == wide.max_len(plan)
