@@ -157,6 +157,13 @@ PROTOTYPES = {
     "dmt_copy_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),
+    "dmt_selftest_tf32_rows": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
+                                         C.c_int64, _fp, _fp, C.c_int64, _fp, C.c_int64, C.c_float, C.c_int32,
+                                         C.c_int32, _fp]),
+    "dmt_selftest_tf32_wgrad_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "dmt_selftest_tf32_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
+                                          C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),
+    "dmt_selftest_tf32_colsum": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int32, _fp, C.c_int32, _fp, _fp]),
 }
 
 

@@ -22,6 +22,7 @@ namespace umma {
 
 constexpr uint32_t kLayoutNone = 0;
 constexpr uint32_t kLayoutSW128 = 2;
+constexpr uint32_t kLayoutSW128Base32B = 1;   // 128-byte swizzle of 32-byte atoms: MN-major 32-bit (tf32) operands
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -61,6 +62,26 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
                                                        bool b_mn_major = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32 instruction descriptor: fp32 operands in shared memory (the tensor core uses sign, exponent and the
+// top 10 mantissa bits), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major = false,
+                                                       bool b_mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 (K = 8 per instruction); issued by ONE thread.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
@@ -187,6 +208,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a descriptor / protocol bug must fail the launch (trap), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -425,6 +425,23 @@ DMT_API int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float
 DMT_API int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float* C, int32_t N,
                               int32_t K, void* stream);
 
+/* The TMA-fed tf32 tcgen05 GEMM engine of the training pipeline (DMT_PRECISION_TF32), exposed on raw device
+ * pointers so that its shared-memory descriptors are pinned by unit tests (tests/test_gpu_tf32.py):
+ *   rows  : C[M,N] (+)= mask(relu((A[M,K] Bt[N,K]^T + addend) * alpha + bias))     N % 16 == 0, N <= 256, K % 4 == 0
+ *   wgrad : C (+)= P[T,MA]^T Q[T,NB]  (transposed: C[n][m], else C[m][n]); workspace of .._wgrad_bytes
+ *   colsum: out[W] (+)= column sums of X[T,W]; scratch >= 296 * W floats
+ * All matrices fp32 row-major, 16-byte aligned, row strides multiples of 4 floats. */
+DMT_API int dmt_selftest_tf32_rows(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t M, int32_t N,
+                                   int32_t K, float* C, int64_t ldc, const float* bias, const float* addend,
+                                   int64_t ld_add, const float* mask, int64_t ld_mask, float alpha, int32_t relu,
+                                   int32_t accumulate, void* stream);
+DMT_API size_t dmt_selftest_tf32_wgrad_bytes(int64_t T, int32_t MA, int32_t NB);
+DMT_API int dmt_selftest_tf32_wgrad(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t T, int32_t MA,
+                                    int32_t NB, float* C, int64_t ldc, int32_t transposed, int32_t accumulate,
+                                    void* workspace, void* stream);
+DMT_API int dmt_selftest_tf32_colsum(const float* X, int64_t ldx, int64_t T, int32_t W, float* out,
+                                     int32_t accumulate, void* scratch, void* stream);
+
 /* Diagnostics: when `device_counters` (16 x uint64 on the device) is non-NULL, the bf16 sequence kernel
  * adds the SM cycles thread 0 of every CTA spends in each of its phases (gather-convert, QKV MMA, QKV
  * epilogue, ... decoder).  Pass NULL to switch it off.  Process-wide debug switch, not for production. */
