@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--small-tables", action="store_true", help="debug: tiny vocabularies")
     ap.add_argument("--train-batch", type=int, default=8192, help="per-GPU training batch (BASELINE configs 3/4: 8192)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps of the `train` block")
-    ap.add_argument("--train-gemm", default="bf16", choices=["f32", "bf16", "bf16x3"],
+    ap.add_argument("--train-gemm", default="bf16", choices=["f32", "bf16", "bf16x3", "tf32"],
                     help="GEMM engine of the training step (BASELINE config 3 names bf16)")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs 3/4)")
     ap.add_argument("--no-f32", action="store_true", help="skip the `f32` forward block")
@@ -393,7 +393,9 @@ def run_train(args, world, rank, local_rank, device, timed):
         "value": world * B * args.train_steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / args.train_steps,
         "steps": args.train_steps, "warmup": 3, "scaling": "weak",
         "dtype": {"f32": "f32", "bf16": "bf16 GEMM operands on tcgen05 / fp32 accumulate + storage",
-                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate + storage"}[args.train_gemm],
+                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate + storage",
+                  "tf32": "tf32 GEMM operands (TMA-fed tcgen05 kind::tf32 straight from fp32 activations; MMoE split-bf16) / "
+                          "fp32 accumulate + storage"}[args.train_gemm],
         "stage_ms": {k: round(t / args.train_steps, 4) for k, (t, _) in sorted(stage.items())},
         "gpu_launches": int(launches),
         "allreduce_bytes": trainer.allreduce_bytes if world > 1 else 0,

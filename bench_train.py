@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--small-tables", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="debug: gradients only")
     ap.add_argument("--no-dropout", action="store_true", help="set the conf's dropout rates to 0")
-    ap.add_argument("--train-gemm", default="bf16x3", choices=["f32", "bf16", "bf16x3"],
+    ap.add_argument("--train-gemm", default="bf16x3", choices=["f32", "bf16", "bf16x3", "tf32"],
                     help="engine of the training-path GEMMs: fp32 SIMT | tcgen05 bf16 | tcgen05 split-bf16 (fp32-grade)")
     return ap.parse_args()
 
@@ -133,7 +133,8 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak",
         "dtype": {"f32": "f32", "bf16": "bf16 GEMM operands / fp32 accumulate+storage",
-                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate+storage"}[args.train_gemm],
+                  "bf16x3": "split-bf16 (hi+lo) GEMM operands on tcgen05 / fp32 accumulate+storage",
+                  "tf32": "tf32 GEMM operands (TMA-fed tcgen05 kind::tf32) / fp32 accumulate+storage"}[args.train_gemm],
         "data": "synthetic",
         "config": {"workload": "BASELINE config %d: DMT training step (fwd + bwd + TF-1 Adam, dense over every row), "
                                "615 dense + all id sequences, MMoE 2 tasks, per-GPU batch %d, d_model=%d, %d heads, "

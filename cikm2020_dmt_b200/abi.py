@@ -11,7 +11,7 @@ from . import build as _build
 
 MAX_SEQ_FEATS, MAX_BLOCKS, MAX_POOL_FEATS = 8, 4, 64
 MAX_EXPERTS, MAX_TASKS, MAX_LAYERS, MAX_SEQ_LEN = 8, 4, 4, 64
-PRECISION_F32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
+PRECISION_F32, PRECISION_BF16, PRECISION_BF16X3, PRECISION_TF32 = 0, 1, 2, 3
 ABI_VERSION = 6
 
 _fp = C.c_void_p   # device pointers travel as integers
@@ -160,6 +160,8 @@ PROTOTYPES = {
     "dmt_selftest_tf32_rows": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
                                          C.c_int64, _fp, _fp, C.c_int64, _fp, C.c_int64, C.c_float, C.c_int32,
                                          C.c_int32, _fp]),
+    "dmt_selftest_tf32_gemm": (C.c_int, [_fp, C.c_int64, C.c_int32, _fp, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                         C.c_int32, _fp, C.c_int64, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),
     "dmt_selftest_tf32_wgrad_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "dmt_selftest_tf32_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
                                           C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),

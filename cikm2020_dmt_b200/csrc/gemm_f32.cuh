@@ -59,10 +59,13 @@ struct GemmGroup {
                 // operands (hi*hi + hi*lo + lo*hi) on tcgen05 -- fp32-grade results
 };
 
-// dmt_precision -> GemmGroup::use_tc
+// dmt_precision -> GemmGroup::use_tc (DMT_PRECISION_TF32: the grouped problems that have no tf32 route -- the MMoE
+// GEMMs, the per-sample rows of the decoder -- run on the split-bf16 engine)
 inline int gemm_engine(int precision) {
-  return precision == DMT_PRECISION_BF16 ? 1 : (precision == DMT_PRECISION_BF16X3 ? 3 : 0);
+  return precision == DMT_PRECISION_BF16 ? 1
+                                         : ((precision == DMT_PRECISION_BF16X3 || precision == DMT_PRECISION_TF32) ? 3 : 0);
 }
+inline bool gemm_tf32(int precision) { return precision == DMT_PRECISION_TF32; }
 
 inline void gemm_prob_init(GemmProb& p) {
   p = GemmProb{};

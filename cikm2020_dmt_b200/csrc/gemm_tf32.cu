@@ -304,6 +304,146 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tf32_wgrad_kernel(const __gr
   if (warp == 1) tmem_dealloc(tbase, ncols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// General tiled GEMM: one 128 x BN tile per CTA, K streamed in chunks of 32 through a TMA ring.
+constexpr int kGemmThreadsG = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int GKC = 32;                  // K per stage
+
+struct GemmArgsG {
+  CUtensorMap tmA[4], tmB[4];
+  Tf32Gemm p;
+  int BN, stages, nkc;
+};
+
+__global__ void __launch_bounds__(kGemmThreadsG, 1) tf32_gemm_kernel(const __grid_constant__ GemmArgsG g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Tf32Gemm& p = g.p;
+  const int BN = g.BN, S = g.stages, nkc = g.nkc;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * RBM;
+  const int z0 = p.reduce_z ? 0 : blockIdx.z, nzl = p.reduce_z ? p.nz : 1;   // problems this CTA walks
+  const int total = nzl * nkc;
+  const uint32_t a_bytes = RBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = a_bytes + b_bytes;
+  const uint32_t s0 = smem_u32(smem);
+  uint32_t ncols = 32;
+  while ((int)ncols < BN) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int z = z0 + it / nkc, kc = it % nkc, s = it % S;
+        mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1);
+        const uint32_t sa = s0 + s * stage_bytes, sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        if (p.a_mn) {                       // [K, M] storage: four {32 m, 32 k} boxes
+          for (int i = 0; i < 4; ++i) tma_load_2d(sa + i * 4096, &g.tmA[z], m0 + i * 32, kc * GKC, &full_bar[s]);
+        } else {                            // [M, K] storage: one {32 k, 128 m} box
+          tma_load_2d(sa, &g.tmA[z], kc * GKC, m0, &full_bar[s]);
+        }
+        if (p.b_mn) {
+          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 4096, &g.tmB[z], n0 + i * 32, kc * GKC, &full_bar[s]);
+        } else {
+          tma_load_2d(sb, &g.tmB[z], kc * GKC, n0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(RBM, BN, p.a_mn != 0, p.b_mn != 0);
+      for (int it = 0; it < total; ++it) {
+        const int kc = it % nkc, s = it % S;
+        mbar_wait(&full_bar[s], (it / S) & 1);
+        fence_after_sync();
+        const uint32_t sa = s0 + s * stage_bytes, sb = sa + a_bytes;
+        const int rem = p.K - kc * GKC;
+        const int ksteps = rem >= GKC ? GKC / 8 : (rem + 7) / 8;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 1024, 4096, 512, kLayoutSW128Base32B)
+                                     : make_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
+          const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 1024, 4096, 512, kLayoutSW128Base32B)
+                                     : make_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
+          mma_tf32_ss(tbase, da, db, idesc, (it | k) != 0);
+        }
+        commit(&empty_bar[s]);
+      }
+      commit(&accum_bar);
+    }
+  } else {
+    mbar_wait(&accum_bar, 0);
+    fence_after_sync();
+    const int zc = p.reduce_z ? 0 : blockIdx.z;
+    const int64_t m = (int64_t)m0 + (warp & 3) * 32 + lane;
+    const bool ok = m < p.M;
+    float* crow = p.C[zc] + m * p.ldc;
+    const float* mrow = p.mask[zc] ? p.mask[zc] + m * p.ld_mask : nullptr;
+    const float* bias = p.bias[zc];
+    const bool vec = ((((uintptr_t)p.C[zc]) & 15) == 0) && (p.ldc % 4 == 0) &&
+                     (!p.mask[zc] || (((((uintptr_t)p.mask[zc]) & 15) == 0) && p.ld_mask % 4 == 0));
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;                               // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, c0), r);
+      tmem_ld_wait();
+      if (!ok) continue;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const int n = n0 + c0 + v * 4;
+        if (n >= p.N) break;
+        float y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = __uint_as_float(r[v * 4 + e]) + ((bias && n + e < p.N) ? __ldg(bias + n + e) : 0.f);
+          if (p.relu) t = fmaxf(t, 0.f);
+          y[e] = t;
+        }
+        if (vec && n + 4 <= p.N) {
+          if (mrow) {
+            const float4 mk = ld_stream4(mrow + n);
+            if (!(mk.x > 0.f)) y[0] = 0.f;
+            if (!(mk.y > 0.f)) y[1] = 0.f;
+            if (!(mk.z > 0.f)) y[2] = 0.f;
+            if (!(mk.w > 0.f)) y[3] = 0.f;
+          }
+          float4 o = make_float4(y[0], y[1], y[2], y[3]);
+          if (p.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(crow + n);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(crow + n) = o;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < p.N) {
+              float t = y[e];
+              if (mrow && !(__ldg(mrow + n + e) > 0.f)) t = 0.f;
+              crow[n + e] = (p.accumulate ? crow[n + e] : 0.f) + t;
+            }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, ncols);
+}
+
 struct WgradReduceArgs {
   const float* partial;
   Tf32WgradSeg seg[4];
@@ -360,13 +500,50 @@ __global__ void __launch_bounds__(256) tf32_colsum_kernel(const float* __restric
   }
 }
 
+// one warp per column: lanes stride the per-CTA partials, then a fixed-order shuffle tree (deterministic)
 __global__ void __launch_bounds__(256) tf32_colsum_reduce_kernel(const float* __restrict__ partial, int n_part, int W,
                                                                  float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= W) return;
   float s = 0.f;
-  for (int k = 0; k < n_part; ++k) s += partial[(int64_t)k * W + c];
-  out[c] = (accumulate ? out[c] : 0.f) + s;
+  for (int k = lane; k < n_part; k += 32) s += partial[(int64_t)k * W + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = (accumulate ? out[c] : 0.f) + s;
+}
+
+struct PackArgs {
+  Tf32PackMat m[4];
+  Tf32PackVec v[4];
+  int n_mats, n_vecs;
+  float* dst;
+  int64_t ldd;
+  float* dstv;
+};
+
+// blockIdx.y = source; consecutive threads walk the SOURCE's contiguous dimension (coalesced reads; the destination
+// is a few hundred KB at most and L2-resident)
+__global__ void __launch_bounds__(256) tf32_pack_kernel(const __grid_constant__ PackArgs a) {
+  const int which = blockIdx.y;
+  if (which < a.n_mats) {
+    const Tf32PackMat& s = a.m[which];
+    const int total = s.rows * s.cols;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+      int r, c;
+      if (s.transpose) {            // source is [cols, rows]: i = c * rows + r
+        c = i / s.rows;
+        r = i - c * s.rows;
+        a.dst[(int64_t)(s.dst_row + r) * a.ldd + s.dst_col + c] = __ldg(s.W + (int64_t)c * s.ldw + r);
+      } else {
+        r = i / s.cols;
+        c = i - r * s.cols;
+        a.dst[(int64_t)(s.dst_row + r) * a.ldd + s.dst_col + c] = __ldg(s.W + (int64_t)r * s.ldw + c);
+      }
+    }
+  } else if (which - a.n_mats < a.n_vecs) {
+    const Tf32PackVec& s = a.v[which - a.n_mats];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < s.n; i += gridDim.x * 256)
+      a.dstv[s.dst + i] = s.v ? __ldg(s.v + i) : 0.f;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -409,8 +586,88 @@ int make_map_f32(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols,
 
 }  // namespace
 
+int tf32_pack(const Tf32PackMat* mats, int n_mats, float* dst, int64_t ldd, const Tf32PackVec* vecs, int n_vecs,
+              float* dstv, cudaStream_t st) {
+  DMT_REQUIRE(n_mats >= 0 && n_mats <= 4 && n_vecs >= 0 && n_vecs <= 4 && (n_mats == 0 || dst) && (n_vecs == 0 || dstv),
+              DMT_ERR_INVALID_ARGUMENT, "tf32_pack: %d matrices, %d vectors", n_mats, n_vecs);
+  if (n_mats + n_vecs == 0) return DMT_OK;
+  PackArgs a{};
+  int biggest = 1;
+  for (int i = 0; i < n_mats; ++i) {
+    a.m[i] = mats[i];
+    if (mats[i].rows * mats[i].cols > biggest) biggest = mats[i].rows * mats[i].cols;
+  }
+  for (int i = 0; i < n_vecs; ++i) a.v[i] = vecs[i];
+  a.n_mats = n_mats;
+  a.n_vecs = n_vecs;
+  a.dst = dst;
+  a.ldd = ldd;
+  a.dstv = dstv;
+  int bx = (biggest + 255) / 256;
+  if (bx > 64) bx = 64;
+  tf32_pack_kernel<<<dim3(bx, n_mats + n_vecs), 256, 0, st>>>(a);
+  DMT_CUDA_LAUNCH_CHECK("tf32_pack_kernel");
+  return DMT_OK;
+}
+
+int tf32_gemm(const Tf32Gemm& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.nz <= 0) return DMT_OK;
+  DMT_REQUIRE(p.nz <= 4 && p.K > 0 && p.lda % 4 == 0 && p.ldb % 4 == 0, DMT_ERR_INVALID_ARGUMENT,
+              "tf32_gemm: nz=%d K=%d lda=%lld ldb=%lld", p.nz, p.K, (long long)p.lda, (long long)p.ldb);
+  DMT_REQUIRE(p.M < ((int64_t)1 << 31) - RBM, DMT_ERR_UNSUPPORTED_SHAPE, "tf32_gemm: M=%lld", (long long)p.M);
+  GemmArgsG g;
+  g.p = p;
+  int BN = ((p.N + 31) / 32) * 32;           // a tile is a whole number of 32-column boxes
+  if (BN > 256) BN = 256;
+  if (BN == 96 || BN == 160 || BN == 224) BN += 32;   // keep N of the MMA a multiple of 64 / power-of-two friendly
+  g.BN = BN;
+  g.nkc = (p.K + GKC - 1) / GKC;
+  const int stage_bytes = RBM * 128 + BN * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  g.stages = stages;
+  for (int z = 0; z < p.nz; ++z) {
+    DMT_REQUIRE(p.A[z] && p.B[z] && (p.reduce_z ? (z > 0 || p.C[0]) : (p.C[z] != nullptr)), DMT_ERR_INVALID_ARGUMENT,
+                "tf32_gemm: problem %d is incomplete", z);
+    int rc = p.a_mn ? make_map_f32(&g.tmA[z], p.A[z], p.K, p.M, p.lda, GKC, true)
+                    : make_map_f32(&g.tmA[z], p.A[z], p.M, p.K, p.lda, RBM, false);
+    if (rc != DMT_OK) return rc;
+    rc = p.b_mn ? make_map_f32(&g.tmB[z], p.B[z], p.K, p.N, p.ldb, GKC, true)
+                : make_map_f32(&g.tmB[z], p.B[z], p.N, p.K, p.ldb, BN, false);
+    if (rc != DMT_OK) return rc;
+  }
+  for (int z = p.nz; z < 4; ++z) {
+    g.tmA[z] = g.tmA[0];
+    g.tmB[z] = g.tmB[0];
+  }
+  const int smem = stages * stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tf32_gemm_kernel)");
+  dim3 grid((p.N + BN - 1) / BN, (unsigned)((p.M + RBM - 1) / RBM), p.reduce_z ? 1 : p.nz);
+  tf32_gemm_kernel<<<grid, kGemmThreadsG, smem, st>>>(g);
+  DMT_CUDA_LAUNCH_CHECK("tf32_gemm_kernel");
+  return DMT_OK;
+}
+
 int tf32_rows(const Tf32Rows& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return DMT_OK;
+  if (p.N > 256) {            // wider outputs run as column blocks of <= 256 (each re-reads A)
+    DMT_REQUIRE(p.N % 16 == 0, DMT_ERR_UNSUPPORTED_SHAPE, "tf32_rows: N=%d must be a multiple of 16", p.N);
+    const int blocks = (p.N + 255) / 256;
+    const int per = ((p.N / 16 + blocks - 1) / blocks) * 16;
+    for (int n0 = 0; n0 < p.N; n0 += per) {
+      Tf32Rows q = p;
+      q.N = p.N - n0 < per ? p.N - n0 : per;
+      q.Bt = p.Bt + (int64_t)n0 * p.ldb;
+      q.C = p.C + n0;
+      if (p.bias) q.bias = p.bias + n0;
+      if (p.addend) q.addend = p.addend + n0;
+      if (p.mask) q.mask = p.mask + n0;
+      const int rc = tf32_rows(q, st);
+      if (rc != DMT_OK) return rc;
+    }
+    return DMT_OK;
+  }
   DMT_REQUIRE(p.N % 16 == 0 && p.N <= 256 && p.K > 0 && p.K % 4 == 0, DMT_ERR_UNSUPPORTED_SHAPE,
               "tf32_rows: N=%d (multiple of 16, <= 256) K=%d (multiple of 4)", p.N, p.K);
   DMT_REQUIRE(p.A && p.Bt && p.C && p.ldc % 4 == 0 && ((uintptr_t)p.C & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
@@ -523,7 +780,7 @@ int tf32_colsum(const float* X, int64_t ldx, int64_t T, int W, float* out, int a
   if (T < ctas) ctas = T > 0 ? (int)T : 1;
   tf32_colsum_kernel<<<ctas, 256, 0, st>>>(X, ldx, T, W, scratch);
   DMT_CUDA_LAUNCH_CHECK("tf32_colsum_kernel");
-  tf32_colsum_reduce_kernel<<<(W + 255) / 256, 256, 0, st>>>(scratch, ctas, W, out, accumulate);
+  tf32_colsum_reduce_kernel<<<(W + 7) / 8, 256, 0, st>>>(scratch, ctas, W, out, accumulate);
   DMT_CUDA_LAUNCH_CHECK("tf32_colsum_reduce_kernel");
   return DMT_OK;
 }
@@ -539,6 +796,16 @@ int dmt_selftest_tf32_rows(const float* A, int64_t lda, const float* Bt, int64_t
                            void* stream) {
   dmt::Tf32Rows p{A, lda, Bt, ldb, M, N, K, C, ldc, bias, addend, ld_add, mask, ld_mask, alpha, relu, accumulate};
   return dmt::tf32_rows(p, (cudaStream_t)stream);
+}
+
+int dmt_selftest_tf32_gemm(const float* A, int64_t lda, int32_t a_mn, const float* B, int64_t ldb, int32_t b_mn,
+                           int64_t M, int32_t N, int32_t K, float* C, int64_t ldc, const float* bias, const float* mask,
+                           int64_t ld_mask, int32_t relu, int32_t accumulate, void* stream) {
+  dmt::Tf32Gemm p{};
+  p.A[0] = A; p.B[0] = B; p.lda = lda; p.ldb = ldb; p.a_mn = a_mn; p.b_mn = b_mn; p.nz = 1;
+  p.M = M; p.N = N; p.K = K; p.C[0] = C; p.ldc = ldc; p.bias[0] = bias; p.mask[0] = mask; p.ld_mask = ld_mask;
+  p.relu = relu; p.accumulate = accumulate;
+  return dmt::tf32_gemm(p, (cudaStream_t)stream);
 }
 
 size_t dmt_selftest_tf32_wgrad_bytes(int64_t T, int32_t MA, int32_t NB) { return dmt::tf32_wgrad_partial_bytes(T, MA, NB); }

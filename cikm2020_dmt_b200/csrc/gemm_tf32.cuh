@@ -22,7 +22,7 @@ struct Tf32Rows {
   const float* Bt;     // [N, K] row-major (element (n, k) = weight of input k -> output n), row stride ldb
   int64_t ldb;
   int64_t M;
-  int N, K;            // N % 16 == 0, N <= 256; K % 4 == 0
+  int N, K;            // N % 16 == 0 (N > 256 runs as several column blocks); K % 4 == 0
   float* C;            // [M, N], row stride ldc (multiple of 4), 16-byte aligned
   int64_t ldc;
   const float* bias;   // [N] or null
@@ -54,6 +54,46 @@ struct Tf32Wgrad {
   int accumulate;      // C += D (shared weights collect several contributions per step)
   float* partial;      // workspace of tf32_wgrad_partial_bytes(...)
 };
+
+// Weight packing (tiny, once per use): dst[dst_row + r][dst_col + c] = transpose ? W[c * ldw + r] : W[r * ldw + c]
+// for r < rows, c < cols (rows / cols of the DESTINATION block); vectors: dstv[dst + i] = v[i].  The TF-layout
+// kernels [in, out] become the K-major [out, in] operand `Bt` of tf32_rows, and the Q|K|V (K|V) projections are
+// concatenated so that one GEMM serves them.
+struct Tf32PackMat {
+  const float* W;
+  int64_t ldw;
+  int rows, cols, transpose, dst_row, dst_col;
+};
+struct Tf32PackVec {
+  const float* v;
+  int n, dst;
+};
+int tf32_pack(const Tf32PackMat* mats, int n_mats, float* dst, int64_t ldd, const Tf32PackVec* vecs, int n_vecs,
+              float* dstv, cudaStream_t st);
+
+// General tiled GEMM (both operands streamed by TMA), batched over up to 4 independent problems `z` (the MMoE
+// experts) or -- reduce_z -- summed over them into one output (dX of a layer whose output feeds several experts):
+//   C_z[M, N] (+)= mask(relu( A_z . B_z + bias_z ))
+// A_z: a_mn == 0: [M, K] row-major (lda);  a_mn == 1: stored [K, M] row-major (lda) -- the activation of a weight
+//      gradient, contracted over its rows
+// B_z: b_mn == 0: stored [N, K] row-major (ldb) -- a TF kernel used as dX operand;  b_mn == 1: stored [K, N]
+//      row-major (ldb) -- a TF kernel in the forward, or the gradient matrix of a weight gradient
+struct Tf32Gemm {
+  const float* A[4];
+  const float* B[4];
+  int64_t lda, ldb;
+  int a_mn, b_mn;
+  int nz, reduce_z;
+  int64_t M;
+  int N, K;
+  float* C[4];
+  int64_t ldc;
+  const float* bias[4];
+  const float* mask[4];
+  int64_t ld_mask;
+  int relu, accumulate;
+};
+int tf32_gemm(const Tf32Gemm& p, cudaStream_t st);
 
 size_t tf32_wgrad_partial_bytes(int64_t T, int MA, int NB);
 int tf32_rows(const Tf32Rows& p, cudaStream_t st);

@@ -15,6 +15,7 @@
 // seq_encode_f32.cu for the fused fp32 statement); only the GEMM operands are rounded (bf16 or split-bf16).
 #include "dropout.cuh"
 #include "gemm_f32.cuh"
+#include "gemm_tf32.cuh"
 #include "seq_train.cuh"
 
 namespace dmt {
@@ -331,6 +332,30 @@ inline void fwd_prob(GemmProb& p, const float* A, int64_t lda, int K, const dmt_
   p.ld_add = ld_add;
 }
 
+// DMT_PRECISION_TF32: C[rows, N] = act(A[rows, K] W + b (+ addend)) on the TMA-fed tf32 engine.  `Bt` = the packed
+// K-major operand [N, K] (row stride K), `bias` its packed bias.
+inline int tf32_dense(const float* A, int64_t lda, int K, const float* Bt, const float* bias, int N, int64_t rows,
+                      float* C, int64_t ldc, bool relu, const float* addend, int64_t ld_add, cudaStream_t st) {
+  Tf32Rows p{};
+  p.A = A; p.lda = lda; p.Bt = Bt; p.ldb = K; p.M = rows; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
+  p.bias = bias; p.addend = addend; p.ld_add = ld_add; p.alpha = 1.0f; p.relu = relu ? 1 : 0;
+  return tf32_rows(p, st);
+}
+
+// Bt = [W_0^T ; W_1^T ; ...] (each TF kernel [K, n_i] -> rows of the K-major operand), bias = [b_0 | b_1 | ...]
+inline int tf32_pack_dense(const dmt_dense* const* w, const int* n_out, int n, int K, float* Bt, float* bias,
+                           cudaStream_t st) {
+  Tf32PackMat m[4];
+  Tf32PackVec v[4];
+  int row = 0;
+  for (int i = 0; i < n; ++i) {
+    m[i] = Tf32PackMat{w[i]->w, (int64_t)n_out[i], n_out[i], K, 1, row, 0};
+    v[i] = Tf32PackVec{w[i]->b, n_out[i], row};
+    row += n_out[i];
+  }
+  return tf32_pack(m, n, Bt, K, v, n, bias, st);
+}
+
 }  // namespace
 
 int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
@@ -338,6 +363,19 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
   const dmt_seq_cfg& c = *cfg;
   const int d = c.d_model, dff = c.d_ff, B = c.batch, H = c.num_heads, LP = seq_lp(c);
   const int use_tc = gemm_engine(c.precision);
+  const bool tf = gemm_tf32(c.precision);          // per-token GEMMs on the TMA-fed tf32 engine
+  // weight-pack scratch of the tf32 route: [Q|K|V (or K|V) operand + bias | W1^T + b1 | W2^T + b2]
+  float* pk_qkv = sv.pack;
+  float* pk_qkv_b = pk_qkv + (size_t)3 * d * d;
+  float* pk_w1 = pk_qkv_b + 4 * d;
+  float* pk_w1_b = pk_w1 + (size_t)d * dff;
+  float* pk_w2 = pk_w1_b + dff;
+  float* pk_w2_b = pk_w2 + (size_t)d * dff;
+  float* pk_q = pk_w2_b + 4 * d;                   // decoder query projection [d, d] + bias
+  float* pk_q_b = pk_q + (size_t)d * d;
+  if (tf)
+    DMT_REQUIRE(d % 16 == 0 && dff % 16 == 0, DMT_ERR_UNSUPPORTED_SHAPE,
+                "DMT_PRECISION_TF32 needs d_model and d_ff that are multiples of 16 (got %d, %d)", d, dff);
   const int32_t* offsets = in->offsets[c.n_feats - 1];
   const int ln_grid = 4 * sm_count_cached();
   int rc;
@@ -362,7 +400,13 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
   for (int blk = 0; blk < c.n_enc_blocks && T > 0; ++blk) {
     const dmt_attn_weights& aw = w->enc_attn[blk];
     const dmt_ff_weights& fw = w->ff[blk];
-    {
+    if (tf) {   // one GEMM for Q | K | V: hin is read once
+      const dmt_dense* ws3[3] = {&aw.q, &aw.k, &aw.v};
+      const int n3[3] = {d, d, d};
+      if ((rc = tf32_pack_dense(ws3, n3, 3, d, pk_qkv, pk_qkv_b, st))) return rc;
+      if ((rc = tf32_dense(sv.hin[blk], d, d, pk_qkv, pk_qkv_b, 3 * d, T, sv.qkv[blk], 3 * d, false, nullptr, 0, st)))
+        return rc;
+    } else {
       GemmGroup grp{};
       grp.use_tc = use_tc;
       fwd_prob(grp.p[0], sv.hin[blk], d, d, aw.q, d, T, sv.qkv[blk], 3 * d, false, nullptr, 0);
@@ -381,19 +425,30 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
       attn_fwd_kernel<<<B, 256, smem, st>>>(a);
       DMT_CUDA_LAUNCH_CHECK("attn_fwd_kernel");
     }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      fwd_prob(grp.p[0], sv.a[blk], d, d, fw.w1, dff, T, sv.f1[blk], dff, true, nullptr, 0);
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
-    }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      fwd_prob(grp.p[0], sv.f1[blk], dff, dff, fw.w2, d, T, sv.z2[blk], d, false, sv.a[blk], d);
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    if (tf) {
+      const dmt_dense* w1p[1] = {&fw.w1};
+      const dmt_dense* w2p[1] = {&fw.w2};
+      const int n1[1] = {dff}, n2[1] = {d};
+      if ((rc = tf32_pack_dense(w1p, n1, 1, d, pk_w1, pk_w1_b, st))) return rc;
+      if ((rc = tf32_pack_dense(w2p, n2, 1, dff, pk_w2, pk_w2_b, st))) return rc;
+      if ((rc = tf32_dense(sv.a[blk], d, d, pk_w1, pk_w1_b, dff, T, sv.f1[blk], dff, true, nullptr, 0, st))) return rc;
+      if ((rc = tf32_dense(sv.f1[blk], dff, dff, pk_w2, pk_w2_b, d, T, sv.z2[blk], d, false, sv.a[blk], d, st)))
+        return rc;
+    } else {
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        fwd_prob(grp.p[0], sv.a[blk], d, d, fw.w1, dff, T, sv.f1[blk], dff, true, nullptr, 0);
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        fwd_prob(grp.p[0], sv.f1[blk], dff, dff, fw.w2, d, T, sv.z2[blk], d, false, sv.a[blk], d);
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     ln_fwd_rows_kernel<<<ln_grid, 256, 0, st>>>(sv.z2[blk], T, d, fw.ln.gamma, fw.ln.beta, sv.hin[blk + 1], nullptr, 0);
     DMT_CUDA_LAUNCH_CHECK("ln_fwd_rows_kernel");
@@ -402,7 +457,18 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
   for (int blk = 0; blk < c.n_dec_blocks; ++blk) {
     const dmt_attn_weights& aw = w->dec_attn[blk];
     const dmt_ff_weights& fw = w->ff[blk];
-    {
+    if (tf) {
+      const dmt_dense* wq[1] = {&aw.q};
+      const dmt_dense* wkv[2] = {&aw.k, &aw.v};
+      const int nq[1] = {d}, nkv[2] = {d, d};
+      if ((rc = tf32_pack_dense(wq, nq, 1, d, pk_q, pk_q_b, st))) return rc;
+      if ((rc = tf32_dense(sv.din[blk], d, d, pk_q, pk_q_b, d, B, sv.qd[blk], d, false, nullptr, 0, st))) return rc;
+      if (T > 0) {
+        if ((rc = tf32_pack_dense(wkv, nkv, 2, d, pk_qkv, pk_qkv_b, st))) return rc;
+        if ((rc = tf32_dense(mem, d, d, pk_qkv, pk_qkv_b, 2 * d, T, sv.kvd[blk], 2 * d, false, nullptr, 0, st)))
+          return rc;
+      }
+    } else {
       GemmGroup grp{};
       grp.use_tc = use_tc;
       int n = 0;
@@ -423,19 +489,30 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
       dec_attn_fwd_kernel<<<B, 128, smem, st>>>(a);
       DMT_CUDA_LAUNCH_CHECK("dec_attn_fwd_kernel");
     }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      fwd_prob(grp.p[0], sv.ad[blk], d, d, fw.w1, dff, B, sv.f1d[blk], dff, true, nullptr, 0);
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
-    }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      fwd_prob(grp.p[0], sv.f1d[blk], dff, dff, fw.w2, d, B, sv.z2d[blk], d, false, sv.ad[blk], d);
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    if (tf) {
+      const dmt_dense* w1p[1] = {&fw.w1};
+      const dmt_dense* w2p[1] = {&fw.w2};
+      const int n1[1] = {dff}, n2[1] = {d};
+      if ((rc = tf32_pack_dense(w1p, n1, 1, d, pk_w1, pk_w1_b, st))) return rc;
+      if ((rc = tf32_pack_dense(w2p, n2, 1, dff, pk_w2, pk_w2_b, st))) return rc;
+      if ((rc = tf32_dense(sv.ad[blk], d, d, pk_w1, pk_w1_b, dff, B, sv.f1d[blk], dff, true, nullptr, 0, st))) return rc;
+      if ((rc = tf32_dense(sv.f1d[blk], dff, dff, pk_w2, pk_w2_b, d, B, sv.z2d[blk], d, false, sv.ad[blk], d, st)))
+        return rc;
+    } else {
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        fwd_prob(grp.p[0], sv.ad[blk], d, d, fw.w1, dff, B, sv.f1d[blk], dff, true, nullptr, 0);
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        fwd_prob(grp.p[0], sv.f1d[blk], dff, dff, fw.w2, d, B, sv.z2d[blk], d, false, sv.ad[blk], d);
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     const bool last = blk == c.n_dec_blocks - 1;
     ln_fwd_rows_kernel<<<ln_grid, 256, 0, st>>>(sv.z2d[blk], B, d, fw.ln.gamma, fw.ln.beta, sv.din[blk + 1],

@@ -10,6 +10,7 @@
 // GEMMs with a fixed-order reduction (gemm_f32.cuh).  Nothing here uses floating-point atomics.
 #include "dropout.cuh"
 #include "gemm_f32.cuh"
+#include "gemm_tf32.cuh"
 #include "seq_train.cuh"
 
 namespace dmt {
@@ -397,6 +398,9 @@ struct BwdWs {
   float *ln_partial;                // [ln_grid][2d]
   float *pos_partial;               // [kPosSplits][LP][d]
   float *gpart[8];  // split-K scratch of the weight-gradient contractions (one block's worth)
+  float *tf_pack;   // DMT_PRECISION_TF32: concatenated [Wq|Wk|Wv] / [Wk|Wv] operand of the dX GEMMs
+  float *tf_colsum; //                     scratch of the bias-gradient column sums
+  float *tf_wgrad;  //                     split partials of the token-contraction GEMMs
   int ln_grid;
   int splits_T[8], splits_B[8];
 };
@@ -443,6 +447,20 @@ size_t bwd_carve(const dmt_seq_cfg& c, int64_t T, void* base, BwdWs* out) {
     const int s = w.splits_T[i] > w.splits_B[i] ? w.splits_T[i] : w.splits_B[i];
     w.gpart[i] = cv.take((size_t)s * (M + 1) * N);
   }
+  if (gemm_tf32(c.precision)) {
+    const int di = (int)d, dffi = (int)dff;
+    w.tf_pack = cv.take(3 * d * d + 64);
+    const int wmax = dffi > 3 * di ? dffi : 3 * di;
+    w.tf_colsum = cv.take(tf32_colsum_scratch_bytes(wmax) / sizeof(float));
+    size_t pb = 0;
+    const int64_t rows[2] = {T, (int64_t)B};
+    for (int r = 0; r < 2; ++r) {
+      const size_t cand[3] = {tf32_wgrad_partial_bytes(rows[r], dffi, di), tf32_wgrad_partial_bytes(rows[r], 3 * di, di),
+                              tf32_wgrad_partial_bytes(rows[r], 2 * di, di)};
+      for (int k = 0; k < 3; ++k) pb = cand[k] > pb ? cand[k] : pb;
+    }
+    w.tf_wgrad = cv.take(pb / sizeof(float));
+  }
   if (out) *out = w;
   return cv.off + 256;
 }
@@ -480,6 +498,57 @@ inline void dgrad_prob(GemmProb& p, int n_parts, const float* const* grad, const
   p.ldc = ldc;
 }
 
+
+// ---- DMT_PRECISION_TF32 helpers ---------------------------------------------------------------------
+// C[rows, N] (+)= mask((grad[rows, K] Bt[N, K]^T + addend) * alpha): dX of a dense layer; Bt = the TF kernel [N, K]
+// itself (rows = inputs) or a packed concatenation of several
+inline int tf32_dgrad(const float* grad, int64_t ld_grad, int K, const float* Bt, int64_t ldb, int N, int64_t rows,
+                      float* C, int64_t ldc, const float* addend, int64_t ld_add, const float* mask, int64_t ld_mask,
+                      float alpha, bool accumulate, cudaStream_t st) {
+  Tf32Rows p{};
+  p.A = grad; p.lda = ld_grad; p.Bt = Bt; p.ldb = ldb; p.M = rows; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
+  p.addend = addend; p.ld_add = ld_add; p.mask = mask; p.ld_mask = ld_mask; p.alpha = alpha;
+  p.accumulate = accumulate ? 1 : 0;
+  return tf32_rows(p, st);
+}
+
+// dW_i (+)= act^T grad_i for the column blocks grad_i = grad[:, i*n : (i+1)*n] (n_w weight tensors [K_act, n] that share
+// the activation), db_i (+)= column sums of grad_i.  The wider matrix is the row operand of the contraction.
+inline int tf32_wgrads(const float* act, int64_t ld_act, int k_act, const float* grad, int64_t ld_grad, int n,
+                       int n_w, const dmt_dense* const* g, int64_t rows, const BwdWs& ws, cudaStream_t st) {
+  int rc;
+  Tf32Wgrad p{};
+  p.T = rows;
+  p.partial = ws.tf_wgrad;
+  p.accumulate = 1;
+  if (n_w == 1 && k_act > n) {       // e.g. W2 [dff, d]: D[m = act column][n = grad column] = dW as stored
+    p.P = act; p.ldp = ld_act; p.MA = k_act;
+    p.Q = grad; p.ldq = ld_grad; p.NB = n;
+    p.seg[0] = Tf32WgradSeg{const_cast<float*>(g[0]->w), (int64_t)n, 0, k_act};
+    p.n_seg = 1;
+    p.transposed = 0;
+  } else {                           // D[m = grad column][n = act column] = dW^T, one segment per weight tensor
+    p.P = grad; p.ldp = ld_grad; p.MA = n * n_w;
+    p.Q = act; p.ldq = ld_act; p.NB = k_act;
+    for (int i = 0; i < n_w; ++i) p.seg[i] = Tf32WgradSeg{const_cast<float*>(g[i]->w), (int64_t)n, i * n, (i + 1) * n};
+    p.n_seg = n_w;
+    p.transposed = 1;
+  }
+  if ((rc = tf32_wgrad(p, st))) return rc;
+  for (int i = 0; i < n_w; ++i)
+    if ((rc = tf32_colsum(grad + (int64_t)i * n, ld_grad, rows, n, const_cast<float*>(g[i]->b), 1, ws.tf_colsum, st)))
+      return rc;
+  return DMT_OK;
+}
+
+// Bt[n][i*K + k] = W_i[n][k]: the [N, K] kernels of several projections side by side (dX = sum_i grad_i W_i^T as ONE
+// GEMM over the concatenated gradient columns)
+inline int tf32_pack_cat(const dmt_dense* const* w, int n_w, int N, int K, float* Bt, cudaStream_t st) {
+  Tf32PackMat m[4];
+  for (int i = 0; i < n_w; ++i) m[i] = Tf32PackMat{w[i]->w, (int64_t)K, N, K, 0, 0, i * K};
+  return tf32_pack(m, n_w, Bt, (int64_t)n_w * K, nullptr, 0, nullptr, st);
+}
+
 }  // namespace
 
 size_t seq_bwd_workspace_bytes(const dmt_seq_cfg* cfg, int64_t T) { return bwd_carve(*cfg, T, nullptr, nullptr); }
@@ -494,6 +563,10 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
   const int d = c.d_model, dff = c.d_ff, B = c.batch, H = c.num_heads, LP = seq_lp(c);
   const float sqrt_d = sqrtf((float)d);
   const int use_tc = gemm_engine(c.precision);   // GEMMs on tcgen05 (bf16 operands, fp32 accumulate)
+  const bool tf = gemm_tf32(c.precision);        // per-token GEMMs on the TMA-fed tf32 engine (gemm_tf32.cu)
+  if (tf)
+    DMT_REQUIRE(d % 16 == 0 && dff % 16 == 0, DMT_ERR_UNSUPPORTED_SHAPE,
+                "DMT_PRECISION_TF32 needs d_model and d_ff that are multiples of 16 (got %d, %d)", d, dff);
   const int32_t* offsets = in->offsets[c.n_feats - 1];
   int rc;
 
@@ -511,31 +584,38 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     rc = ln_bwd_launch(sv.z2d[blk], d, dcur, dcur_ld, fw.ln.gamma, ws.dz2d, d, B, d, ws.ln_partial, ws.ln_grid,
                        const_cast<float*>(fg.ln.gamma), const_cast<float*>(fg.ln.beta), st);
     if (rc) return rc;
-    {   // dF1 = (dZ2 W2^T) * (F1 > 0)
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[1] = {ws.dz2d};
-      const int64_t lg[1] = {d};
-      const float* W[1] = {fw.w2.w};
-      const int K[1] = {d};
-      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, dff, ws.df1d, dff);
-      grp.p[0].mask = sv.f1d[blk];
-      grp.p[0].ld_mask = dff;
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
-    }
-    {   // dA = dZ2 + dF1 W1^T
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[1] = {ws.df1d};
-      const int64_t lg[1] = {dff};
-      const float* W[1] = {fw.w1.w};
-      const int K[1] = {dff};
-      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, ws.dad, d);
-      grp.p[0].addend = ws.dz2d;
-      grp.p[0].ld_add = d;
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    if (tf) {   // dF1 = (dZ2 W2^T) * (F1 > 0) ;  dA = dZ2 + dF1 W1^T   (the TF kernels are the K-major operands as stored)
+      if ((rc = tf32_dgrad(ws.dz2d, d, d, fw.w2.w, d, dff, B, ws.df1d, dff, nullptr, 0, sv.f1d[blk], dff, 1.0f, false, st)))
+        return rc;
+      if ((rc = tf32_dgrad(ws.df1d, dff, dff, fw.w1.w, dff, d, B, ws.dad, d, ws.dz2d, d, nullptr, 0, 1.0f, false, st)))
+        return rc;
+    } else {
+      {   // dF1 = (dZ2 W2^T) * (F1 > 0)
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[1] = {ws.dz2d};
+        const int64_t lg[1] = {d};
+        const float* W[1] = {fw.w2.w};
+        const int K[1] = {d};
+        dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, dff, ws.df1d, dff);
+        grp.p[0].mask = sv.f1d[blk];
+        grp.p[0].ld_mask = dff;
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
+      {   // dA = dZ2 + dF1 W1^T
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[1] = {ws.df1d};
+        const int64_t lg[1] = {dff};
+        const float* W[1] = {fw.w1.w};
+        const int K[1] = {dff};
+        dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, ws.dad, d);
+        grp.p[0].addend = ws.dz2d;
+        grp.p[0].ld_add = d;
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     // attention LayerNorm: input z1d = context + block input
     rc = ln_bwd_launch(sv.z1d[blk], d, ws.dad, d, aw.ln.gamma, ws.dz1d, d, B, d, ws.ln_partial, ws.ln_grid,
@@ -551,44 +631,70 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
       DMT_CUDA_LAUNCH_CHECK("dec_attn_bwd_kernel");
     }
     float* dnext = ws.dd[blk & 1];
-    {   // dD_in = dZ1 + dQd Wq^T (x sqrt(d) into d_target for the first block) ; dMemory (+)= dKd Wk^T + dVd Wv^T
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[1] = {ws.dqd};
-      const int64_t lg[1] = {d};
-      const float* W[1] = {aw.q.w};
-      const int K[1] = {d};
-      dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, blk == 0 ? d_target : dnext, d);
-      grp.p[0].addend = ws.dz1d;
-      grp.p[0].ld_add = d;
-      if (blk == 0) grp.p[0].alpha = sqrt_d;
-      grp.n = 1;
+    if (tf) {
+      // dD_in = dZ1 + dQd Wq^T (x sqrt(d) into d_target for the first block) ; dMemory (+)= [dKd | dVd] [Wk | Wv]^T
+      if ((rc = tf32_dgrad(ws.dqd, d, d, aw.q.w, d, d, B, blk == 0 ? d_target : dnext, d, ws.dz1d, d, nullptr, 0,
+                           blk == 0 ? sqrt_d : 1.0f, false, st)))
+        return rc;
       if (T > 0) {
-        const float* gr2[2] = {ws.dkvd, ws.dkvd + d};
-        const int64_t lg2[2] = {2 * d, 2 * d};
-        const float* W2[2] = {aw.k.w, aw.v.w};
-        const int K2[2] = {d, d};
-        dgrad_prob(grp.p[1], 2, gr2, lg2, W2, K2, T, d, dmem, d);
-        grp.p[1].accumulate = dmem_written ? 1 : 0;
-        grp.n = 2;
+        const dmt_dense* kv[2] = {&aw.k, &aw.v};
+        if ((rc = tf32_pack_cat(kv, 2, d, d, ws.tf_pack, st))) return rc;
+        if ((rc = tf32_dgrad(ws.dkvd, 2 * d, 2 * d, ws.tf_pack, 2 * d, d, T, dmem, d, nullptr, 0, nullptr, 0, 1.0f,
+                             dmem_written, st)))
+          return rc;
       }
-      if ((rc = gemm_group_launch(grp, st))) return rc;
       dmem_written = true;
-    }
-    {   // weight gradients of this block
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      int n = 0;
-      wgrad_prob(grp.p[n++], sv.ad[blk], d, ws.df1d, dff, B, d, dff, fg.w1, ws.splits_B[0], ws.gpart[0]);
-      wgrad_prob(grp.p[n++], sv.f1d[blk], dff, ws.dz2d, d, B, dff, d, fg.w2, ws.splits_B[1], ws.gpart[1]);
-      wgrad_prob(grp.p[n++], sv.din[blk], d, ws.dqd, d, B, d, d, ag.q, ws.splits_B[2], ws.gpart[2]);
+      // weight gradients of this block
+      const dmt_dense* g1[1] = {&fg.w1};
+      const dmt_dense* g2[1] = {&fg.w2};
+      const dmt_dense* gq[1] = {&ag.q};
+      if ((rc = tf32_wgrads(sv.ad[blk], d, d, ws.df1d, dff, dff, 1, g1, B, ws, st))) return rc;
+      if ((rc = tf32_wgrads(sv.f1d[blk], dff, dff, ws.dz2d, d, d, 1, g2, B, ws, st))) return rc;
+      if ((rc = tf32_wgrads(sv.din[blk], d, d, ws.dqd, d, d, 1, gq, B, ws, st))) return rc;
       if (T > 0) {
-        const float* mem = sv.hin[c.n_enc_blocks];
-        wgrad_prob(grp.p[n++], mem, d, ws.dkvd, 2 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
-        wgrad_prob(grp.p[n++], mem, d, ws.dkvd + d, 2 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
+        const dmt_dense* gkv[2] = {&ag.k, &ag.v};
+        if ((rc = tf32_wgrads(sv.hin[c.n_enc_blocks], d, d, ws.dkvd, 2 * d, d, 2, gkv, T, ws, st))) return rc;
       }
-      grp.n = n;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    } else {
+      {   // dD_in = dZ1 + dQd Wq^T (x sqrt(d) into d_target for the first block) ; dMemory (+)= dKd Wk^T + dVd Wv^T
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[1] = {ws.dqd};
+        const int64_t lg[1] = {d};
+        const float* W[1] = {aw.q.w};
+        const int K[1] = {d};
+        dgrad_prob(grp.p[0], 1, gr, lg, W, K, B, d, blk == 0 ? d_target : dnext, d);
+        grp.p[0].addend = ws.dz1d;
+        grp.p[0].ld_add = d;
+        if (blk == 0) grp.p[0].alpha = sqrt_d;
+        grp.n = 1;
+        if (T > 0) {
+          const float* gr2[2] = {ws.dkvd, ws.dkvd + d};
+          const int64_t lg2[2] = {2 * d, 2 * d};
+          const float* W2[2] = {aw.k.w, aw.v.w};
+          const int K2[2] = {d, d};
+          dgrad_prob(grp.p[1], 2, gr2, lg2, W2, K2, T, d, dmem, d);
+          grp.p[1].accumulate = dmem_written ? 1 : 0;
+          grp.n = 2;
+        }
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+        dmem_written = true;
+      }
+      {   // weight gradients of this block
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        int n = 0;
+        wgrad_prob(grp.p[n++], sv.ad[blk], d, ws.df1d, dff, B, d, dff, fg.w1, ws.splits_B[0], ws.gpart[0]);
+        wgrad_prob(grp.p[n++], sv.f1d[blk], dff, ws.dz2d, d, B, dff, d, fg.w2, ws.splits_B[1], ws.gpart[1]);
+        wgrad_prob(grp.p[n++], sv.din[blk], d, ws.dqd, d, B, d, d, ag.q, ws.splits_B[2], ws.gpart[2]);
+        if (T > 0) {
+          const float* mem = sv.hin[c.n_enc_blocks];
+          wgrad_prob(grp.p[n++], mem, d, ws.dkvd, 2 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
+          wgrad_prob(grp.p[n++], mem, d, ws.dkvd + d, 2 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
+        }
+        grp.n = n;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     dcur = dnext;
     dcur_ld = d;
@@ -620,31 +726,38 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     rc = ln_bwd_launch(sv.z2[blk], d, dh, d, fw.ln.gamma, ws.dz2, d, T, d, ws.ln_partial, ws.ln_grid,
                        const_cast<float*>(fg.ln.gamma), const_cast<float*>(fg.ln.beta), st);
     if (rc) return rc;
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[1] = {ws.dz2};
-      const int64_t lg[1] = {d};
-      const float* W[1] = {fw.w2.w};
-      const int K[1] = {d};
-      dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, dff, ws.df1, dff);
-      grp.p[0].mask = sv.f1[blk];
-      grp.p[0].ld_mask = dff;
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
-    }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[1] = {ws.df1};
-      const int64_t lg[1] = {dff};
-      const float* W[1] = {fw.w1.w};
-      const int K[1] = {dff};
-      dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, d, ws.da, d);
-      grp.p[0].addend = ws.dz2;
-      grp.p[0].ld_add = d;
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    if (tf) {
+      if ((rc = tf32_dgrad(ws.dz2, d, d, fw.w2.w, d, dff, T, ws.df1, dff, nullptr, 0, sv.f1[blk], dff, 1.0f, false, st)))
+        return rc;
+      if ((rc = tf32_dgrad(ws.df1, dff, dff, fw.w1.w, dff, d, T, ws.da, d, ws.dz2, d, nullptr, 0, 1.0f, false, st)))
+        return rc;
+    } else {
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[1] = {ws.dz2};
+        const int64_t lg[1] = {d};
+        const float* W[1] = {fw.w2.w};
+        const int K[1] = {d};
+        dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, dff, ws.df1, dff);
+        grp.p[0].mask = sv.f1[blk];
+        grp.p[0].ld_mask = dff;
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[1] = {ws.df1};
+        const int64_t lg[1] = {dff};
+        const float* W[1] = {fw.w1.w};
+        const int K[1] = {dff};
+        dgrad_prob(grp.p[0], 1, gr, lg, W, K, T, d, ws.da, d);
+        grp.p[0].addend = ws.dz2;
+        grp.p[0].ld_add = d;
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     rc = ln_bwd_launch(sv.z1[blk], d, ws.da, d, aw.ln.gamma, ws.dz1, d, T, d, ws.ln_partial, ws.ln_grid,
                        const_cast<float*>(ag.ln.gamma), const_cast<float*>(ag.ln.beta), st);
@@ -661,31 +774,46 @@ int seq_bwd_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_se
     }
     ping ^= 1;
     float* dhin = blk == 0 ? d_tokens : ws.dh[ping];
-    {   // dH_in = dZ1 + dQ Wq^T + dK Wk^T + dV Wv^T   (x sqrt(d) for the first block: row gradients)
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      const float* gr[3] = {ws.dqkv, ws.dqkv + d, ws.dqkv + 2 * d};
-      const int64_t lg[3] = {3 * d, 3 * d, 3 * d};
-      const float* W[3] = {aw.q.w, aw.k.w, aw.v.w};
-      const int K[3] = {d, d, d};
-      dgrad_prob(grp.p[0], 3, gr, lg, W, K, T, d, dhin, d);
-      grp.p[0].addend = ws.dz1;
-      grp.p[0].ld_add = d;
-      if (blk == 0) grp.p[0].alpha = sqrt_d;
-      grp.n = 1;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
-    }
-    {
-      GemmGroup grp{};
-      grp.use_tc = use_tc;
-      int n = 0;
-      wgrad_prob(grp.p[n++], sv.a[blk], d, ws.df1, dff, T, d, dff, fg.w1, ws.splits_T[0], ws.gpart[0]);
-      wgrad_prob(grp.p[n++], sv.f1[blk], dff, ws.dz2, d, T, dff, d, fg.w2, ws.splits_T[1], ws.gpart[1]);
-      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv, 3 * d, T, d, d, ag.q, ws.splits_T[2], ws.gpart[2]);
-      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + d, 3 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
-      wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + 2 * d, 3 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
-      grp.n = n;
-      if ((rc = gemm_group_launch(grp, st))) return rc;
+    if (tf) {
+      // dH_in = dZ1 + [dQ | dK | dV] [Wq | Wk | Wv]^T   (x sqrt(d) for the first block: row gradients)
+      const dmt_dense* qkvw[3] = {&aw.q, &aw.k, &aw.v};
+      if ((rc = tf32_pack_cat(qkvw, 3, d, d, ws.tf_pack, st))) return rc;
+      if ((rc = tf32_dgrad(ws.dqkv, 3 * d, 3 * d, ws.tf_pack, 3 * d, d, T, dhin, d, ws.dz1, d, nullptr, 0,
+                           blk == 0 ? sqrt_d : 1.0f, false, st)))
+        return rc;
+      const dmt_dense* g1[1] = {&fg.w1};
+      const dmt_dense* g2[1] = {&fg.w2};
+      const dmt_dense* gqkv[3] = {&ag.q, &ag.k, &ag.v};
+      if ((rc = tf32_wgrads(sv.a[blk], d, d, ws.df1, dff, dff, 1, g1, T, ws, st))) return rc;
+      if ((rc = tf32_wgrads(sv.f1[blk], dff, dff, ws.dz2, d, d, 1, g2, T, ws, st))) return rc;
+      if ((rc = tf32_wgrads(sv.hin[blk], d, d, ws.dqkv, 3 * d, d, 3, gqkv, T, ws, st))) return rc;
+    } else {
+      {   // dH_in = dZ1 + dQ Wq^T + dK Wk^T + dV Wv^T   (x sqrt(d) for the first block: row gradients)
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        const float* gr[3] = {ws.dqkv, ws.dqkv + d, ws.dqkv + 2 * d};
+        const int64_t lg[3] = {3 * d, 3 * d, 3 * d};
+        const float* W[3] = {aw.q.w, aw.k.w, aw.v.w};
+        const int K[3] = {d, d, d};
+        dgrad_prob(grp.p[0], 3, gr, lg, W, K, T, d, dhin, d);
+        grp.p[0].addend = ws.dz1;
+        grp.p[0].ld_add = d;
+        if (blk == 0) grp.p[0].alpha = sqrt_d;
+        grp.n = 1;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
+      {
+        GemmGroup grp{};
+        grp.use_tc = use_tc;
+        int n = 0;
+        wgrad_prob(grp.p[n++], sv.a[blk], d, ws.df1, dff, T, d, dff, fg.w1, ws.splits_T[0], ws.gpart[0]);
+        wgrad_prob(grp.p[n++], sv.f1[blk], dff, ws.dz2, d, T, dff, d, fg.w2, ws.splits_T[1], ws.gpart[1]);
+        wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv, 3 * d, T, d, d, ag.q, ws.splits_T[2], ws.gpart[2]);
+        wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + d, 3 * d, T, d, d, ag.k, ws.splits_T[3], ws.gpart[3]);
+        wgrad_prob(grp.p[n++], sv.hin[blk], d, ws.dqkv + 2 * d, 3 * d, T, d, d, ag.v, ws.splits_T[4], ws.gpart[4]);
+        grp.n = n;
+        if ((rc = gemm_group_launch(grp, st))) return rc;
+      }
     }
     dh = dhin;
   }

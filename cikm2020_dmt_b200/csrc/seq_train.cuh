@@ -24,7 +24,14 @@ struct SeqSaved {
   float* ad[DMT_MAX_BLOCKS];        // [B, d]
   float* f1d[DMT_MAX_BLOCKS];       // [B, dff]
   float* z2d[DMT_MAX_BLOCKS];       // [B, d]
+  float* pack;                      // DMT_PRECISION_TF32: packed / transposed weights of the GEMM in flight
 };
+
+// floats of the weight-pack scratch: the largest set alive at once is one block's Q|K|V + W1 + W2 packs
+inline size_t seq_pack_floats(const dmt_seq_cfg& c) {
+  const size_t d = c.d_model, dff = c.d_ff;
+  return 3 * d * d + 2 * d * dff + 3 * d * d + 16 * d + 2 * dff + 1024;
+}
 
 inline int seq_lp(const dmt_seq_cfg& c) { return c.maxlen < DMT_MAX_SEQ_LEN ? c.maxlen : DMT_MAX_SEQ_LEN; }
 
@@ -62,6 +69,7 @@ inline size_t seq_saved_carve(const dmt_seq_cfg& c, int64_t T, void* base, SeqSa
     s.f1d[b] = cv.take(B * dff);
     s.z2d[b] = cv.take(B * d);
   }
+  s.pack = cv.take(seq_pack_floats(c));
   if (sv) *sv = s;
   return cv.off + 256;
 }

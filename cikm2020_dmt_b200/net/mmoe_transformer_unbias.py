@@ -25,8 +25,10 @@ def _is_host(t):
 class mmoe_transformer_unbias(object):
     def __init__(self, wnd_conf, device=None, params=None, precision="f32", seed=20201019, train_gemm=None):
         """precision: 'f32' (CUDA cores, exact-parity path) | 'bf16' (tcgen05 inference kernels).
-        train_gemm: engine of the GEMMs of the TRAINING path -- 'f32' (SIMT), 'bf16' (tcgen05, bf16 operands) or
-        'bf16x3' (tcgen05, split hi+lo operands: fp32-grade).  Default: 'f32' with precision 'f32', else 'bf16x3'."""
+        train_gemm: engine of the GEMMs of the TRAINING path -- 'f32' (SIMT), 'bf16' (tcgen05, bf16 operands),
+        'bf16x3' (tcgen05, split hi+lo operands: fp32-grade) or 'tf32' (the per-token GEMMs of the sequence pipeline on
+        the TMA-fed tcgen05 kind::tf32 engine, no operand conversion pass; MMoE on bf16x3).
+        Default: 'f32' with precision 'f32', else 'bf16x3'."""
         self.wnd_conf = wnd_conf
         self.plan = wnd_conf if hasattr(wnd_conf, "mmoe_in") else build_plan(wnd_conf)
         if not torch.cuda.is_available():
@@ -39,7 +41,7 @@ class mmoe_transformer_unbias(object):
         if train_gemm is None:
             train_gemm = "f32" if precision == "f32" else "bf16x3"
         self.train_precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16,
-                                "bf16x3": abi.PRECISION_BF16X3}[train_gemm]
+                                "bf16x3": abi.PRECISION_BF16X3, "tf32": abi.PRECISION_TF32}[train_gemm]
         self.params = params if params is not None else ParamStore(self.plan, device=self.device, seed=seed)
         pdev = self.params.dense.device
         if pdev.type != "cuda" or pdev.index != self.device.index:

@@ -64,6 +64,11 @@ typedef enum dmt_precision {
   DMT_PRECISION_BF16X3 = 2 /* training entry points only (fwd_train / bwd): every GEMM operand is split
                               x = hi + lo into two bf16 images and each product is hi*hi + hi*lo + lo*hi on
                               tcgen05 -- fp32-grade gradients at tensor-core speed                       */
+  ,
+  DMT_PRECISION_TF32 = 3   /* training entry points only: the per-token GEMMs of the sequence pipeline run on the
+                              TMA-fed tcgen05 kind::tf32 engine straight from the fp32 activations (no operand
+                              conversion pass; 10-bit operand mantissa, fp32 accumulate); the MMoE GEMMs use the
+                              bf16x3 engine                                                             */
 } dmt_precision;
 
 /* one tf.layers.dense / base.dense_layer: kernel [in,out] + bias [out] */
@@ -434,6 +439,11 @@ DMT_API int dmt_selftest_umma(int32_t mode, const void* A, const void* B, float*
 DMT_API int dmt_selftest_tf32_rows(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t M, int32_t N,
                                    int32_t K, float* C, int64_t ldc, const float* bias, const float* addend,
                                    int64_t ld_add, const float* mask, int64_t ld_mask, float alpha, int32_t relu,
+                                   int32_t accumulate, void* stream);
+/* gemm: C[M,N] (+)= mask(relu(op(A) op(B) + bias)); a_mn: A stored [K,M], else [M,K]; b_mn: B stored [K,N], else [N,K] */
+DMT_API int dmt_selftest_tf32_gemm(const float* A, int64_t lda, int32_t a_mn, const float* B, int64_t ldb,
+                                   int32_t b_mn, int64_t M, int32_t N, int32_t K, float* C, int64_t ldc,
+                                   const float* bias, const float* mask, int64_t ld_mask, int32_t relu,
                                    int32_t accumulate, void* stream);
 DMT_API size_t dmt_selftest_tf32_wgrad_bytes(int64_t T, int32_t MA, int32_t NB);
 DMT_API int dmt_selftest_tf32_wgrad(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t T, int32_t MA,

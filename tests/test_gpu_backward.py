@@ -91,7 +91,9 @@ def test_gradients_two_blocks_and_ctr_rel_multiply():
 
 @pytest.mark.parametrize("conf_file,batch,engine,rel_tol,cos_tol",
                          [("dmt_d64.conf", 200, "bf16x3", 2e-3, 0.99999), ("dmt.conf", 72, "bf16x3", 2e-3, 0.99999),
-                          ("dmt_d64.conf", 200, "bf16", 1e-1, 0.995)])
+                          ("dmt_d64.conf", 200, "bf16", 1e-1, 0.995),
+                          ("dmt_d64.conf", 200, "tf32", 6e-2, 0.999), ("dmt.conf", 72, "tf32", 6e-2, 0.999),
+                          ("dmt_d64.conf", 2100, "tf32", 6e-2, 0.999)])
 def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol):
     """Training with every GEMM of the path (MMoE forward, all dgrad / wgrad contractions) on tcgen05, fp32
     accumulation, everything else fp32.
@@ -99,13 +101,16 @@ def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol)
         relative Frobenius error <= 2e-3 and cosine >= 0.99999 against the fp64 oracle gradient;
       * 'bf16': plain bf16 operands (2^-9 rounding per operand through a chain of up to eight GEMMs and a
         loss whose class weights reach 400): relative error <= 1e-1, cosine >= 0.995.
+      * 'tf32': the per-token GEMMs of the sequence pipeline on the TMA-fed kind::tf32 engine straight from the
+        fp32 activations (operand mantissa truncated to 10 bits), the MMoE GEMMs on bf16x3: relative error <= 6e-2,
+        cosine >= 0.999 (bf16-class tolerance, cos-sim >= 0.999; 2100 samples: several row tiles per persistent CTA and several token splits).
     Variables whose exact gradient is ~0 are compared absolutely."""
     plan, model, store, host, dev, O = _setup(conf_file, batch, seed=31, precision="bf16", train_gemm=engine)
     P = O.params_from_store(store)
     loss_ref, grads_ref, _ = O.loss_and_grads(plan, P, host)
     loss, G = model.compute_gradients(dev)
     torch.cuda.synchronize()
-    assert abs(loss.item() - loss_ref.item()) <= (1e-2 if engine == "bf16" else 1e-4) * abs(loss_ref.item())
+    assert abs(loss.item() - loss_ref.item()) <= {"bf16": 1e-2, "tf32": 3e-3}.get(engine, 1e-4) * abs(loss_ref.item())
     scale = max(float(g.abs().max()) for g in grads_ref.values())
     bad = []
     for name in [s.name for s in store.specs] + list(store.tables):
@@ -125,8 +130,9 @@ def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol)
     assert not bad, bad
 
 
-def test_bf16_gemm_gradients_are_deterministic():
-    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 300, seed=5, precision="bf16")
+@pytest.mark.parametrize("engine", ["bf16x3", "tf32"])
+def test_bf16_gemm_gradients_are_deterministic(engine):
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 300, seed=5, precision="bf16", train_gemm=engine)
     _, G = model.compute_gradients(dev)
     first = G.dense.clone()
     _, G = model.compute_gradients(dev)

@@ -100,3 +100,36 @@ def test_tf32_colsum(T, W):
     torch.cuda.synchronize()
     want = 1.0 + X[:, :W].double().sum(0)
     assert (out.double() - want).abs().max().item() <= 1e-4 * max(1.0, math.sqrt(max(T, 1)))
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (0, 0), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(8192, 512, 1087), (1000, 128, 256), (1087, 512, 3000), (300, 472, 512), (130, 4, 40)])
+def test_tf32_gemm_all_operand_orders(a_mn, b_mn, M, N, K):
+    """The general tiled kernel through every operand storage order (K-major / MN-major, i.e. SWIZZLE_128B /
+    SWIZZLE_128B_ATOM_32B boxes), ragged M / N / K, bias + ReLU + mask + accumulate, misaligned output columns."""
+    abi, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + a_mn * 2 + b_mn)
+    pad = lambda n: (n + 3) // 4 * 4
+    A = torch.randn(K, pad(M), device="cuda", generator=g)[:, :M] if a_mn else torch.randn(M, pad(K), device="cuda", generator=g)[:, :K]
+    B = torch.randn(K, pad(N), device="cuda", generator=g)[:, :N] if b_mn else torch.randn(N, pad(K), device="cuda", generator=g)[:, :K]
+    bias = torch.randn(N, device="cuda", generator=g)
+    mask = torch.randn(M, pad(N), device="cuda", generator=g)
+    wide = torch.randn(M, pad(N) + 8, device="cuda", generator=g)
+    old = wide.clone()
+    Cv = wide[:, 3:3 + N]                                   # misaligned first column: scalar store path
+    st = torch.cuda.current_stream().cuda_stream
+    abi.check(lib.dmt_selftest_tf32_gemm(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn, M, N, K,
+                                         Cv.data_ptr(), wide.stride(0), bias.data_ptr(), mask.data_ptr(), mask.stride(0),
+                                         1, 1, st))
+    torch.cuda.synchronize()
+    Am = A.double().t() if a_mn else A.double()
+    Bm = B.double() if b_mn else B.double().t()
+    want = torch.relu(Am @ Bm + bias.double()) * (mask[:, :N] > 0).double() + old[:, 3:3 + N].double()
+    assert (wide[:, 3:3 + N].double() - want).abs().max().item() <= _tol(K, 1.0)
+    assert torch.equal(wide[:, :3], old[:, :3]) and torch.equal(wide[:, 3 + N:], old[:, 3 + N:])
+    # aligned output: vector store path
+    C2 = torch.zeros(M, pad(N), device="cuda")
+    abi.check(lib.dmt_selftest_tf32_gemm(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn, M, N, K,
+                                         C2.data_ptr(), C2.stride(0), None, None, 0, 0, 0, st))
+    torch.cuda.synchronize()
+    assert (C2[:, :N].double() - Am @ Bm).abs().max().item() <= _tol(K, 1.0)
