@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--small-tables", action="store_true", help="debug: tiny vocabularies")
     ap.add_argument("--train-batch", type=int, default=8192, help="per-GPU training batch (BASELINE configs 3/4: 8192)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps of the `train` block")
-    ap.add_argument("--train-gemm", default="bf16", choices=["f32", "bf16", "bf16x3", "tf32"],
-                    help="GEMM engine of the training step (BASELINE config 3 names bf16)")
+    ap.add_argument("--train-gemm", default="tf32", choices=["f32", "bf16", "bf16x3", "tf32"],
+                    help="GEMM engine of the training step (BASELINE config 3 names bf16; tf32 keeps more operand bits)")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs 3/4)")
     ap.add_argument("--no-f32", action="store_true", help="skip the `f32` forward block")
     ap.add_argument("--wide-batch", action="store_true",
@@ -292,6 +292,47 @@ def run_f32_forward(args, plan, store, dev_batches, timed, world):
             "note": "same workload and batches as `value`, inputs resident in HBM"}
 
 
+def run_tf32_forward(args, conf_file, rank, device, timed, world):
+    """A `tf32` block: the forward workload through precision='tf32' -- the row-batched pipeline whose dense
+    projections, feed-forward and MMoE experts run on the TMA-fed tcgen05 kind::tf32 engine straight from fp32
+    activations (no bf16 rounding of activations or weights; attention / LayerNorm fp32 on CUDA cores).  Runs any
+    d_model / d_ff that are multiples of 16: `conf_file` = the bench conf (d_model 64) or the reference's own
+    dmt.conf (d_model 80, 4 heads, d_ff 320).  Logits within atol 2e-2 + rtol 1e-2 of the fp64 oracle (tests)."""
+    import torch
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to, SEED
+    from cikm2020_dmt_b200.params import ParamStore
+    from cikm2020_dmt_b200.plan import build_plan
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    conf = Conf(os.path.join(ROOT, "conf", "settings") + "/", conf_file)
+    plan = build_plan(conf)
+    rows = None
+    if args.small_tables:
+        rows = SMALL_ROWS
+        for t in list(plan.tables.values()) + list(plan.bias_tables.values()):
+            if t.name in rows:
+                t.rows = rows[t.name]
+    store = ParamStore(plan, device=device)
+    model = mmoe_transformer_unbias(plan, params=store, precision="tf32")
+    batches = [batch_to(synthetic_batch(plan, args.batch, seed=SEED + 70000 + 1000 * rank + i, id_mode=args.id_mode,
+                                        table_rows=rows), device) for i in range(3)]
+    step = lambda i: model.inference(batches[i % len(batches)], is_train=False)
+    for i in range(3):
+        step(i)
+    l0 = model.launches
+    ms = timed(step, args.f32_steps)
+    out = {"conf": conf_file, "d_model": plan.d_model, "num_heads": plan.num_heads, "d_ff": plan.d_ff,
+           "mmoe_in": plan.mmoe_in, "value": world * args.batch * args.f32_steps / (ms / 1e3), "unit": "samples/s",
+           "ms_per_step": ms / args.f32_steps, "steps": args.f32_steps, "warmup": 3,
+           "dtype": "tf32 operands (fp32 storage, 10-bit operand mantissa in the tensor core) / fp32 accumulate",
+           "gpu_launches": int(model.launches - l0),
+           "kernels": "tf32_rows_kernel / tf32_gemm_kernel (TMA + tcgen05 kind::tf32) + fp32 SIMT attention, LayerNorm",
+           "tolerance": "logits atol 2e-2 + rtol 1e-2 vs the fp64 oracle (tests/test_gpu_parity.py)"}
+    del model, store, batches
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_dp_parity(args, world, rank, device):
     """N ranks on 1/N of a global batch each (row-sharded Sku, one allreduce bucket) vs ONE rank on the whole batch,
     2 optimizer steps, dropout off, small vocabularies: max / mean |delta parameter| over every variable (the
@@ -515,6 +556,10 @@ def main():
             return {"error": "%s: %s" % (type(exc).__name__, exc), "trace": traceback.format_exc()[-800:]}
 
     f32_block = None if args.no_f32 else guarded(run_f32_forward, args, plan, store, dev_batches, timed, world)
+    tf32_block = tf32_dmt_block = None
+    if not args.no_f32:
+        tf32_block = guarded(run_tf32_forward, args, args.conf, rank, device, timed, world)
+        tf32_dmt_block = guarded(run_tf32_forward, args, "dmt.conf", rank, device, timed, world)
     train_block = None
     if not args.no_train:
         dev_batches = None
@@ -650,7 +695,7 @@ def main():
                             "step i computes; one H2D copy and one D2H read (side stream) per step inside the timed region; the host "
                             "waits for step i-1's scores after launching step i"},
         "embed_gather": embed_gather,
-        "f32": f32_block, "train": train_block,
+        "f32": f32_block, "tf32": tf32_block, "tf32_dmt_conf": tf32_dmt_block, "train": train_block,
         "gpu_launches": int(gpu_launches), "clocks": clocks,
         "tokens_per_step": sum(batch_tokens(plan, b) for b in batches) / len(batches),
     }

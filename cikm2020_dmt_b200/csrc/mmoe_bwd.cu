@@ -7,6 +7,7 @@
 //                          multi-part problem, so dx is written once.
 #include "dropout.cuh"
 #include "gemm_f32.cuh"
+#include "gemm_tf32.cuh"
 #include "seq_train.cuh"   // Carver
 
 namespace dmt {
@@ -169,6 +170,7 @@ struct MmoeBwdWs {
   float* part_expert[DMT_MAX_EXPERTS];   // split-K scratch, one per expert (largest layer)
   float* part_gate[DMT_MAX_TASKS];
   float* part_tower[DMT_MAX_TASKS][DMT_MAX_LAYERS + 1];
+  float* tf_colsum;                      // DMT_PRECISION_TF32: scratch of the bias-gradient column sums
   int splits_layer[DMT_MAX_LAYERS];
   int splits_gate, splits_tower[DMT_MAX_LAYERS + 1];
 };
@@ -203,6 +205,11 @@ size_t mmoe_bwd_carve(const dmt_mmoe_cfg& c, void* base, MmoeBwdWs* out) {
     w.splits_tower[l] = gemm_pick_splits(in_dim, units, (int64_t)B, tc);
     for (size_t t = 0; t < T; ++t) w.part_tower[t][l] = cv.take((size_t)w.splits_tower[l] * (in_dim + 1) * units);
     in_dim = units;
+  }
+  if (gemm_tf32(c.precision)) {
+    int wmax = 4;
+    for (int l = 0; l < c.n_layers; ++l) wmax = c.units[l] > wmax ? c.units[l] : wmax;
+    w.tf_colsum = cv.take(tf32_colsum_scratch_bytes((wmax + 3) / 4 * 4) / sizeof(float));
   }
   if (out) *out = w;
   return cv.off + 256;
@@ -298,10 +305,37 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
     if ((rc = gemm_group_launch(grp, st))) return rc;
   }
   // expert layers, last to first
+  const bool tf = gemm_tf32(c.precision);
+  bool tf_ok = tf && E <= 4;
+  for (int l = 0; l < NL && tf_ok; ++l) tf_ok = c.units[l] % 4 == 0;
   for (int l = NL - 1; l >= 0; --l) {
     const int units = c.units[l];
     const int in_dim = l == 0 ? c.in_dim : c.units[l - 1];
-    {
+    if (tf_ok) {
+      // dW_e (+)= in_e^T dH_e: both operands MN-major straight from the row-major activations (contraction over
+      // the batch), the four experts in one launch; db_e (+)= column sums of dH_e
+      Tf32Gemm p{};
+      p.nz = E;
+      p.a_mn = 1;
+      p.b_mn = 1;
+      p.lda = l == 0 ? x_ld : in_dim;
+      p.ldb = units;
+      p.M = in_dim;
+      p.N = units;
+      p.K = B;
+      p.ldc = units;
+      p.accumulate = 1;
+      for (int e = 0; e < E; ++e) {
+        p.A[e] = l == 0 ? x : H[l - 1] + (int64_t)e * B * in_dim;
+        p.B[e] = ws.dH[l] + (int64_t)e * B * units;
+        p.C[e] = const_cast<float*>(g->expert[e][l].w);
+      }
+      if ((rc = tf32_gemm(p, st))) return rc;
+      for (int e = 0; e < E; ++e)
+        if ((rc = tf32_colsum(ws.dH[l] + (int64_t)e * B * units, units, B, units, const_cast<float*>(g->expert[e][l].b), 1,
+                              ws.tf_colsum, st)))
+          return rc;
+    } else {
       GemmGroup grp{};
       grp.use_tc = use_tc;
       for (int e = 0; e < E; ++e) {
@@ -312,7 +346,25 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
       grp.n = E;
       if ((rc = gemm_group_launch(grp, st))) return rc;
     }
-    if (l > 0) {
+    if (l > 0 && tf_ok) {
+      // dH_{l-1,e} = (dH_{l,e} W_e^T) * (H_{l-1,e} > 0): the TF kernel [in, units] is the K-major operand as stored
+      Tf32Gemm p{};
+      p.nz = E;
+      p.lda = units;
+      p.ldb = units;
+      p.M = B;
+      p.N = in_dim;
+      p.K = units;
+      p.ldc = in_dim;
+      p.ld_mask = in_dim;
+      for (int e = 0; e < E; ++e) {
+        p.A[e] = ws.dH[l] + (int64_t)e * B * units;
+        p.B[e] = w->expert[e][l].w;
+        p.C[e] = ws.dH[l - 1] + (int64_t)e * B * in_dim;
+        p.mask[e] = H[l - 1] + (int64_t)e * B * in_dim;
+      }
+      if ((rc = tf32_gemm(p, st))) return rc;
+    } else if (l > 0) {
       GemmGroup grp{};
       grp.use_tc = use_tc;
       for (int e = 0; e < E; ++e) {
@@ -333,15 +385,33 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
     } else if (dx && dx_col0 < c.in_dim) {
       DMT_REQUIRE(E + NT <= kGemmMaxParts, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_bwd: experts + tasks = %d > %d", E + NT,
                   kGemmMaxParts);
+      if (tf_ok) {   // dx[:, col0:] = sum_e dH_{0,e} W_{0,e}[col0:, :]^T (one launch, summed over the experts) ...
+        Tf32Gemm q{};
+        q.nz = E;
+        q.reduce_z = 1;
+        q.lda = units;
+        q.ldb = units;
+        q.M = B;
+        q.N = c.in_dim - dx_col0;
+        q.K = units;
+        q.C[0] = dx + dx_col0;
+        q.ldc = dx_ld;
+        for (int e = 0; e < E; ++e) {
+          q.A[e] = ws.dH[0] + (int64_t)e * B * units;
+          q.B[e] = w->expert[e][0].w + (int64_t)dx_col0 * units;
+        }
+        if ((rc = tf32_gemm(q, st))) return rc;
+      }
       GemmGroup grp{};
       grp.use_tc = use_tc;
       GemmProb& p = grp.p[0];
       gemm_prob_init(p);
       int n = 0;
-      for (int e = 0; e < E; ++e)
-        p.part[n++] = GemmPart{ws.dH[0] + (int64_t)e * B * units, w->expert[e][0].w + (int64_t)dx_col0 * units, units,
-                               units, units, 0};
-      for (int t = 0; t < NT; ++t)
+      if (!tf_ok)
+        for (int e = 0; e < E; ++e)
+          p.part[n++] = GemmPart{ws.dH[0] + (int64_t)e * B * units, w->expert[e][0].w + (int64_t)dx_col0 * units, units,
+                                 units, units, 0};
+      for (int t = 0; t < NT; ++t)      // ... + the gates' share (K = experts per task: a few columns)
         p.part[n++] = GemmPart{ws.dgl + t * E, w->gate[t].w + (int64_t)dx_col0 * E, (int64_t)NT * E, E, E, 0};
       p.n_parts = n;
       p.M = B;
@@ -349,6 +419,7 @@ int mmoe_bwd_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const fl
       p.transB = 1;
       p.C = dx + dx_col0;
       p.ldc = dx_ld;
+      p.accumulate = tf_ok ? 1 : 0;
       grp.n = 1;
       if ((rc = gemm_group_launch(grp, st))) return rc;
     }
@@ -371,25 +442,48 @@ int mmoe_fwd_train_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, co
   int64_t in_ld = x_ld, in_stride = 0;
   int in_dim = c.in_dim;
   float* out = ws;
+  bool tf_ok = gemm_tf32(c.precision) && E <= 4 && x_ld % 4 == 0;
+  for (int l = 0; l < c.n_layers && tf_ok; ++l) tf_ok = c.units[l] % 4 == 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const int units = c.units[l];
-    GemmGroup grp{};
-    grp.use_tc = gemm_engine(c.precision);
-    for (int e = 0; e < E; ++e) {
-      GemmProb& p = grp.p[e];
-      gemm_prob_init(p);
-      p.n_parts = 1;
-      p.part[0] = GemmPart{in + in_stride * e, w->expert[e][l].w, in_ld, units, in_dim, 0};
+    if (tf_ok) {   // H_{l,e} = relu(in_e W_e + b_e): the TF kernel [in, units] is the MN-major operand as stored
+      Tf32Gemm p{};
+      p.nz = E;
+      p.b_mn = 1;
+      p.lda = in_ld;
+      p.ldb = units;
       p.M = B;
       p.N = units;
-      p.C = out + (int64_t)e * B * units;
+      p.K = in_dim;
       p.ldc = units;
-      p.bias = w->expert[e][l].b;
       p.relu = 1;
+      for (int e = 0; e < E; ++e) {
+        p.A[e] = in + in_stride * e;
+        p.B[e] = w->expert[e][l].w;
+        p.C[e] = out + (int64_t)e * B * units;
+        p.bias[e] = w->expert[e][l].b;
+      }
+      int rc = tf32_gemm(p, st);
+      if (rc) return rc;
+    } else {
+      GemmGroup grp{};
+      grp.use_tc = gemm_engine(c.precision);
+      for (int e = 0; e < E; ++e) {
+        GemmProb& p = grp.p[e];
+        gemm_prob_init(p);
+        p.n_parts = 1;
+        p.part[0] = GemmPart{in + in_stride * e, w->expert[e][l].w, in_ld, units, in_dim, 0};
+        p.M = B;
+        p.N = units;
+        p.C = out + (int64_t)e * B * units;
+        p.ldc = units;
+        p.bias = w->expert[e][l].b;
+        p.relu = 1;
+      }
+      grp.n = E;
+      int rc = gemm_group_launch(grp, st);
+      if (rc) return rc;
     }
-    grp.n = E;
-    int rc = gemm_group_launch(grp, st);
-    if (rc) return rc;
     in = out;
     in_ld = units;
     in_dim = units;

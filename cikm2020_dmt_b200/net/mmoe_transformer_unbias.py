@@ -24,7 +24,10 @@ def _is_host(t):
 
 class mmoe_transformer_unbias(object):
     def __init__(self, wnd_conf, device=None, params=None, precision="f32", seed=20201019, train_gemm=None):
-        """precision: 'f32' (CUDA cores, exact-parity path) | 'bf16' (tcgen05 inference kernels).
+        """precision: 'f32' (CUDA cores, exact-parity path) | 'bf16' (fused tcgen05 tile kernels; d_model 64 / 2 heads)
+        | 'tf32' (any d_model / d_ff that are multiples of 16, e.g. dmt.conf's 80 / 320 with 4 heads: the row-batched
+        pipeline -- every dense projection, the feed-forward and the MMoE experts on the TMA-fed tcgen05 kind::tf32
+        engine straight from fp32 activations, attention / LayerNorm on CUDA cores in fp32).
         train_gemm: engine of the GEMMs of the TRAINING path -- 'f32' (SIMT), 'bf16' (tcgen05, bf16 operands),
         'bf16x3' (tcgen05, split hi+lo operands: fp32-grade) or 'tf32' (the per-token GEMMs of the sequence pipeline on
         the TMA-fed tcgen05 kind::tf32 engine, no operand conversion pass; MMoE on bf16x3).
@@ -37,9 +40,9 @@ class mmoe_transformer_unbias(object):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = abi.load()
-        self.precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16}[precision]
+        self.precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16, "tf32": abi.PRECISION_TF32}[precision]
         if train_gemm is None:
-            train_gemm = "f32" if precision == "f32" else "bf16x3"
+            train_gemm = {"f32": "f32", "tf32": "tf32"}.get(precision, "bf16x3")
         self.train_precision = {"f32": abi.PRECISION_F32, "bf16": abi.PRECISION_BF16,
                                 "bf16x3": abi.PRECISION_BF16X3, "tf32": abi.PRECISION_TF32}[train_gemm]
         self.params = params if params is not None else ParamStore(self.plan, device=self.device, seed=seed)
@@ -361,6 +364,15 @@ class mmoe_transformer_unbias(object):
         plan = self.plan
         seq = plan.sequences[seq_index]
         cfg = self._seq_cfg(inputs, seq, batch, self.precision)
+        if self.precision == abi.PRECISION_TF32:      # row-batched pipeline (its intermediates live in `saved`)
+            si, keep = self._seq_input(inputs, seq, batch)
+            n_tok = self._sparse(inputs, seq.user_features[-1], "seq%d" % seq.index).values.numel()
+            saved = self._scratch("seq_saved_%d" % seq_index, self.lib.dmt_seq_saved_bytes(C.byref(cfg), n_tok))
+            with self._Stage(self, "seq_encode", 1):
+                abi.check(self.lib.dmt_seq_encode_fwd_train(C.byref(cfg), C.byref(si), C.byref(self._seq_w[seq_index]),
+                                                            out, out_ld, n_tok, saved.data_ptr(), saved.numel(),
+                                                            self._stream()))
+            return keep
         ws_ptr, ws_bytes = None, 0
         if self.precision == abi.PRECISION_BF16:
             ws, ws_bytes = self._prepared_for(seq_index, cfg)
@@ -488,16 +500,19 @@ class mmoe_transformer_unbias(object):
             plan = self.plan
             if is_train and (plan.dropout_rate > 0 or any(r > 0 for r in plan.dropout_rate_bias)):
                 return self._inference_train(inputs, is_predict, dropout_seed)
+            if self.precision == abi.PRECISION_TF32:      # the row-batched pipeline, dropout off
+                return self._inference_train(inputs, is_predict, 0, dropout=False, engine=abi.PRECISION_TF32)
             return self._inference(inputs, is_train, is_predict)
         finally:
             self._stream_h = None
 
-    def _inference_train(self, inputs, is_predict, dropout_seed):
-        """Forward of the training graph (dropout active); no activations are kept for a backward."""
+    def _inference_train(self, inputs, is_predict, dropout_seed, dropout=True, engine=None):
+        """Forward of the training graph through the row-batched pipeline (dropout active unless dropout=False); the
+        activations it leaves in the `saved` scratch are not kept for a backward."""
         from .. import dropout as DO
         plan, lib = self.plan, self.lib
-        rate = float(plan.dropout_rate)
-        rates_bias = [float(r) for r in plan.dropout_rate_bias]
+        rate = float(plan.dropout_rate) if dropout else 0.0
+        rates_bias = [float(r) for r in plan.dropout_rate_bias] if dropout else []
         if dropout_seed is None:
             self._train_calls = getattr(self, "_train_calls", 0) + 1
             dropout_seed = DO.step_seed(getattr(self, "dropout_base_seed", 20201019), self._train_calls)
@@ -506,7 +521,7 @@ class mmoe_transformer_unbias(object):
         feats = inputs["features"] if plan.is_use_feature else None
         batch = inputs[plan.pooled[0].feature].offsets.numel() - 1
         stream = self._stream()
-        F32 = self.train_precision
+        F32 = self.train_precision if engine is None else engine
         x_ld = (plan.mmoe_in + 3) // 4 * 4
         x = self._buf("x", (batch, x_ld))
         keep = []

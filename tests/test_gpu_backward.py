@@ -92,7 +92,7 @@ def test_gradients_two_blocks_and_ctr_rel_multiply():
 @pytest.mark.parametrize("conf_file,batch,engine,rel_tol,cos_tol",
                          [("dmt_d64.conf", 200, "bf16x3", 2e-3, 0.99999), ("dmt.conf", 72, "bf16x3", 2e-3, 0.99999),
                           ("dmt_d64.conf", 200, "bf16", 1e-1, 0.995),
-                          ("dmt_d64.conf", 200, "tf32", 6e-2, 0.999), ("dmt.conf", 72, "tf32", 6e-2, 0.999),
+                          ("dmt_d64.conf", 200, "tf32", 1e-1, 0.998), ("dmt.conf", 72, "tf32", 1e-1, 0.998),
                           ("dmt_d64.conf", 2100, "tf32", 6e-2, 0.999)])
 def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol):
     """Training with every GEMM of the path (MMoE forward, all dgrad / wgrad contractions) on tcgen05, fp32
@@ -102,8 +102,8 @@ def test_gradients_tensor_core_gemms(conf_file, batch, engine, rel_tol, cos_tol)
       * 'bf16': plain bf16 operands (2^-9 rounding per operand through a chain of up to eight GEMMs and a
         loss whose class weights reach 400): relative error <= 1e-1, cosine >= 0.995.
       * 'tf32': the per-token GEMMs of the sequence pipeline on the TMA-fed kind::tf32 engine straight from the
-        fp32 activations (operand mantissa truncated to 10 bits), the MMoE GEMMs on bf16x3: relative error <= 6e-2,
-        cosine >= 0.999 (bf16-class tolerance, cos-sim >= 0.999; 2100 samples: several row tiles per persistent CTA and several token splits).
+        fp32 activations (operand mantissa truncated to 10 bits), MMoE included: a bf16-class engine -- relative error
+        <= 1e-1, cosine >= 0.998 on the small batches and <= 6e-2 / >= 0.999 on 2100 samples (2100 samples: several row tiles per persistent CTA and several token splits).
     Variables whose exact gradient is ~0 are compared absolutely."""
     plan, model, store, host, dev, O = _setup(conf_file, batch, seed=31, precision="bf16", train_gemm=engine)
     P = O.params_from_store(store)

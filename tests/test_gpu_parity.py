@@ -444,3 +444,35 @@ def test_compact_packed_batch_widen_and_bf16_features():
     # the fp32 path refuses bf16 features instead of silently widening them
     with pytest.raises(ValueError):
         model.inference(packed, is_train=False)
+
+
+@pytest.mark.parametrize("conf_file,batch", [("dmt.conf", 300), ("dmt_d64.conf", 300)])
+def test_inference_tf32_pipeline_matches_oracle(conf_file, batch):
+    """precision='tf32': the row-batched pipeline (dense projections / feed-forward / MMoE experts on the TMA-fed
+    tcgen05 kind::tf32 engine, attention and LayerNorm fp32 on CUDA cores) -- the tensor-core path for ANY shape
+    with d_model, d_ff multiples of 16, in particular the reference's own dmt.conf (d_model 80, 4 heads of 20,
+    d_ff 320, MMoE input 1199).  tf32 keeps 10 operand mantissa bits: interest vectors atol 2e-2 / mean 3e-3,
+    logits atol 2e-2 + rtol 1e-2, loss rtol 5e-3 against the fp64 oracle."""
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    plan, model, host, dev, P, O = _setup(conf_file, batch, seed=83)
+    tf = mmoe_transformer_unbias(plan, params=model.params, precision="tf32")
+    want = O.trans_core(plan, P, O.generate_data(plan, P, host), training=False)
+    out = torch.zeros(batch, len(plan.sequences) * plan.d_model, device="cuda")
+    for s in range(len(plan.sequences)):
+        tf.seq_encode(dev, s, out.data_ptr() + 4 * s * plan.d_model, out.stride(0), batch)
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - want.double()).abs()
+    assert err.max().item() < 2e-2 and err.mean().item() < 3e-3, (err.max().item(), err.mean().item())
+    (yr, yb) = tf.inference(dev, is_train=False)
+    (wr, wb) = O.inference(plan, P, host, is_train=False)
+    torch.cuda.synchronize()
+    _close(yr[0], wr[0], atol=2e-2, rtol=1e-2)
+    _close(yr[1], wr[1], atol=2e-2, rtol=1e-2)
+    _close(yb, wb, atol=1e-5)
+    loss = tf.loss((yr, yb), dev["mask"])
+    want_loss = O.logit_loss_unbias(plan, (wr, wb), host["mask"])
+    assert abs(loss.item() - want_loss.item()) <= 5e-3 * max(1.0, abs(want_loss.item()))
+    # is_predict returns the logit pair only, from the same kernels
+    (pc, po) = tf.inference(dev, is_train=False, is_predict=True)
+    torch.cuda.synchronize()
+    assert torch.equal(pc, yr[0]) and torch.equal(po, yr[1])
