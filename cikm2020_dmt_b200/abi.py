@@ -164,7 +164,7 @@ PROTOTYPES = {
                                          C.c_int32, _fp, C.c_int64, _fp, _fp, C.c_int64, C.c_int32, C.c_int32, _fp]),
     "dmt_selftest_tf32_wgrad_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "dmt_selftest_tf32_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
-                                          C.c_int64, C.c_int32, C.c_int32, _fp, _fp]),
+                                          C.c_int64, C.c_int32, C.c_int32, _fp, _fp, _fp]),
     "dmt_selftest_tf32_colsum": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int32, _fp, C.c_int32, _fp, _fp]),
 }
 

@@ -203,6 +203,7 @@ struct WgradArgs {
   int64_t T, tps;       // tokens per split (multiple of WKT)
   int MA, NB, m_tiles, splits, stages;
   float* partial;       // [splits][m_tiles * 128][NB]
+  float* partial_cs;    // non-null: [splits][m_tiles * 128] column sums of P (one extra MMA per K step)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1) tf32_wgrad_kernel(const __grid_constant__ WgradArgs g) {
@@ -220,8 +221,15 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tf32_wgrad_kernel(const __gr
   int64_t t1 = t0 + g.tps;
   if (t1 > g.T) t1 = g.T;
   const int nkb = t1 > t0 ? (int)((t1 - t0 + WKT - 1) / WKT) : 0;
+  const bool want_cs = g.partial_cs != nullptr;
+  const int cs_col = nbq * 32;                             // TMEM column of the column-sum accumulator
   uint32_t ncols = 32;
-  while ((int)ncols < NB) ncols <<= 1;
+  while ((int)ncols < (want_cs ? cs_col + 16 : NB)) ncols <<= 1;
+  const uint32_t ones = s0 + S * stage_bytes;              // 1 KB of 1.0f: 8 k-rows x 128 B (any swizzle of ones is ones)
+  if (want_cs) {
+    for (int i = threadIdx.x; i < 256; i += kWgradThreads) reinterpret_cast<float*>(smem + S * stage_bytes)[i] = 1.0f;
+    fence_proxy_async();
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -253,16 +261,19 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tf32_wgrad_kernel(const __gr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(RBM, NB, true, true);
+      const uint32_t idesc = make_idesc_tf32(RBM, NB, true, true), idesc_cs = make_idesc_tf32(RBM, 16, true, true);
+      const uint64_t d_ones = make_smem_desc(ones, kBox, 512, kLayoutSW128Base32B);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         mbar_wait(&full_bar[s], (kb / S) & 1);
         fence_after_sync();
         const uint32_t sp = s0 + s * stage_bytes, sq = sp + 4 * kBox;
 #pragma unroll
-        for (int k = 0; k < WKT / 8; ++k)
-          mma_tf32_ss(tbase, make_smem_desc(sp + k * 1024, kBox, 512, kLayoutSW128Base32B),
-                      make_smem_desc(sq + k * 1024, kBox, 512, kLayoutSW128Base32B), idesc, (kb | k) != 0);
+        for (int k = 0; k < WKT / 8; ++k) {
+          const uint64_t dp = make_smem_desc(sp + k * 1024, kBox, 512, kLayoutSW128Base32B);
+          mma_tf32_ss(tbase, dp, make_smem_desc(sq + k * 1024, kBox, 512, kLayoutSW128Base32B), idesc, (kb | k) != 0);
+          if (want_cs) mma_tf32_ss(tbase + cs_col, dp, d_ones, idesc_cs, (kb | k) != 0);   // sum_t P[t, m] * 1
+        }
         commit(&empty_bar[s]);
       }
       commit(&accum_bar);
@@ -273,6 +284,14 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tf32_wgrad_kernel(const __gr
     const int row = (warp & 3) * 32 + lane;
     const int m = mt * RBM + row;
     float* prow = g.partial + ((int64_t)split * g.m_tiles * RBM + m) * NB;
+    if (want_cs) {
+      uint32_t r8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (nkb > 0) {
+        tmem_ld8(tmem_addr(tbase, cs_col), r8);
+        tmem_ld_wait();
+      }
+      if (m < g.MA) g.partial_cs[(int64_t)split * g.m_tiles * RBM + m] = __uint_as_float(r8[0]);
+    }
     for (int c0 = 0; c0 < NB; c0 += 32) {
       const int w = NB - c0 < 32 ? NB - c0 : 32;
       uint32_t r[32];
@@ -446,6 +465,7 @@ __global__ void __launch_bounds__(kGemmThreadsG, 1) tf32_gemm_kernel(const __gri
 
 struct WgradReduceArgs {
   const float* partial;
+  const float* partial_cs;
   Tf32WgradSeg seg[4];
   int n_seg, MA, NB, m_tiles, splits, transposed, accumulate;
 };
@@ -453,6 +473,16 @@ struct WgradReduceArgs {
 // fixed-order sum over the splits (deterministic), scattered into the weight tensors
 __global__ void __launch_bounds__(256) tf32_wgrad_reduce_kernel(const __grid_constant__ WgradReduceArgs a) {
   const int i = blockIdx.x * 256 + threadIdx.x;
+  if (a.partial_cs && i >= a.MA * a.NB && i < a.MA * a.NB + a.MA) {      // the column sums (bias gradients)
+    const int m = i - a.MA * a.NB;
+    float s = 0.f;
+    for (int k = 0; k < a.splits; ++k) s += a.partial_cs[(int64_t)k * a.m_tiles * RBM + m];
+    for (int q = 0; q < a.n_seg; ++q) {
+      const Tf32WgradSeg& sg = a.seg[q];
+      if (m >= sg.m0 && m < sg.m1 && sg.colsum) sg.colsum[m - sg.m0] = (a.accumulate ? sg.colsum[m - sg.m0] : 0.f) + s;
+    }
+    return;
+  }
   if (i >= a.MA * a.NB) return;
   const int m = i / a.NB, n = i - m * a.NB;
   const int64_t stride = (int64_t)a.m_tiles * RBM * a.NB;
@@ -720,7 +750,7 @@ size_t tf32_wgrad_partial_bytes(int64_t T, int MA, int NB) {
   int mt, s;
   int64_t per;
   wgrad_plan(T, MA, NB, &mt, &s, &per);
-  return ((size_t)s * mt * RBM * NB * sizeof(float) + 255) & ~(size_t)255;
+  return (((size_t)s * mt * RBM * (NB + 1) * sizeof(float) + 255) & ~(size_t)255) + 256;   // + column-sum partials
 }
 
 int tf32_wgrad(const Tf32Wgrad& p, cudaStream_t st) {
@@ -735,9 +765,13 @@ int tf32_wgrad(const Tf32Wgrad& p, cudaStream_t st) {
   g.MA = p.MA;
   g.NB = p.NB;
   g.partial = p.partial;
+  bool want_cs = false;
+  for (int i = 0; i < p.n_seg; ++i) want_cs = want_cs || p.seg[i].colsum != nullptr;
+  g.partial_cs = want_cs ? p.partial + (((size_t)g.splits * g.m_tiles * RBM * p.NB + 63) & ~(size_t)63) : nullptr;
   const int nbq = (p.NB + 31) / 32;
+  DMT_REQUIRE(!want_cs || nbq * 32 + 16 <= 512, DMT_ERR_UNSUPPORTED_SHAPE, "tf32_wgrad: NB=%d with column sums", p.NB);
   const int stage_bytes = (4 + nbq) * WKT * 128;
-  int stages = (220 * 1024) / stage_bytes;
+  int stages = (219 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   DMT_REQUIRE(stages >= 2, DMT_ERR_UNSUPPORTED_SHAPE, "tf32_wgrad: NB=%d stage does not fit", p.NB);
   g.stages = stages;
@@ -746,7 +780,7 @@ int tf32_wgrad(const Tf32Wgrad& p, cudaStream_t st) {
     if (rc != DMT_OK) return rc;
     rc = make_map_f32(&g.tmQ, p.Q, p.T, p.NB, p.ldq, WKT, true);
     if (rc != DMT_OK) return rc;
-    const int smem = stages * stage_bytes + 1024;
+    const int smem = stages * stage_bytes + 1024 + 1024;     // + the block of ones
     cudaError_t e = cudaFuncSetAttribute(tf32_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tf32_wgrad_kernel)");
     tf32_wgrad_kernel<<<dim3(g.splits, g.m_tiles), kWgradThreads, smem, st>>>(g);
@@ -756,6 +790,7 @@ int tf32_wgrad(const Tf32Wgrad& p, cudaStream_t st) {
   }
   WgradReduceArgs r;
   r.partial = p.partial;
+  r.partial_cs = g.partial_cs;
   for (int i = 0; i < 4; ++i) r.seg[i] = p.seg[i < p.n_seg ? i : 0];
   r.n_seg = p.n_seg;
   r.MA = p.MA;
@@ -764,7 +799,7 @@ int tf32_wgrad(const Tf32Wgrad& p, cudaStream_t st) {
   r.splits = g.splits;
   r.transposed = p.transposed;
   r.accumulate = p.accumulate;
-  tf32_wgrad_reduce_kernel<<<(p.MA * p.NB + 255) / 256, 256, 0, st>>>(r);
+  tf32_wgrad_reduce_kernel<<<(p.MA * p.NB + (want_cs ? p.MA : 0) + 255) / 256, 256, 0, st>>>(r);
   DMT_CUDA_LAUNCH_CHECK("tf32_wgrad_reduce_kernel");
   return DMT_OK;
 }
@@ -811,11 +846,11 @@ int dmt_selftest_tf32_gemm(const float* A, int64_t lda, int32_t a_mn, const floa
 size_t dmt_selftest_tf32_wgrad_bytes(int64_t T, int32_t MA, int32_t NB) { return dmt::tf32_wgrad_partial_bytes(T, MA, NB); }
 
 int dmt_selftest_tf32_wgrad(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t T, int32_t MA, int32_t NB,
-                            float* C, int64_t ldc, int32_t transposed, int32_t accumulate, void* workspace,
-                            void* stream) {
+                            float* C, int64_t ldc, int32_t transposed, int32_t accumulate, float* colsum,
+                            void* workspace, void* stream) {
   dmt::Tf32Wgrad p{};
   p.P = P; p.ldp = ldp; p.Q = Q; p.ldq = ldq; p.T = T; p.MA = MA; p.NB = NB;
-  p.seg[0] = dmt::Tf32WgradSeg{C, ldc, 0, MA};
+  p.seg[0] = dmt::Tf32WgradSeg{C, ldc, 0, MA, colsum};
   p.n_seg = 1;
   p.transposed = transposed;
   p.accumulate = accumulate;

@@ -39,6 +39,8 @@ struct Tf32WgradSeg {  // rows [m0, m1) of D go to one weight tensor
   float* C;            // transposed == 0: C[(m - m0) * ldc + n];  transposed == 1: C[n * ldc + (m - m0)]
   int64_t ldc;
   int m0, m1;
+  float* colsum;       // non-null: colsum[m - m0] (+)= sum_t P[t, m] (the bias gradient when P is the gradient
+                       // matrix) -- rides along as one extra N = 16 MMA per K step against a block of ones
 };
 
 struct Tf32Wgrad {

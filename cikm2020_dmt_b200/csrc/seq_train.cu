@@ -524,21 +524,21 @@ inline int tf32_wgrads(const float* act, int64_t ld_act, int k_act, const float*
   if (n_w == 1 && k_act > n) {       // e.g. W2 [dff, d]: D[m = act column][n = grad column] = dW as stored
     p.P = act; p.ldp = ld_act; p.MA = k_act;
     p.Q = grad; p.ldq = ld_grad; p.NB = n;
-    p.seg[0] = Tf32WgradSeg{const_cast<float*>(g[0]->w), (int64_t)n, 0, k_act};
+    p.seg[0] = Tf32WgradSeg{const_cast<float*>(g[0]->w), (int64_t)n, 0, k_act, nullptr};
     p.n_seg = 1;
     p.transposed = 0;
-  } else {                           // D[m = grad column][n = act column] = dW^T, one segment per weight tensor
-    p.P = grad; p.ldp = ld_grad; p.MA = n * n_w;
-    p.Q = act; p.ldq = ld_act; p.NB = k_act;
-    for (int i = 0; i < n_w; ++i) p.seg[i] = Tf32WgradSeg{const_cast<float*>(g[i]->w), (int64_t)n, i * n, (i + 1) * n};
-    p.n_seg = n_w;
-    p.transposed = 1;
+    if ((rc = tf32_wgrad(p, st))) return rc;
+    return tf32_colsum(grad, ld_grad, rows, n, const_cast<float*>(g[0]->b), 1, ws.tf_colsum, st);
   }
-  if ((rc = tf32_wgrad(p, st))) return rc;
+  // D[m = grad column][n = act column] = dW^T, one segment per weight tensor; the bias gradients (column sums of the
+  // gradient matrix = the row operand) ride along inside the same kernel
+  p.P = grad; p.ldp = ld_grad; p.MA = n * n_w;
+  p.Q = act; p.ldq = ld_act; p.NB = k_act;
   for (int i = 0; i < n_w; ++i)
-    if ((rc = tf32_colsum(grad + (int64_t)i * n, ld_grad, rows, n, const_cast<float*>(g[i]->b), 1, ws.tf_colsum, st)))
-      return rc;
-  return DMT_OK;
+    p.seg[i] = Tf32WgradSeg{const_cast<float*>(g[i]->w), (int64_t)n, i * n, (i + 1) * n, const_cast<float*>(g[i]->b)};
+  p.n_seg = n_w;
+  p.transposed = 1;
+  return tf32_wgrad(p, st);
 }
 
 // Bt[n][i*K + k] = W_i[n][k]: the [N, K] kernels of several projections side by side (dX = sum_i grad_i W_i^T as ONE

@@ -448,7 +448,8 @@ DMT_API int dmt_selftest_tf32_gemm(const float* A, int64_t lda, int32_t a_mn, co
 DMT_API size_t dmt_selftest_tf32_wgrad_bytes(int64_t T, int32_t MA, int32_t NB);
 DMT_API int dmt_selftest_tf32_wgrad(const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t T, int32_t MA,
                                     int32_t NB, float* C, int64_t ldc, int32_t transposed, int32_t accumulate,
-                                    void* workspace, void* stream);
+                                    float* colsum /* [MA] (+)= column sums of P, or NULL */, void* workspace,
+                                    void* stream);
 DMT_API int dmt_selftest_tf32_colsum(const float* X, int64_t ldx, int64_t T, int32_t W, float* out,
                                      int32_t accumulate, void* scratch, void* stream);
 

@@ -70,21 +70,26 @@ def test_tf32_wgrad(T, MA, NB, transposed):
     shape = (NB, MA) if transposed else (MA, NB)
     C = torch.randn(shape, device="cuda", generator=g)
     old = C.clone()
+    cs = torch.randn(MA, device="cuda", generator=g)            # bias gradient riding along: column sums of P
     ws = torch.empty(lib.dmt_selftest_tf32_wgrad_bytes(T, MA, NB), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for acc in (0, 1):
         abi.check(lib.dmt_selftest_tf32_wgrad(P.data_ptr() if T else ws.data_ptr(), MA, Q.data_ptr() if T else ws.data_ptr(),
-                                              NB, T, MA, NB, C.data_ptr(), shape[1], transposed, acc, ws.data_ptr(), st))
+                                              NB, T, MA, NB, C.data_ptr(), shape[1], transposed, acc, cs.data_ptr(),
+                                              ws.data_ptr(), st))
     torch.cuda.synchronize()
     D = P.double().t() @ Q.double()
     want = 2 * (D.t() if transposed else D)                    # written once, accumulated once
     err = (C.double() - want).abs().max().item()
     assert err <= 2 * _tol(max(T, 1), 1.0), err
+    err_cs = (cs.double() - 2 * P.double().sum(0)).abs().max().item()
+    assert err_cs <= 2 * _tol(max(T, 1), 1.0), err_cs
     # deterministic: the same call twice gives the same bits
     C2 = old.clone()
     for acc in (0, 1):
         abi.check(lib.dmt_selftest_tf32_wgrad(P.data_ptr() if T else ws.data_ptr(), MA, Q.data_ptr() if T else ws.data_ptr(),
-                                              NB, T, MA, NB, C2.data_ptr(), shape[1], transposed, acc, ws.data_ptr(), st))
+                                              NB, T, MA, NB, C2.data_ptr(), shape[1], transposed, acc, None,
+                                              ws.data_ptr(), st))
     torch.cuda.synchronize()
     assert torch.equal(C, C2)
 
