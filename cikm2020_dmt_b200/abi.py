@@ -102,6 +102,13 @@ class GradSource(C.Structure):
                 ("mean", C.c_int32)]
 
 MAX_GRAD_SOURCES = 16
+MAX_ADAM_TABLES, MAX_MULTI_GRAD_SOURCES = 16, 64
+
+
+class AdamTable(C.Structure):
+    _fields_ = [("table", _fp), ("m", _fp), ("v", _fp), ("touched", _fp), ("rows", C.c_int64), ("dim", C.c_int32),
+                ("_pad", C.c_int32)]
+
 
 
 # name -> (restype, argtypes); must list every DMT_API symbol of include/dmt_b200.h
@@ -152,6 +159,13 @@ PROTOTYPES = {
     "dmt_embed_grad_scatter_rows": (C.c_int, [C.c_int32, C.POINTER(GradSource), _fp, _fp, _fp, C.c_int64, C.c_int32,
                                               _fp, _fp]),
     "dmt_adam_rows_untouched": (C.c_int, [C.POINTER(AdamCfg), _fp, _fp, _fp, C.c_int64, C.c_int32, _fp, _fp]),
+    "dmt_embed_grad_expand_multi": (C.c_int, [C.c_int32, C.POINTER(AdamTable), C.c_int32, C.POINTER(GradSource),
+                                              C.POINTER(C.c_int32), _fp, _fp, _fp, _fp]),
+    "dmt_embed_sorted_multi_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "dmt_embed_adam_sorted_multi": (C.c_int, [C.POINTER(AdamCfg), C.c_int32, C.POINTER(AdamTable), C.c_int32,
+                                              C.POINTER(GradSource), _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp,
+                                              C.c_size_t, _fp]),
+    "dmt_adam_rows_untouched_multi": (C.c_int, [C.POINTER(AdamCfg), C.c_int32, C.POINTER(AdamTable), _fp]),
     "dmt_build_digest": (C.c_char_p, []),
     "dmt_widen_u16": (C.c_int, [C.c_int32, C.POINTER(WidenDesc), _fp]),
     "dmt_copy_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),

@@ -118,7 +118,14 @@ class TFAdam(object):
         self.v_dense = torch.zeros_like(self.store.dense)
         self.m_tab = {k: torch.zeros_like(t) for k, t in self.store.tables.items()}
         self.v_tab = {k: torch.zeros_like(t) for k, t in self.store.tables.items()}
-        self.touched = {k: torch.zeros(t.shape[0], dtype=torch.uint8, device=dev) for k, t in self.store.tables.items()}
+        # the "row got a gradient this step" marks of all tables live in ONE buffer (cleared with one memset)
+        sizes = {k: (t.shape[0] + 255) // 256 * 256 for k, t in self.store.tables.items()}
+        self._touched_all = torch.zeros(sum(sizes.values()), dtype=torch.uint8, device=dev)
+        self.touched, off = {}, 0
+        for k, t in self.store.tables.items():
+            self.touched[k] = self._touched_all[off:off + t.shape[0]]
+            off += sizes[k]
+        self._multi = None            # cached descriptors of the multi-table path
 
     def current_lr(self, step=None):
         """Learning rate of the step that starts at `global_step` (default: the next one)."""
@@ -141,11 +148,59 @@ class TFAdam(object):
 
     def apply_gradients(self, grads, lr=None, grad_scale=1.0):
         """`optimizer.apply_gradients` (run_dnn.py:203-207): one TF-Adam step over every variable; tables
-        without a lookup this step still decay (dense semantics)."""
+        without a lookup this step still decay (dense semantics).  All embedding tables go through ONE expand /
+        sort / segmented-Adam / untouched-rows sequence (dmt_*_multi); a table too large for the packed keys, or
+        more tables / lookups groups than the multi entry points take, falls back to the per-table calls."""
         self.begin_step()
         self.step_dense(grads.dense, lr=lr, grad_scale=grad_scale)
-        for name in self.store.tables:
+        names = list(self.store.tables)
+        n_src = sum(len(grads.lookups.get(k, [])) for k in names)
+        if (len(names) <= abi.MAX_ADAM_TABLES and 0 < n_src <= abi.MAX_MULTI_GRAD_SOURCES
+                and all(self.store.tables[k].shape[0] <= (1 << 24) and self.store.tables[k].shape[1] <= 128 for k in names)):
+            self.step_tables_multi(names, grads.lookups, lr=lr, grad_scale=grad_scale)
+            return
+        for name in names:
             self.step_table(name, grads.lookups.get(name, []), lr=lr, grad_scale=grad_scale)
+
+    def step_tables_multi(self, names, lookups, lr=None, grad_scale=1.0):
+        """Every table of `names` in one pass: keys = (table index << 24) | row."""
+        cfg = self._cfg(lr)
+        dev = self.store.dense.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._multi is None or self._multi[0] != tuple(names):
+            tabs = (abi.AdamTable * len(names))()
+            for i, k in enumerate(names):
+                t = self.store.tables[k]
+                tabs[i].table, tabs[i].m, tabs[i].v = t.data_ptr(), self.m_tab[k].data_ptr(), self.v_tab[k].data_ptr()
+                tabs[i].touched, tabs[i].rows, tabs[i].dim = self.touched[k].data_ptr(), t.shape[0], t.shape[1]
+            self._multi = (tuple(names), tabs)
+        tabs = self._multi[1]
+        for i, k in enumerate(names):          # the tables may have been re-bound (row-sharded exchange)
+            tabs[i].table = self.store.tables[k].data_ptr()
+        sources, owner = [], []
+        for i, k in enumerate(names):
+            for lg in lookups.get(k, []):
+                sources.append(lg)
+                owner.append(i)
+        arr = (abi.GradSource * len(sources))(*[s.to_c() for s in sources])
+        own = (C.c_int32 * len(owner))(*owner)
+        total = sum(s.ids.numel() for s in sources)
+        buf = self.model._scratch("adam_multi", total * 16 + 1024)
+        keys = buf[:total * 4].view(torch.int32)
+        scale = buf[total * 4:total * 8].view(torch.float32)
+        refs = buf[total * 8:total * 16].view(torch.int64)
+        abi.check(self.lib.dmt_embed_grad_expand_multi(len(names), tabs, len(sources), arr, own, keys.data_ptr(),
+                                                       refs.data_ptr(), scale.data_ptr(), stream))
+        skeys, perm = torch.sort(keys, stable=True)
+        ws = self.model._scratch("sorted_ws", self.lib.dmt_embed_sorted_multi_workspace_bytes(total))
+        abi.check(self.lib.dmt_embed_adam_sorted_multi(C.byref(cfg), len(names), tabs, len(sources), arr, skeys.data_ptr(),
+                                                       perm.data_ptr(), refs.data_ptr(), scale.data_ptr(), total,
+                                                       float(grad_scale), ws.data_ptr(), ws.numel(), stream))
+        abi.check(self.lib.dmt_adam_rows_untouched_multi(C.byref(cfg), len(names), tabs, stream))
+        self._touched_all.zero_()
+        self.model.launches += 5
+        self._keep = (arr, own, keys, refs, scale, skeys, perm, sources)
+        self.model.invalidate_prepared()
 
     def step_dense(self, grad_flat, lr=None, grad_scale=1.0):
         cfg = self._cfg(lr)

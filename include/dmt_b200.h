@@ -422,6 +422,34 @@ DMT_API int dmt_embed_grad_scatter_rows(int32_t n_sources, const dmt_grad_source
 DMT_API int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float* m, float* v,
                                     int64_t rows, int32_t dim, uint8_t* touched, void* stream);
 
+/* Multi-table variants of the three calls above: every embedding table of one optimizer step (run_dnn.py:203-207
+ * applies ONE Adam op over all variables) in one expand, one key sort (caller), one segmented-reduction + Adam pair
+ * and one untouched-rows pass.  Keys are (table index << 24) | row, so tables hold at most 2^24 rows here; `sources`
+ * and `tables` are HOST arrays, source_table[s] = the table source s looks up.  dmt_adam_rows_untouched_multi leaves
+ * the `touched` marks set: the caller clears them (one memset when they live in one buffer). */
+#define DMT_MAX_ADAM_TABLES 16
+#define DMT_MAX_MULTI_GRAD_SOURCES 64
+typedef struct dmt_adam_table {
+  float* table;
+  float* m;
+  float* v;
+  uint8_t* touched;   /* [rows] */
+  int64_t rows;
+  int32_t dim;
+  int32_t _pad;
+} dmt_adam_table;
+DMT_API int dmt_embed_grad_expand_multi(int32_t n_tables, const dmt_adam_table* tables, int32_t n_sources,
+                                        const dmt_grad_source* sources, const int32_t* source_table, int32_t* keys,
+                                        int64_t* refs, float* scale, void* stream);
+DMT_API size_t dmt_embed_sorted_multi_workspace_bytes(int64_t n);
+DMT_API int dmt_embed_adam_sorted_multi(const dmt_adam_cfg* cfg, int32_t n_tables, const dmt_adam_table* tables,
+                                        int32_t n_sources, const dmt_grad_source* sources,
+                                        const int32_t* sorted_keys, const int64_t* perm, const int64_t* refs,
+                                        const float* scale, int64_t n, float grad_scale, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+DMT_API int dmt_adam_rows_untouched_multi(const dmt_adam_cfg* cfg, int32_t n_tables, const dmt_adam_table* tables,
+                                          void* stream);
+
 /* ---- diagnostics -------------------------------------------------------------------
  * One 128 x N x K bf16 tcgen05 GEMM through each shared-memory operand layout the tensor-core
  * kernels use (mode 0: K-major/K-major no-swizzle, A [128,K], B [N,K]; mode 1: B MN-major,
