@@ -34,6 +34,7 @@ class FFWeights(C.Structure):
 
 
 SEQ_DEFER_TAIL = 1
+SEQ_LEN_EXACT = 2
 MAX_TAIL_SEQS = 4
 
 

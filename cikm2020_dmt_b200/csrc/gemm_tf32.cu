@@ -616,6 +616,11 @@ int make_map_f32(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols,
 
 }  // namespace
 
+int make_map_f32_public(CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                        bool mn_major) {
+  return make_map_f32(tm, base, rows, cols, ld, box_rows, mn_major);
+}
+
 int tf32_pack(const Tf32PackMat* mats, int n_mats, float* dst, int64_t ldd, const Tf32PackVec* vecs, int n_vecs,
               float* dstv, cudaStream_t st) {
   DMT_REQUIRE(n_mats >= 0 && n_mats <= 4 && n_vecs >= 0 && n_vecs <= 4 && (n_mats == 0 || dst) && (n_vecs == 0 || dstv),

@@ -20,6 +20,11 @@
 
 namespace dmt {
 
+bool attn_fwd_tc_supported(const dmt_seq_cfg& c);
+int attn_fwd_tc_launch(const dmt_seq_cfg& c, const float* qkv, const float* h, const float* gamma, const float* beta,
+                       float* z1, float* a, const int32_t* offsets, int64_t T, int LP, const Dropout& drop,
+                       cudaStream_t st);
+
 namespace {
 
 struct GatherArgs {
@@ -415,7 +420,11 @@ int seq_fwd_train_pipeline(const dmt_seq_cfg* cfg, const dmt_seq_input* in, cons
       grp.n = 3;
       if ((rc = gemm_group_launch(grp, st))) return rc;
     }
-    {
+    if (tf && attn_fwd_tc_supported(c)) {   // tcgen05 attention: whole-sample tiles cut from the packed token rows
+      if ((rc = attn_fwd_tc_launch(c, sv.qkv[blk], sv.hin[blk], aw.ln.gamma, aw.ln.beta, sv.z1[blk], sv.a[blk], offsets,
+                                   T, LP, Dropout(c.dropout_rate, c.dropout_seed, kSiteSelfProbs + blk), st)))
+        return rc;
+    } else {
       AttnFwdArgs a{sv.qkv[blk], sv.hin[blk], aw.ln.gamma, aw.ln.beta, sv.z1[blk], sv.a[blk], offsets, d, H, LP,
                     Dropout(c.dropout_rate, c.dropout_seed, kSiteSelfProbs + blk)};
       const size_t smem = ((size_t)3 * LP * (d + 1) + LP * (LP + 1)) * sizeof(float);

@@ -300,6 +300,11 @@ class mmoe_transformer_unbias(object):
         are still host tensors.  Otherwise transformer_maxlen_k -- the feature-name suffix (`..._12m_10`) is NOT
         a bound: the reference sizes the sequence by the batch's own longest row
         (mmoe_transformer_unbias.py:141-146)."""
+        return self._seq_len_bound(inputs, seq)[0]
+
+    def _seq_len_bound(self, inputs, seq):
+        """(bound, exact): `exact` = the bound is the batch's true longest sequence and it does not exceed
+        transformer_maxlen_k (DMT_SEQ_LEN_EXACT)."""
         name = seq.user_features[-1]
         hints = inputs.get("__max_len__")
         hint = None
@@ -310,9 +315,10 @@ class mmoe_transformer_unbias(object):
             off = getattr(sp, "offsets", None)
             if torch.is_tensor(off) and _is_host(off) and off.numel() > 1:
                 hint = int((off[1:] - off[:-1]).max())
+        exact = hint is not None and int(hint) <= seq.maxlen
         if hint is None:
             hint = seq.maxlen
-        return max(1, min(int(hint), seq.maxlen))
+        return max(1, min(int(hint), seq.maxlen)), exact
 
     def _prepared_for(self, seq_index, cfg):
         ver, buf = self._prepared.get(seq_index, (-1, None))
@@ -331,9 +337,10 @@ class mmoe_transformer_unbias(object):
 
     def _seq_cfg(self, inputs, seq, batch, precision, dropout_rate=0.0, dropout_seed=0):
         plan = self.plan
+        bound, exact = self._seq_len_bound(inputs, seq)
         return abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
                           plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0,
-                          len(seq.user_features), precision, self._seq_len_hint(inputs, seq), 0,
+                          len(seq.user_features), precision, bound, abi.SEQ_LEN_EXACT if exact else 0,
                           float(dropout_rate), int(dropout_seed) & 0xFFFFFFFF)
 
     def _seq_input(self, inputs, seq, batch):
@@ -379,7 +386,7 @@ class mmoe_transformer_unbias(object):
             ws_ptr = ws.data_ptr()
         defer = deferred is not None and self.precision == abi.PRECISION_BF16 and self._v2_ok
         if defer:
-            cfg.flags = abi.SEQ_DEFER_TAIL
+            cfg.flags |= abi.SEQ_DEFER_TAIL
         si, keep = self._seq_input(inputs, seq, batch)
         stream = self._stream()
         # bf16: the fused tile kernel (+ the row-batched decoder tail kernel unless deferred)

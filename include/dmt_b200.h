@@ -99,6 +99,11 @@ typedef struct dmt_ff_weights {
  * later dmt_seq_tail_fwd, which runs the tails of several sequences as ONE launch.  Without the bit,
  * dmt_seq_encode_fwd is self-contained. */
 #define DMT_SEQ_DEFER_TAIL 1
+/* dmt_seq_cfg.flags: the caller guarantees that NO sequence of the batch is longer than min(slot_len, maxlen) (it
+ * knows the lengths: they came through its host memory).  Lets the training pipeline cut whole-sample tiles out of
+ * the packed token rows without a pass over the offsets (tensor-core attention); without it the per-sample kernels
+ * run, which cap over-long sequences themselves. */
+#define DMT_SEQ_LEN_EXACT 2
 
 typedef struct dmt_seq_cfg {
   int32_t batch;        /* B                                                          */

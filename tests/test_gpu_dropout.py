@@ -102,6 +102,39 @@ def test_training_mode_matches_oracle_dmt_conf_pipeline_bf16x3():
     _compare(plan, model, store, host, dev, O, seed=12345, rel_tol=3e-3)
 
 
+def test_training_mode_matches_oracle_tf32_tensor_core_attention():
+    """dmt_d64.conf on the tf32 engine, whose self-attention runs in the tcgen05 kernel (attn_tc.cu): the kernel must
+    draw the attention-probability keep masks per (sample, head, query, key) exactly like the per-sample fp32 kernels.
+    (i) training-mode forward with the same seed: interest vectors of the tf32 model within 1e-2 of the fp32 model's
+    (one wrong mask index moves an interest vector by O(0.1 .. 1)); (ii) loss within 3e-3 and gradient cosine >= 0.99
+    against the oracle driven with the same masks (tf32 is a bf16-class engine; dropout + 400x class weights amplify
+    its operand truncation)."""
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 200, seed=21, precision="bf16", train_gemm="tf32")
+    exact = mmoe_transformer_unbias(plan, params=store, precision="f32")
+    c0, c1 = plan.interest_col, plan.interest_col + len(plan.sequences) * plan.d_model
+    model.inference(dev, is_train=True, dropout_seed=4242)
+    got = model._last["x"][:, c0:c1].clone()
+    exact.inference(dev, is_train=True, dropout_seed=4242)
+    want = exact._last["x"][:, c0:c1].clone()
+    torch.cuda.synchronize()
+    assert (got - want).abs().max().item() < 1e-2
+    P = O.params_from_store(store)
+    O.DROPOUT_HOOK = _hook(plan, host, 4242)
+    try:
+        loss_ref, grads_ref, _ = O.loss_and_grads(plan, P, host, is_train=True)
+    finally:
+        O.DROPOUT_HOOK = None
+    loss, G = model.compute_gradients(dev, is_train=True, dropout_seed=4242)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= 3e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    for name in ("DnnModel/embedding_trans/Sku/embedding", "DnnModel/mmoe_layers/expert-0/expert-layer-0/weights"):
+        want = grads_ref[name].double()
+        got = (G.table_dense(store, name) if name in store.tables else G[name]).detach().double().cpu().reshape(want.shape)
+        cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-300))
+        assert cos >= 0.99, (name, cos)
+
+
 def test_training_mode_two_blocks():
     ov = {("model", "transformer_num_blocks_encode"): "2", ("model", "transformer_num_blocks_decode"): "2"}
     plan, model, store, host, dev, O = _setup("dmt_d64.conf", 24, seed=9, overrides=ov)
