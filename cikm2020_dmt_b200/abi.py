@@ -108,7 +108,7 @@ MAX_ADAM_TABLES, MAX_MULTI_GRAD_SOURCES = 16, 64
 
 class AdamTable(C.Structure):
     _fields_ = [("table", _fp), ("m", _fp), ("v", _fp), ("touched", _fp), ("rows", C.c_int64), ("dim", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32), ("dense_out", _fp)]
 
 
 

@@ -391,6 +391,12 @@ __device__ __forceinline__ void finish_row_multi(const SortedMultiArgs& a, int32
   const int D = t.dim;
   const int64_t row = key & ((1 << kMultiRowBits) - 1);
   const int64_t base = row * D;
+  if (t.dense_out) {
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c)
+      if (lane + 32 * c < D) t.dense_out[base + lane + 32 * c] = acc[c] * a.gscale;
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < kMaxCols; ++c) {
     const int col = lane + 32 * c;
@@ -694,8 +700,8 @@ static int check_tables(const char* who, int32_t n_tables, const dmt_adam_table*
   DMT_REQUIRE(tables && n_tables > 0 && n_tables <= DMT_MAX_ADAM_TABLES, DMT_ERR_INVALID_ARGUMENT,
               "%s: n_tables=%d (max %d)", who, n_tables, DMT_MAX_ADAM_TABLES);
   for (int t = 0; t < n_tables; ++t) {
-    DMT_REQUIRE(tables[t].table && tables[t].m && tables[t].v && tables[t].touched && tables[t].dim > 0 &&
-                    tables[t].dim <= dmt::kMultiMaxDim && tables[t].rows > 0,
+    DMT_REQUIRE((tables[t].dense_out || (tables[t].table && tables[t].m && tables[t].v && tables[t].touched)) &&
+                    tables[t].dim > 0 && tables[t].dim <= dmt::kMultiMaxDim && tables[t].rows > 0,
                 DMT_ERR_INVALID_ARGUMENT, "%s: table %d is incomplete", who, t);
     DMT_REQUIRE(tables[t].rows <= ((int64_t)1 << dmt::kMultiRowBits), DMT_ERR_UNSUPPORTED_SHAPE,
                 "%s: table %d has %lld rows (the packed keys hold 2^%d; use the per-table entry points)", who, t,
@@ -747,8 +753,10 @@ int dmt_embed_adam_sorted_multi(const dmt_adam_cfg* cfg, int32_t n_tables, const
                                 float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_tables("dmt_embed_adam_sorted_multi", n_tables, tables);
   if (rc != DMT_OK) return rc;
-  DMT_REQUIRE(cfg && cfg->step >= 1 && sources && sorted_keys && perm && refs && scale && n_sources > 0 &&
-                  n_sources <= dmt::kMaxMultiSources,
+  bool any_adam = false;
+  for (int t = 0; t < n_tables; ++t) any_adam = any_adam || tables[t].dense_out == nullptr;
+  DMT_REQUIRE((!any_adam || (cfg && cfg->step >= 1)) && sources && sorted_keys && perm && refs && scale &&
+                  n_sources > 0 && n_sources <= dmt::kMaxMultiSources,
               DMT_ERR_INVALID_ARGUMENT, "dmt_embed_adam_sorted_multi: bad arguments");
   if (n == 0) return DMT_OK;
   DMT_REQUIRE(workspace && workspace_bytes >= dmt_embed_sorted_multi_workspace_bytes(n), DMT_ERR_WORKSPACE_TOO_SMALL,
@@ -759,7 +767,7 @@ int dmt_embed_adam_sorted_multi(const dmt_adam_cfg* cfg, int32_t n_tables, const
   for (int t = 0; t < n_tables; ++t) a.tab[t] = tables[t];
   a.keys = sorted_keys; a.perm = perm; a.refs = refs; a.scale = scale;
   a.n = n; a.gscale = grad_scale;
-  a.s = dmt::adam_scalars(cfg);
+  if (any_adam) a.s = dmt::adam_scalars(cfg);
   a.carry = (float*)workspace;
   const int64_t chunks = (n + dmt::kChunk - 1) / dmt::kChunk;
   const int64_t blocks = (chunks * 32 + 255) / 256;

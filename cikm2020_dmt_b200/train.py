@@ -175,24 +175,54 @@ class Trainer(object):
         inv_world = 1.0 / self.world
         # replicated tables: densify into the allreduce bucket (the bucket's dense part was zeroed and filled by
         # compute_gradients; zero the table part here)
-        with self._stage("densify", 2 * len(self.replicated)):
+        with self._stage("densify", 3):
             n_dense = self.store.dense.numel()
             self.bucket[n_dense:].zero_()
             keep = []
-            for scope in self.replicated:
-                srcs = grads.lookups.get(scope, [])
-                if not srcs:
-                    continue
-                table = self.store.tables[scope]
-                keys, refs, scale, arr = self._expand(srcs, table.shape[0], stream)
+            scopes = [k for k in self.replicated if grads.lookups.get(k)]
+            n_src = sum(len(grads.lookups[k]) for k in scopes)
+            if scopes and (len(scopes) > abi.MAX_ADAM_TABLES or n_src > abi.MAX_MULTI_GRAD_SOURCES or
+                           any(self.store.tables[k].shape[0] > (1 << 24) or self.store.tables[k].shape[1] > 128
+                               for k in scopes)):
+                for scope in scopes:       # beyond the limits of the multi-table entry points: one table at a time
+                    srcs = grads.lookups[scope]
+                    table = self.store.tables[scope]
+                    keys, refs, scale, arr = self._expand(srcs, table.shape[0], stream)
+                    skeys, perm = torch.sort(keys, stable=True)
+                    ws = model._scratch("sorted_ws", self.lib.dmt_embed_sorted_workspace_bytes(keys.numel(), table.shape[1]))
+                    abi.check(self.lib.dmt_embed_grad_densify_sorted(table.shape[0], table.shape[1], len(srcs), arr,
+                                                                     skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),
+                                                                     scale.data_ptr(), keys.numel(), 1.0,
+                                                                     self.table_grad[scope].data_ptr(), ws.data_ptr(),
+                                                                     ws.numel(), stream))
+                    keep.append((keys, refs, scale, arr, skeys, perm, srcs))
+            elif scopes:
+                # all replicated tables in ONE expand / sort / segmented reduction, written straight into the bucket
+                tabs = (abi.AdamTable * len(scopes))()
+                sources, owner = [], []
+                for i, scope in enumerate(scopes):
+                    t = self.store.tables[scope]
+                    tabs[i].rows, tabs[i].dim = t.shape[0], t.shape[1]
+                    tabs[i].dense_out = self.table_grad[scope].data_ptr()
+                    for lg in grads.lookups[scope]:
+                        sources.append(lg)
+                        owner.append(i)
+                arr = (abi.GradSource * len(sources))(*[s_.to_c() for s_ in sources])
+                own = (C.c_int32 * len(owner))(*owner)
+                total = sum(s_.ids.numel() for s_ in sources)
+                buf = model._scratch("densify_multi", total * 16 + 1024)
+                keys = buf[:total * 4].view(torch.int32)
+                scale = buf[total * 4:total * 8].view(torch.float32)
+                refs = buf[total * 8:total * 16].view(torch.int64)
+                abi.check(self.lib.dmt_embed_grad_expand_multi(len(scopes), tabs, len(sources), arr, own, keys.data_ptr(),
+                                                               refs.data_ptr(), scale.data_ptr(), stream))
                 skeys, perm = torch.sort(keys, stable=True)
-                ws = model._scratch("sorted_ws", self.lib.dmt_embed_sorted_workspace_bytes(keys.numel(), table.shape[1]))
-                abi.check(self.lib.dmt_embed_grad_densify_sorted(table.shape[0], table.shape[1], len(srcs), arr,
-                                                                 skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),
-                                                                 scale.data_ptr(), keys.numel(), 1.0,
-                                                                 self.table_grad[scope].data_ptr(), ws.data_ptr(),
-                                                                 ws.numel(), stream))
-                keep.append((keys, refs, scale, arr, skeys, perm, srcs))
+                ws = model._scratch("sorted_ws", self.lib.dmt_embed_sorted_multi_workspace_bytes(total))
+                abi.check(self.lib.dmt_embed_adam_sorted_multi(None, len(scopes), tabs, len(sources), arr,
+                                                               skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),
+                                                               scale.data_ptr(), total, 1.0, ws.data_ptr(), ws.numel(),
+                                                               stream))
+                keep.append((tabs, arr, own, keys, refs, scale, skeys, perm, sources))
         with self._stage("allreduce"):
             if self.world > 1:
                 dist.all_reduce(self.bucket, group=self.group)

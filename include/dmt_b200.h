@@ -442,6 +442,9 @@ typedef struct dmt_adam_table {
   int64_t rows;
   int32_t dim;
   int32_t _pad;
+  float* dense_out;   /* dmt_embed_adam_sorted_multi: non-NULL = write the summed gradient rows (x grad_scale) into this
+                         zero-initialised [rows, dim] matrix instead of applying Adam (the replicated tables of a
+                         data-parallel step: densified into the allreduce bucket); table / m / v / touched unused */
 } dmt_adam_table;
 DMT_API int dmt_embed_grad_expand_multi(int32_t n_tables, const dmt_adam_table* tables, int32_t n_sources,
                                         const dmt_grad_source* sources, const int32_t* source_table, int32_t* keys,
