@@ -42,7 +42,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (BASELINE config 2: 4096)")
     ap.add_argument("--conf", default="dmt_d64.conf")
     ap.add_argument("--id-mode", default="uniform", choices=["uniform", "zipf"])
-    ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["f32", "bf16", "tf32"],
+                    help="headline path: bf16 = fused tcgen05 tile kernels (d_model 64 / 2 heads); tf32 = row-batched "
+                         "tcgen05 pipeline (any shape, e.g. --conf dmt.conf); f32 = CUDA cores")
     ap.add_argument("--n-batches", type=int, default=4, help="distinct batches rotated through the timed loop")
     ap.add_argument("--cpu-batch", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time budget")
@@ -583,17 +585,19 @@ def main():
     dom = max(stage, key=lambda k: stage[k][0])
     steps_used = args.steps
     mean_b = lambda fn: sum(fn(plan, batches[i % len(batches)]) for i in range(steps_used))
-    if dom == "seq_encode":
-        t_ms, _ = stage["seq_encode"]
+    if dom in ("seq_encode", "seq_encode_train"):
+        t_ms, _ = stage[dom]
         n = steps_used * len(plan.sequences)                     # one fused tile-kernel launch per sequence and step
         #                                                          (its share of the batched tail launch is in t_ms)
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
         fl = mean_b(flops_seq)                                   # algorithmic FLOPs (valid tokens only)
         hbm = alg / (t_ms / 1e3) / 1e9
         tfl = fl / (t_ms / 1e3) / 1e12
-        name = ("seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM"
-                if args.precision == "bf16" else "seq_encode_f32_kernel (fp32 CUDA cores") + \
-               ", fused gather->encoder->decoder, per sequence)"
+        name = {"bf16": "seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM, fused "
+                        "gather->encoder->decoder, per sequence)",
+                "tf32": "row-batched pipeline: seq_gather + tf32_rows_kernel x5 + attention + LayerNorm kernels (tcgen05 "
+                        "kind::tf32 GEMMs, per sequence)",
+                "f32": "seq_encode_f32_kernel (fp32 CUDA cores, fused gather->encoder->decoder, per sequence)"}[args.precision]
         if args.precision == "bf16":
             # SURVEY 8d crossover: the fully fused kernel has 432 FLOP/B against a 209 FLOP/B ridge -> the tensor
             # roofline is the binding one; the HBM reading is kept as a secondary field
@@ -624,7 +628,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tr = json.load(fh).get("seq_encode_tc_kernel")
         wl = tr["workload"]
-        if (dom == "seq_encode" and wl["conf"] == args.conf and wl["per_gpu_batch"] == args.batch
+        if (dom in ("seq_encode", "seq_encode_train") and wl["conf"] == args.conf and wl["per_gpu_batch"] == args.batch
                 and wl["precision"] == args.precision and wl["id_mode"] == args.id_mode and not args.small_tables):
             roofline["traffic"] = tr["mean_dram_bytes_per_launch"]
             roofline["traffic_source"] = tr["source"]

@@ -476,3 +476,44 @@ def test_inference_tf32_pipeline_matches_oracle(conf_file, batch):
     (pc, po) = tf.inference(dev, is_train=False, is_predict=True)
     torch.cuda.synchronize()
     assert torch.equal(pc, yr[0]) and torch.equal(po, yr[1])
+
+
+def test_bench_size_bf16_and_tf32_against_fp32_path_and_oracle():
+    """The bench's own size and tables (BASELINE config 2: B = 4096, Sku 5,000,000 x 32 and the other full
+    vocabularies): every sample's logits from the bf16 fused tcgen05 kernels and from the tf32 pipeline against
+    the fp32 CUDA path on the same device batch (bf16: atol 5e-2 + rtol 2e-2; tf32: atol 2e-2 + rtol 1e-2), and
+    a strided subsample of all three against the fp64 oracle."""
+    from cikm2020_dmt_b200.conf import Conf
+    from cikm2020_dmt_b200.data import SparseIds, batch_to, synthetic_batch
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    from cikm2020_dmt_b200.params import ParamStore
+    from cikm2020_dmt_b200.plan import build_plan
+    from conftest import CONF_DIR
+    from oracle import dmt_oracle as O
+    plan = build_plan(Conf(CONF_DIR, "dmt_d64.conf"))
+    assert plan.tables["Sku"].rows == 5000000
+    store = ParamStore(plan, device="cuda", seed=3).randomize_(4)
+    host = synthetic_batch(plan, 4096, seed=17)
+    dev = batch_to(host, "cuda")
+    outs = {}
+    for prec in ("f32", "bf16", "tf32"):
+        m = mmoe_transformer_unbias(plan, params=store, precision=prec)
+        (yr, yb) = m.inference(dev, is_train=False)
+        torch.cuda.synchronize()
+        outs[prec] = (yr[0].clone(), yr[1].clone(), yb.clone())
+        del m
+    for prec, atol, rtol in (("bf16", 5e-2, 2e-2), ("tf32", 2e-2, 1e-2)):
+        for t in range(2):
+            _close(outs[prec][t], outs["f32"][t], atol=atol, rtol=rtol)
+        _close(outs[prec][2], outs["f32"][2], atol=1e-5)
+    idx = list(range(0, 4096, 173))
+    sub = {}
+    for k, v in host.items():
+        if isinstance(v, SparseIds):
+            sub[k] = SparseIds.from_lists([v.values[int(v.offsets[b]):int(v.offsets[b + 1])].tolist() for b in idx])
+        else:
+            sub[k] = v[idx]
+    (wr, wb) = O.inference(plan, O.params_from_store(store, torch.float32), sub, is_train=False, lean=True)
+    for prec, atol, rtol in (("f32", 2e-4, 2e-4), ("bf16", 5e-2, 2e-2), ("tf32", 2e-2, 1e-2)):
+        _close(outs[prec][0][idx], wr[0], atol=atol, rtol=rtol)
+        _close(outs[prec][1][idx], wr[1], atol=atol, rtol=rtol)
