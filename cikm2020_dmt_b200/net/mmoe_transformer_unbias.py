@@ -55,6 +55,7 @@ class mmoe_transformer_unbias(object):
         self._events = None          # bench hook: {stage: [(start, stop), ...]} CUDA events
         self.launches = 0            # kernels of this library enqueued so far
         self._stream_h = None        # set for the duration of inference() / compute_gradients()
+        self.seq_streams = os.environ.get("DMT_SEQ_STREAMS", "1") != "0"   # one stream per behaviour sequence
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
         self._v2_ok = True           # bf16 path: the decoder tails of all sequences run as one deferred launch
         self._bind_weights()
@@ -153,6 +154,22 @@ class mmoe_transformer_unbias(object):
             t = torch.empty((int(nbytes * 1.25) + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.device)
             self._buffers[("scratch", name)] = t
         return t
+
+    def _seq_side_streams(self, n):
+        st = getattr(self, "_side_streams", None)
+        if st is None or len(st) < n:
+            st = self._side_streams = [torch.cuda.Stream(self.device) for _ in range(n)]
+        return st
+
+    def _ev_pool(self, name):
+        """Reusable (timing-free) events for the fork / join of the side streams."""
+        pool = getattr(self, "_events_pool", None)
+        if pool is None:
+            pool = self._events_pool = {}
+        ev = pool.get(name)
+        if ev is None:
+            ev = pool[name] = torch.cuda.Event()
+        return ev
 
     def _stream(self):
         """Raw handle of the current CUDA stream; looked up once per public entry point (the torch call costs
@@ -532,6 +549,11 @@ class mmoe_transformer_unbias(object):
         x_ld = (plan.mmoe_in + 3) // 4 * 4
         x = self._buf("x", (batch, x_ld))
         keep = []
+        side = self._seq_side_streams(len(plan.sequences)) if self._events is None and self.seq_streams else None
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:     # one stream per behaviour sequence; the dense copy / pooled means overlap on `main`
+            fork = self._ev_pool("fork")
+            fork.record(main)
         if feats is not None:
             if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
                 raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
@@ -549,10 +571,16 @@ class mmoe_transformer_unbias(object):
             nbytes = lib.dmt_seq_saved_bytes(C.byref(cfg), n_tok)
             saved = self._scratch("seq_saved_%d" % s, nbytes)
             col = plan.interest_col + s * plan.d_model
+            if side is not None:
+                side[s].wait_event(fork)
             with self._Stage(self, "seq_encode_train", 1):
                 abi.check(lib.dmt_seq_encode_fwd_train(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]),
                                                        x.data_ptr() + 4 * col, x_ld, n_tok, saved.data_ptr(),
-                                                       saved.numel(), stream))
+                                                       saved.numel(), side[s].cuda_stream if side is not None else stream))
+            if side is not None:
+                ev = self._ev_pool("join%d" % s)
+                ev.record(side[s])
+                main.wait_event(ev)
         mcfg = self._mmoe_cfg(batch, F32)
         mws_bytes = lib.dmt_mmoe_train_workspace_bytes(C.byref(mcfg))
         mws = self._buf("mmoe_ws_f32", ((mws_bytes + 255) // 256 * 256,), torch.uint8)
@@ -587,13 +615,37 @@ class mmoe_transformer_unbias(object):
         x_ld = (plan.mmoe_in + 3) // 4 * 4
         x = self._buf("x", (batch, x_ld))
         keep = []
+        deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
+        # The behaviour sequences are independent of each other and of the dense / pooled columns until the MMoE
+        # input: each runs on its own stream, so the CTAs of the next sequence's (persistent, one-CTA-per-SM) kernel
+        # start on an SM the moment the previous kernel's CTA there retires -- no tail bubble, prologues (weight
+        # images, TMEM allocation) hidden.  Per-stage timing (bench hook) serialises them so that each kernel's
+        # duration is its own.
+        side = self._seq_side_streams(len(plan.sequences)) if self._events is None and self.seq_streams else None
+        if side is not None:
+            main = torch.cuda.current_stream(self.device)
+            fork = self._ev_pool("fork")
+            fork.record(main)
+            joins = []
+            for s in range(len(plan.sequences)):
+                side[s].wait_event(fork)
+                self._stream_h = side[s].cuda_stream
+                col = plan.interest_col + s * plan.d_model
+                keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
+                ev = self._ev_pool("join%d" % s)
+                ev.record(side[s])
+                joins.append(ev)
+            self._stream_h = main.cuda_stream
         if feats is not None:
             self._copy_dense(feats, batch, x, x_ld, keep, self.precision)
         keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
-        deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
-        for s in range(len(plan.sequences)):
-            col = plan.interest_col + s * plan.d_model
-            keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
+        if side is not None:
+            for ev in joins:
+                main.wait_event(ev)
+        else:
+            for s in range(len(plan.sequences)):
+                col = plan.interest_col + s * plan.d_model
+                keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
         if deferred:
             self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
         # scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can
@@ -706,6 +758,11 @@ class mmoe_transformer_unbias(object):
         x_ld = (plan.mmoe_in + 3) // 4 * 4
         x = self._buf("x", (batch, x_ld))
         keep = []
+        side = self._seq_side_streams(len(plan.sequences)) if self._events is None and self.seq_streams else None
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:     # the sequence pipelines fork here: the dense copy / pooled means overlap them on `main`
+            fork = self._ev_pool("fork")
+            fork.record(main)
         if feats is not None:
             if feats.dtype != torch.float32 or feats.shape != (batch, plan.feature_dim):
                 raise ValueError("'features' must be fp32 [%d, %d]" % (batch, plan.feature_dim))
@@ -716,6 +773,8 @@ class mmoe_transformer_unbias(object):
             keep.append(feats)
         keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
         seq_state = []
+        # one stream per behaviour sequence (independent pipelines of many short kernels: their tails and the
+        # low-occupancy ones overlap); serial under per-stage timing
         for s, seq in enumerate(plan.sequences):
             cfg = self._seq_cfg(inputs, seq, batch, F32, rate, DO.step_seed(dropout_seed, 0, 1 + seq.index))
             si, kp = self._seq_input(inputs, seq, batch)
@@ -727,10 +786,16 @@ class mmoe_transformer_unbias(object):
             nbytes = lib.dmt_seq_saved_bytes(C.byref(cfg), n_tok)
             saved = self._scratch("seq_saved_%d" % s, nbytes)
             col = plan.interest_col + s * plan.d_model
+            if side is not None:
+                side[s].wait_event(fork)
             with self._Stage(self, "seq_encode_train", 1):
                 abi.check(lib.dmt_seq_encode_fwd_train(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]),
                                                        x.data_ptr() + 4 * col, x_ld, n_tok, saved.data_ptr(),
-                                                       saved.numel(), stream))
+                                                       saved.numel(), side[s].cuda_stream if side is not None else stream))
+            if side is not None:
+                ev = self._ev_pool("join%d" % s)
+                ev.record(side[s])
+                main.wait_event(ev)
             seq_state.append((cfg, si, users, n_tok, saved, col))
         mcfg = self._mmoe_cfg(batch, F32)
         mws_bytes = lib.dmt_mmoe_train_workspace_bytes(C.byref(mcfg))
@@ -781,18 +846,28 @@ class mmoe_transformer_unbias(object):
             add(plan.bias_tables[p.table].scope,
                 LookupGrad(sp.values, d_bias_in, p.col, 0, sp.offsets, sp.weights, True))
         id_off = -1 if plan.zero_pad else 0
+        if side is not None:
+            fork = self._ev_pool("fork_bwd")
+            fork.record(main)
         for s, seq in enumerate(plan.sequences):
             cfg, si, users, n_tok, saved, col = seq_state[s]
             d_tok = self._scratch("d_tokens_%d" % s, max(n_tok, 1) * plan.d_model * 4)
             d_tok = d_tok[:max(n_tok, 1) * plan.d_model * 4].view(torch.float32).view(max(n_tok, 1), plan.d_model)
             d_tar = self._buf("d_target_%d" % s, (batch, plan.d_model))
             nb = lib.dmt_seq_bwd_workspace_bytes(C.byref(cfg), n_tok)
-            sws = self._scratch("seq_bwd_ws", nb)
+            sws = self._scratch("seq_bwd_ws_%d" % s if side is not None else "seq_bwd_ws", nb)
+            if side is not None:
+                side[s].wait_event(fork)
             with self._Stage(self, "seq_bwd", 30):
                 abi.check(lib.dmt_seq_encode_bwd(C.byref(cfg), C.byref(si), C.byref(self._seq_w[s]), n_tok,
                                                  saved.data_ptr(), saved.numel(), dx.data_ptr() + 4 * col, x_ld,
                                                  C.byref(self._seq_g[s]), d_tok.data_ptr(), d_tar.data_ptr(),
-                                                 sws.data_ptr(), sws.numel(), stream))
+                                                 sws.data_ptr(), sws.numel(),
+                                                 side[s].cuda_stream if side is not None else stream))
+            if side is not None:
+                ev = self._ev_pool("join_bwd%d" % s)
+                ev.record(side[s])
+                main.wait_event(ev)
             for f, u in enumerate(users):
                 scope = plan.tables[seq.tables[f]].scope
                 if n_tok:
