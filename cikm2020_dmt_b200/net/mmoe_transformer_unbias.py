@@ -96,7 +96,13 @@ class mmoe_transformer_unbias(object):
         for seq in plan.sequences:
             w = abi.SeqWeights()
             S = seq.scope
-            w.pos = abi.ptr(P[S + "/positional_encoding_k_position_learn/embedding_position_learn"])
+            if plan.position_encoding_method == "position_sin_cos":
+                # a constant of the graph (TransformerModel_util.py:237-278): no variable, its "gradient" lands in a
+                # scratch table that nothing reads
+                w.pos = abi.ptr(self.params.position_table(seq) if P is self.params else
+                                self._buf("pos_grad_sink_%d" % seq.index, (plan.maxlen_k, plan.d_model)))
+            else:
+                w.pos = abi.ptr(P[S + "/positional_encoding_k_position_learn/embedding_position_learn"])
 
             def attn(dst, base):
                 dst.q = abi.dense(P[base + "/dense/kernel"], P[base + "/dense/bias"])

@@ -41,10 +41,26 @@ class ParamSpec:
         return n
 
 
+POS_LEARN = "/positional_encoding_k_position_learn/embedding_position_learn"
+POS_SIN_COS = "/positional_encoding_k_position_sin_cos/position_enc"     # a constant, not a TF variable
+
+
+def sin_cos_table(maxlen, d):
+    """positional_encoding (TransformerModel_util.py:237-278): pos / 10000^((i - i % 2) / E), sin on the even
+    columns, cos on the odd ones; built in fp64 like the reference's numpy code, then cast to fp32."""
+    import numpy as np
+    i = np.arange(d)
+    enc = np.arange(maxlen)[:, None] / np.power(10000.0, (i - i % 2) / float(d))[None, :]
+    enc[:, 0::2] = np.sin(enc[:, 0::2])
+    enc[:, 1::2] = np.cos(enc[:, 1::2])
+    return torch.from_numpy(enc.astype(np.float32))
+
+
 def seq_param_specs(plan, seq) -> List[ParamSpec]:
     d, dff, S = plan.d_model, plan.d_ff, seq.scope
-    out = [ParamSpec(S + "/positional_encoding_k_position_learn/embedding_position_learn",
-                     (plan.maxlen_k, d), "xavier")]
+    out = []
+    if plan.position_encoding_method == "position_learn":        # position_sin_cos has no variable (:61-65)
+        out.append(ParamSpec(S + POS_LEARN, (plan.maxlen_k, d), "xavier"))
 
     def attn(block, kind):
         base = "%s/num_blocks_%d/%s" % (S, block, kind)
@@ -182,6 +198,18 @@ class ParamStore:
         for s in self.specs:
             self.views[s.name] = self.dense[s.offset:s.offset + s.numel].view(s.shape)
         self.views.update(self.tables)
+        # constants of the graph that are not variables (never saved, never updated): the sinusoid position table
+        self.consts: Dict[str, torch.Tensor] = {}
+        if plan.position_encoding_method == "position_sin_cos":
+            tab = sin_cos_table(plan.maxlen_k, plan.d_model).to(self.device)
+            for seq in plan.sequences:
+                self.consts[seq.scope + POS_SIN_COS] = tab
+
+    def position_table(self, seq):
+        """[maxlen_k, d_model] added to the scaled token embeddings of `seq` (TransformerModel.py:61-69)."""
+        if self.plan.position_encoding_method == "position_sin_cos":
+            return self.consts[seq.scope + POS_SIN_COS]
+        return self.views[seq.scope + POS_LEARN]
 
     def named_parameters(self):
         return self.views.items()

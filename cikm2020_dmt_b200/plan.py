@@ -111,9 +111,9 @@ def build_plan(conf) -> ModelPlan:
     if conf.is_trans_input_by_mlp or conf.is_trans_out_concat_item or conf.is_trans_out_by_mlp:
         raise PlanError("transformer_is_trans_input_by_mlp / _out_concat_item / _out_by_mlp "
                         "are off in dmt.conf and not built (mmoe_transformer_unbias.py:197-216)")
-    if conf.position_encoding_method != "position_learn":
-        raise PlanError("only transformer_position_encoding_method=position_learn is built "
-                        "(TransformerModel.py:63-79 lists the others)")
+    if conf.position_encoding_method not in ("position_learn", "position_sin_cos"):
+        raise PlanError("transformer_position_encoding_method=%r: position_learn and position_sin_cos are built; "
+                        "time_add / time_concat (TransformerModel.py:71-79) are not" % conf.position_encoding_method)
     if conf.is_decoder_add_pos_emb:
         raise PlanError("transformer_is_decoder_add_pos_emb=true is not built (TransformerModel.py:148-149)")
     if model.get(K.IS_BN) or conf.sim_embed:

@@ -179,11 +179,24 @@ def _dropout(x, rate, training, site=None):
     return x
 
 
+def sin_cos_position_table(maxlen, E):
+    """positional_encoding (TransformerModel_util.py:237-278): numpy fp64 table, cast to fp32 by
+    tf.convert_to_tensor(position_enc, tf.float32)."""
+    import numpy as np
+    position_enc = np.array([[pos / np.power(10000, (i - i % 2) / E) for i in range(E)] for pos in range(maxlen)])
+    position_enc[:, 0::2] = np.sin(position_enc[:, 0::2])
+    position_enc[:, 1::2] = np.cos(position_enc[:, 1::2])
+    return torch.from_numpy(position_enc.astype(np.float32))
+
+
 def encode(plan, P, scope, seq_emb, seqlens, training):
     """TransformerModel.py:84-123 + positional_encoding_learn (util:281-316)."""
     enc = seq_emb * plan.d_model ** 0.5                                               # :97
     T = enc.shape[1]
-    pos = P[scope + "/positional_encoding_k_position_learn/embedding_position_learn"]
+    if getattr(plan, "position_encoding_method", "position_learn") == "position_sin_cos":
+        pos = sin_cos_position_table(plan.maxlen_k, plan.d_model).to(enc.dtype)         # :63-65, a constant
+    else:
+        pos = P[scope + "/positional_encoding_k_position_learn/embedding_position_learn"]
     enc = enc + pos[torch.arange(T)][None, :, :]                                      # :67-69
     enc = _dropout(enc, plan.dropout_rate, training, ("enc_in", scope))               # :101
     for i in range(plan.num_blocks_encode):

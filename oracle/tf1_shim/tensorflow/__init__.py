@@ -293,6 +293,11 @@ def constant(value, dtype=None, **_kw):
 
 
 def convert_to_tensor(value, dtype=None, **_kw):
+    # the one place the reference turns a numpy fp64 array into a tf.float32 constant (the sinusoid position table,
+    # TransformerModel_util.py:262): the shim computes in fp64 but keeps the fp32 rounding of that constant
+    import numpy as _np
+    if dtype is not None and isinstance(value, _np.ndarray) and value.dtype == _np.float64:
+        value = value.astype(_np.float32).astype(_np.float64)
     return _t(value, dtype)
 
 

@@ -35,9 +35,17 @@ MODEL_EDITS = {"hidden_units_bottom": "48,24,16", "hidden_units_task": "8", "tra
                "feature_dimension": "16", "batch_size": "8"}
 
 
+VARIANT = sys.argv[1] if len(sys.argv) > 1 else ""          # "" | "sincos" (transformer_position_encoding_method)
+STEM = "ref_graph" + ("_" + VARIANT if VARIANT else "")
+
+
 def small_reference_conf_text():
     with open(os.path.join(REF_CODE, "conf/settings/dmt.conf")) as fh:
         text = fh.read()
+    if VARIANT == "sincos":
+        text, n = re.subn(r"(?m)^transformer_position_encoding_method\s*=.*$",
+                          "transformer_position_encoding_method=position_sin_cos", text)
+        assert n == 1
     for a, b in SMALL.items():
         text = text.replace(a, b)
     for k, v in MODEL_EDITS.items():
@@ -71,7 +79,7 @@ def golden_graph():
     from cikm2020_dmt_b200.plan import build_plan
 
     text = small_reference_conf_text()
-    conf_out = os.path.join(HERE, "ref_graph.conf")
+    conf_out = os.path.join(HERE, STEM + ".conf")
     with open(conf_out, "w") as fh:
         fh.write(re.sub(r"(?m)^train_data_stat_path\s*=.*$", "train_data_stat_path =", text))
 
@@ -87,7 +95,7 @@ def golden_graph():
             os.chdir(cwd)
 
     # inputs: our synthetic generator on the same (small) plan, then edge cases by hand
-    plan = build_plan(Conf(HERE + "/", "ref_graph.conf"))
+    plan = build_plan(Conf(HERE + "/", STEM + ".conf"))
     rows = {n: t.rows for n, t in plan.tables.items()}
     B = 8
     batch = synthetic_batch(plan, B, seed=424242, table_rows=rows)
@@ -157,9 +165,9 @@ def golden_graph():
     out["out/interest_state"] = interest.numpy()
     for k, v in losses.items():
         out["out/loss/" + k] = np.float64(v.item())
-    np.savez_compressed(os.path.join(HERE, "ref_graph.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, STEM + ".npz"), **out)
     n_par = sum(v.numel() for _, v in tf.global_variables())
-    print("wrote ref_graph.npz: %d variables, %d parameters, click_logit[:3] = %s, loss = %.6f"
+    print("wrote " + STEM + ".npz: %d variables, %d parameters, click_logit[:3] = %s, loss = %.6f"
           % (len(tf.global_variables()), n_par, y_rel[0][:3].flatten().tolist(), losses["two_head_add/ctr_rel"].item()))
 
 

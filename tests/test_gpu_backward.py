@@ -82,6 +82,20 @@ def test_gradients_match_oracle_autograd_dmt_conf_d80_h4():
     _compare_all(plan, model, store, host, dev, O)
 
 
+def test_gradients_position_sin_cos():
+    """transformer_position_encoding_method=position_sin_cos (the reference parser's default): the position table is
+    a constant of the graph -- no variable, no gradient; everything else differentiates as before (fp32 and tf32)."""
+    ov = {("model", "transformer_position_encoding_method"): "position_sin_cos"}
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 48, overrides=ov)
+    assert not any("positional_encoding" in s.name for s in store.specs)
+    _compare_all(plan, model, store, host, dev, O)
+    plan, model, store, host, dev, O = _setup("dmt.conf", 40, overrides=ov, precision="bf16", train_gemm="tf32")
+    loss, G = model.compute_gradients(dev)
+    torch.cuda.synchronize()
+    loss_ref, grads_ref, _ = O.loss_and_grads(plan, O.params_from_store(store), host)
+    assert abs(loss.item() - loss_ref.item()) <= 3e-3 * abs(loss_ref.item())
+
+
 def test_gradients_two_blocks_and_ctr_rel_multiply():
     ov = {("model", "transformer_num_blocks_encode"): "2", ("model", "transformer_num_blocks_decode"): "2"}
     plan, model, store, host, dev, O = _setup("dmt_d64.conf", 24, seed=7, overrides=ov)
