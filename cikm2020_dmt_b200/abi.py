@@ -94,7 +94,10 @@ class WidenDesc(C.Structure):
 
 class AdamCfg(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
-                ("step", C.c_int32), ("_pad", C.c_int32)]
+                ("step", C.c_int32), ("kind", C.c_int32)]
+
+
+OPT_ADAM, OPT_SGD, OPT_ADAGRAD = 0, 1, 2
 
 
 class GradSource(C.Structure):

@@ -40,6 +40,7 @@ def save(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
             arrays["%s@rows%d-%d" % (name, lo, hi)] = t.detach().cpu().numpy()
         elif rank == 0:
             arrays[name] = t.detach().cpu().numpy()
+    slot_m, slot_v = getattr(optimizer, "SLOT_NAMES", ("Adam", "Adam_1"))   # TF slot names of the two state buffers
     if optimizer is not None:
         arrays["global_step"] = np.asarray(optimizer.t, dtype=np.int64)
         if hasattr(optimizer, "global_step"):      # the learning-rate schedule's clock (run_dnn.py:122-126)
@@ -47,13 +48,17 @@ def save(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
         if rank == 0:
             for spec in store.specs:
                 sl = slice(spec.offset, spec.offset + spec.numel)
-                arrays[spec.name + "/Adam"] = optimizer.m_dense[sl].detach().cpu().numpy().reshape(spec.shape)
-                arrays[spec.name + "/Adam_1"] = optimizer.v_dense[sl].detach().cpu().numpy().reshape(spec.shape)
+                if slot_m:
+                    arrays[spec.name + "/" + slot_m] = optimizer.m_dense[sl].detach().cpu().numpy().reshape(spec.shape)
+                if slot_v:
+                    arrays[spec.name + "/" + slot_v] = optimizer.v_dense[sl].detach().cpu().numpy().reshape(spec.shape)
         for name in store.tables:
             if name in shards or rank == 0:
                 sfx = "@rows%d-%d" % shards[name] if name in shards else ""
-                arrays[name + "/Adam" + sfx] = optimizer.m_tab[name].detach().cpu().numpy()
-                arrays[name + "/Adam_1" + sfx] = optimizer.v_tab[name].detach().cpu().numpy()
+                if slot_m:
+                    arrays[name + "/" + slot_m + sfx] = optimizer.m_tab[name].detach().cpu().numpy()
+                if slot_v:
+                    arrays[name + "/" + slot_v + sfx] = optimizer.v_tab[name].detach().cpu().numpy()
     for k, v in (extra or {}).items():
         arrays["extra/" + k] = np.asarray(v)
     path = _ckpt_path(directory, step) if rank == 0 else _ckpt_path(directory, step)[:-4] + ".rank%d.npz" % rank
@@ -116,20 +121,23 @@ def load(directory: str, step: int, store, optimizer=None, shards: Optional[Dict
         t.copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(t.device).reshape(t.shape))
     if strict and missing:
         raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (files[0], len(missing), missing[0]))
+    slot_m, slot_v = getattr(optimizer, "SLOT_NAMES", ("Adam", "Adam_1"))
     if optimizer is not None and "global_step" in data:
         optimizer.t = int(data["global_step"])
         if hasattr(optimizer, "global_step"):
             optimizer.global_step = int(data.get("lr_global_step", data["global_step"]))
         for spec in store.specs:
             sl = slice(spec.offset, spec.offset + spec.numel)
-            if spec.name + "/Adam" in data:
-                optimizer.m_dense[sl].copy_(torch.from_numpy(data[spec.name + "/Adam"]).reshape(-1))
-                optimizer.v_dense[sl].copy_(torch.from_numpy(data[spec.name + "/Adam_1"]).reshape(-1))
+            if slot_m and spec.name + "/" + slot_m in data:
+                optimizer.m_dense[sl].copy_(torch.from_numpy(data[spec.name + "/" + slot_m]).reshape(-1))
+            if slot_v and spec.name + "/" + slot_v in data:
+                optimizer.v_dense[sl].copy_(torch.from_numpy(data[spec.name + "/" + slot_v]).reshape(-1))
         for name in store.tables:
-            m = fetch(name + "/Adam", shard_of=name)
-            v = fetch(name + "/Adam_1", shard_of=name)
-            if m is not None and v is not None:
+            m = fetch(name + "/" + slot_m, shard_of=name) if slot_m else None
+            v = fetch(name + "/" + slot_v, shard_of=name) if slot_v else None
+            if m is not None:
                 optimizer.m_tab[name].copy_(torch.from_numpy(np.ascontiguousarray(m)))
+            if v is not None:
                 optimizer.v_tab[name].copy_(torch.from_numpy(np.ascontiguousarray(v)))
     if model is None and optimizer is not None:
         model = getattr(optimizer, "model", None)

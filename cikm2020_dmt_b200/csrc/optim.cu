@@ -21,12 +21,16 @@ namespace dmt {
 
 struct AdamScalars {
   float lr_t, b1, b2, eps, one_minus_b1, one_minus_b2;
+  int kind;       // DMT_OPT_ADAM | DMT_OPT_SGD | DMT_OPT_ADAGRAD
 };
 
 static AdamScalars adam_scalars(const dmt_adam_cfg* c) {
   AdamScalars s;
   const double t = (double)c->step;
-  s.lr_t = (float)((double)c->lr * sqrt(1.0 - pow((double)c->beta2, t)) / (1.0 - pow((double)c->beta1, t)));
+  s.kind = c->kind;
+  s.lr_t = c->kind == DMT_OPT_ADAM
+               ? (float)((double)c->lr * sqrt(1.0 - pow((double)c->beta2, t)) / (1.0 - pow((double)c->beta1, t)))
+               : c->lr;
   s.b1 = c->beta1;
   s.b2 = c->beta2;
   s.eps = c->epsilon;
@@ -36,6 +40,15 @@ static AdamScalars adam_scalars(const dmt_adam_cfg* c) {
 }
 
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamScalars& s) {
+  if (s.kind == DMT_OPT_SGD) {               // tf.train.GradientDescentOptimizer
+    p -= s.lr_t * g;
+    return;
+  }
+  if (s.kind == DMT_OPT_ADAGRAD) {           // tf.train.AdagradOptimizer: the accumulator lives in m
+    m = fmaf(g, g, m);
+    p -= s.lr_t * g / sqrtf(m);
+    return;
+  }
   m = fmaf(s.b1, m, s.one_minus_b1 * g);
   v = fmaf(s.b2, v, s.one_minus_b2 * g * g);
   p -= s.lr_t * m / (sqrtf(v) + s.eps);
@@ -680,6 +693,11 @@ int dmt_adam_rows_untouched(const dmt_adam_cfg* cfg, float* table, float* m, flo
   DMT_REQUIRE(cfg && table && m && v && touched && cfg->step >= 1, DMT_ERR_INVALID_ARGUMENT,
               "dmt_adam_rows_untouched: bad arguments");
   if (rows == 0) return DMT_OK;
+  if (cfg->kind != DMT_OPT_ADAM) {             // a row without gradient does not move: only clear the marks
+    cudaError_t e0 = cudaMemsetAsync(touched, 0, (size_t)rows, (cudaStream_t)stream);
+    if (e0 != cudaSuccess) return dmt::cuda_fail(e0, "cudaMemsetAsync(touched)");
+    return DMT_OK;
+  }
   const bool vec = dim % 4 == 0 && (((uintptr_t)table | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   int64_t blocks = (rows * (vec ? dim / 4 : dim) + 255) / 256;
   const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
@@ -783,6 +801,7 @@ int dmt_adam_rows_untouched_multi(const dmt_adam_cfg* cfg, int32_t n_tables, con
   int rc = check_tables("dmt_adam_rows_untouched_multi", n_tables, tables);
   if (rc != DMT_OK) return rc;
   DMT_REQUIRE(cfg && cfg->step >= 1, DMT_ERR_INVALID_ARGUMENT, "dmt_adam_rows_untouched_multi: bad arguments");
+  if (cfg->kind != DMT_OPT_ADAM) return DMT_OK;   // a row without gradient does not move
   dmt::UntouchedMultiArgs a{};
   int64_t biggest = 1;
   for (int t = 0; t < n_tables; ++t) {

@@ -50,9 +50,15 @@ class Inference(object):
         if optimizer == "adam":
             from .optim import TFAdam   # tf.train.AdamOptimizer semantics (inference_mlp.py:272-273)
             return TFAdam(self.model, learning_rate)
-        if optimizer in ("sgd", "adadelta", "adagrad", "ftrl", "rmsprop"):
+        if optimizer == "sgd":
+            from .optim import TFGradientDescent     # inference_mlp.py:266-267
+            return TFGradientDescent(self.model, learning_rate)
+        if optimizer == "adagrad":
+            from .optim import TFAdagrad             # inference_mlp.py:270-271
+            return TFAdagrad(self.model, learning_rate)
+        if optimizer in ("adadelta", "ftrl", "rmsprop"):
             raise NotImplementedError("optimizer %r is accepted by the reference (inference_mlp.py:264-277) "
-                                      "but only 'adam' (dmt.conf) is built" % optimizer)
+                                      "but only 'adam' (dmt.conf), 'sgd' and 'adagrad' are built" % optimizer)
         print("Unknow optimizer, exit now")
         sys.exit(1)
 

@@ -88,6 +88,9 @@ def piecewise_constant(step, boundaries, values):
 
 
 class TFAdam(object):
+    KIND = abi.OPT_ADAM
+    SLOT_NAMES = ("Adam", "Adam_1")        # TF slot names of m / v
+
     def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, step_boundary=None,
                  global_step=0):
         """learning_rate: a float, or the conf's comma list (`[model] learning_rate = 0.001,0.0001`) together
@@ -139,7 +142,7 @@ class TFAdam(object):
             lr = self._lr_now if self._lr_now is not None else self.current_lr()
         elif isinstance(lr, (list, tuple)):
             raise TypeError("pass a scalar learning rate per step; schedules belong to the constructor")
-        return abi.AdamCfg(float(lr), self.beta1, self.beta2, self.epsilon, int(self.t), 0)
+        return abi.AdamCfg(float(lr), self.beta1, self.beta2, self.epsilon, int(self.t), self.KIND)
 
     def begin_step(self):
         self._lr_now = self.current_lr()       # evaluated at the pre-increment global_step, like the TF graph
@@ -239,3 +242,24 @@ class TFAdam(object):
                                                    self.touched[name].data_ptr(), stream))
         self.model.launches += 1
         self.model.invalidate_prepared()
+
+
+class TFGradientDescent(TFAdam):
+    """`tf.train.GradientDescentOptimizer(learning_rate)` (inference_mlp.py:266-267): theta -= lr * g.  Same host
+    path and kernels as TFAdam (`dmt_adam_cfg.kind = DMT_OPT_SGD`); rows without a gradient do not move, so the
+    untouched-rows pass is a no-op and the moment buffers stay unused."""
+    KIND = abi.OPT_SGD
+    SLOT_NAMES = (None, None)
+
+
+class TFAdagrad(TFAdam):
+    """`tf.train.AdagradOptimizer(learning_rate)` (inference_mlp.py:270-271): acc += g^2 (initial accumulator 0.1, TF's
+    default), theta -= lr * g / sqrt(acc).  The accumulator lives in the `m` buffers."""
+    KIND = abi.OPT_ADAGRAD
+    SLOT_NAMES = ("Adagrad", None)
+
+    def __init__(self, model, learning_rate, initial_accumulator_value=0.1, **kw):
+        super().__init__(model, learning_rate, **kw)
+        self.m_dense.fill_(initial_accumulator_value)
+        for t in self.m_tab.values():
+            t.fill_(initial_accumulator_value)

@@ -370,8 +370,14 @@ typedef struct dmt_adam_cfg {
   float beta2;    /* 0.999 */
   float epsilon;  /* 1e-8  */
   int32_t step;   /* t >= 1 */
-  int32_t _pad;
+  int32_t kind;   /* which optimizer of inference_mlp.py:264-277 the update kernels apply:
+                     0 = tf.train.AdamOptimizer (dmt.conf), 1 = GradientDescentOptimizer (theta -= lr g),
+                     2 = AdagradOptimizer (acc += g^2, theta -= lr g / sqrt(acc); acc lives in `m`, initial value 0.1).
+                     1 and 2 leave a row without gradient unchanged, so the untouched-rows passes are no-ops. */
 } dmt_adam_cfg;
+#define DMT_OPT_ADAM 0
+#define DMT_OPT_SGD 1
+#define DMT_OPT_ADAGRAD 2
 
 /* One group of lookups into a table whose gradient is needed: the backward of tf.nn.embedding_lookup
  * (sequence / target path, base.py:81-91: id_offset = -1 with zero_pad, index 0 has no gradient) or of

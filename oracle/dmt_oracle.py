@@ -387,6 +387,41 @@ class TFAdam:
                 p.sub_(lr_t * self.m[k] / (self.v[k].sqrt() + self.eps))
 
 
+class TFGradientDescent:
+    """tf.train.GradientDescentOptimizer(lr) (inference_mlp.py:266-267): theta -= lr * g."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], lr=1e-3):
+        self.params, self.lr = params, float(torch.tensor(lr, dtype=torch.float32))
+
+    def step(self, grads: Dict[str, torch.Tensor], lr=None):
+        lr = self.lr if lr is None else float(torch.tensor(lr, dtype=torch.float32))
+        with torch.no_grad():
+            for k, p in self.params.items():
+                g = grads.get(k)
+                if g is not None:
+                    p.sub_(lr * (g.to_dense() if g.is_sparse else g))
+
+
+class TFAdagrad:
+    """tf.train.AdagradOptimizer(lr) (inference_mlp.py:270-271; TF-1.12 default initial_accumulator_value = 0.1):
+    acc += g^2 ; theta -= lr * g / sqrt(acc)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], lr=1e-3, initial_accumulator_value=0.1):
+        self.params, self.lr = params, float(torch.tensor(lr, dtype=torch.float32))
+        self.acc = {k: torch.full_like(v, initial_accumulator_value) for k, v in params.items()}
+
+    def step(self, grads: Dict[str, torch.Tensor], lr=None):
+        lr = self.lr if lr is None else float(torch.tensor(lr, dtype=torch.float32))
+        with torch.no_grad():
+            for k, p in self.params.items():
+                g = grads.get(k)
+                if g is None:
+                    continue
+                g = g.to_dense() if g.is_sparse else g
+                self.acc[k].addcmul_(g, g)
+                p.sub_(lr * g / self.acc[k].sqrt())
+
+
 def piecewise_constant(step, boundaries, values):
     """tf.train.piecewise_constant (run_dnn.py:125-126): values[0] while step <= boundaries[0]."""
     for b, v in zip(boundaries, values):

@@ -201,3 +201,39 @@ def test_train_steps_follow_oracle_adam():
         # (|step| ~ lr * |g| / (|g| + eps)); everything else must track closely
         assert err.max().item() <= 1e-3, "%s drifted by %.3e after 3 steps" % (name, err.max().item())
         assert err.mean().item() <= 2e-5, "%s mean drift %.3e after 3 steps" % (name, err.mean().item())
+
+
+@pytest.mark.parametrize("name", ["sgd", "adagrad"])
+def test_train_steps_follow_oracle_sgd_and_adagrad(name):
+    """`get_optimizer('sgd' | 'adagrad', lr)` (inference_mlp.py:266-271): three full steps through the same sorted
+    segmented-reduction kernels (`dmt_adam_cfg.kind`) track tf.train.GradientDescentOptimizer / AdagradOptimizer
+    (initial accumulator 0.1) restated in the oracle; rows without a gradient do not move."""
+    from cikm2020_dmt_b200.inference import Inference
+    from cikm2020_dmt_b200.optim import TFAdagrad, TFGradientDescent
+    from cikm2020_dmt_b200.data import synthetic_batch, batch_to
+    plan, model, store, host, dev, O = _setup("dmt_d64.conf", 32, seed=23)
+    lr = 0.05
+    opt = {"sgd": TFGradientDescent, "adagrad": TFAdagrad}[name](model, lr)
+    P = O.params_from_store(store)
+    ref = {"sgd": O.TFGradientDescent, "adagrad": O.TFAdagrad}[name](P, lr=lr)
+    sku = "DnnModel/embedding_trans/Sku/embedding"
+    before = store.tables[sku].clone()
+    touched = torch.zeros(before.shape[0], dtype=torch.bool)
+    for step in range(3):
+        h = synthetic_batch(plan, 32, seed=300 + step, table_rows=SMALL_ROWS)
+        h["mask"] = torch.nn.functional.one_hot((torch.arange(32) + step) % 5, 5).float()
+        loss_ref, grads_ref, _ = O.loss_and_grads(plan, P, h)
+        ref.step(grads_ref)
+        loss, G = model.compute_gradients(batch_to(h, "cuda"))
+        opt.apply_gradients(G)
+        assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item()) + 1e-5
+        g = grads_ref[sku]
+        touched |= (g.to_dense() if g.is_sparse else g).abs().sum(1) > 0
+    torch.cuda.synchronize()
+    for pname, v in store.named_parameters():
+        if pname.endswith("attention/dense_1/bias"):        # exact gradient 0: fp32 noise (Adagrad normalises it up)
+            continue
+        err = (v.detach().double().cpu() - P[pname].detach()).abs()
+        assert err.max().item() <= 2e-3 and err.mean().item() <= 2e-5, (pname, err.max().item(), err.mean().item())
+    after = store.tables[sku].cpu()
+    assert torch.equal(after[~touched], before.cpu()[~touched])      # no gradient, no movement
