@@ -527,9 +527,17 @@ def main():
         if prev is not None:
             prev.synchronize()
 
-    # ---- warm-up, then the timed device-resident region (with per-stage events + clock sampling)
+    # ---- warm-up, then the timed device-resident region (with per-stage events + clock sampling).  The W warm-up
+    #      steps are followed by an untimed pre-heat of at least 0.3 s of back-to-back steps: 20 steps of this workload
+    #      are 9 ms, too short for the SM clock to leave its idle state on a cold box
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    torch.cuda.synchronize()
+    t_heat = time.perf_counter()
+    while time.perf_counter() - t_heat < 0.3:
+        for i in range(10):
+            step_resident(i)
+        torch.cuda.synchronize()
     model.enable_stage_timing(True)
     launches0 = model.launches
     sampler = ClockSampler(local_rank) if rank == 0 else None
