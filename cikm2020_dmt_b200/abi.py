@@ -126,6 +126,7 @@ PROTOTYPES = {
     "dmt_seq_encode_fwd": (C.c_int, [C.POINTER(SeqCfg), C.POINTER(SeqInput), C.POINTER(SeqWeights), _fp,
                                      C.c_int64, _fp, C.c_size_t, _fp]),
     "dmt_seq_tail_fwd": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "dmt_seq_encode_multi_fwd": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
     "dmt_copy_dense_features": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_mmoe_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),

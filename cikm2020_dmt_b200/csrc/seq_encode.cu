@@ -18,6 +18,8 @@ void seq_tc_set_profile(unsigned long long* p);
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                          int64_t out_ld, void* workspace, cudaStream_t st);
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg);
+int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
 int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
                  float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
 }
@@ -103,6 +105,33 @@ int dmt_seq_tail_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_se
     DMT_REQUIRE(dmt::seq_tc_supported(cfgs[i], ins[i], &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_tail_fwd: %s", why);
   }
   return dmt::seq_tc_tails(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, (cudaStream_t)stream);
+}
+
+int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                             const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                             void* const* workspaces, const size_t* workspace_bytes, void* stream) {
+  DMT_REQUIRE(n_seq >= 0 && n_seq <= DMT_MAX_TAIL_SEQS, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_encode_multi_fwd: n_seq=%d (max %d)", n_seq, DMT_MAX_TAIL_SEQS);
+  if (n_seq == 0) return DMT_OK;
+  DMT_REQUIRE(cfgs && ins && ws && outs && out_lds && workspaces && workspace_bytes, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_seq_encode_multi_fwd: null pointer");
+  for (int i = 0; i < n_seq; ++i) {
+    int rc = validate_seq(cfgs[i], ins[i], ws[i]);
+    if (rc != DMT_OK) return rc;
+    DMT_REQUIRE(cfgs[i]->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT,
+                "dmt_seq_encode_multi_fwd: sequence %d: only the bf16 path has a multi-sequence launch", i);
+    DMT_REQUIRE(outs[i] && out_lds[i] >= cfgs[i]->d_model, DMT_ERR_INVALID_ARGUMENT,
+                "dmt_seq_encode_multi_fwd: sequence %d: bad output", i);
+    DMT_REQUIRE(cfgs[i]->batch > 0, DMT_ERR_INVALID_ARGUMENT, "dmt_seq_encode_multi_fwd: sequence %d: empty batch", i);
+    const char* why = nullptr;
+    DMT_REQUIRE(dmt::seq_tc_supported(cfgs[i], ins[i], &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_multi_fwd: %s", why);
+    DMT_REQUIRE(workspaces[i] && workspace_bytes[i] >= dmt::seq_tc_workspace_bytes(cfgs[i]), DMT_ERR_WORKSPACE_TOO_SMALL,
+                "dmt_seq_encode_multi_fwd: sequence %d: workspace %zu < %zu bytes (dmt_seq_encode_workspace_bytes)", i,
+                workspace_bytes[i], dmt::seq_tc_workspace_bytes(cfgs[i]));
+    DMT_REQUIRE(((uintptr_t)workspaces[i] & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
+                "dmt_seq_encode_multi_fwd: sequence %d: unaligned workspace", i);
+  }
+  return dmt::seq_tc_multi(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, (cudaStream_t)stream);
 }
 
 size_t dmt_seq_saved_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens) {

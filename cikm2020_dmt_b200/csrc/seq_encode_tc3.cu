@@ -24,6 +24,9 @@
 // interest vector out.
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "dmt_common.cuh"
 #include "seq_tc.cuh"
@@ -786,6 +789,782 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __g
   if (tid < 32) tmem_dealloc(tmem_base_s, 512);
 }
 
+// =====================================================================================================================
+// One launch for ALL behaviour sequences, with length-bucketed tiles (round 2).
+//
+// The per-sequence launches above pad every sample to the slot size of the batch's LONGEST sequence (64 rows for
+// dmt.conf's 50-token histories although the mean length is 34: ~47 % of every MMA / softmax / LayerNorm row is
+// padding) and pay the pipeline ramp (weight images, first gather, last read-out) and the wave quantisation of a
+// persistent grid three times.  Here `seq_bucket_kernel` first orders the samples of every sequence by length class
+// (> 32 | 17..32 | <= 16 tokens; `perm`, `counts` in the per-sequence workspace -- no host round trip), and ONE
+// persistent kernel walks the concatenated tile list of all (sequence, class) SEGMENTS: 2 / 4 / 8 samples per 128-row
+// tile.  Global tile g belongs to tile group (g mod 2*gridDim.x); a group runs the per-tile program of the segment's
+// slot size (the three instantiations of the generic lambda below: same memory plan, same tensor-memory plan), drains
+// its software pipeline at a segment boundary and, at a SEQUENCE boundary, the whole CTA swaps the 88 KB of weight
+// images / biases / positions / gather descriptors.
+// =====================================================================================================================
+struct SeqMultiArgs {
+  SeqTcArgs a[DMT_MAX_TAIL_SEQS];
+  const int32_t* perm[DMT_MAX_TAIL_SEQS];     // [batch] sample indices ordered by length class
+  const int32_t* counts[DMT_MAX_TAIL_SEQS];   // [3] samples in the 64- / 32- / 16-row classes
+  int32_t n_seq;
+};
+
+struct BucketArgs {
+  const int32_t* offs[DMT_MAX_TAIL_SEQS];     // CSR offsets [B + 1] that define the sequence lengths
+  int32_t* perm[DMT_MAX_TAIL_SEQS];
+  int32_t* counts[DMT_MAX_TAIL_SEQS];
+  int32_t batch[DMT_MAX_TAIL_SEQS];
+  int32_t maxlen[DMT_MAX_TAIL_SEQS];
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ int len_class(int len) { return len > 32 ? 0 : (len > 16 ? 1 : 2); }
+
+// one CTA per sequence: stable counting sort of the samples by length class (thread t owns a contiguous run of samples)
+__global__ void __launch_bounds__(1024) seq_bucket_kernel(const __grid_constant__ BucketArgs ba) {
+  __shared__ int wsum[32][3];
+  __shared__ int tot_s[3];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = ba.batch[q], maxlen = ba.maxlen[q];
+  const int32_t* offs = ba.offs[q];
+  const int per = (B + 1023) / 1024;
+  const int lo = min(tid * per, B), hi = min(lo + per, B);
+  int c[3] = {0, 0, 0};
+  for (int b = lo; b < hi; ++b) {
+    const int k = len_class(min(__ldg(offs + b + 1) - __ldg(offs + b), maxlen));
+    c[0] += k == 0; c[1] += k == 1; c[2] += k == 2;
+  }
+  int ex[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int v = c[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    ex[k] = v - c[k];
+    if (lane == 31) wsum[warp][k] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int mine = wsum[lane][k];
+      int v = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      wsum[lane][k] = v - mine;
+      if (lane == 31) tot_s[k] = v;
+    }
+  }
+  __syncthreads();
+  int pos[3];
+  pos[0] = wsum[warp][0] + ex[0];
+  pos[1] = tot_s[0] + wsum[warp][1] + ex[1];
+  pos[2] = tot_s[0] + tot_s[1] + wsum[warp][2] + ex[2];
+  int32_t* perm = ba.perm[q];
+  for (int b = lo; b < hi; ++b) {
+    const int k = len_class(min(__ldg(offs + b + 1) - __ldg(offs + b), maxlen));
+    const int p = k == 0 ? pos[0]++ : (k == 1 ? pos[1]++ : pos[2]++);
+    perm[p] = b;
+  }
+  if (tid < 3) ba.counts[q][tid] = tot_s[tid];
+}
+
+#define T3_TICK(idx)                                                    \
+  do {                                                                  \
+    if (dbgp && tid == 0) {                                             \
+      const long long _now = clock64();                                 \
+      atomicAdd(dbgp + (idx), (unsigned long long)(_now - t_last));     \
+      t_last = _now;                                                    \
+    }                                                                   \
+  } while (0)
+
+template <int N>
+using ic = std::integral_constant<int, N>;
+
+__global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const __grid_constant__ SeqMultiArgs m) {
+  using L0 = Tc2Layout<64>;                           // the byte offsets of the memory plan do not depend on the slot size
+  constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
+  constexpr int HC = KC / 2;                          // gather chunks per half
+  constexpr int tFF2 = 64;                            // H W2 accumulator (v3 plan)
+  constexpr int oExLN = 6144, oExSc = 4096;           // exchange scratch inside the Q region (see Tc2Layout aliases)
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2], cbars[2], wbar;        // per group: phase MMAs | context MMA; weights landed
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int slen_s[2][2][8];
+  __shared__ ChunkDesc sd[KC];
+  __shared__ float mxs_s[2][32];                      // (see seq_encode_tc3_kernel)
+
+  const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, row = gt & 127, hf = gt >> 7;
+  const int wq = (gt >> 5) & 3, lane = tid & 31;      // wq: warp inside the half = TMEM lane quarter
+  uint8_t* gbase = smem + L0::oGrp + grp * L0::szGrp;
+  uint8_t* sXA = gbase + L0::gXA;
+  uint8_t* sQ = gbase + L0::gQ;
+  uint8_t* sK = gbase + L0::gK;
+  float* fv = reinterpret_cast<float*>(smem + L0::oFV);
+  const uint4* spos = reinterpret_cast<const uint4*>(smem + L0::oPos);
+  uint64_t* bar = &bars[grp];
+  uint64_t* cbar = &cbars[grp];
+  const uint32_t bar_id = 1 + grp;
+
+  // diagnostics (dmt_debug_seq_profile): [q*16 + phase] cycles of CTA 0 / group 0 per sequence, [64 + cta] cycles of
+  // the whole CTA, [320 + cta] / [576 + cta] %globaltimer at entry / exit
+  unsigned long long* const dbg0 = m.a[0].dbg;
+  const long long t_entry = clock64();
+  if (dbg0 && tid == 0) dbg0[320 + blockIdx.x] = globaltimer_ns();
+
+  if (tid < 32) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&cbars[0], 1);
+    mbar_init(&cbars[1], 1);
+    mbar_init(&wbar, 1);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s + grp * 256;
+  const uint32_t aXA = smem_u32(sXA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(gbase + L0::gV);
+  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
+  const uint32_t dXA = desc_lo(aXA, ROWB), dQ = desc_lo(aQ, ROWB), dK = desc_lo(aK, ROWB);
+  const uint32_t dWqkv = desc_lo(smem_u32(smem + L0::oWqkv), 3 * D * 16), dW1 = desc_lo(smem_u32(smem + L0::oW1), DFF * 16),
+                 dW2 = desc_lo(smem_u32(smem + L0::oW2), D * 16);
+  const float sqrt_d = sqrtf((float)D);
+  const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;
+  const int c0h = hf * HC;                             // first gather chunk / 8-column group of this half
+  uint32_t phase = 0, cphase = 0;
+  // exchange slots: [row][half] pairs of floats
+  float2* exLN = reinterpret_cast<float2*>(sQ + oExLN);
+  float2* exSc = reinterpret_cast<float2*>(sQ + oExSc);
+  const int G = blockIdx.x * 2 + grp, S = 2 * gridDim.x;   // this tile group | tile groups of the grid
+  int seg_g0 = 0;                                      // global index of the current segment's first tile
+
+  for (int q = 0; q < m.n_seq; ++q) {
+    const SeqTcArgs& a = m.a[q];
+    const long long t_seq = clock64();
+    // ---- sequence prologue: gather descriptors, weight images, biases / LayerNorm vectors, positions.  Every group
+    //      has waited for its last context MMA (ctx_readout), i.e. for every MMA it issued: nothing reads the old
+    //      images any more once all threads are here ----
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid < KC) {
+      const int f = a.chunk_feat[tid];
+      sd[tid].ids = a.in.ids[f];
+      sd[tid].offs = a.in.offsets[f];
+      sd[tid].item_ids = a.in.item_ids[f];
+      sd[tid].tab = a.in.table[f] + a.chunk_off[tid];
+      sd[tid].rows = a.in.rows[f];
+      sd[tid].dim = a.in.dim[f];
+      sd[tid].dup = (tid > 0 && (tid % HC) != 0 && f == a.chunk_feat[tid - 1]) ? 1 : 0;   // dup only inside a half
+    }
+    if (tid == 0) {
+      mbar_expect_tx(&wbar, L0::oGrp);
+      bulk_g2s(smem + L0::oWqkv, a.prepared, L0::oGrp, &wbar);
+    }
+    {
+      for (int i = tid; i < D; i += kT3Threads) {
+        fv[L0::vBQKV + i] = a.bq[i];
+        fv[L0::vBQKV + D + i] = a.bk[i];
+        fv[L0::vBQKV + 2 * D + i] = a.bv[i];
+        fv[L0::vB2 + i] = a.b2[i];
+        fv[L0::vLN + 0 * D + i] = a.ln1_g[i];
+        fv[L0::vLN + 1 * D + i] = a.ln1_b[i];
+        fv[L0::vLN + 2 * D + i] = a.ln2_g[i];
+        fv[L0::vLN + 3 * D + i] = a.ln2_b[i];
+      }
+      for (int i = tid; i < DFF; i += kT3Threads) fv[L0::vB1 + i] = a.b1[i];
+      uint4* pdst = reinterpret_cast<uint4*>(smem + L0::oPos);
+      for (int i = tid; i < a.cfg.maxlen * KC; i += kT3Threads) {
+        const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
+        const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        pdst[i] = f8_to_bf16(f);
+      }
+    }
+    __syncthreads();
+    const __nv_bfloat16* gDec = a.prepared + prep_off_dec(D, DFF);
+    const uint4* gG = reinterpret_cast<const uint4*>(gDec);
+    const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
+    const int32_t* const len_offs = a.in.offsets[a.cfg.n_feats - 1];
+    const int maxlen = a.cfg.maxlen;
+    const int zp = a.cfg.zero_pad ? 1 : 0;
+    const int32_t* const perm = m.perm[q];
+    void* const ctxp = a.ctx;
+    unsigned long long* const dbgp = a.dbg ? a.dbg + q * 16 : nullptr;
+    if (dbgp && tid == 0) atomicAdd(dbgp + 15, (unsigned long long)(clock64() - t_seq));   // sequence prologue
+    bool wpending = gt == 0;                           // the MMA issuer waits for the images before its first MMA
+    const uint32_t wpar = q & 1;
+
+    auto run_segment = [&](auto slot_c, auto kw_c, const int seg_cnt, const int seg_base) {
+      constexpr int SLOT = decltype(slot_c)::value, KW = decltype(kw_c)::value;
+      using L = Tc2Layout<SLOT>;
+      static_assert(KW % 8 == 0 && KW <= L::CW && (SLOT == 64 || KW == L::CW), "key window");
+      constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
+      const int n_tiles = (seg_cnt + NS - 1) / NS;
+      int first = (G - seg_g0) % S;                    // this group's first tile of the segment (global striding)
+      if (first < 0) first += S;
+      seg_g0 += n_tiles;
+      if (first >= n_tiles) return;
+      const int lmax = maxlen < SLOT ? maxlen : SLOT;
+      const int slot = row / SLOT, tpos = row % SLOT;
+      long long t_last = clock64();
+      // ---- software-pipelined gather: this thread loads chunks c0h .. c0h+HC-1 of its token row ----
+      int pf_o0[HC], pf_o1[HC], pf_id[HC];
+      int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
+      bool pf_valid = false;
+      f8 pf_e[HC];
+      int pf_tid = kInvalidId;
+      float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
+
+      auto stage_offsets = [&](int nt) {
+        pf_l0 = pf_l1 = 0;
+        pf_tid = kInvalidId;
+#pragma unroll
+        for (int k = 0; k < HC; ++k) pf_o0[k] = pf_o1[k] = 0;
+        if (nt >= n_tiles) return;
+        const int si = nt * NS + slot;
+        if (si < seg_cnt) {
+          const int b = __ldg(perm + seg_base + si);
+          pf_l0 = __ldg(len_offs + b);
+          pf_l1 = __ldg(len_offs + b + 1);
+#pragma unroll
+          for (int k = 0; k < HC; ++k) {
+            if (k > 0 && sd[c0h + k].dup) {
+              pf_o0[k] = pf_o0[k - 1];
+              pf_o1[k] = pf_o1[k - 1];
+            } else {
+              const int32_t* of = sd[c0h + k].offs;
+              pf_o0[k] = __ldg(of + b);
+              pf_o1[k] = __ldg(of + b + 1);
+            }
+          }
+        }
+        if (gt < NS * KC) {
+          const int st = nt * NS + gt / KC;
+          if (st < seg_cnt) pf_tid = __ldg(sd[gt % KC].item_ids + __ldg(perm + seg_base + st));
+        }
+      };
+      auto stage_ids = [&](int nt, int par) {
+        pf_len = min(pf_l1 - pf_l0, lmax);
+        pf_valid = tpos < pf_len;
+        if (tpos == 0 && hf == 0) slen_s[grp][par][slot] = pf_len;
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+          pf_id[k] = kInvalidId;
+          if (pf_valid) {
+            if (k > 0 && sd[c0h + k].dup) pf_id[k] = pf_id[k - 1];
+            else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(sd[c0h + k].ids + pf_o0[k] + tpos) : 0;
+          }
+        }
+      };
+      auto stage_rows = [&]() {
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+          pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
+          pf_e[k].hi = pf_e[k].lo;
+          const int64_t rw = (int64_t)pf_id[k] - zp;
+          if (pf_id[k] != kInvalidId && rw >= 0 && rw < sd[c0h + k].rows)
+            pf_e[k] = ld_stream8(sd[c0h + k].tab + rw * sd[c0h + k].dim);
+        }
+        pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        pf_t1 = pf_t0;
+        if (gt < NS * KC) {
+          const int c = gt % KC;
+          const int64_t rw = (int64_t)pf_tid - zp;
+          if (pf_tid != kInvalidId && rw >= 0 && rw < sd[c].rows) {
+            const f8 t = ld_stream8(sd[c].tab + rw * sd[c].dim);
+            pf_t0 = t.lo;
+            pf_t1 = t.hi;
+          }
+        }
+      };
+      // decoder contexts of the tile whose first sample is rb0.  The context MMA is issued TRANSPOSED (A = the memory
+      // image read MN-major, B = the 16-row probability image): accumulator row k = feature k, column (part, head), so
+      // the read-out is 16 values in each of 64 lanes (two warps) instead of 64 values in each of 8-16 lanes of one
+      // warp, and the two partial softmaxes of a 64-row slot sit in the same lane (no shuffles).
+      auto ctx_readout = [&](int rb0) {
+        if (gt >= D) return;
+        mbar_wait(cbar, cphase);
+        cphase ^= 1;
+        fence_after_sync();
+        uint32_t c[16];
+        tmem_ld16(tmem_addr(tbase, L::tCtx), c);
+        tmem_ld_wait();
+        const float* mxs = mxs_s[grp];
+        const int kf = gt;                                 // feature column = TMEM lane
+        uint8_t* dst0 = reinterpret_cast<uint8_t*>(ctxp) + (size_t)(kf >> 3) * (128 * 16) + (kf & 7) * 2;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int si = rb0 + s;
+          const int b = si < seg_cnt ? __ldg(perm + seg_base + si) : -1;
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            float num, den;
+            if constexpr (PPS == 2) {
+              const int ia = (2 * s) * H + h, ib = (2 * s + 1) * H + h;
+              const float ma = mxs[ia], mb = mxs[ib];
+              const float m = fmaxf(ma, mb);
+              const float wa = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m), wb = (mb == -INFINITY) ? 0.f : ex2_approx(mb - m);
+              num = __uint_as_float(c[ia]) * wa + __uint_as_float(c[ib]) * wb;
+              den = mxs[NR + ia] * wa + mxs[NR + ib] * wb;
+            } else {
+              num = __uint_as_float(c[s * H + h]);
+              den = mxs[NR + s * H + h];
+            }
+            const float v = den > 0.f ? num / den : 0.f;    // empty sequence: context 0
+            if (b >= 0)
+              *reinterpret_cast<unsigned short*>(dst0 + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(h * KC) * (128 * 16) +
+                                                 (size_t)(b & 127) * 16) = __bfloat16_as_ushort(__float2bfloat16(v));
+          }
+        }
+        fence_before_sync();
+      };
+      // concat + sqrt(d) scale + learned position -> bf16, in registers: done early (in an MMA shadow) so that P0 is
+      // four stores
+      uint4 px[HC];
+      auto convert_rows = [&]() {
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = 0.f;
+          if (pf_valid) {
+            float p[8];
+            bf16x8_to_f(spos[tpos * KC + c0h + k], p);
+            x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
+            x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
+            x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
+            x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
+          }
+          px[k] = f8_to_bf16(x);
+        }
+      };
+      int n_done = 0;
+      const int tile0 = first, tstride = S;
+      stage_offsets(tile0);
+      stage_ids(tile0, 0);
+      stage_rows();
+      convert_rows();
+      T3_TICK(12);                                       // pipeline prime (offsets -> ids -> rows of the first tile)
+
+      for (int it = 0;; ++it) {
+        const int tile = tile0 + it * tstride;
+        if (tile >= n_tiles) break;
+        const int par = it & 1;
+        const int b0 = tile * NS;                          // segment-local index of the tile's first sample
+        const int next_tile = tile + tstride;
+
+        // ---- P0: this half's four (already converted) chunks -> X image ----
+#pragma unroll
+        for (int k = 0; k < HC; ++k) *reinterpret_cast<uint4*>(sXA + (c0h + k) * ROWB + row * 16) = px[k];
+        const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;
+        fence_proxy_async();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(0);
+
+        // ---- P1: [Q|K|V] = X Wqkv ----
+        if (gt == 0) {
+          if (wpending) {                                // this sequence's weight images landed (bulk copy issued in
+            mbar_wait(&wbar, wpar);                      // its prologue)
+            wpending = false;
+          }
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                        desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
+          commit(bar);
+        }
+        if (it > 0) ctx_readout(b0 - tstride * NS);
+        stage_offsets(next_tile);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        T3_TICK(1);
+
+        // ---- P2: + bias, bf16 -> Q / K / V images; half hf converts columns [96 hf, 96 hf + 96) ----
+#pragma unroll 1
+        for (int blk = 0; blk < 3; ++blk) {
+          const int n0 = hf * 96 + blk * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_addr(tbase, L::tQKV + n0), r);
+          tmem_ld_wait();
+          const int m = n0 >> 6;                           // 0: Q, 1: K, 2: V image
+          uint8_t* dstm = sQ + m * 16384 + row * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
+            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
+            float y[8];
+            y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
+            y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
+            y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
+            y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
+            const int ch = ((n0 & 63) >> 3) + g;
+            *reinterpret_cast<uint4*>(dstm + ch * ROWB) = f8_to_bf16(y);
+          }
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(2);
+
+        // ---- P3: S_h = Q_h K_h^T ----
+        if (gt == 0) {
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+#pragma unroll
+          for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int ks = 0; ks < DK / 16; ++ks) {
+              const uint32_t ch = (h * DK) / 8 + ks * 2;
+              mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dQ + ch * (ROWB / 16), dHi),
+                          desc_join(dK + ch * (ROWB / 16), dHi), idesc, ks > 0);
+            }
+          commit(bar);
+        }
+        stage_ids(next_tile, par ^ 1);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        T3_TICK(3);
+
+        // ---- P4: masked softmax of head hf; unnormalised P_hf packed IN PLACE ----
+        const int len = slen_s[grp][par][slot];
+        float inv_h = 0.f;
+        {
+          const int col0 = (row / CW) * CW;
+          const int lo = (SLOT == CW) ? 0 : slot * SLOT - col0;
+          const uint32_t sbase = tmem_addr(tbase, L::tS + hf * 128);
+          uint32_t r[CW];
+          tmem_ld32(sbase + col0, r);
+          if constexpr (KW >= 48) tmem_ld16(sbase + col0 + 32, r + 32);
+          if constexpr (KW == 56) tmem_ld8(sbase + col0 + 48, r + 48);
+          if constexpr (KW == 64) tmem_ld16(sbase + col0 + 48, r + 48);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < KW; ++j) {
+            const bool ok = (unsigned)(j - lo) < (unsigned)len;
+            const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
+            r[j] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+          const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < KW; j += 4) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), sl2, -mxs));
+            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+            r[j / 2] = pack_bf16x2(e0, e1);                 // (j/2 <= j: the packed words trail the reads)
+            r[j / 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          const float sum = (s0 + s1) + (s2 + s3);
+          inv_h = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+          for (int j = KW / 2; j < CW; ++j) r[j] = 0u;
+          if constexpr (CW == 64) {
+            tmem_st32(sbase + col0 / 2, r);
+            tmem_st32(sbase + (32 - col0 / 2), r + 32);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 16 == col0 / 2) tmem_st16(sbase + q * 16, r);
+              else tmem_st16(sbase + q * 16, r + 16);
+            }
+          }
+        }
+        if (gt < NS * KC) {
+          float* dv = reinterpret_cast<float*>(gbase + L::gDvec) + (gt / KC) * D + (gt % KC) * 8;
+          *reinterpret_cast<float4*>(dv) = make_float4(cur_t0.x * sqrt_d, cur_t0.y * sqrt_d, cur_t0.z * sqrt_d, cur_t0.w * sqrt_d);
+          *reinterpret_cast<float4*>(dv + 4) = make_float4(cur_t1.x * sqrt_d, cur_t1.y * sqrt_d, cur_t1.z * sqrt_d, cur_t1.w * sqrt_d);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(4);
+
+        // ---- P5: O_h = P_h V_h ----
+        if (gt == 0) {
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const uint32_t dV = desc_lo(aV + ((h * DK) / 8) * ROWB, 128);
+#pragma unroll
+            for (int ks = 0; ks < 128 / 16; ++ks)
+              mma_bf16_ts(tbase + L::tO + h * 128, tbase + L::tS + h * 128 + ks * 8,
+                          desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
+          }
+          commit(bar);
+        }
+        // folded decoder queries qt[s][n] = dvec[s] . G[n] + g[n]: thread (n = row, hf) computes the samples s = hf,
+        // hf + 2, ...; the contraction is split between the shadows of the P.V and the H.W2 MMAs
+        constexpr int NSH = NS / 2;
+        float qacc[NSH];
+        auto qt_part = [&](int jc0) {
+          const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
+#pragma unroll
+          for (int jc = jc0; jc < jc0 + KC / 2; ++jc) {
+            float w[8];
+            bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
+#pragma unroll
+            for (int s = 0; s < NSH; ++s) {
+              const float4 d0 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8);
+              const float4 d1 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8 + 4);
+              qacc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], qacc[s]))));
+              qacc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], qacc[s]))));
+            }
+          }
+        };
+        {
+          const float gb = __ldg(gGb + row);
+#pragma unroll
+          for (int s = 0; s < NSH; ++s) qacc[s] = gb;
+          qt_part(0);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        T3_TICK(5);
+
+        // ---- P6: A = LN(O + X): half hf owns columns [32 hf, 32 hf + 32) = head hf ----
+        {
+          float y[DK];
+          uint32_t r[32];
+          tmem_ld32(tmem_addr(tbase, L::tO + hf * 128), r);
+#pragma unroll
+          for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
+          tmem_ld_wait();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < DK; e += 2) {
+            y[e] = fmaf(__uint_as_float(r[e]), inv_h, y[e]);
+            y[e + 1] = fmaf(__uint_as_float(r[e + 1]), inv_h, y[e + 1]);
+            s0 += y[e]; s1 += y[e + 1];
+            q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
+          }
+          exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+          named_sync(bar_id, 256);
+          const float2 o = exLN[row * 2 + (hf ^ 1)];
+          const float mean = ((s0 + s1) + o.x) * (1.0f / D);
+          const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
+          const float rstd = 1.0f / sqrtf(var + kLnEps);
+          const float* g = fv + L::vLN + 0 * D + hf * DK;
+          const float* bt = fv + L::vLN + 1 * D + hf * DK;
+#pragma unroll
+          for (int e = 0; e < DK; e += 4) {
+            const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
+            y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
+            y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
+            y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
+            y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
+          }
+#pragma unroll
+          for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sXA + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(6);
+
+        // ---- P7: hidden = A W1 ----
+        if (gt == 0) {
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
+                        desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
+          commit(bar);
+        }
+        stage_rows();
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        T3_TICK(7);
+
+        // ---- P8: relu(+b1): half hf packs accumulator columns [128 hf, 128 hf + 128) into [128 hf, 128 hf + 64) ----
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          uint32_t r[32];
+          tmem_ld32(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 32), r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + hf * 128 + blk * 32 + g * 4);
+            pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
+            pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
+          }
+          tmem_st16(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 16), pk);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(8);
+
+        // ---- P9: F = H W2; the K = 256 A operand is two 64-column pieces of tensor memory ----
+        if (gt == 0) {
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, D);
+#pragma unroll
+          for (int ks = 0; ks < DFF / 16; ++ks)
+            mma_bf16_ts(tbase + tFF2, tbase + L::tFF1 + (ks / 8) * 128 + (ks % 8) * 8, desc_join(dW2 + ks * (2 * D), dHi),
+                        idesc, ks > 0);
+          commit(bar);
+        }
+        convert_rows();                                      // next tile's rows (requested in P7) -> bf16 registers
+        {
+          qt_part(KC / 2);
+          float* qt = reinterpret_cast<float*>(gbase + L::gQt);
+#pragma unroll
+          for (int s = 0; s < NSH; ++s) qt[(2 * s + hf) * (H * D) + row] = qacc[s];
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        T3_TICK(9);                                          // (qt is read after P10's LayerNorm-exchange barrier)
+
+        // ---- P10: memory = LN(F + b2 + A); decoder scores; partial softmax of head hf; images for the context MMA ----
+        {
+          float y[DK];
+          uint32_t r[32];
+          tmem_ld32(tmem_addr(tbase, tFF2 + hf * DK), r);
+#pragma unroll
+          for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
+          tmem_ld_wait();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < DK; e += 2) {
+            y[e] += __uint_as_float(r[e]) + fv[L::vB2 + hf * DK + e];
+            y[e + 1] += __uint_as_float(r[e + 1]) + fv[L::vB2 + hf * DK + e + 1];
+            s0 += y[e]; s1 += y[e + 1];
+            q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
+          }
+          exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+          named_sync(bar_id, 256);
+          {
+            const float2 o = exLN[row * 2 + (hf ^ 1)];
+            const float mean = ((s0 + s1) + o.x) * (1.0f / D);
+            const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
+            const float rstd = 1.0f / sqrtf(var + kLnEps);
+            const float* g = fv + L::vLN + 2 * D + hf * DK;
+            const float* bt = fv + L::vLN + 3 * D + hf * DK;
+#pragma unroll
+            for (int e = 0; e < DK; e += 4) {
+              const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
+              y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
+              y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
+              y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
+              y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
+            }
+          }
+          // memory image: this half's four chunks
+#pragma unroll
+          for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sK + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
+          // partial decoder scores over this half's 32 columns, both heads; exchanged with the other half
+          const float* qt = reinterpret_cast<const float*>(gbase + L::gQt) + slot * (H * D) + hf * DK;
+          float pu[H];
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < DK; k += 4) {
+              const float4 q = *reinterpret_cast<const float4*>(qt + h * D + k);
+              a0 = fmaf(y[k], q.x, a0); a1 = fmaf(y[k + 1], q.y, a1);
+              a0 = fmaf(y[k + 2], q.z, a0); a1 = fmaf(y[k + 3], q.w, a1);
+            }
+            pu[h] = a0 + a1;
+          }
+          exSc[row * 2 + hf] = make_float2(pu[0], pu[1]);
+          named_sync(bar_id, 256);
+          const float2 os = exSc[row * 2 + (hf ^ 1)];
+          // this half finishes head hf
+          const float dot = (hf == 0 ? pu[0] + os.x : pu[1] + os.y);
+          const float u = (tpos < len) ? dot * sl2 : -INFINITY;
+          const int part = (SLOT >= 32) ? wq : (wq * (32 / W) + lane / W);
+          float m = u;
+#pragma unroll
+          for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          float e = (tpos < len) ? ex2_approx(u - m) : 0.f;
+          e = __bfloat162float(__float2bfloat16(e));
+          float dsum = e;
+#pragma unroll
+          for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+          if ((lane % W) == 0) {
+            mxs_s[grp][part * H + hf] = m;
+            mxs_s[grp][NR + part * H + hf] = dsum;
+          }
+          // transposed probabilities: rows (p, hf) for every part p, column = this token
+          const unsigned short eb = __bfloat16_as_ushort(__float2bfloat16(e));
+          uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2 + hf * 16;
+#pragma unroll
+          for (int p = 0; p < NR / H; ++p)
+            *reinterpret_cast<unsigned short*>(pd + p * (H * 16)) = (p == part) ? eb : (unsigned short)0;
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        named_sync(bar_id, 256);
+        T3_TICK(10);
+
+        // ---- P11: context MMA, transposed: D[feature][(part, head)] = sum_t M_t[feature] e_t  (A = memory image read
+        //      MN-major, B = the compact probability image); read out in the shadow of the next tile's X Wqkv ----
+        if (gt == 0) {
+          fence_after_sync();
+          constexpr uint32_t idesc = make_idesc_bf16(128, 16, true, false);
+          const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
+#pragma unroll
+          for (int ks = 0; ks < 128 / 16; ++ks)
+            mma_bf16_ss(tbase + L::tCtx, desc_join(dM + ks * (256 / 16), dHiV), desc_join(dPd + ks * (2 * 256 / 16), dHi),
+                        idesc, ks > 0);
+          commit(cbar);
+        }
+        n_done = it + 1;
+        T3_TICK(11);
+      }
+
+
+      if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
+      T3_TICK(13);                                       // pipeline drain (last context read-out)
+      if (dbgp && tid == 0) atomicAdd(dbgp + 14, (unsigned long long)n_done);
+    };
+
+    const int c64 = __ldg(m.counts[q]), c32 = __ldg(m.counts[q] + 1), c16 = __ldg(m.counts[q] + 2);
+    run_segment(ic<64>{}, ic<56>{}, c64, 0);
+    run_segment(ic<32>{}, ic<32>{}, c32, c64);
+    run_segment(ic<16>{}, ic<32>{}, c16, c64 + c32);
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base_s, 512);
+  if (dbg0 && tid == 0) {
+    dbg0[64 + blockIdx.x] = (unsigned long long)(clock64() - t_entry);
+    dbg0[576 + blockIdx.x] = globaltimer_ns();
+  }
+}
+
 // ---- per-sample decoder tail, row-batched: 128 samples per CTA (one thread = one sample = one TMEM lane) ----
 //   o  = [ctx_0 | ctx_1] WvBD + bv (bv only for non-empty sequences) ; y = o + dvec ; av = LN3(y)
 //   u  = LN2(relu(av W1 + b1) W2 + b2 + av)                                   (TransformerModel.py:157-171)
@@ -1066,6 +1845,46 @@ int seq_tails_launch(int n, const SeqTcArgs* args, cudaStream_t st) {
   for (int i = n; i <= DMT_MAX_TAIL_SEQS; ++i) tb.first_tile[i] = t;
   if (t == 0) return DMT_OK;
   return launch_tails(tb, st);
+}
+
+// workspace tail of the bucketed launch: [perm: batch int32 | counts: 4 int32]
+size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg) { return ((size_t)cfg->batch * 4 + 16 + 255) / 256 * 256; }
+
+// dmt_seq_encode_multi_fwd: every behaviour sequence of the step -- length classes, ONE tile-kernel launch, one tail
+// launch
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, cudaStream_t st) {
+  SeqMultiArgs m;
+  BucketArgs ba;
+  memset(&m, 0, sizeof(m));
+  memset(&ba, 0, sizeof(ba));
+  m.n_seq = n;
+  long long ub_tiles = 0;                             // upper bound of the tile count (the classes are known on the device only)
+  int maxlen = 0;
+  for (int i = 0; i < n; ++i) {
+    m.a[i] = args[i];
+    int32_t* perm = static_cast<int32_t*>(scheds[i]);
+    int32_t* counts = perm + args[i].cfg.batch;
+    m.perm[i] = perm;
+    m.counts[i] = counts;
+    ba.offs[i] = args[i].in.offsets[args[i].cfg.n_feats - 1];
+    ba.perm[i] = perm;
+    ba.counts[i] = counts;
+    ba.batch[i] = args[i].cfg.batch;
+    ba.maxlen[i] = args[i].cfg.maxlen;
+    ub_tiles += (args[i].cfg.batch + 1) / 2 + 2;
+    if (args[i].cfg.maxlen > maxlen) maxlen = args[i].cfg.maxlen;
+  }
+  seq_bucket_kernel<<<n, 1024, 0, st>>>(ba);
+  DMT_CUDA_LAUNCH_CHECK("seq_bucket_kernel");
+  const int total = Tc2Layout<64>::oPos + maxlen * kD * 2 + 64;
+  const int sms = sm_count_cached();
+  const long long pairs = (ub_tiles + 1) / 2;
+  const int grid = pairs < sms ? (int)pairs : sms;
+  cudaError_t e = cudaFuncSetAttribute(seq_encode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_multi_kernel)");
+  seq_encode_multi_kernel<<<grid, kT3Threads, total, st>>>(m);
+  DMT_CUDA_LAUNCH_CHECK("seq_encode_multi_kernel");
+  return seq_tails_launch(n, args, st);
 }
 
 }  // namespace dmt

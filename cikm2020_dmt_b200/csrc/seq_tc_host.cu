@@ -96,9 +96,12 @@ bool seq_tc2_supported(const dmt_seq_cfg* cfg);
 size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg);
 int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st);
 
-// workspace = [prepared weight images | v2: decoder contexts [B][H*D] fp32]
+size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg);
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, cudaStream_t st);
+
+// workspace = [prepared weight images | decoder-context images | length-class schedule (perm, counts)]
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg) {
-  return seq_tc_prepared_bytes(cfg) + seq_tc2_ctx_bytes(cfg);
+  return seq_tc_prepared_bytes(cfg) + seq_tc2_ctx_bytes(cfg) + seq_tc_sched_bytes(cfg);
 }
 
 bool seq_tc_supported(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const char** why) {
@@ -163,6 +166,17 @@ int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* con
     fill_args(cfgs[i], ins[i], ws[i], outs[i], out_lds[i], workspaces[i], args[i]);
   }
   return seq_tails_launch(n, args, st);
+}
+
+int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st) {
+  SeqTcArgs args[DMT_MAX_TAIL_SEQS];
+  void* scheds[DMT_MAX_TAIL_SEQS];
+  for (int i = 0; i < n; ++i) {
+    fill_args(cfgs[i], ins[i], ws[i], outs[i], out_lds[i], workspaces[i], args[i]);
+    scheds[i] = static_cast<uint8_t*>(workspaces[i]) + seq_tc_prepared_bytes(cfgs[i]) + seq_tc2_ctx_bytes(cfgs[i]);
+  }
+  return seq_encode_multi_launch(n, args, scheds, st);
 }
 
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,

@@ -56,6 +56,7 @@ class mmoe_transformer_unbias(object):
         self.launches = 0            # kernels of this library enqueued so far
         self._stream_h = None        # set for the duration of inference() / compute_gradients()
         self.seq_streams = os.environ.get("DMT_SEQ_STREAMS", "1") != "0"   # one stream per behaviour sequence
+        self.seq_multi = os.environ.get("DMT_SEQ_MULTI", "1") != "0"       # bf16: one launch over all sequences
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
         self._v2_ok = True           # bf16 path: the decoder tails of all sequences run as one deferred launch
         self._bind_weights()
@@ -420,6 +421,32 @@ class mmoe_transformer_unbias(object):
             deferred.append((cfg, si, self._seq_w[seq_index], out, out_ld, ws_ptr))
         return keep
 
+    def seq_encode_multi(self, inputs, x, x_ld, batch):
+        """A2-A8 for ALL behaviour sequences (bf16 path): `dmt_seq_encode_multi_fwd` -- length classes on the
+        device, one persistent tile-kernel launch over every (sequence, class) segment, one tail launch; writes
+        the interest vectors into their columns of the MMoE input `x`."""
+        plan = self.plan
+        n = len(plan.sequences)
+        items, keep = [], []
+        for s, seq in enumerate(plan.sequences):
+            cfg = self._seq_cfg(inputs, seq, batch, self.precision)
+            ws, ws_bytes = self._prepared_for(s, cfg)
+            si, kp = self._seq_input(inputs, seq, batch)
+            keep += kp
+            col = plan.interest_col + s * plan.d_model
+            items.append((cfg, si, self._seq_w[s], x.data_ptr() + 4 * col, x_ld, ws.data_ptr(), ws_bytes))
+        keep.append(items)
+        cfgs = (C.c_void_p * n)(*[C.addressof(d[0]) for d in items])
+        ins = (C.c_void_p * n)(*[C.addressof(d[1]) for d in items])
+        wts = (C.c_void_p * n)(*[C.addressof(d[2]) for d in items])
+        outs = (C.c_void_p * n)(*[d[3] for d in items])
+        lds = (C.c_int64 * n)(*[d[4] for d in items])
+        wss = (C.c_void_p * n)(*[d[5] for d in items])
+        wsb = (C.c_size_t * n)(*[d[6] for d in items])
+        with self._Stage(self, "seq_encode", 3):
+            abi.check(self.lib.dmt_seq_encode_multi_fwd(n, cfgs, ins, wts, outs, lds, wss, wsb, self._stream()))
+        return keep
+
     def seq_tails(self, deferred):
         """dmt_seq_tail_fwd over the sequences collected by `seq_encode(..., deferred=list)`."""
         n = len(deferred)
@@ -622,6 +649,14 @@ class mmoe_transformer_unbias(object):
         x = self._buf("x", (batch, x_ld))
         keep = []
         deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
+        if (self.precision == abi.PRECISION_BF16 and self._v2_ok and self.seq_multi and batch > 0
+                and 0 < len(plan.sequences) <= abi.MAX_TAIL_SEQS):
+            # bf16: all sequences in ONE persistent tile-kernel launch over length-bucketed tiles
+            keep += self.seq_encode_multi(inputs, x, x_ld, batch)
+            if feats is not None:
+                self._copy_dense(feats, batch, x, x_ld, keep, self.precision)
+            keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
+            return self._inference_head(inputs, x, batch, keep, is_predict)
         # The behaviour sequences are independent of each other and of the dense / pooled columns until the MMoE
         # input: each runs on its own stream, so the CTAs of the next sequence's (persistent, one-CTA-per-SM) kernel
         # start on an SM the moment the previous kernel's CTA there retires -- no tail bubble, prologues (weight
@@ -654,6 +689,12 @@ class mmoe_transformer_unbias(object):
                 keep += self.seq_encode(inputs, s, x.data_ptr() + 4 * col, x_ld, batch, deferred)
         if deferred:
             self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
+        return self._inference_head(inputs, x, batch, keep, is_predict)
+
+    def _inference_head(self, inputs, x, batch, keep, is_predict):
+        """MMoE + towers + bias tower on the assembled MMoE input (mmoe_transformer_unbias.py:218-316)."""
+        plan = self.plan
+        stream = self._stream()
         # scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can
         # read them back with a single copy; two buffers alternate, so the result of call i stays valid while
         # call i + 1 runs

@@ -244,6 +244,16 @@ DMT_API int dmt_seq_encode_fwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in,
 DMT_API int dmt_seq_tail_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
                              const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
                              void* const* workspaces, void* stream);
+/* DMT_PRECISION_BF16: A2-A8 for ALL behaviour sequences of the step (trans_core x 3, mmoe_transformer_unbias.py:
+ * 150-216) as three launches in total: the samples of every sequence are ordered by length class on the device
+ * (> 32 | 17..32 | <= 16 tokens -> 2 / 4 / 8 samples per 128-row tile instead of padding everything to the longest
+ * history), ONE persistent tile kernel walks the tiles of all (sequence, class) segments, one launch runs the decoder
+ * tails.  Arguments as dmt_seq_tail_fwd; each workspace is that sequence's prepared buffer
+ * (dmt_seq_encode_workspace_bytes / dmt_seq_prepare_weights).  Results per sample are those of dmt_seq_encode_fwd
+ * up to the summation order of the softmax (bf16 tolerance). */
+DMT_API int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                                     const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                                     void* const* workspaces, const size_t* workspace_bytes, void* stream);
 
 /* ---- A9/A11: pooled embeddings ----------------------------------------------------
  * Replaces embedding_combiner (model/net/base.py:93-124) and embedding_combiner_bias

@@ -120,4 +120,10 @@ def test_argument_errors_need_no_gpu():
     assert lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0) > 128 * 1024       # weight images + context image
     big = abi.SeqCfg(4096, 64, 256, 2, 1, 1, 50, 1, 5, abi.PRECISION_BF16, 0, 0, 0.0, 0)
     grow = lib.dmt_seq_encode_workspace_bytes(C.byref(big), 0) - lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0)
-    assert grow == (4096 // 128 - 1) * 128 * 128 * 2                             # one 32 KB image per 128 samples
+    sched = lambda b: (b * 4 + 16 + 255) // 256 * 256                            # length-class schedule: perm + counts
+    assert grow == (4096 // 128 - 1) * 128 * 128 * 2 + sched(4096) - sched(4)    # one 32 KB image per 128 samples
+    rc = lib.dmt_seq_encode_multi_fwd(abi.MAX_TAIL_SEQS + 1, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"n_seq" in lib.dmt_last_error()
+    assert lib.dmt_seq_encode_multi_fwd(0, None, None, None, None, None, None, None, None) == 0
+    rc = lib.dmt_seq_encode_multi_fwd(1, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"null" in lib.dmt_last_error()
