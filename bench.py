@@ -504,13 +504,18 @@ def main():
     def step_resident(i):
         infer(dev_batches[i % len(dev_batches)], is_train=False)
 
-    staged_next = [None]
+    staged = []         # batches whose copy is in flight: [step i, step i + 1]
 
     def step_e2e(i):
-        # every step copies ONE batch host->device (the next step's, on the copy stream, overlapping this step's
-        # kernels -- a data-loader prefetch) and reads this step's scores back
-        cur = staged_next[0] if staged_next[0] is not None else model.prefetch(packed[i % len(packed)], views=False)
-        staged_next[0] = model.prefetch(packed[(i + 1) % len(packed)], views=False)
+        # every step copies ONE batch host->device (the batch of step i + 2, on the copy stream, overlapping the
+        # kernels of steps i and i + 1 -- a data-loader prefetch two batches deep, the model rotates three device
+        # buffers) and reads this step's scores back
+        while len(staged) < 2:
+            staged.append(model.prefetch(packed[(i + len(staged)) % len(packed)], views=False))
+        # (before this step's launches: the copy into the third buffer then only waits for step i - 1, the buffer's
+        # previous consumer)
+        staged.append(model.prefetch(packed[(i + 2) % len(packed)], views=False))
+        cur = staged.pop(0)
         (yr, yb) = infer(cur, is_train=False)
         # one device->host read of the step's scores ([click logit; order logit; y_bias] x B), on a side stream so
         # the next step's kernels do not queue behind the copy (the model alternates two score buffers)
@@ -601,14 +606,19 @@ def main():
     mean_b = lambda fn: sum(fn(plan, batches[i % len(batches)]) for i in range(steps_used))
     if dom in ("seq_encode", "seq_encode_train"):
         t_ms, _ = stage[dom]
-        n = steps_used * len(plan.sequences)                     # one fused tile-kernel launch per sequence and step
-        #                                                          (its share of the batched tail launch is in t_ms)
+        multi = args.precision == "bf16" and getattr(model, "seq_multi", False)
+        # bf16: ONE persistent tile-kernel launch per step over all sequences (+ length-class and tail launches, whose
+        # time is in t_ms); other paths: one launch chain per sequence
+        n = steps_used * (1 if multi else len(plan.sequences))
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
         fl = mean_b(flops_seq)                                   # algorithmic FLOPs (valid tokens only)
         hbm = alg / (t_ms / 1e3) / 1e9
         tfl = fl / (t_ms / 1e3) / 1e12
-        name = {"bf16": "seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM, fused "
-                        "gather->encoder->decoder, per sequence)",
+        name = {"bf16": ("seq_bucket_kernel + seq_encode_multi_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight "
+                         "per SM, fused gather->encoder->decoder, all sequences in one persistent launch over "
+                         "length-bucketed tiles)") if multi else
+                        ("seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM, fused "
+                         "gather->encoder->decoder, per sequence)"),
                 "tf32": "row-batched pipeline: seq_gather + tf32_rows_kernel x5 + attention + LayerNorm kernels (tcgen05 "
                         "kind::tf32 GEMMs, per sequence)",
                 "f32": "seq_encode_f32_kernel (fp32 CUDA cores, fused gather->encoder->decoder, per sequence)"}[args.precision]
@@ -709,9 +719,10 @@ def main():
                            "only; widened on the device by dmt_widen_u16 (1 launch, copy stream)") if compact else
                           "int32 ids + fp32 features, one pinned buffer",
                 "pinned_numa_node": numa_node,
-                "pipeline": "double-buffered prefetch: step i+1's packed batch is copied on a side stream while "
-                            "step i computes; one H2D copy and one D2H read (side stream) per step inside the timed region; the host "
-                            "waits for step i-1's scores after launching step i"},
+                "pipeline": "prefetch two batches deep (three rotating device buffers): step i+2's packed batch is "
+                            "copied on a side stream while steps i and i+1 compute; one H2D copy and one D2H read "
+                            "(side stream) per step inside the timed region; the host waits for step i-1's scores "
+                            "after launching step i"},
         "embed_gather": embed_gather,
         "f32": f32_block, "tf32": tf32_block, "tf32_dmt_conf": tf32_dmt_block, "train": train_block,
         "gpu_launches": int(gpu_launches), "clocks": clocks,

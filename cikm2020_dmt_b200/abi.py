@@ -35,6 +35,7 @@ class FFWeights(C.Structure):
 
 SEQ_DEFER_TAIL = 1
 SEQ_LEN_EXACT = 2
+SEQ_OUT_BF16 = 4
 MAX_TAIL_SEQS = 4
 
 
@@ -128,12 +129,16 @@ PROTOTYPES = {
     "dmt_seq_tail_fwd": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "dmt_seq_encode_multi_fwd": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "dmt_pool_mean_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
+    "dmt_pool_mean_fwd_bf16": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(PoolFeat), _fp, C.c_int64, _fp]),
     "dmt_copy_dense_features": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
+    "dmt_stage_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_mmoe_workspace_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
     "dmt_mmoe_prepared_bytes": (C.c_size_t, [C.POINTER(MmoeCfg)]),
     "dmt_mmoe_prepare_weights": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_size_t, _fp]),
     "dmt_mmoe_fwd": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp, C.c_size_t,
                                _fp, _fp]),
+    "dmt_mmoe_fwd_bf16in": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp,
+                                      C.c_size_t, _fp, _fp]),
     "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
                                     _fp, _fp, _fp, _fp, _fp]),

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(128) bias_loss_kernel(const __grid_constant__ 
   if (sub != 0 || b >= B) return;
   const float yb = cur[0];
   a.y_bias[b] = yb;
+  if (!a.probs && !a.mask) return;     // inference: the tower alone (the logits may still be in flight on another stream)
 
   const float lc = __ldg(a.logits + b), lo = __ldg(a.logits + B + b);
   const float sc = sigmoidf_(lc), so = sigmoidf_(lo), sb = sigmoidf_(yb);

@@ -357,8 +357,9 @@ size_t mmoe_tc_prepared_bytes(const dmt_mmoe_cfg* cfg);
 size_t mmoe_tc_workspace_bytes(const dmt_mmoe_cfg* cfg);
 bool mmoe_tc_supported(const dmt_mmoe_cfg* cfg, const char** why);
 int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* prepared, cudaStream_t st);
-int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
-                   void* workspace, const void* prepared, cudaStream_t st);
+int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                   const void* xb_in, int64_t xb_ld, float* logits, void* workspace, const void* prepared,
+                   cudaStream_t st);
 
 }  // namespace dmt
 
@@ -413,7 +414,31 @@ int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float
               "dmt_mmoe_fwd(bf16): pass the buffer written by dmt_mmoe_prepare_weights");
   DMT_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)prepared & 255) == 0, DMT_ERR_INVALID_ARGUMENT,
               "dmt_mmoe_fwd(bf16): workspace / prepared must be 256-byte aligned");
-  return dmt::mmoe_tc_launch(cfg, w, x, x_ld, logits, workspace, prepared, (cudaStream_t)stream);
+  return dmt::mmoe_tc_launch(cfg, w, x, x_ld, nullptr, 0, logits, workspace, prepared, (cudaStream_t)stream);
+}
+
+int dmt_mmoe_fwd_bf16in(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const void* xb, int64_t xb_ld, float* logits,
+                        void* workspace, size_t workspace_bytes, const void* prepared, void* stream) {
+  DMT_REQUIRE(cfg && w && xb && logits, DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd_bf16in: null pointer");
+  DMT_REQUIRE(cfg->batch >= 0 && cfg->in_dim > 0 && cfg->n_experts > 0 && cfg->n_experts <= DMT_MAX_EXPERTS &&
+                  cfg->n_layers > 0 && cfg->n_layers <= DMT_MAX_LAYERS && cfg->n_tasks > 0 &&
+                  cfg->n_tasks <= DMT_MAX_TASKS && cfg->n_tower_layers >= 0 && cfg->n_tower_layers <= DMT_MAX_LAYERS,
+              DMT_ERR_INVALID_ARGUMENT, "dmt_mmoe_fwd_bf16in: configuration out of range");
+  DMT_REQUIRE(cfg->precision == DMT_PRECISION_BF16, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd_bf16in: only the bf16 path reads a bf16 input (precision %d)", cfg->precision);
+  DMT_REQUIRE(xb_ld >= cfg->in_dim && xb_ld % 8 == 0 && ((uintptr_t)xb & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd_bf16in: xb_ld=%lld must be a multiple of 8 and >= in_dim, xb 16-byte aligned",
+              (long long)xb_ld);
+  DMT_REQUIRE(workspace && workspace_bytes >= dmt_mmoe_workspace_bytes(cfg), DMT_ERR_WORKSPACE_TOO_SMALL,
+              "dmt_mmoe_fwd_bf16in: workspace %zu < %zu bytes", workspace_bytes, dmt_mmoe_workspace_bytes(cfg));
+  if (cfg->batch == 0) return DMT_OK;
+  const char* why = nullptr;
+  DMT_REQUIRE(dmt::mmoe_tc_supported(cfg, &why), DMT_ERR_UNSUPPORTED_SHAPE, "dmt_mmoe_fwd_bf16in: %s", why);
+  DMT_REQUIRE(prepared, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd_bf16in: pass the buffer written by dmt_mmoe_prepare_weights");
+  DMT_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)prepared & 255) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_mmoe_fwd_bf16in: workspace / prepared must be 256-byte aligned");
+  return dmt::mmoe_tc_launch(cfg, w, nullptr, 0, xb, xb_ld, logits, workspace, prepared, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,6 +28,10 @@ struct GemmTcArgs {
   int32_t b_rows_per_z;        // row offset of expert z inside the Bt tensor map
   int64_t ldc, c_stride_z;
   int32_t relu;
+  // layer 0 of dmt_mmoe_fwd_bf16in: slab z == gate_z holds the n_tasks x n_experts gate kernels as extra B rows
+  // (mmoe_transformer_unbias.py:85-94); its epilogue writes the gate softmaxes instead of an activation tile
+  int32_t gate_z, n_tasks, n_experts;
+  float* gates;                // [n_tasks][M][n_experts]
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -46,6 +50,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM, z = blockIdx.z;
   const int nkb = (g.K + GBK - 1) / GBK;
+  if (z == g.gate_z && n0 > 0) return;           // the gate slab is one (mostly empty) N tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GSTAGES; ++s) {
@@ -100,6 +105,36 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
     const int row = (warp & 3) * 32 + lane;
     const int m = m0 + row;
     const float* __restrict__ bias = g.bias + (int64_t)z * g.N;
+    if (z == g.gate_z) {
+      // gates: columns [t * E, t * E + E) of this row are task t's logits
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, 0), r);
+      tmem_ld_wait();
+      if (m < g.M) {
+        const int E = g.n_experts;
+        for (int t = 0; t < g.n_tasks; ++t) {
+          float v[DMT_MAX_EXPERTS];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < DMT_MAX_EXPERTS; ++e) {
+            v[e] = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)               // (register arrays want compile-time indices)
+              if (e < E && j == t * E + e) v[e] = __uint_as_float(r[j]) + __ldg(bias + j);
+            mx = fmaxf(mx, v[e]);
+          }
+          float den = 0.f;
+#pragma unroll
+          for (int e = 0; e < DMT_MAX_EXPERTS; ++e) {
+            v[e] = e < E ? expf(v[e] - mx) : 0.f;
+            den += v[e];
+          }
+#pragma unroll
+          for (int e = 0; e < DMT_MAX_EXPERTS; ++e)
+            if (e < E) g.gates[((int64_t)t * g.M + m) * E + e] = v[e] / den;
+        }
+      }
+    } else {
     __nv_bfloat16* crow = g.C + (int64_t)z * g.c_stride_z + (int64_t)m * g.ldc;
 #pragma unroll
     for (int c0 = 0; c0 < GBN; c0 += 32) {
@@ -132,6 +167,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
           }
         }
       }
+    }
     }
   }
   fence_before_sync();
@@ -269,18 +305,31 @@ __global__ void __launch_bounds__(kCastWarps * 32) mmoe_cast_gate4_kernel(const 
   }
 }
 
-// Bt[z][n][k] = W_z[k][n] (bf16, K padded to ldk with zeros): the K-major B operand of layer l.
-__global__ void mmoe_prepare_kernel(dmt_mmoe_weights w, int layer, int E, int K, int N, int ldk,
+// `gate_rows` (layer 0 only) = n_tasks * E extra rows after the experts': row t * E + e = gate t's kernel column e
+__global__ void mmoe_prepare_kernel(dmt_mmoe_weights w, int layer, int E, int K, int N, int ldk, int gate_rows,
                                     __nv_bfloat16* __restrict__ out) {
-  const int64_t total = (int64_t)E * N * ldk;
+  const int64_t total = ((int64_t)E * N + gate_rows) * ldk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = i % ldk, n = (i / ldk) % N, z = i / ((int64_t)ldk * N);
-    out[i] = __float2bfloat16(k < K ? w.expert[z][layer].w[(int64_t)k * N + n] : 0.f);
+    const int k = i % ldk;
+    const int64_t row = i / ldk;
+    float v = 0.f;
+    if (k < K) {
+      if (row < (int64_t)E * N) {
+        const int n = row % N, z = row / N;
+        v = w.expert[z][layer].w[(int64_t)k * N + n];
+      } else {
+        const int j = (int)(row - (int64_t)E * N), t = j / E, e = j % E;
+        v = w.gate[t].w[(int64_t)k * E + e];
+      }
+    }
+    out[i] = __float2bfloat16(v);
   }
 }
-__global__ void mmoe_prepare_bias_kernel(dmt_mmoe_weights w, int layer, int E, int N, float* __restrict__ out) {
+__global__ void mmoe_prepare_bias_kernel(dmt_mmoe_weights w, int layer, int E, int N, int gate_rows,
+                                         float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < E * N) out[i] = w.expert[i / N][layer].b[i % N];
+  else if (i < E * N + gate_rows) out[i] = w.gate[(i - E * N) / E].b[(i - E * N) % E];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -317,18 +366,26 @@ static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t col
 
 static inline int pad8(int k) { return (k + 7) & ~7; }
 
-// prepared = [Bt_0 | Bt_1 | ... ] bf16 then [bias_0 | bias_1 | ...] fp32 (256-byte aligned sections)
+// the gate kernels ride along as extra rows of layer 0's B operand (dmt_mmoe_fwd_bf16in reads them; the fp32-input
+// entry computes its gates in fp32 while it converts x)
+static inline int gate_rows(const dmt_mmoe_cfg* cfg, int layer) {
+  static_assert(DMT_MAX_TASKS * DMT_MAX_EXPERTS <= 32, "the gate logits must fit one 32-column accumulator chunk");
+  return layer == 0 ? cfg->n_tasks * cfg->n_experts : 0;
+}
+
+// prepared = [Bt_0 (+ gate rows) | Bt_1 | ... ] bf16 then [bias_0 (+ gate biases) | bias_1 | ...] fp32 (256-byte aligned
+// sections)
 static size_t prepared_layout(const dmt_mmoe_cfg* cfg, size_t* w_off, size_t* b_off) {
   size_t off = 0;
   int K = cfg->in_dim;
   for (int l = 0; l < cfg->n_layers; ++l) {
     if (w_off) w_off[l] = off;
-    off += ((size_t)cfg->n_experts * cfg->units[l] * pad8(K) * 2 + 255) & ~(size_t)255;
+    off += (((size_t)cfg->n_experts * cfg->units[l] + gate_rows(cfg, l)) * pad8(K) * 2 + 255) & ~(size_t)255;
     K = cfg->units[l];
   }
   for (int l = 0; l < cfg->n_layers; ++l) {
     if (b_off) b_off[l] = off;
-    off += ((size_t)cfg->n_experts * cfg->units[l] * 4 + 255) & ~(size_t)255;
+    off += (((size_t)cfg->n_experts * cfg->units[l] + gate_rows(cfg, l)) * 4 + 255) & ~(size_t)255;
   }
   return off;
 }
@@ -362,11 +419,11 @@ int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* pr
   uint8_t* base = (uint8_t*)prepared;
   int K = cfg->in_dim;
   for (int l = 0; l < cfg->n_layers; ++l) {
-    const int N = cfg->units[l], E = cfg->n_experts, ldk = pad8(K);
-    const int64_t total = (int64_t)E * N * ldk;
-    mmoe_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*w, l, E, K, N, ldk,
+    const int N = cfg->units[l], E = cfg->n_experts, ldk = pad8(K), gr = gate_rows(cfg, l);
+    const int64_t total = ((int64_t)E * N + gr) * ldk;
+    mmoe_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*w, l, E, K, N, ldk, gr,
                                                                          (__nv_bfloat16*)(base + w_off[l]));
-    mmoe_prepare_bias_kernel<<<(E * N + 255) / 256, 256, 0, st>>>(*w, l, E, N, (float*)(base + b_off[l]));
+    mmoe_prepare_bias_kernel<<<(E * N + gr + 255) / 256, 256, 0, st>>>(*w, l, E, N, gr, (float*)(base + b_off[l]));
     K = N;
   }
   DMT_CUDA_LAUNCH_CHECK("mmoe_prepare_kernel");
@@ -376,8 +433,10 @@ int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* pr
 int mmoe_head_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
                      const void* h_last, int h_is_bf16, const float* gates, float* logits, cudaStream_t st);
 
-int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld, float* logits,
-                   void* workspace, const void* prepared, cudaStream_t st) {
+// x: fp32 input (converted to bf16 into the workspace here) -- or xb_in: the input is bf16 already
+int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x, int64_t x_ld,
+                   const void* xb_in, int64_t xb_ld, float* logits, void* workspace, const void* prepared,
+                   cudaStream_t st) {
   size_t w_off[DMT_MAX_LAYERS], b_off[DMT_MAX_LAYERS], h_off[DMT_MAX_LAYERS], gate_off;
   prepared_layout(cfg, w_off, b_off);
   workspace_layout(cfg, h_off, &gate_off);
@@ -390,7 +449,10 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
   const size_t gsm = (size_t)cfg->n_tasks * ((cfg->in_dim + 127) & ~127) * sizeof(float4);
   bool gate_al = true;
   for (int t = 0; t < cfg->n_tasks; ++t) gate_al = gate_al && ((uintptr_t)w->gate[t].w & 15) == 0;
-  if (E == 4 && gate_al && x_ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gates & 15) == 0 && gsm <= 160 * 1024) {
+  const bool fold_gates = xb_in != nullptr;                  // gates computed by the layer-0 GEMM itself
+  if (fold_gates) {
+    // (nothing to launch: slab z = E of the layer-0 GEMM below)
+  } else if (E == 4 && gate_al && x_ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gates & 15) == 0 && gsm <= 160 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mmoe_cast_gate4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_cast_gate4_kernel)");
     int grid = (B + kCastWarps - 1) / kCastWarps;
@@ -410,15 +472,16 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
   }
-  const __nv_bfloat16* a = xb;
+  const __nv_bfloat16* a = xb_in ? (const __nv_bfloat16*)xb_in : xb;
   int64_t a_rows = B;          // rows in the A tensor map
-  int a_rows_per_z = 0, K = cfg->in_dim, lda = ldx;
+  int a_rows_per_z = 0, K = cfg->in_dim;
+  int64_t lda = xb_in ? xb_ld : ldx;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const int N = cfg->units[l];
     GemmTcArgs g;
     int rc = make_map(&g.tmA, a, a_rows, K, lda);
     if (rc != DMT_OK) return rc;
-    rc = make_map(&g.tmB, pw + w_off[l], (int64_t)E * N, K, pad8(K));
+    rc = make_map(&g.tmB, pw + w_off[l], (int64_t)E * N + gate_rows(cfg, l), K, pad8(K));
     if (rc != DMT_OK) return rc;
     g.bias = (const float*)(pw + b_off[l]);
     g.C = (__nv_bfloat16*)(ws + h_off[l]);
@@ -428,7 +491,12 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
     g.ldc = N;
     g.c_stride_z = (int64_t)B * N;
     g.relu = 1;
-    dim3 grid((N + GBN - 1) / GBN, (B + GBM - 1) / GBM, E);
+    const bool gz = fold_gates && l == 0;
+    g.gate_z = gz ? E : -1;
+    g.n_tasks = cfg->n_tasks;
+    g.n_experts = E;
+    g.gates = gates;
+    dim3 grid((N + GBN - 1) / GBN, (B + GBM - 1) / GBM, gz ? E + 1 : E);
     gemm_tc_kernel<<<grid, kGemmThreads, smem_bytes, st>>>(g);
     DMT_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
     a = g.C;

@@ -808,6 +808,7 @@ struct SeqMultiArgs {
   const int32_t* perm[DMT_MAX_TAIL_SEQS];     // [batch] sample indices ordered by length class
   const int32_t* counts[DMT_MAX_TAIL_SEQS];   // [3] samples in the 64- / 32- / 16-row classes
   int32_t n_seq;
+  int32_t stagger;                            // cycles the second tile group of every CTA starts late
 };
 
 struct BucketArgs {
@@ -888,6 +889,8 @@ __global__ void __launch_bounds__(1024) seq_bucket_kernel(const __grid_constant_
       atomicAdd(dbgp + (idx), (unsigned long long)(_now - t_last));     \
       t_last = _now;                                                    \
     }                                                                   \
+    if (dbgp && gt == 0 && blockIdx.x == 0 && tl_tile < 6 && (idx) < 12) \
+      dbg0[1024 + grp * 128 + tl_tile * 16 + (idx)] = (unsigned long long)(clock64() - t_entry); \
   } while (0)
 
 template <int N>
@@ -951,6 +954,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
   float2* exLN = reinterpret_cast<float2*>(sQ + oExLN);
   float2* exSc = reinterpret_cast<float2*>(sQ + oExSc);
   const int G = blockIdx.x * 2 + grp, S = 2 * gridDim.x;   // this tile group | tile groups of the grid
+  int tl_tile = 0;                                     // diagnostics: tiles this group has finished (timeline capture)
+  // (tuning knob) the second tile group starts every sequence `stagger` cycles late: do the groups' SIMT epilogues
+  // then fall into each other's MMA round trips instead of both groups computing and waiting at the same time?
   int seg_g0 = 0;                                      // global index of the current segment's first tile
 
   for (int q = 0; q < m.n_seq; ++q) {
@@ -1006,6 +1012,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
     void* const ctxp = a.ctx;
     unsigned long long* const dbgp = a.dbg ? a.dbg + q * 16 : nullptr;
     if (dbgp && tid == 0) atomicAdd(dbgp + 15, (unsigned long long)(clock64() - t_seq));   // sequence prologue
+    if (grp == 1 && m.stagger > 0) {                   // (the CTA-wide barriers above re-align the groups)
+      const long long t0 = clock64();
+      while (clock64() - t0 < m.stagger) __nanosleep(200);
+    }
     bool wpending = gt == 0;                           // the MMA issuer waits for the images before its first MMA
     const uint32_t wpar = q & 1;
 
@@ -1542,6 +1552,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
         }
         n_done = it + 1;
         T3_TICK(11);
+        ++tl_tile;
       }
 
 
@@ -1764,8 +1775,14 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
     const int bb = tile * 128 + r;
     if (bb >= B) break;
     const float* so = reinterpret_cast<const float*>(smem + L::oOut) + r * (D + 1);
-    a.out[(int64_t)bb * a.out_ld + lane] = so[lane];
-    a.out[(int64_t)bb * a.out_ld + 32 + lane] = so[32 + lane];
+    if (a.cfg.flags & DMT_SEQ_OUT_BF16) {             // straight into the bf16 MMoE input
+      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)bb * a.out_ld;
+      ob[lane] = __float2bfloat16(so[lane]);
+      ob[32 + lane] = __float2bfloat16(so[32 + lane]);
+    } else {
+      a.out[(int64_t)bb * a.out_ld + lane] = so[lane];
+      a.out[(int64_t)bb * a.out_ld + 32 + lane] = so[32 + lane];
+    }
   }
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
@@ -1858,6 +1875,14 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, c
   memset(&m, 0, sizeof(m));
   memset(&ba, 0, sizeof(ba));
   m.n_seq = n;
+  {
+    static int stagger = -1;                          // tuning knob (cycles)
+    if (stagger < 0) {
+      const char* e = getenv("DMT_SEQ_STAGGER");
+      stagger = e ? atoi(e) : 0;
+    }
+    m.stagger = stagger;
+  }
   long long ub_tiles = 0;                             // upper bound of the tile count (the classes are known on the device only)
   int maxlen = 0;
   for (int i = 0; i < n; ++i) {

@@ -49,9 +49,67 @@ copy_dense_bf16_kernel(const __nv_bfloat16* __restrict__ src, int batch, int dim
   }
 }
 
+// dense features -> bf16 columns [0, dim) of the bf16 MMoE input; the source rows are contiguous ([batch, dim]), so a
+// thread takes 8 consecutive source elements (one 16-byte / two 16-byte loads) and scatters them to their rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+stage_dense_bf16_kernel(const T* __restrict__ src, int64_t total, int dim, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total; i0 += stride) {
+    __nv_bfloat16 v[8];
+    if (i0 + 8 <= total) {
+      if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(src + i0));
+      } else {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(src + i0));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(src + i0 + 4));
+        v[0] = __float2bfloat16(a.x); v[1] = __float2bfloat16(a.y); v[2] = __float2bfloat16(a.z); v[3] = __float2bfloat16(a.w);
+        v[4] = __float2bfloat16(b.x); v[5] = __float2bfloat16(b.y); v[6] = __float2bfloat16(b.z); v[7] = __float2bfloat16(b.w);
+      }
+    } else {
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u < total) {
+          if constexpr (sizeof(T) == 2) v[u] = src[i0 + u];
+          else v[u] = __float2bfloat16(src[i0 + u]);
+        }
+    }
+    int64_t b = i0 / dim;
+    int c = (int)(i0 - b * dim);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u < total) dst[b * ld + c] = v[u];
+      if (++c == dim) {
+        c = 0;
+        ++b;
+      }
+    }
+  }
+}
+
 }  // namespace dmt
 
 extern "C" {
+
+int dmt_stage_dense_features_bf16(const void* features, int32_t features_are_bf16, int32_t batch, int32_t dim,
+                                  void* out_bf16, int64_t out_ld, void* stream) {
+  DMT_REQUIRE(features && out_bf16 && batch >= 0 && dim > 0 && out_ld >= dim, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_stage_dense_features_bf16: bad arguments");
+  DMT_REQUIRE(((uintptr_t)features & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_stage_dense_features_bf16: features must be 16-byte aligned");
+  if (batch == 0) return DMT_OK;
+  const int64_t total = (int64_t)batch * dim;
+  int64_t blocks = (total / 8 + 255) / 256 + 1;
+  const int64_t cap = (int64_t)dmt::sm_count_cached() * 8;
+  if (blocks > cap) blocks = cap;
+  if (features_are_bf16)
+    dmt::stage_dense_bf16_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)features, total, dim, (__nv_bfloat16*)out_bf16, out_ld);
+  else
+    dmt::stage_dense_bf16_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)features, total, dim, (__nv_bfloat16*)out_bf16, out_ld);
+  DMT_CUDA_LAUNCH_CHECK("stage_dense_bf16_kernel");
+  return DMT_OK;
+}
 
 int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* stream) {
   DMT_REQUIRE(n_arrays >= 0 && (arrays || n_arrays == 0), DMT_ERR_INVALID_ARGUMENT, "dmt_widen_u16: bad arguments");

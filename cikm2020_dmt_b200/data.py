@@ -83,15 +83,44 @@ def batch_to(batch: Dict, device, non_blocking=False) -> Dict:
     `__max_len__` (feature name -> length) so the model never needs a device->host read to size its row slots."""
     out = {}
     max_len = dict(batch.get("__max_len__") or {})
+    moved = {}      # offsets tensors that share storage in the source (the id lists of one behaviour sequence) stay
+                    # ONE tensor on the device: the pooled-lookup kernel walks such features together
+
+    def move_offsets(t):
+        key = (t.data_ptr(), t.dtype, tuple(t.shape))
+        if key not in moved:
+            moved[key] = t.to(device, non_blocking=non_blocking)
+        return moved[key]
+
     for k, v in batch.items():
         if k == "__max_len__":
             continue
         if isinstance(v, SparseIds) and v.offsets.device.type == "cpu" and k not in max_len:
             off = v.offsets
             max_len[k] = int((off[1:] - off[:-1]).max()) if off.numel() > 1 else 0
-        out[k] = v.to(device, non_blocking=non_blocking) if hasattr(v, "to") else v
+        if isinstance(v, SparseIds):
+            out[k] = SparseIds(v.values.to(device, non_blocking=non_blocking), move_offsets(v.offsets),
+                               None if v.weights is None else v.weights.to(device, non_blocking=non_blocking))
+        else:
+            out[k] = v.to(device, non_blocking=non_blocking) if hasattr(v, "to") else v
     out["__max_len__"] = max_len
     return out
+
+
+def share_offsets(batch: Dict) -> Dict:
+    """CSR features of a HOST batch whose offsets arrays are equal (the parallel id lists of one behaviour sequence:
+    sku / time bucket / category / brand / shop of the same events) are made to share ONE offsets tensor, in place.
+    `PackedBatch` then stores it once and `batch_to` moves it once, and `dmt_pool_mean_fwd` walks those features
+    together (it groups by offsets pointer, which proves equal lengths without reading device memory)."""
+    seen = {}
+    for k, v in batch.items():
+        if isinstance(v, SparseIds) and v.offsets.device.type == "cpu":
+            key = (v.offsets.numel(), v.offsets.dtype, v.offsets.contiguous().numpy().tobytes())
+            if key in seen:
+                v.offsets = seen[key]
+            else:
+                seen[key] = v.offsets
+    return batch
 
 
 def _seq_lengths(rng, B, max_len, kind):

@@ -57,6 +57,7 @@ class mmoe_transformer_unbias(object):
         self._stream_h = None        # set for the duration of inference() / compute_gradients()
         self.seq_streams = os.environ.get("DMT_SEQ_STREAMS", "1") != "0"   # one stream per behaviour sequence
         self.seq_multi = os.environ.get("DMT_SEQ_MULTI", "1") != "0"       # bf16: one launch over all sequences
+        self.x_bf16 = os.environ.get("DMT_X_BF16", "1") != "0"             # bf16: MMoE input assembled in bf16
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
         self._v2_ok = True           # bf16 path: the decoder tails of all sequences run as one deferred launch
         self._bind_weights()
@@ -317,6 +318,18 @@ class mmoe_transformer_unbias(object):
             abi.check(fn(feats.data_ptr(), batch, plan.feature_dim, x.data_ptr(), x_ld, self._stream()))
         keep.append(feats)
 
+    def _stage_dense_bf16(self, feats, batch, xb, xb_ld, keep):
+        """base.py:95-96 for the bf16 MMoE input: fp32 or bf16 `features` -> bf16 columns [0, feature_dim)."""
+        plan = self.plan
+        if tuple(feats.shape) != (batch, plan.feature_dim) or feats.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("'features' must be fp32 (or bf16) [%d, %d]" % (batch, plan.feature_dim))
+        feats = feats.contiguous()
+        with self._Stage(self, "copy_dense", 1):
+            abi.check(self.lib.dmt_stage_dense_features_bf16(feats.data_ptr(), 1 if feats.dtype == torch.bfloat16 else 0,
+                                                             batch, plan.feature_dim, xb.data_ptr(), xb_ld,
+                                                             self._stream()))
+        keep.append(feats)
+
     def _seq_len_hint(self, inputs, seq):
         """Upper bound on this sequence's lengths (selects the row-slot size of the bf16 tile kernels, which clamp
         every sequence to it).  Exact when known: `inputs['__max_len__']` ({sequence index | feature name: longest
@@ -424,17 +437,20 @@ class mmoe_transformer_unbias(object):
     def seq_encode_multi(self, inputs, x, x_ld, batch):
         """A2-A8 for ALL behaviour sequences (bf16 path): `dmt_seq_encode_multi_fwd` -- length classes on the
         device, one persistent tile-kernel launch over every (sequence, class) segment, one tail launch; writes
-        the interest vectors into their columns of the MMoE input `x`."""
+        the interest vectors into their columns of the MMoE input `x` (fp32, or bf16: DMT_SEQ_OUT_BF16)."""
         plan = self.plan
         n = len(plan.sequences)
         items, keep = [], []
+        esz = x.element_size()
         for s, seq in enumerate(plan.sequences):
             cfg = self._seq_cfg(inputs, seq, batch, self.precision)
+            if x.dtype == torch.bfloat16:
+                cfg.flags |= abi.SEQ_OUT_BF16
             ws, ws_bytes = self._prepared_for(s, cfg)
             si, kp = self._seq_input(inputs, seq, batch)
             keep += kp
             col = plan.interest_col + s * plan.d_model
-            items.append((cfg, si, self._seq_w[s], x.data_ptr() + 4 * col, x_ld, ws.data_ptr(), ws_bytes))
+            items.append((cfg, si, self._seq_w[s], x.data_ptr() + esz * col, x_ld, ws.data_ptr(), ws_bytes))
         keep.append(items)
         cfgs = (C.c_void_p * n)(*[C.addressof(d[0]) for d in items])
         ins = (C.c_void_p * n)(*[C.addressof(d[1]) for d in items])
@@ -479,11 +495,12 @@ class mmoe_transformer_unbias(object):
             e.ids, e.offsets = sp.values.data_ptr(), sp.offsets.data_ptr()
             e.weights = None if sp.weights is None else sp.weights.data_ptr()
         stream = self._stream()
+        fn = self.lib.dmt_pool_mean_fwd_bf16 if out.dtype == torch.bfloat16 else self.lib.dmt_pool_mean_fwd
         for s in range(0, len(specs), abi.MAX_POOL_FEATS):
             n = min(abi.MAX_POOL_FEATS, len(specs) - s)
             sub = C.cast(C.byref(arr, s * C.sizeof(abi.PoolFeat)), C.POINTER(abi.PoolFeat))
             with self._Stage(self, "pool_mean", 1):
-                abi.check(self.lib.dmt_pool_mean_fwd(batch, n, sub, out.data_ptr(), out.stride(0), stream))
+                abi.check(fn(batch, n, sub, out.data_ptr(), out.stride(0), stream))
         return keep
 
     def _mmoe_cfg(self, batch, precision):
@@ -519,9 +536,10 @@ class mmoe_transformer_unbias(object):
                 self._prepared["mmoe"] = (self.params_version, prep)
             prep_ptr = prep.data_ptr()
             launches = cfg.n_layers + 2
+        fwd = self.lib.dmt_mmoe_fwd_bf16in if x.dtype == torch.bfloat16 else self.lib.dmt_mmoe_fwd
         with self._Stage(self, "mmoe", launches):
-            abi.check(self.lib.dmt_mmoe_fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),
-                                            logits.data_ptr(), ws.data_ptr(), nbytes, prep_ptr, stream))
+            abi.check(fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),
+                          logits.data_ptr(), ws.data_ptr(), nbytes, prep_ptr, stream))
 
     def _bias_cfg(self, batch, passthrough=False, loss_unbias_method=None, loss_ctr_rel_method=None,
                   dropout_rates=None, dropout_seed=0):
@@ -651,12 +669,44 @@ class mmoe_transformer_unbias(object):
         deferred = [] if len(plan.sequences) <= abi.MAX_TAIL_SEQS else None
         if (self.precision == abi.PRECISION_BF16 and self._v2_ok and self.seq_multi and batch > 0
                 and 0 < len(plan.sequences) <= abi.MAX_TAIL_SEQS):
-            # bf16: all sequences in ONE persistent tile-kernel launch over length-bucketed tiles
+            # bf16: all sequences in ONE persistent tile-kernel launch over length-bucketed tiles; the MMoE input is
+            # assembled in bf16 by its producers (no fp32 copy of x, no conversion pass)
+            if self.x_bf16:
+                x_ld = (plan.mmoe_in + 7) // 8 * 8
+                x = self._buf("xb", (batch, x_ld), torch.bfloat16)
+            # the sequence launches run on a side stream: the dense copy / pooled lookups fill the SMs while the
+            # 3-CTA length-class kernel runs and as the persistent kernel's CTAs retire (they write disjoint columns)
+            side = self._seq_side_streams(2) if self._events is None and self.seq_streams else None
+            scores, y_bias = self._next_scores(batch), None
+            if side is not None:
+                main = torch.cuda.current_stream(self.device)
+                fork = self._ev_pool("fork")
+                fork.record(main)
+                if not is_predict:                   # the bias branch depends on nothing else: its own stream
+                    side[1].wait_event(fork)
+                    self._stream_h = side[1].cuda_stream
+                    y_bias = self._bias_branch(inputs, batch, scores, keep)
+                    join_b = self._ev_pool("join1")
+                    join_b.record(side[1])
+                side[0].wait_event(fork)
+                self._stream_h = side[0].cuda_stream
             keep += self.seq_encode_multi(inputs, x, x_ld, batch)
+            if side is not None:
+                join = self._ev_pool("join0")
+                join.record(side[0])
+                self._stream_h = main.cuda_stream
             if feats is not None:
-                self._copy_dense(feats, batch, x, x_ld, keep, self.precision)
+                if self.x_bf16:
+                    self._stage_dense_bf16(feats, batch, x, x_ld, keep)
+                else:
+                    self._copy_dense(feats, batch, x, x_ld, keep, self.precision)
             keep += self.pool_mean(inputs, plan.pooled, False, x, batch)
-            return self._inference_head(inputs, x, batch, keep, is_predict)
+            if side is not None:
+                main.wait_event(join)
+            out = self._inference_head(inputs, x, batch, keep, is_predict, scores, y_bias)
+            if side is not None and not is_predict:
+                main.wait_event(join_b)
+            return out
         # The behaviour sequences are independent of each other and of the dense / pooled columns until the MMoE
         # input: each runs on its own stream, so the CTAs of the next sequence's (persistent, one-CTA-per-SM) kernel
         # start on an SM the moment the previous kernel's CTA there retires -- no tail bubble, prologues (weight
@@ -691,30 +741,43 @@ class mmoe_transformer_unbias(object):
             self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
         return self._inference_head(inputs, x, batch, keep, is_predict)
 
-    def _inference_head(self, inputs, x, batch, keep, is_predict):
-        """MMoE + towers + bias tower on the assembled MMoE input (mmoe_transformer_unbias.py:218-316)."""
-        plan = self.plan
-        stream = self._stream()
-        # scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can
-        # read them back with a single copy; two buffers alternate, so the result of call i stays valid while
-        # call i + 1 runs
+    def _next_scores(self, batch):
+        """Scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can
+        read them back with a single copy; two buffers alternate, so the result of call i stays valid while call
+        i + 1 runs."""
         self._score_flip = getattr(self, "_score_flip", 0) ^ 1
-        scores = self._buf("scores%d" % self._score_flip, (plan.num_tasks + 1, batch))
+        scores = self._buf("scores%d" % self._score_flip, (self.plan.num_tasks + 1, batch))
         self.last_scores = scores
-        logits = scores[:plan.num_tasks]
-        self.mmoe(x, batch, logits)
-        self._last = {"x": x, "batch": batch, "keep": keep}
-        y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
-        if is_predict:
-            return y_rel
+        return scores
+
+    def _bias_branch(self, inputs, batch, scores, keep):
+        """embedding_combiner_bias + embedding_mlp_bias (mmoe_transformer_unbias.py:235-289, eval mode) -> y_bias =
+        scores[num_tasks].  Reads nothing the rest of the forward writes: it may run on its own stream."""
+        plan = self.plan
         bias_in = self._buf("bias_in", (batch, plan.bias_width))
         keep += self.pool_mean(inputs, plan.bias_pooled, True, bias_in, batch)
         y_bias = scores[plan.num_tasks]
         cfg = self._bias_cfg(batch)
         with self._Stage(self, "bias_tower", 1):
             abi.check(self.lib.dmt_bias_loss_fwd(C.byref(cfg), C.byref(self._bias_w), bias_in.data_ptr(),
-                                                 bias_in.stride(0), logits.data_ptr(), None, y_bias.data_ptr(),
-                                                 None, None, None, None, stream))
+                                                 bias_in.stride(0), scores.data_ptr(), None, y_bias.data_ptr(),
+                                                 None, None, None, None, self._stream()))
+        return y_bias
+
+    def _inference_head(self, inputs, x, batch, keep, is_predict, scores=None, y_bias=None):
+        """MMoE + towers (+ the bias tower unless it already ran) on the assembled MMoE input
+        (mmoe_transformer_unbias.py:218-316)."""
+        plan = self.plan
+        if scores is None:
+            scores = self._next_scores(batch)
+        logits = scores[:plan.num_tasks]
+        self.mmoe(x, batch, logits)
+        self._last = {"x": x, "batch": batch, "keep": keep}
+        y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
+        if is_predict:
+            return y_rel
+        if y_bias is None:
+            y_bias = self._bias_branch(inputs, batch, scores, keep)
         return (y_rel, y_bias.view(batch, 1))
 
     def loss(self, logits, mask, loss_unbias_method=None, loss_ctr_rel_method=None, want_probs=False,

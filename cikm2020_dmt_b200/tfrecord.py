@@ -28,7 +28,7 @@ from typing import Dict, Iterator, List, Optional
 import numpy as np
 import torch
 
-from .data import SparseIds
+from .data import SparseIds, share_offsets
 
 # ----------------------------------------------------------------------------- TFRecord framing
 _CRC_TABLE = None
@@ -391,7 +391,7 @@ class ExampleBatcher(object):
             if w.size != len(flat):                 # a feature without Wts: unit weights (base.py:107-111)
                 w = np.ones(len(flat), np.float32)
             out[f] = SparseIds(torch.from_numpy(values.astype(np.int32)), torch.from_numpy(off), torch.from_numpy(w))
-        return out
+        return share_offsets(out)       # the parallel id lists of one behaviour sequence: one offsets tensor
 
 
 def list_files(prefix: str) -> List[str]:

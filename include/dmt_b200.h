@@ -104,6 +104,9 @@ typedef struct dmt_ff_weights {
  * the packed token rows without a pass over the offsets (tensor-core attention); without it the per-sample kernels
  * run, which cap over-long sequences themselves. */
 #define DMT_SEQ_LEN_EXACT 2
+/* dmt_seq_cfg.flags (bf16 path: dmt_seq_encode_fwd / dmt_seq_tail_fwd / dmt_seq_encode_multi_fwd): `out` is a bf16
+ * array (out_ld in bf16 elements) -- the interest vectors go straight into the bf16 MMoE input (dmt_mmoe_fwd_bf16in). */
+#define DMT_SEQ_OUT_BF16 4
 
 typedef struct dmt_seq_cfg {
   int32_t batch;        /* B                                                          */
@@ -261,6 +264,11 @@ DMT_API int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cf
  * `feats` is a HOST array of n_feats <= DMT_MAX_POOL_FEATS descriptors. */
 DMT_API int dmt_pool_mean_fwd(int32_t batch, int32_t n_feats, const dmt_pool_feat* feats,
                               float* out, int64_t out_ld, void* stream);
+/* same, bf16 output (out_ld in bf16 elements): the pooled columns of the bf16 MMoE input (dmt_mmoe_fwd_bf16in).
+ * Needs row widths that are multiples of 4 and 16-byte aligned tables.  Features that share ONE offsets array
+ * (pointer equality: the parallel id lists of one behaviour sequence) are walked together, one warp per sample. */
+DMT_API int dmt_pool_mean_fwd_bf16(int32_t batch, int32_t n_feats, const dmt_pool_feat* feats,
+                                   void* out_bf16, int64_t out_ld, void* stream);
 
 /* strided 2-D copy of the dense `features` block into the MMoE input (base.py:95-96) */
 DMT_API int dmt_copy_dense_features(const float* features, int32_t batch, int32_t dim,
@@ -282,6 +290,10 @@ DMT_API int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* 
  * dmt_copy_dense_features (base.py:95-96) */
 DMT_API int dmt_copy_dense_features_bf16(const void* features_bf16, int32_t batch, int32_t dim,
                                          float* out, int64_t out_ld, void* stream);
+/* fp32 or bf16 [batch, dim] (dense, 16-byte aligned) -> bf16 columns [0, dim) of the bf16 MMoE input (row stride
+ * out_ld elements); base.py:95-96 for the bf16 tensor-core path */
+DMT_API int dmt_stage_dense_features_bf16(const void* features, int32_t features_are_bf16, int32_t batch, int32_t dim,
+                                          void* out_bf16, int64_t out_ld, void* stream);
 
 /* ---- A10: MMoE experts + gates + task towers --------------------------------------
  * Replaces expert_gate + build_tower (mmoe_transformer_unbias.py:63-126,293-310).
@@ -296,6 +308,14 @@ DMT_API int dmt_mmoe_prepare_weights(const dmt_mmoe_cfg* cfg, const dmt_mmoe_wei
 DMT_API int dmt_mmoe_fwd(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const float* x,
                          int64_t x_ld, float* logits, void* workspace, size_t workspace_bytes,
                          const void* prepared, void* stream);
+/* DMT_PRECISION_BF16: the MMoE input is already bf16 -- [batch, xb_ld] with xb_ld a multiple of 8 and >= in_dim,
+ * written in place by its producers (dmt_stage_dense_features_bf16, dmt_pool_mean_fwd_bf16, the sequence tails with
+ * DMT_SEQ_OUT_BF16): no fp32 copy of x and no conversion pass.  The gate logits are extra output columns of the
+ * layer-0 expert GEMM (gate kernels rounded to bf16 like the expert kernels, fp32 accumulation), softmaxed in its
+ * epilogue.  Workspace / prepared as for dmt_mmoe_fwd. */
+DMT_API int dmt_mmoe_fwd_bf16in(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const void* xb,
+                                int64_t xb_ld, float* logits, void* workspace, size_t workspace_bytes,
+                                const void* prepared, void* stream);
 
 /* ---- A11/A12: bias tower + unbiased multi-task loss -------------------------------
  * Replaces embedding_mlp_bias (mmoe_transformer_unbias.py:259-289, eval mode),

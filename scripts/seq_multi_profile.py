@@ -24,7 +24,7 @@ names = ["P0 convert+sync", "P1 QKV mma wait", "P2 QKV epilogue+sync", "P3 S mma
          "P10 LN2+scores+images+sync", "P11 ctx mma issue", "prime (per segment)", "drain (per segment)"]
 lib = abi.load()
 for it in range(3):
-    cnt = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(2048, dtype=torch.int64, device="cuda")
     lib.dmt_debug_seq_profile(cnt.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -49,3 +49,9 @@ print("CTAs %d: cycles min %d mean %.0f max %d" % (ncta, min(cyc), sum(cyc) / nc
 print("globaltimer: first entry -> last exit %.1f us; entry skew %.1f us; exit skew %.1f us; mean CTA life %.1f us"
       % ((max(t1) - min(t0)) / 1e3, (max(t0) - min(t0)) / 1e3, (max(t1) - min(t1)) / 1e3,
          sum(b - a for a, b in zip(t0, t1)) / ncta / 1e3))
+
+print("timeline of CTA 0 (cycles since kernel entry at the END of each phase), group 0 | group 1:")
+for t in range(6):
+    for i in range(12):
+        a, b = c[1024 + t * 16 + i], c[1024 + 128 + t * 16 + i]
+        print("  tile %d %-28s %8d | %8d" % (t, names[i], a, b))
