@@ -7,6 +7,7 @@
 //                      tiles, 3-stage mbarrier ring), warp 1 = MMA issuer, warps 2-5 = epilogue
 //   mmoe_head_kernel : gate mixture + task towers (shared with the fp32 path, mmoe_f32.cu)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "dmt_common.cuh"
 #include "umma.cuh"
@@ -332,6 +333,214 @@ __global__ void mmoe_prepare_bias_kernel(dmt_mmoe_weights w, int layer, int E, i
   else if (i < E * N + gate_rows) out[i] = w.gate[(i - E * N) / E].b[(i - E * N) % E];
 }
 
+// =====================================================================================================================
+// Expert layers 2 + 3 + the first tower layer in ONE kernel (hidden_units_bottom = x, 256, 128; one tower layer):
+// a CTA owns 128 samples of ONE expert.  h2 = relu(h1 W2 + b2) never leaves the SM: the layer-2 accumulator
+// (256 TMEM columns) is packed to bf16 IN PLACE and is the tensor-memory A operand of layer 3; h3 likewise feeds the
+// tower contraction u_e = h3_e [Wt_0 | Wt_1 ...] (linear, so it commutes with the gate mixture:
+// z_t Wt = sum_e g_te (h3_e Wt), mmoe_transformer_unbias.py:99-126).  Only u [E][B][64] fp32 goes back to HBM; the
+// mixture + bias + ReLU + output unit are mmoe_mix_kernel.  Replaces two GEMM launches + the head kernel
+// (15 + 13 + 26 us at B = 4096) and the round trip of h2 / h3 through HBM.
+// Warp roles as gemm_tc_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (thread = sample row).
+// =====================================================================================================================
+constexpr int kT2N2 = 256, kT2N3 = 128, kT2NT = 64, kT2Stages = 3;
+constexpr int kT2StageBytes = (GBM * GBK + kT2N2 * GBK) * 2;        // 48 KB: A 128 x 64 | B 256 x 64
+constexpr int kT2W3Bytes = kT2N3 * kT2N2 * 2;                        // 64 KB: 4 k-blocks of 128 rows x 64
+constexpr int kT2WtBytes = kT2NT * kT2N3 * 2;                        // 16 KB: 2 k-blocks of 64 rows x 64
+constexpr int kT2Smem = kT2Stages * kT2StageBytes + kT2W3Bytes + kT2WtBytes + 1024;
+
+struct MmoeTailArgs {
+  CUtensorMap tmA;             // h1  [E * B, K1]     box {64, 128}
+  CUtensorMap tmB2;            // W2t [E * 256, K1]   box {64, 128}
+  CUtensorMap tmB3;            // W3t [E * 128, 256]  box {64, 128}
+  CUtensorMap tmBt;            // Wt  [64, 128]       box {64, 64}    rows t * U + j, zero rows beyond n_tasks * U
+  const float* b2;             // [E][256]
+  const float* b3;             // [E][128]
+  float* u;                    // [E][B][64]
+  int32_t B, K1;
+};
+
+__global__ void __launch_bounds__(kGemmThreads) mmoe_tail_kernel(const __grid_constant__ MmoeTailArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kT2Stages], empty_bar[kT2Stages], wbar, acc2_bar, a3_bar, acc3_bar, a4_bar, acc4_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW3 = smem + kT2Stages * kT2StageBytes;
+  uint8_t* sWt = sW3 + kT2W3Bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GBM, z = blockIdx.y;
+  const int nkb = (g.K1 + GBK - 1) / GBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kT2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&wbar, 1);
+    mbar_init(&acc2_bar, 1);
+    mbar_init(&acc3_bar, 1);
+    mbar_init(&acc4_bar, 1);
+    mbar_init(&a3_bar, 128);
+    mbar_init(&a4_bar, 128);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmBt) : "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  constexpr int tH2 = 0, tH3 = 256, tU = 384;          // accumulators; the packed A operands reuse [0, 128) / [0, 64)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: layer-3 / tower kernels once, then the layer-2 operand ring =====
+      mbar_expect_tx(&wbar, kT2W3Bytes + kT2WtBytes);
+      for (int kb = 0; kb < kT2N2 / GBK; ++kb) tma_load_2d(sW3 + kb * (kT2N3 * GBK * 2), &g.tmB3, kb * GBK, z * kT2N3, &wbar);
+      for (int kb = 0; kb < kT2N3 / GBK; ++kb) tma_load_2d(sWt + kb * (kT2NT * GBK * 2), &g.tmBt, kb * GBK, 0, &wbar);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kT2Stages;
+        mbar_wait(&empty_bar[s], ((kb / kT2Stages) & 1) ^ 1);
+        uint8_t* sa = smem + s * kT2StageBytes;
+        uint8_t* sb = sa + GBM * GBK * 2;
+        mbar_expect_tx(&full_bar[s], kT2StageBytes);
+        tma_load_2d(sa, &g.tmA, kb * GBK, z * g.B + m0, &full_bar[s]);
+        tma_load_2d(sb, &g.tmB2, kb * GBK, z * kT2N2, &full_bar[s]);
+        tma_load_2d(sb + GBM * GBK * 2, &g.tmB2, kb * GBK, z * kT2N2 + GBM, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      {
+        constexpr uint32_t idesc = make_idesc_bf16(GBM, kT2N2);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % kT2Stages;
+          mbar_wait(&full_bar[s], (kb / kT2Stages) & 1);
+          fence_after_sync();
+          const uint32_t sa = smem_u32(smem + s * kT2StageBytes), sb = sa + GBM * GBK * 2;
+#pragma unroll
+          for (int k = 0; k < GBK / 16; ++k)
+            mma_bf16_ss(tbase + tH2, make_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128),
+                        make_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128), idesc, (kb | k) != 0);
+          commit(&empty_bar[s]);
+        }
+        commit(&acc2_bar);
+      }
+      {  // layer 3: A = relu(h2) packed in tensor memory columns [0, 128)
+        mbar_wait(&wbar, 0);
+        mbar_wait(&a3_bar, 0);
+        fence_after_sync();
+        constexpr uint32_t idesc = make_idesc_bf16(GBM, kT2N3);
+        const uint32_t sw = smem_u32(sW3);
+#pragma unroll
+        for (int ks = 0; ks < kT2N2 / 16; ++ks)
+          mma_bf16_ts(tbase + tH3, tbase + ks * 8,
+                      make_smem_desc(sw + (ks / 4) * (kT2N3 * GBK * 2) + (ks % 4) * 32, 16, 1024, kLayoutSW128), idesc, ks > 0);
+        commit(&acc3_bar);
+      }
+      {  // tower contraction: A = relu(h3) packed in columns [0, 64)
+        mbar_wait(&a4_bar, 0);
+        fence_after_sync();
+        constexpr uint32_t idesc = make_idesc_bf16(GBM, kT2NT);
+        const uint32_t sw = smem_u32(sWt);
+#pragma unroll
+        for (int ks = 0; ks < kT2N3 / 16; ++ks)
+          mma_bf16_ts(tbase + tU, tbase + ks * 8,
+                      make_smem_desc(sw + (ks / 4) * (kT2NT * GBK * 2) + (ks % 4) * 32, 16, 1024, kLayoutSW128), idesc, ks > 0);
+        commit(&acc4_bar);
+      }
+    }
+  } else {
+    // ===== epilogue warps: thread = sample row = TMEM lane =====
+    const int row = (warp & 3) * 32 + lane;
+    const int m = m0 + row;
+    auto relu_pack = [&](int acc_col, int ncols, const float* __restrict__ bias) {
+      // fp32 accumulator columns [acc_col, acc_col + ncols) -> relu(+bias) -> bf16 pairs, packed into columns
+      // [0, ncols / 2): the packed words trail the columns already read (same thread = same lane)
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_addr(tbase, acc_col + c0), r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
+          pk[q * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[q * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[q * 4 + 1]) + bb.y, 0.f));
+          pk[q * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[q * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[q * 4 + 3]) + bb.w, 0.f));
+        }
+        tmem_st16(tmem_addr(tbase, c0 / 2), pk);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+    };
+    mbar_wait(&acc2_bar, 0);
+    fence_after_sync();
+    relu_pack(tH2, kT2N2, g.b2 + z * kT2N2);
+    mbar_arrive(&a3_bar);
+    mbar_wait(&acc3_bar, 0);
+    fence_after_sync();
+    relu_pack(tH3, kT2N3, g.b3 + z * kT2N3);
+    mbar_arrive(&a4_bar);
+    mbar_wait(&acc4_bar, 0);
+    fence_after_sync();
+    float* urow = g.u + ((int64_t)z * g.B + m) * kT2NT;
+#pragma unroll
+    for (int c0 = 0; c0 < kT2NT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_addr(tbase, tU + c0), r);
+      tmem_ld_wait();
+      if (m < g.B) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(urow + c0 + q * 4) =
+              make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                          __uint_as_float(r[q * 4 + 3]));
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// logits[t][b] = relu(sum_e g[t][b][e] u[e][b][t U + :] + b_t) . w_out_t + b_out_t   (mmoe_transformer_unbias.py:99-126)
+struct MmoeMixArgs {
+  const float* u;              // [E][B][64]
+  const float* gates;          // [T][B][E]
+  dmt_dense tower[DMT_MAX_TASKS], tower_out[DMT_MAX_TASKS];
+  float* logits;               // [T][B]
+  int32_t B, E, T, U;
+};
+__global__ void __launch_bounds__(256) mmoe_mix_kernel(const __grid_constant__ MmoeMixArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= a.B) return;
+  for (int t = 0; t < a.T; ++t) {
+    float part = 0.f;
+    for (int j = lane; j < a.U; j += 32) {
+      float acc = 0.f;
+      for (int e = 0; e < a.E; ++e)
+        acc = fmaf(__ldg(a.gates + ((int64_t)t * a.B + b) * a.E + e), __ldg(a.u + ((int64_t)e * a.B + b) * kT2NT + t * a.U + j), acc);
+      part = fmaf(fmaxf(acc + __ldg(a.tower[t].b + j), 0.f), __ldg(a.tower_out[t].w + j), part);
+    }
+    part = warp_sum(part);
+    if (lane == 0) a.logits[(int64_t)t * a.B + b] = part + __ldg(a.tower_out[t].b);
+  }
+}
+
+// tower image for the tail kernel: Wt[n = t U + j][k] = tower_t kernel [k][j]  (bf16, zero rows up to 64)
+__global__ void mmoe_prepare_tower_kernel(dmt_mmoe_weights w, int T, int U, int Hd, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kT2NT * Hd) return;
+  const int k = i % Hd, n = i / Hd, t = n / U, j = n % U;
+  out[i] = __float2bfloat16(t < T ? w.tower[t][0].w[(int64_t)k * U + j] : 0.f);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -349,12 +558,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (row stride ld elements), box 64 x 128, 128-byte swizzle, OOB -> 0.
-static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+static int make_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = GBM) {
   EncodeTiledFn fn = encode_fn();
   DMT_REQUIRE(fn, DMT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {GBK, GBM};
+  cuuint32_t box[2] = {GBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -390,7 +599,16 @@ static size_t prepared_layout(const dmt_mmoe_cfg* cfg, size_t* w_off, size_t* b_
   return off;
 }
 
-size_t mmoe_tc_prepared_bytes(const dmt_mmoe_cfg* cfg) { return prepared_layout(cfg, nullptr, nullptr) + 256; }
+// hidden_units_bottom = (x, 256, 128), one tower layer of <= 64 / n_tasks units: layers 2 + 3 + tower fused
+static bool tail_fused(const dmt_mmoe_cfg* cfg) {
+  return cfg->n_layers == 3 && cfg->units[1] == kT2N2 && cfg->units[2] == kT2N3 && cfg->n_tower_layers == 1 &&
+         cfg->tower_units[0] > 0 && cfg->n_tasks * cfg->tower_units[0] <= kT2NT;
+}
+
+// (+ the bf16 tower image of the fused tail kernel after the sections of prepared_layout)
+size_t mmoe_tc_prepared_bytes(const dmt_mmoe_cfg* cfg) {
+  return prepared_layout(cfg, nullptr, nullptr) + (tail_fused(cfg) ? kT2WtBytes : 0) + 256;
+}
 
 // activations: xb | h_0 | h_1 | ... (bf16) | gates (fp32)
 static size_t workspace_layout(const dmt_mmoe_cfg* cfg, size_t* h_off, size_t* gate_off) {
@@ -425,6 +643,11 @@ int mmoe_tc_prepare(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, void* pr
                                                                          (__nv_bfloat16*)(base + w_off[l]));
     mmoe_prepare_bias_kernel<<<(E * N + gr + 255) / 256, 256, 0, st>>>(*w, l, E, N, gr, (float*)(base + b_off[l]));
     K = N;
+  }
+  if (tail_fused(cfg)) {
+    const size_t wt_off = prepared_layout(cfg, nullptr, nullptr);
+    mmoe_prepare_tower_kernel<<<(kT2NT * kT2N3 + 255) / 256, 256, 0, st>>>(*w, cfg->n_tasks, cfg->tower_units[0], kT2N3,
+                                                                          (__nv_bfloat16*)(base + wt_off));
   }
   DMT_CUDA_LAUNCH_CHECK("mmoe_prepare_kernel");
   return DMT_OK;
@@ -476,7 +699,9 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
   int64_t a_rows = B;          // rows in the A tensor map
   int a_rows_per_z = 0, K = cfg->in_dim;
   int64_t lda = xb_in ? xb_ld : ldx;
-  for (int l = 0; l < cfg->n_layers; ++l) {
+  static const bool fuse_env = !(getenv("DMT_MMOE_FUSED_TAIL") && atoi(getenv("DMT_MMOE_FUSED_TAIL")) == 0);
+  const bool fused = tail_fused(cfg) && fuse_env;
+  for (int l = 0; l < (fused ? 1 : cfg->n_layers); ++l) {
     const int N = cfg->units[l];
     GemmTcArgs g;
     int rc = make_map(&g.tmA, a, a_rows, K, lda);
@@ -504,6 +729,39 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
     a_rows_per_z = B;
     K = N;
     lda = N;
+  }
+  if (fused) {
+    const int K1 = cfg->units[0];
+    MmoeTailArgs t;
+    int rc = make_map(&t.tmA, ws + h_off[0], (int64_t)E * B, K1, K1);
+    if (rc != DMT_OK) return rc;
+    rc = make_map(&t.tmB2, pw + w_off[1], (int64_t)E * kT2N2, K1, pad8(K1));
+    if (rc != DMT_OK) return rc;
+    rc = make_map(&t.tmB3, pw + w_off[2], (int64_t)E * kT2N3, kT2N2, kT2N2);
+    if (rc != DMT_OK) return rc;
+    rc = make_map(&t.tmBt, pw + prepared_layout(cfg, nullptr, nullptr), kT2NT, kT2N3, kT2N3, kT2NT);
+    if (rc != DMT_OK) return rc;
+    t.b2 = (const float*)(pw + b_off[1]);
+    t.b3 = (const float*)(pw + b_off[2]);
+    t.u = (float*)(ws + h_off[1]);                       // h2 never exists in HBM: its slot holds u [E][B][64] fp32
+    t.B = B;
+    t.K1 = K1;
+    cudaError_t e = cudaFuncSetAttribute(mmoe_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_tail_kernel)");
+    mmoe_tail_kernel<<<dim3((B + GBM - 1) / GBM, E), kGemmThreads, kT2Smem, st>>>(t);
+    DMT_CUDA_LAUNCH_CHECK("mmoe_tail_kernel");
+    MmoeMixArgs mx;
+    mx.u = t.u;
+    mx.gates = gates;
+    for (int tt = 0; tt < DMT_MAX_TASKS; ++tt) {
+      mx.tower[tt] = w->tower[tt][0];
+      mx.tower_out[tt] = w->tower_out[tt];
+    }
+    mx.logits = logits;
+    mx.B = B; mx.E = E; mx.T = cfg->n_tasks; mx.U = cfg->tower_units[0];
+    mmoe_mix_kernel<<<(B + 7) / 8, 256, 0, st>>>(mx);
+    DMT_CUDA_LAUNCH_CHECK("mmoe_mix_kernel");
+    return DMT_OK;
   }
   return mmoe_head_launch(cfg, w, x, x_ld, ws + h_off[cfg->n_layers - 1], 1, gates, logits, st);
 }
