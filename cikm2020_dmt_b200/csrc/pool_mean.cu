@@ -80,18 +80,23 @@ __global__ void __launch_bounds__(1024) pool_mean_kernel(const __grid_constant__
 }
 
 
-// Grouped version (every row width a multiple of 4): features that share one CSR offsets array (the 6 lookups of one behaviour sequence;
-// the 5 single-id item features) are ONE job per sample.  Lane l of the warp owns one float4 of the group's
-// concatenated row (feature, float4 index) and walks the sample's tokens in order, eight tokens in flight: no
-// shuffle reduction, no idle token lanes for the 8-wide tables, 1/6 of the per-job index math of the
-// warp-per-(sample, feature) kernel of round 1 -- that one was issue-bound (68 % of the issue slots busy).
-// The sum runs in token order like the scalar kernel (and the oracle).  Output fp32 or bf16 (the bf16 tensor-core
-// MMoE reads its input as bf16: the columns are written in that type directly, no conversion pass).
+// Grouped version (every row width a multiple of 4): features that share one CSR offsets array (the 6 lookups of one
+// behaviour sequence; the 5 single-id item features) are walked together, one warp per (sample, group).  A group has
+// P float4 "parts" per token (a 32-wide Sku row = 8 parts, five 8-wide rows = 10 parts); the warp processes
+// 3 tokens per step (2 / 1 for rows wider than 40 / 64 floats) -- lane = (token slot, part) -- and keeps eight steps
+// in flight, ids requested one round ahead of the rows, the next sample's first round during this sample's last.
+// Every lane sums the tokens of its slot in token order; the slot sums are added in slot order (fixed order that
+// depends on the feature's row width only: bit-identical run to run, in any batch, with any grouping).  Round 1's warp-per-(sample, feature) kernel spent most of its
+// issue slots on per-job index math (68 % busy, 39 us at B = 4096); a first grouped version with ONE token per step
+// had too few loads in flight (38 us).  Output fp32 or bf16 (the bf16 tensor-core MMoE reads its input as bf16: the
+// columns are written in that type directly, no conversion pass).
 constexpr int kPoolMaxGroups = DMT_MAX_POOL_FEATS;    // worst case: no two features share their offsets
 struct PoolGroupArgs {
   dmt_pool_feat f[DMT_MAX_POOL_FEATS];
-  uint8_t lane_feat[kPoolMaxGroups][32];              // feature of lane l (0xff: idle)
-  uint8_t lane_part[kPoolMaxGroups][32];              // float4 index inside that feature's row
+  uint8_t part_feat[kPoolMaxGroups][32];              // part p of a token of group g -> feature
+  uint8_t part_idx[kPoolMaxGroups][32];               //                              -> float4 index inside its row
+  uint8_t n_parts[kPoolMaxGroups];                    // P
+  uint8_t n_slots[kPoolMaxGroups];                    // token slots per step (pool_slots of the group's features)
   int32_t batch;
   void* out;
   int64_t out_ld;
@@ -99,56 +104,111 @@ struct PoolGroupArgs {
 };
 
 template <bool WTS>
-__device__ __forceinline__ void pool_group_walk(const int32_t* __restrict__ ids, const float* __restrict__ wts,
-                                                const float* __restrict__ tab, int64_t rows, int dim, int beg, int end,
-                                                float4& num, float& den) {
-  // software pipeline: the ids (and weights) of round r + 1 are requested before the rows of round r are consumed,
-  // so a round costs ONE dependent-load latency instead of two
+__device__ __forceinline__ void pool_group_samples(const PoolGroupArgs& a, const int32_t* __restrict__ ids,
+                                                   const int32_t* __restrict__ offs, const float* __restrict__ wts,
+                                                   const float* __restrict__ tab, int64_t rows, int dim, int col, int P,
+                                                   int tps, bool active, int slot) {
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  // Software pipeline over tokens AND samples: the ids (and weights) of the next round -- the first round of the NEXT
+  // sample after the last round of this one -- are requested before the rows of the current round are consumed, and
+  // the next sample's offsets one sample ahead: a round costs ONE dependent-load latency, a new sample none.
   int nrow[8];
   float nw[8];
-  auto fetch_ids = [&](int t0) {
+  auto fetch_ids = [&](int t0, int end) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u * tps;
       nrow[u] = -1;
       nw[u] = 0.f;
-      if (t0 + u < end) {
-        nrow[u] = __ldg(ids + t0 + u);
-        nw[u] = WTS ? __ldg(wts + t0 + u) : 1.0f;
+      if (active && t < end) {
+        nrow[u] = __ldg(ids + t);
+        nw[u] = WTS ? __ldg(wts + t) : 1.0f;
       }
     }
   };
-  fetch_ids(beg);
-  for (int t0 = beg; t0 < end; t0 += 8) {
-    int row[8];
-    float w[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      row[u] = nrow[u];
-      w[u] = nw[u];
+  int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int beg = 0, end = 0;
+  if (b < a.batch) {
+    beg = __ldg(offs + b);
+    end = __ldg(offs + b + 1);
+  }
+  fetch_ids(beg + slot, end);
+  while (b < a.batch) {
+    const int nb = b + stride;
+    int nbeg = 0, nend = 0;
+    if (nb < a.batch) {
+      nbeg = __ldg(offs + nb);
+      nend = __ldg(offs + nb + 1);
     }
-    float4 e[8];
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+    float den = 0.f;
+    int t0 = beg + slot;
+    do {                                               // (an empty sample runs one round of nothing)
+      int row[8];
+      float w[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row[u] >= 0 && row[u] < rows) e[u] = ldg4(tab + (int64_t)row[u] * dim);
-    }
-    if (t0 + 8 < end) fetch_ids(t0 + 8);
+      for (int u = 0; u < 8; ++u) {
+        row[u] = nrow[u];
+        w[u] = nw[u];
+      }
+      float4 e[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      num.x = fmaf(w[u], e[u].x, num.x);
-      num.y = fmaf(w[u], e[u].y, num.y);
-      num.z = fmaf(w[u], e[u].z, num.z);
-      num.w = fmaf(w[u], e[u].w, num.w);
-      den += w[u];
+      for (int u = 0; u < 8; ++u) {
+        e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row[u] >= 0 && row[u] < rows) e[u] = ldg4(tab + (int64_t)row[u] * dim);
+      }
+      t0 += 8 * tps;
+      if (t0 - slot < end) fetch_ids(t0, end);          // (warp-uniform: t0 - slot is the round's first token)
+      else fetch_ids(nbeg + slot, nend);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        num.x = fmaf(w[u], e[u].x, num.x);
+        num.y = fmaf(w[u], e[u].y, num.y);
+        num.z = fmaf(w[u], e[u].z, num.z);
+        num.w = fmaf(w[u], e[u].w, num.w);
+        den += w[u];
+      }
+    } while (t0 - slot < end);
+    for (int sl = 1; sl < tps; ++sl) {                 // slot sums -> the slot-0 lanes, in slot order
+      const int src = lane + sl * P;
+      const float vx = __shfl_sync(0xffffffffu, num.x, src), vy = __shfl_sync(0xffffffffu, num.y, src);
+      const float vz = __shfl_sync(0xffffffffu, num.z, src), vw = __shfl_sync(0xffffffffu, num.w, src);
+      const float vd = __shfl_sync(0xffffffffu, den, src);
+      if (slot == 0) {
+        num.x += vx; num.y += vy; num.z += vz; num.w += vw;
+        den += vd;
+      }
     }
+    if (active && slot == 0) {
+      // tf.nn.embedding_lookup_sparse(combiner='mean'): sum(w*row)/sum(w); an absent row comes out as 0
+      const float inv = (end > beg) ? 1.0f / den : 0.f;
+      if (a.out_bf16) {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + (int64_t)b * a.out_ld + col;
+        o[0] = __float2bfloat16(num.x * inv);
+        o[1] = __float2bfloat16(num.y * inv);
+        o[2] = __float2bfloat16(num.z * inv);
+        o[3] = __float2bfloat16(num.w * inv);
+      } else {
+        float* o = static_cast<float*>(a.out) + (int64_t)b * a.out_ld + col;
+        o[0] = num.x * inv;
+        o[1] = num.y * inv;
+        o[2] = num.z * inv;
+        o[3] = num.w * inv;
+      }
+    }
+    b = nb;
+    beg = nbeg;
+    end = nend;
   }
 }
 
-__global__ void __launch_bounds__(256, 3) pool_group_kernel(const __grid_constant__ PoolGroupArgs a) {
+__global__ void __launch_bounds__(256, 2) pool_group_kernel(const __grid_constant__ PoolGroupArgs a) {
   const int lane = threadIdx.x & 31, g = blockIdx.y;
-  const int fi = a.lane_feat[g][lane];
-  if (fi == 0xff) return;
-  const int part = a.lane_part[g][lane];
+  const int P = a.n_parts[g], tps = a.n_slots[g];
+  const bool active = lane < tps * P;
+  const int slot = active ? lane / P : 0, pi = active ? lane - slot * P : 0;
+  const int fi = a.part_feat[g][pi], part = a.part_idx[g][pi];
   // this lane's lookup, read once (lanes of different features read different descriptors)
   const int32_t* __restrict__ ids = a.f[fi].ids;
   const int32_t* __restrict__ offs = a.f[fi].offsets;
@@ -157,56 +217,55 @@ __global__ void __launch_bounds__(256, 3) pool_group_kernel(const __grid_constan
   const int64_t rows = a.f[fi].rows;
   const int dim = a.f[fi].dim;
   const int col = a.f[fi].out_col + part * 4;
-  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < a.batch; b += gridDim.x * 8) {
-    const int beg = __ldg(offs + b), end = __ldg(offs + b + 1);
-    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
-    float den = 0.f;
-    if (wts) pool_group_walk<true>(ids, wts, tab, rows, dim, beg, end, num, den);
-    else pool_group_walk<false>(ids, wts, tab, rows, dim, beg, end, num, den);
-    // tf.nn.embedding_lookup_sparse(combiner='mean'): sum(w*row)/sum(w); an absent row comes out as 0
-    const float inv = (end > beg) ? 1.0f / den : 0.f;
-    if (a.out_bf16) {
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + (int64_t)b * a.out_ld + col;
-      o[0] = __float2bfloat16(num.x * inv);
-      o[1] = __float2bfloat16(num.y * inv);
-      o[2] = __float2bfloat16(num.z * inv);
-      o[3] = __float2bfloat16(num.w * inv);
-    } else {
-      float* o = static_cast<float*>(a.out) + (int64_t)b * a.out_ld + col;
-      o[0] = num.x * inv;
-      o[1] = num.y * inv;
-      o[2] = num.z * inv;
-      o[3] = num.w * inv;
-    }
+  // (lanes of one warp may differ in having weights: both instantiations run, each with its lanes)
+  const bool any_w = __any_sync(0xffffffffu, wts != nullptr), all_w = __all_sync(0xffffffffu, wts != nullptr || !active);
+  if (!any_w) pool_group_samples<false>(a, ids, offs, wts, tab, rows, dim, col, P, tps, active, slot);
+  else if (all_w) pool_group_samples<true>(a, ids, offs, wts, tab, rows, dim, col, P, tps, active, slot);
+  else {
+    pool_group_samples<true>(a, ids, offs, wts, tab, rows, dim, col, P, tps, active && wts != nullptr, slot);
+    pool_group_samples<false>(a, ids, offs, wts, tab, rows, dim, col, P, tps, active && wts == nullptr, slot);
   }
 }
 
-// features -> groups (same offsets array, <= 32 float4 lanes per group); false when the grouped kernel does not apply
+// Token slots per step of a feature: a function of ITS row width only, so that the order in which a sample's rows
+// are summed -- tokens t = slot (mod slots) in token order per slot, then the slots in order -- does not depend on
+// which other features share the group (a sample's output is bit-identical in any batch and any grouping).
+static inline int pool_slots(int parts) { return parts <= 10 ? 3 : (parts <= 16 ? 2 : 1); }
+
+// features -> groups: same offsets array, same slot count, slots x parts <= 32 lanes; a row of >= 8 float4 parts
+// (Sku) is a group of its own.  false when the grouped kernel does not apply.
 static bool pool_build_groups(int n_feats, const dmt_pool_feat* feats, PoolGroupArgs& a, int* n_groups) {
   int ng = 0;
-  int lanes[kPoolMaxGroups];
+  int parts[kPoolMaxGroups];
   const int32_t* goffs[kPoolMaxGroups];
+  bool wide[kPoolMaxGroups];
   for (int f = 0; f < n_feats; ++f) {
     const int d = feats[f].dim;
     if (d % 4 != 0 || ((uintptr_t)feats[f].table & 15) != 0 || d / 4 > 32) return false;
+    const int np = d / 4, sl = pool_slots(np);
     int g = -1;
-    for (int k = 0; k < ng; ++k)
-      if (goffs[k] == feats[f].offsets && lanes[k] + d / 4 <= 32) { g = k; break; }
+    if (np < 8)
+      for (int k = 0; k < ng; ++k)
+        if (goffs[k] == feats[f].offsets && !wide[k] && a.n_slots[k] == sl && (parts[k] + np) * sl <= 32) { g = k; break; }
     if (g < 0) {
       if (ng == kPoolMaxGroups) return false;
       g = ng++;
       goffs[g] = feats[f].offsets;
-      lanes[g] = 0;
-      for (int l = 0; l < 32; ++l) a.lane_feat[g][l] = 0xff, a.lane_part[g][l] = 0;
+      parts[g] = 0;
+      wide[g] = np >= 8;
+      a.n_slots[g] = (uint8_t)sl;
+      for (int l = 0; l < 32; ++l) a.part_feat[g][l] = 0, a.part_idx[g][l] = 0;
     }
-    for (int p = 0; p < d / 4; ++p) {
-      a.lane_feat[g][lanes[g]] = (uint8_t)f;
-      a.lane_part[g][lanes[g]] = (uint8_t)p;
-      ++lanes[g];
+    for (int p = 0; p < np; ++p) {
+      a.part_feat[g][parts[g]] = (uint8_t)f;
+      a.part_idx[g][parts[g]] = (uint8_t)p;
+      ++parts[g];
     }
   }
-  for (int g = ng; g < kPoolMaxGroups; ++g)
-    for (int l = 0; l < 32; ++l) a.lane_feat[g][l] = 0xff, a.lane_part[g][l] = 0;
+  for (int g = 0; g < kPoolMaxGroups; ++g) {
+    a.n_parts[g] = g < ng ? (uint8_t)parts[g] : 1;
+    if (g >= ng) a.n_slots[g] = 1;
+  }
   *n_groups = ng;
   return ng > 0;
 }
@@ -253,8 +312,10 @@ static int pool_mean_impl(const char* fn, int32_t batch, int32_t n_feats, const 
       ga.out = out;
       ga.out_ld = out_ld;
       ga.out_bf16 = out_bf16;
+      // ~two waves of 2 CTAs per SM over all groups: every warp walks several samples (the cross-sample prefetch needs
+      // a next sample), the cheap single-token groups retire early and make room for the sequence groups
       int gx = (batch + 7) / 8;
-      const int cap = (dmt::sm_count_cached() * 16 + ng - 1) / ng;
+      const int cap = (dmt::sm_count_cached() * 4 + ng - 1) / ng;
       if (gx > cap) gx = cap < 1 ? 1 : cap;
       dmt::pool_group_kernel<<<dim3(gx, ng), 256, 0, (cudaStream_t)stream>>>(ga);
       DMT_CUDA_LAUNCH_CHECK("pool_group_kernel");
