@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM, z = blockIdx.z;
+  // the gate slab (if any) is scheduled FIRST (blockIdx.z == 0) so that its 128-row CTAs are not a tail wave of their
+  // own; z = slab index in the B / bias / C layouts (experts 0 .. E-1, gate slab = E)
+  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM;
+  const int z = g.gate_z < 0 ? (int)blockIdx.z : (blockIdx.z == 0 ? g.gate_z : (int)blockIdx.z - 1);
   const int nkb = (g.K + GBK - 1) / GBK;
   if (z == g.gate_z && n0 > 0) return;           // the gate slab is one (mostly empty) N tile
 

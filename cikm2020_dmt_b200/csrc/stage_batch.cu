@@ -49,39 +49,35 @@ copy_dense_bf16_kernel(const __nv_bfloat16* __restrict__ src, int batch, int dim
   }
 }
 
-// dense features -> bf16 columns [0, dim) of the bf16 MMoE input; the source rows are contiguous ([batch, dim]), so a
-// thread takes 8 consecutive source elements (one 16-byte / two 16-byte loads) and scatters them to their rows
+// dense features -> bf16 columns [0, dim) of the bf16 MMoE input: one warp per row, a lane converts two consecutive
+// columns per trip (two coalesced scalar loads -- a 615-wide source row is only element-aligned -- one 4-byte bf16x2
+// store: the destination rows are 16-byte aligned), four trips in flight
+template <typename T>
+__device__ __forceinline__ float dense_ld(const T* p) {
+  if constexpr (sizeof(T) == 2) return __bfloat162float(*p);
+  else return __ldcs(p);
+}
 template <typename T>
 __global__ void __launch_bounds__(256)
-stage_dense_bf16_kernel(const T* __restrict__ src, int64_t total, int dim, __nv_bfloat16* __restrict__ dst, int64_t ld) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
-  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i0 < total; i0 += stride) {
-    __nv_bfloat16 v[8];
-    if (i0 + 8 <= total) {
-      if constexpr (sizeof(T) == 2) {
-        *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(src + i0));
-      } else {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(src + i0));
-        const float4 b = __ldcs(reinterpret_cast<const float4*>(src + i0 + 4));
-        v[0] = __float2bfloat16(a.x); v[1] = __float2bfloat16(a.y); v[2] = __float2bfloat16(a.z); v[3] = __float2bfloat16(a.w);
-        v[4] = __float2bfloat16(b.x); v[5] = __float2bfloat16(b.y); v[6] = __float2bfloat16(b.z); v[7] = __float2bfloat16(b.w);
-      }
-    } else {
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u < total) {
-          if constexpr (sizeof(T) == 2) v[u] = src[i0 + u];
-          else v[u] = __float2bfloat16(src[i0 + u]);
-        }
-    }
-    int64_t b = i0 / dim;
-    int c = (int)(i0 - b * dim);
+stage_dense_bf16_kernel(const T* __restrict__ src, int batch, int dim, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < batch; b += gridDim.x * 8) {
+    const T* __restrict__ s = src + (int64_t)b * dim;
+    __nv_bfloat16* __restrict__ d = dst + (int64_t)b * ld;
+    int c = 2 * lane;
+    for (; c + 192 + 1 < dim; c += 256) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (i0 + u < total) dst[b * ld + c] = v[u];
-      if (++c == dim) {
-        c = 0;
-        ++b;
+      for (int u = 0; u < 4; ++u) {
+        v[2 * u] = dense_ld(s + c + 64 * u);
+        v[2 * u + 1] = dense_ld(s + c + 64 * u + 1);
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<__nv_bfloat162*>(d + c + 64 * u) = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    }
+    for (; c < dim; c += 64) {
+      if (c + 1 < dim) *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(dense_ld(s + c), dense_ld(s + c + 1));
+      else d[c] = __float2bfloat16(dense_ld(s + c));
     }
   }
 }
@@ -94,19 +90,18 @@ int dmt_stage_dense_features_bf16(const void* features, int32_t features_are_bf1
                                   void* out_bf16, int64_t out_ld, void* stream) {
   DMT_REQUIRE(features && out_bf16 && batch >= 0 && dim > 0 && out_ld >= dim, DMT_ERR_INVALID_ARGUMENT,
               "dmt_stage_dense_features_bf16: bad arguments");
-  DMT_REQUIRE(((uintptr_t)features & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
-              "dmt_stage_dense_features_bf16: features must be 16-byte aligned");
   if (batch == 0) return DMT_OK;
-  const int64_t total = (int64_t)batch * dim;
-  int64_t blocks = (total / 8 + 255) / 256 + 1;
-  const int64_t cap = (int64_t)dmt::sm_count_cached() * 8;
+  DMT_REQUIRE(out_ld % 2 == 0 && ((uintptr_t)out_bf16 & 3) == 0, DMT_ERR_INVALID_ARGUMENT,
+              "dmt_stage_dense_features_bf16: out_ld must be even and the output 4-byte aligned");
+  int64_t blocks = ((int64_t)batch + 7) / 8;           // one warp per row
+  const int64_t cap = (int64_t)dmt::sm_count_cached() * 16;
   if (blocks > cap) blocks = cap;
   if (features_are_bf16)
     dmt::stage_dense_bf16_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)features, total, dim, (__nv_bfloat16*)out_bf16, out_ld);
+        (const __nv_bfloat16*)features, batch, dim, (__nv_bfloat16*)out_bf16, out_ld);
   else
     dmt::stage_dense_bf16_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)features, total, dim, (__nv_bfloat16*)out_bf16, out_ld);
+        (const float*)features, batch, dim, (__nv_bfloat16*)out_bf16, out_ld);
   DMT_CUDA_LAUNCH_CHECK("stage_dense_bf16_kernel");
   return DMT_OK;
 }

@@ -290,8 +290,8 @@ DMT_API int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* 
  * dmt_copy_dense_features (base.py:95-96) */
 DMT_API int dmt_copy_dense_features_bf16(const void* features_bf16, int32_t batch, int32_t dim,
                                          float* out, int64_t out_ld, void* stream);
-/* fp32 or bf16 [batch, dim] (dense, 16-byte aligned) -> bf16 columns [0, dim) of the bf16 MMoE input (row stride
- * out_ld elements); base.py:95-96 for the bf16 tensor-core path */
+/* fp32 or bf16 [batch, dim] (dense) -> bf16 columns [0, dim) of the bf16 MMoE input (row stride
+ * out_ld elements, even; out 4-byte aligned); base.py:95-96 for the bf16 tensor-core path */
 DMT_API int dmt_stage_dense_features_bf16(const void* features, int32_t features_are_bf16, int32_t batch, int32_t dim,
                                           void* out_bf16, int64_t out_ld, void* stream);
 
