@@ -140,7 +140,9 @@ def algorithmic_bytes_seq(plan, batch):
     return total
 
 
-def flops_seq(plan, batch):
+def flops_seq(plan, batch, tail=True):
+    """Algorithmic FLOPs (valid tokens only) of A2-A8; tail=False leaves out the per-sample decoder tail
+    (ctx Wv + FF on B rows: seq_tail_kernel's share)."""
     d, dff = plan.d_model, plan.d_ff
     total = 0
     B = batch["features"].shape[0]
@@ -149,7 +151,7 @@ def flops_seq(plan, batch):
         n_tok = float(lens.sum())
         total += n_tok * (2 * d * 3 * d + 4 * d * dff) * plan.num_blocks_encode          # QKV + FF per token
         total += float((lens * lens).sum()) * 4 * d * plan.num_blocks_encode              # QK^T + PV
-        total += (n_tok * (2 * d * 2 * d + 4 * d) + B * (2 * d * d + 4 * d * dff)) * plan.num_blocks_decode
+        total += (n_tok * (2 * d * 2 * d + 4 * d) + (B * (2 * d * d + 4 * d * dff) if tail else 0)) * plan.num_blocks_decode
     return total
 
 
@@ -556,7 +558,20 @@ def main():
     # per-stage pass (CUDA events around every stage, sequences serial): feeds `roofline` and `stage_share` only; it is
     # host-bound (two events per stage), so it runs at least 60 steps to average the idle gaps out
     stage_steps = max(args.steps, 60)
+    # bf16: the dominant kernel's own launches are bracketed by CUDA events on their launch stream inside the library
+    # (dmt_debug_seq_timer) -- in this pass, where nothing runs beside it (in the headline region the dense copy and
+    # the pooled lookups share the SMs with it)
+    import ctypes as _C
+    seq_timer = None
+    use_seq_timer = args.precision == "bf16" and getattr(model, "seq_multi", False)
+    if use_seq_timer:
+        model.lib.dmt_debug_seq_timer(1)
     timed(step_resident, stage_steps)
+    if use_seq_timer:
+        t_k, n_k = _C.c_float(0), _C.c_int32(0)
+        if model.lib.dmt_debug_seq_timer_read(_C.byref(t_k), _C.byref(n_k)) == 0 and n_k.value == stage_steps:
+            seq_timer = (float(t_k.value), int(n_k.value))
+        model.lib.dmt_debug_seq_timer(0)
     gpu_launches = (model.launches - launches0) * args.steps // stage_steps
     torch.cuda.synchronize()
     stage = model.stage_times_ms()
@@ -610,11 +625,19 @@ def main():
         # bf16: ONE persistent tile-kernel launch per step over all sequences (+ length-class and tail launches, whose
         # time is in t_ms); other paths: one launch chain per sequence
         n = steps_used * (1 if multi else len(plan.sequences))
+        stage_ms_per_step = t_ms / steps_used
+        if multi and seq_timer is not None:
+            # the kernel's own events over the K timed steps (the stage time above also holds the length-class and
+            # tail launches and, in the serial per-stage pass, launch gaps)
+            t_ms, n = seq_timer
         alg = mean_b(algorithmic_bytes_seq)                      # bytes over all launches of the region
-        fl = mean_b(flops_seq)                                   # algorithmic FLOPs (valid tokens only)
+        own = multi and seq_timer is not None                    # t_ms is the tile kernel's own time
+        fl = mean_b((lambda p, b: flops_seq(p, b, tail=False)) if own else flops_seq)   # algorithmic FLOPs (valid tokens)
         hbm = alg / (t_ms / 1e3) / 1e9
         tfl = fl / (t_ms / 1e3) / 1e12
-        name = {"bf16": ("seq_bucket_kernel + seq_encode_multi_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight "
+        name = {"bf16": ("seq_encode_multi_kernel (bf16 tcgen05, two tiles in flight per SM, fused gather->encoder->decoder "
+                         "scores / contexts, all sequences in one persistent launch over length-bucketed tiles)") if own else
+                        ("seq_bucket_kernel + seq_encode_multi_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight "
                          "per SM, fused gather->encoder->decoder, all sequences in one persistent launch over "
                          "length-bucketed tiles)") if multi else
                         ("seq_encode_tc3_kernel + seq_tail_kernel (bf16 tcgen05, two tiles in flight per SM, fused "
@@ -629,6 +652,10 @@ def main():
                         "frac": tfl / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
                         "launches": n, "avg_launch_ms": t_ms / n, "flops_per_launch": fl / n,
                         "algorithmic_bytes_per_launch": alg / n,
+                        "timing": ("CUDA events around every seq_encode_multi_kernel launch on its launch stream, in the "
+                                   "per-stage pass (dmt_debug_seq_timer)") if (multi and seq_timer is not None) else
+                                  "CUDA events around the stage's launches in the per-stage pass",
+                        "stage_ms_per_step": stage_ms_per_step,
                         "hbm": {"achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm / pk["hbm_gbs"]},
                         "note": "fully fused kernel: 432 FLOP/B vs a 209 FLOP/B ridge -> tensor-bound by the roofline; "
                                 "at L<=50 it is in practice limited by the SIMT epilogues between its six dependent MMA "

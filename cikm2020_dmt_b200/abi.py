@@ -180,6 +180,8 @@ PROTOTYPES = {
     "dmt_widen_u16": (C.c_int, [C.c_int32, C.POINTER(WidenDesc), _fp]),
     "dmt_copy_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
+    "dmt_debug_seq_timer": (C.c_int, [C.c_int32]),
+    "dmt_debug_seq_timer_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dmt_selftest_umma": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]),
     "dmt_selftest_tf32_rows": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _fp,
                                          C.c_int64, _fp, _fp, C.c_int64, _fp, C.c_int64, C.c_float, C.c_int32,

@@ -20,6 +20,8 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg);
 int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
                  float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
+int seq_timer_enable(int on);
+int seq_timer_read(float* total_ms, int32_t* launches);
 int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
                  float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
 }
@@ -183,6 +185,13 @@ int dmt_seq_encode_bwd(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dm
   dmt::seq_saved_carve(*cfg, n_tokens, const_cast<void*>(saved), &sv);
   return dmt::seq_bwd_launch(cfg, in, w, n_tokens, sv, d_out, d_out_ld, grads, d_tokens, d_target, workspace,
                              (cudaStream_t)stream);
+}
+
+int dmt_debug_seq_timer(int32_t enable) { return dmt::seq_timer_enable(enable); }
+
+int dmt_debug_seq_timer_read(float* total_ms, int32_t* launches) {
+  DMT_REQUIRE(total_ms && launches, DMT_ERR_INVALID_ARGUMENT, "dmt_debug_seq_timer_read: null pointer");
+  return dmt::seq_timer_read(total_ms, launches);
 }
 
 int dmt_debug_seq_profile(void* device_counters) {

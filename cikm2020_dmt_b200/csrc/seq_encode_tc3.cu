@@ -1864,6 +1864,40 @@ int seq_tails_launch(int n, const SeqTcArgs* args, cudaStream_t st) {
   return launch_tails(tb, st);
 }
 
+// diagnostics (dmt_debug_seq_timer): CUDA events around every seq_encode_multi_kernel launch, on its launch stream --
+// bench.py's roofline of the dominant kernel is that kernel's own live duration, not the stage's three launches
+constexpr int kTimerCap = 4096;
+static struct {
+  bool on = false;
+  int n = 0;
+  cudaEvent_t e0[kTimerCap], e1[kTimerCap];
+} g_seq_timer;
+
+int seq_timer_enable(int on) {
+  for (int i = 0; i < g_seq_timer.n; ++i) {
+    cudaEventDestroy(g_seq_timer.e0[i]);
+    cudaEventDestroy(g_seq_timer.e1[i]);
+  }
+  g_seq_timer.n = 0;
+  g_seq_timer.on = on != 0;
+  return DMT_OK;
+}
+
+int seq_timer_read(float* total_ms, int32_t* launches) {
+  float sum = 0.f;
+  for (int i = 0; i < g_seq_timer.n; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_seq_timer.e1[i]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(dmt_debug_seq_timer_read)");
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_seq_timer.e0[i], g_seq_timer.e1[i]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime(dmt_debug_seq_timer_read)");
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = g_seq_timer.n;
+  return DMT_OK;
+}
+
 // workspace tail of the bucketed launch: [perm: batch int32 | counts: 4 int32]
 size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg) { return ((size_t)cfg->batch * 4 + 16 + 255) / 256 * 256; }
 
@@ -1907,7 +1941,14 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, c
   const int grid = pairs < sms ? (int)pairs : sms;
   cudaError_t e = cudaFuncSetAttribute(seq_encode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_multi_kernel)");
+  const bool timed = g_seq_timer.on && g_seq_timer.n < kTimerCap;
+  if (timed) {
+    cudaEventCreate(&g_seq_timer.e0[g_seq_timer.n]);
+    cudaEventCreate(&g_seq_timer.e1[g_seq_timer.n]);
+    cudaEventRecord(g_seq_timer.e0[g_seq_timer.n], st);
+  }
   seq_encode_multi_kernel<<<grid, kT3Threads, total, st>>>(m);
+  if (timed) cudaEventRecord(g_seq_timer.e1[g_seq_timer.n++], st);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_multi_kernel");
   return seq_tails_launch(n, args, st);
 }

@@ -529,6 +529,10 @@ DMT_API int dmt_selftest_tf32_colsum(const float* X, int64_t ldx, int64_t T, int
  * adds the SM cycles thread 0 of every CTA spends in each of its phases (gather-convert, QKV MMA, QKV
  * epilogue, ... decoder).  Pass NULL to switch it off.  Process-wide debug switch, not for production. */
 DMT_API int dmt_debug_seq_profile(void* device_counters);
+/* diagnostics: CUDA events around every seq_encode_multi_kernel launch (on its launch stream) while enabled;
+ * _read waits for them and returns their summed duration and count (then keeps collecting). */
+DMT_API int dmt_debug_seq_timer(int32_t enable);
+DMT_API int dmt_debug_seq_timer_read(float* total_ms, int32_t* launches);
 
 #ifdef __cplusplus
 }
