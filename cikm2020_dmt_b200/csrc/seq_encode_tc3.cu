@@ -808,7 +808,6 @@ struct SeqMultiArgs {
   const int32_t* perm[DMT_MAX_TAIL_SEQS];     // [batch] sample indices ordered by length class
   const int32_t* counts[DMT_MAX_TAIL_SEQS];   // [3] samples in the 64- / 32- / 16-row classes
   int32_t n_seq;
-  int32_t stagger;                            // cycles the second tile group of every CTA starts late
 };
 
 struct BucketArgs {
@@ -883,7 +882,7 @@ __global__ void __launch_bounds__(1024) seq_bucket_kernel(const __grid_constant_
 }
 
 #define T3_TICK(idx)                                                    \
-  do {                                                                  \
+  if constexpr (DBG) {                                                  \
     if (dbgp && tid == 0) {                                             \
       const long long _now = clock64();                                 \
       atomicAdd(dbgp + (idx), (unsigned long long)(_now - t_last));     \
@@ -891,11 +890,14 @@ __global__ void __launch_bounds__(1024) seq_bucket_kernel(const __grid_constant_
     }                                                                   \
     if (dbgp && gt == 0 && blockIdx.x == 0 && tl_tile < 6 && (idx) < 12) \
       dbg0[1024 + grp * 128 + tl_tile * 16 + (idx)] = (unsigned long long)(clock64() - t_entry); \
-  } while (0)
+  }
 
 template <int N>
 using ic = std::integral_constant<int, N>;
 
+// DBG: the diagnostics of dmt_debug_seq_profile (a second instantiation: their counters and clocks cost registers the
+// production kernel does not have)
+template <bool DBG>
 __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const __grid_constant__ SeqMultiArgs m) {
   using L0 = Tc2Layout<64>;                           // the byte offsets of the memory plan do not depend on the slot size
   constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
@@ -924,9 +926,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
 
   // diagnostics (dmt_debug_seq_profile): [q*16 + phase] cycles of CTA 0 / group 0 per sequence, [64 + cta] cycles of
   // the whole CTA, [320 + cta] / [576 + cta] %globaltimer at entry / exit
-  unsigned long long* const dbg0 = m.a[0].dbg;
-  const long long t_entry = clock64();
-  if (dbg0 && tid == 0) dbg0[320 + blockIdx.x] = globaltimer_ns();
+  unsigned long long* const dbg0 = DBG ? m.a[0].dbg : nullptr;
+  const long long t_entry = DBG ? clock64() : 0;
+  if (DBG && dbg0 && tid == 0) dbg0[320 + blockIdx.x] = globaltimer_ns();
 
   if (tid < 32) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -950,18 +952,16 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
   const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;
   const int c0h = hf * HC;                             // first gather chunk / 8-column group of this half
   uint32_t phase = 0, cphase = 0;
-  // exchange slots: [row][half] pairs of floats
+  // exchange slots: [half][row] pairs of floats (consecutive lanes = consecutive 8-byte slots)
   float2* exLN = reinterpret_cast<float2*>(sQ + oExLN);
   float2* exSc = reinterpret_cast<float2*>(sQ + oExSc);
   const int G = blockIdx.x * 2 + grp, S = 2 * gridDim.x;   // this tile group | tile groups of the grid
   int tl_tile = 0;                                     // diagnostics: tiles this group has finished (timeline capture)
-  // (tuning knob) the second tile group starts every sequence `stagger` cycles late: do the groups' SIMT epilogues
-  // then fall into each other's MMA round trips instead of both groups computing and waiting at the same time?
   int seg_g0 = 0;                                      // global index of the current segment's first tile
 
   for (int q = 0; q < m.n_seq; ++q) {
     const SeqTcArgs& a = m.a[q];
-    const long long t_seq = clock64();
+    const long long t_seq = DBG ? clock64() : 0;
     // ---- sequence prologue: gather descriptors, weight images, biases / LayerNorm vectors, positions.  Every group
     //      has waited for its last context MMA (ctx_readout), i.e. for every MMA it issued: nothing reads the old
     //      images any more once all threads are here ----
@@ -998,7 +998,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
       for (int i = tid; i < a.cfg.maxlen * KC; i += kT3Threads) {
         const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
         const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        pdst[i] = f8_to_bf16(f);
+        // 16-byte chunk k of position t lives at chunk k ^ (t & 7) of its 128-byte row: the threads of a warp read
+        // consecutive positions, the same chunk -- unswizzled that is eight lanes on the same four banks
+        pdst[(i & ~7) | ((i & 7) ^ ((i >> 3) & 7))] = f8_to_bf16(f);
       }
     }
     __syncthreads();
@@ -1010,12 +1012,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
     const int zp = a.cfg.zero_pad ? 1 : 0;
     const int32_t* const perm = m.perm[q];
     void* const ctxp = a.ctx;
-    unsigned long long* const dbgp = a.dbg ? a.dbg + q * 16 : nullptr;
-    if (dbgp && tid == 0) atomicAdd(dbgp + 15, (unsigned long long)(clock64() - t_seq));   // sequence prologue
-    if (grp == 1 && m.stagger > 0) {                   // (the CTA-wide barriers above re-align the groups)
-      const long long t0 = clock64();
-      while (clock64() - t0 < m.stagger) __nanosleep(200);
-    }
+    unsigned long long* const dbgp = (DBG && a.dbg) ? a.dbg + q * 16 : nullptr;
+    if (DBG && dbgp && tid == 0) atomicAdd(dbgp + 15, (unsigned long long)(clock64() - t_seq));   // sequence prologue
     bool wpending = gt == 0;                           // the MMA issuer waits for the images before its first MMA
     const uint32_t wpar = q & 1;
 
@@ -1031,7 +1029,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
       if (first >= n_tiles) return;
       const int lmax = maxlen < SLOT ? maxlen : SLOT;
       const int slot = row / SLOT, tpos = row % SLOT;
-      long long t_last = clock64();
+      long long t_last = DBG ? clock64() : 0;
       // ---- software-pipelined gather: this thread loads chunks c0h .. c0h+HC-1 of its token row ----
       int pf_o0[HC], pf_o1[HC], pf_id[HC];
       int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
@@ -1154,7 +1152,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
           for (int e = 0; e < 8; ++e) x[e] = 0.f;
           if (pf_valid) {
             float p[8];
-            bf16x8_to_f(spos[tpos * KC + c0h + k], p);
+            bf16x8_to_f(spos[tpos * KC + ((c0h + k) ^ (tpos & 7))], p);
             x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
             x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
             x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
@@ -1374,9 +1372,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
             s0 += y[e]; s1 += y[e + 1];
             q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
           }
-          exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+          exLN[hf * 128 + row] = make_float2(s0 + s1, q0 + q1);
           named_sync(bar_id, 256);
-          const float2 o = exLN[row * 2 + (hf ^ 1)];
+          const float2 o = exLN[(hf ^ 1) * 128 + row];
           const float mean = ((s0 + s1) + o.x) * (1.0f / D);
           const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
           const float rstd = 1.0f / sqrtf(var + kLnEps);
@@ -1472,10 +1470,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
             s0 += y[e]; s1 += y[e + 1];
             q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
           }
-          exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
+          exLN[hf * 128 + row] = make_float2(s0 + s1, q0 + q1);
           named_sync(bar_id, 256);
           {
-            const float2 o = exLN[row * 2 + (hf ^ 1)];
+            const float2 o = exLN[(hf ^ 1) * 128 + row];
             const float mean = ((s0 + s1) + o.x) * (1.0f / D);
             const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
             const float rstd = 1.0f / sqrtf(var + kLnEps);
@@ -1507,9 +1505,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
             }
             pu[h] = a0 + a1;
           }
-          exSc[row * 2 + hf] = make_float2(pu[0], pu[1]);
+          exSc[hf * 128 + row] = make_float2(pu[0], pu[1]);
           named_sync(bar_id, 256);
-          const float2 os = exSc[row * 2 + (hf ^ 1)];
+          const float2 os = exSc[(hf ^ 1) * 128 + row];
           // this half finishes head hf
           const float dot = (hf == 0 ? pu[0] + os.x : pu[1] + os.y);
           const float u = (tpos < len) ? dot * sl2 : -INFINITY;
@@ -1552,13 +1550,13 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
         }
         n_done = it + 1;
         T3_TICK(11);
-        ++tl_tile;
+        if (DBG) ++tl_tile;
       }
 
 
       if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
       T3_TICK(13);                                       // pipeline drain (last context read-out)
-      if (dbgp && tid == 0) atomicAdd(dbgp + 14, (unsigned long long)n_done);
+      if (DBG && dbgp && tid == 0) atomicAdd(dbgp + 14, (unsigned long long)n_done);
     };
 
     const int c64 = __ldg(m.counts[q]), c32 = __ldg(m.counts[q] + 1), c16 = __ldg(m.counts[q] + 2);
@@ -1570,7 +1568,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
   fence_before_sync();
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_base_s, 512);
-  if (dbg0 && tid == 0) {
+  if (DBG && dbg0 && tid == 0) {
     dbg0[64 + blockIdx.x] = (unsigned long long)(clock64() - t_entry);
     dbg0[576 + blockIdx.x] = globaltimer_ns();
   }
@@ -1909,14 +1907,6 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, c
   memset(&m, 0, sizeof(m));
   memset(&ba, 0, sizeof(ba));
   m.n_seq = n;
-  {
-    static int stagger = -1;                          // tuning knob (cycles)
-    if (stagger < 0) {
-      const char* e = getenv("DMT_SEQ_STAGGER");
-      stagger = e ? atoi(e) : 0;
-    }
-    m.stagger = stagger;
-  }
   long long ub_tiles = 0;                             // upper bound of the tile count (the classes are known on the device only)
   int maxlen = 0;
   for (int i = 0; i < n; ++i) {
@@ -1933,21 +1923,23 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, c
     ub_tiles += (args[i].cfg.batch + 1) / 2 + 2;
     if (args[i].cfg.maxlen > maxlen) maxlen = args[i].cfg.maxlen;
   }
-  seq_bucket_kernel<<<n, 1024, 0, st>>>(ba);
-  DMT_CUDA_LAUNCH_CHECK("seq_bucket_kernel");
   const int total = Tc2Layout<64>::oPos + maxlen * kD * 2 + 64;
   const int sms = sm_count_cached();
   const long long pairs = (ub_tiles + 1) / 2;
   const int grid = pairs < sms ? (int)pairs : sms;
-  cudaError_t e = cudaFuncSetAttribute(seq_encode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+  const bool dbg = args[0].dbg != nullptr;
+  auto kern = dbg ? seq_encode_multi_kernel<true> : seq_encode_multi_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_multi_kernel)");
   const bool timed = g_seq_timer.on && g_seq_timer.n < kTimerCap;
-  if (timed) {
+  if (timed) {      // (created before the launches: the event records then sit back to back with the kernel launch)
     cudaEventCreate(&g_seq_timer.e0[g_seq_timer.n]);
     cudaEventCreate(&g_seq_timer.e1[g_seq_timer.n]);
-    cudaEventRecord(g_seq_timer.e0[g_seq_timer.n], st);
   }
-  seq_encode_multi_kernel<<<grid, kT3Threads, total, st>>>(m);
+  seq_bucket_kernel<<<n, 1024, 0, st>>>(ba);
+  DMT_CUDA_LAUNCH_CHECK("seq_bucket_kernel");
+  if (timed) cudaEventRecord(g_seq_timer.e0[g_seq_timer.n], st);
+  kern<<<grid, kT3Threads, total, st>>>(m);
   if (timed) cudaEventRecord(g_seq_timer.e1[g_seq_timer.n++], st);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_multi_kernel");
   return seq_tails_launch(n, args, st);
