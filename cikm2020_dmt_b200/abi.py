@@ -86,6 +86,23 @@ class BiasWeights(C.Structure):
     _fields_ = [("layer", Dense * (MAX_LAYERS + 1))]
 
 
+class FwdFeature(C.Structure):
+    _fields_ = [("ids", _fp), ("offsets", _fp), ("weights", _fp)]
+
+
+class FwdDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_seq", C.c_int32), ("n_pool", C.c_int32), ("n_bias_pool", C.c_int32),
+                ("feature_dim", C.c_int32), ("is_predict", C.c_int32), ("interest_col", C.c_int32), ("_pad", C.c_int32),
+                ("pool", _fp), ("pool_feature", _fp), ("bias_pool", _fp), ("bias_pool_feature", _fp),
+                ("seq_cfg", _fp * MAX_TAIL_SEQS), ("seq_in", _fp * MAX_TAIL_SEQS),
+                ("seq_user_feature", _fp * MAX_TAIL_SEQS), ("seq_item_feature", _fp * MAX_TAIL_SEQS),
+                ("seq_w", _fp * MAX_TAIL_SEQS), ("seq_ws", _fp * MAX_TAIL_SEQS),
+                ("seq_ws_bytes", C.c_size_t * MAX_TAIL_SEQS),
+                ("mmoe_cfg", _fp), ("mmoe_w", _fp), ("mmoe_ws", _fp), ("mmoe_ws_bytes", C.c_size_t),
+                ("mmoe_prepared", _fp), ("bias_cfg", _fp), ("bias_w", _fp), ("bias_in", _fp), ("bias_ld", C.c_int64),
+                ("xb", _fp), ("xb_ld", C.c_int64)]
+
+
 MAX_WIDEN = 64
 
 
@@ -139,6 +156,7 @@ PROTOTYPES = {
                                _fp, _fp]),
     "dmt_mmoe_fwd_bf16in": (C.c_int, [C.POINTER(MmoeCfg), C.POINTER(MmoeWeights), _fp, C.c_int64, _fp, _fp,
                                       C.c_size_t, _fp, _fp]),
+    "dmt_forward_bf16": (C.c_int, [C.POINTER(FwdDesc), C.c_int32, _fp, _fp, C.c_int32, _fp, _fp]),
     "dmt_loss_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "dmt_bias_loss_fwd": (C.c_int, [C.POINTER(BiasLossCfg), C.POINTER(BiasWeights), _fp, C.c_int64, _fp, _fp, _fp,
                                     _fp, _fp, _fp, _fp, _fp]),

@@ -383,6 +383,34 @@ class PackedBatch:
             out[key] = SparseIds(p["v"], p["o"], p.get("w"))
         return out
 
+    def feature_offsets(self, names):
+        """[len(names), 3] int64 byte offsets of (ids, offsets, weights) of the CSR features `names` inside the packed
+        buffer -- ids of a uint16-stored array: inside the WIDE buffer, flagged by bit 62; no weights: -1 -- plus the
+        element counts [len(names), 2] (ids, offsets).  Computed once per batch when the data loader builds it; the
+        native forward driver (dmt_forward_bf16) turns it into its pointer table with one vector add per call."""
+        key = tuple(names)
+        cache = self.__dict__.setdefault("_feat_offsets", {})
+        hit = cache.get(key)
+        if hit is None:
+            if not hasattr(self, "_ptr_plan"):
+                self.unpack_ptrs(self.host)      # (builds the plan; the descriptors it returns are dropped)
+            sparse = {k: (v, o, w) for k, v, o, w in self._ptr_plan[1]}
+            tab = np.full((len(names), 3), -1, dtype=np.int64)
+            cnt = np.zeros((len(names), 2), dtype=np.int64)
+            for i, n in enumerate(names):
+                if n not in sparse:
+                    raise KeyError("feature %r is not in this packed batch" % n)
+                v, o, w = sparse[n]
+                if v[2] != torch.int32 or o[2] != torch.int32:
+                    raise TypeError("feature %r: ids/offsets must be int32" % n)
+                tab[i, 0] = v[0] | ((1 << 62) if v[3] else 0)
+                tab[i, 1] = o[0]
+                if w is not None:
+                    tab[i, 2] = w[0]
+                cnt[i] = (v[1], o[1])
+            hit = cache[key] = (tab, cnt)
+        return hit
+
     def unpack_ptrs(self, buf: torch.Tensor, wide: Optional[torch.Tensor] = None) -> Dict:
         """Like `unpack`, but the id / offset / weight arrays come back as `DevArray`s (address + length) and only
         the dense tensors ('features', 'mask', ...) as torch views."""
@@ -411,6 +439,7 @@ class PackedBatch:
                                  DevArray(base + off[0], off[1], off[2], dev),
                                  None if w is None else DevArray(base + w[0], w[1], w[2], dev))
         out["__buffer__"] = (buf, wide)  # keeps the storage alive as long as the descriptors
+        out["__packed__"] = self
         return out
 
     def to(self, device, out: Optional[torch.Tensor] = None, views: bool = True,

@@ -10,6 +10,7 @@ stream.  There is no PyTorch math on the path and no CPU fallback.
 import ctypes as C
 import os
 
+import numpy as np
 import torch
 
 from .. import abi
@@ -58,6 +59,8 @@ class mmoe_transformer_unbias(object):
         self.seq_streams = os.environ.get("DMT_SEQ_STREAMS", "1") != "0"   # one stream per behaviour sequence
         self.seq_multi = os.environ.get("DMT_SEQ_MULTI", "1") != "0"       # bf16: one launch over all sequences
         self.x_bf16 = os.environ.get("DMT_X_BF16", "1") != "0"             # bf16: MMoE input assembled in bf16
+        self.fwd_native = os.environ.get("DMT_FWD_NATIVE", "1") != "0"     # bf16: one C call per forward
+        self._fwd_states = {}
         self._pool_static = {}       # (bias, n specs) -> per-feature static descriptor parts
         self._v2_ok = True           # bf16 path: the decoder tails of all sequences run as one deferred launch
         self._bind_weights()
@@ -671,6 +674,10 @@ class mmoe_transformer_unbias(object):
                 and 0 < len(plan.sequences) <= abi.MAX_TAIL_SEQS):
             # bf16: all sequences in ONE persistent tile-kernel launch over length-bucketed tiles; the MMoE input is
             # assembled in bf16 by its producers (no fp32 copy of x, no conversion pass)
+            if self.x_bf16 and self.fwd_native and self._events is None and self.seq_streams:
+                out = self._inference_native(inputs, feats, batch, is_predict)     # the same calls, issued natively
+                if out is not None:
+                    return out
             if self.x_bf16:
                 x_ld = (plan.mmoe_in + 7) // 8 * 8
                 x = self._buf("xb", (batch, x_ld), torch.bfloat16)
@@ -740,6 +747,158 @@ class mmoe_transformer_unbias(object):
         if deferred:
             self.seq_tails(deferred)       # one launch for the decoder tails of every sequence
         return self._inference_head(inputs, x, batch, keep, is_predict)
+
+    # ------------------------------------------------------------------ native forward driver (dmt_forward_bf16)
+    def _fwd_feature_names(self):
+        names = list(self.plan.all_id_features())
+        for seq in self.plan.sequences:
+            for n in list(seq.user_features) + list(seq.item_features):
+                if n not in names:
+                    names.append(n)
+        return names
+
+    def _fwd_state(self, batch, is_predict):
+        """Static half of the forward: `dmt_fwd_desc` + everything it points to (descriptor templates, feature
+        bindings, buffers), built once per (batch size, is_predict, parameter version)."""
+        key = (batch, bool(is_predict))
+        st = self._fwd_states.get(key)
+        if st is not None and st["version"] == self.params_version:
+            return st
+        plan, lib = self.plan, self.lib
+        names = self._fwd_feature_names()
+        index = {n: i for i, n in enumerate(names)}
+        st = {"version": self.params_version, "names": names, "keep": []}
+        d = abi.FwdDesc()
+        d.batch, d.n_seq, d.is_predict = batch, len(plan.sequences), 1 if is_predict else 0
+        d.feature_dim = plan.feature_dim if plan.is_use_feature else 0
+        d.interest_col = plan.interest_col
+
+        def pool_templates(specs, bias):
+            arr = (abi.PoolFeat * max(len(specs), 1))()
+            feat = (C.c_int32 * max(len(specs), 1))()
+            for i, p in enumerate(specs):
+                table = self.params.table(p.table, bias=bias)
+                arr[i].table, arr[i].rows, arr[i].dim, arr[i].out_col = table.data_ptr(), table.shape[0], table.shape[1], p.col
+                feat[i] = index[p.feature]
+            st["keep"] += [arr, feat]
+            return arr, feat
+
+        if len(plan.pooled) > abi.MAX_POOL_FEATS or len(plan.bias_pooled) > abi.MAX_POOL_FEATS:
+            raise ValueError("more than %d pooled lookups" % abi.MAX_POOL_FEATS)
+        arr, feat = pool_templates(plan.pooled, False)
+        d.n_pool, d.pool, d.pool_feature = len(plan.pooled), C.addressof(arr), C.addressof(feat)
+        arr, feat = pool_templates(plan.bias_pooled, True)
+        d.n_bias_pool, d.bias_pool, d.bias_pool_feature = len(plan.bias_pooled), C.addressof(arr), C.addressof(feat)
+        for s, seq in enumerate(plan.sequences):
+            cfg = abi.SeqCfg(batch, plan.d_model, plan.d_ff, plan.num_heads, plan.num_blocks_encode,
+                             plan.num_blocks_decode, plan.maxlen_k, 1 if plan.zero_pad else 0, len(seq.user_features),
+                             abi.PRECISION_BF16, seq.maxlen, abi.SEQ_OUT_BF16, 0.0, 0)
+            ws, ws_bytes = self._prepared_for(s, cfg)
+            si = abi.SeqInput()
+            uf = (C.c_int32 * abi.MAX_SEQ_FEATS)()
+            itf = (C.c_int32 * abi.MAX_SEQ_FEATS)()
+            for f, (u, it) in enumerate(zip(seq.user_features, seq.item_features)):
+                table = self.params.table(seq.tables[f])
+                si.table[f], si.rows[f], si.dim[f] = abi.ptr(table), table.shape[0], table.shape[1]
+                uf[f], itf[f] = index[u], index[it]
+            st["keep"] += [cfg, ws, si, uf, itf]
+            d.seq_cfg[s], d.seq_in[s], d.seq_w[s] = C.addressof(cfg), C.addressof(si), C.addressof(self._seq_w[s])
+            d.seq_user_feature[s], d.seq_item_feature[s] = C.addressof(uf), C.addressof(itf)
+            d.seq_ws[s], d.seq_ws_bytes[s] = ws.data_ptr(), ws_bytes
+        mcfg = self._mmoe_cfg(batch, abi.PRECISION_BF16)
+        nbytes = lib.dmt_mmoe_workspace_bytes(C.byref(mcfg))
+        mws = self._buf("mmoe_ws", ((nbytes + 255) // 256 * 256,), torch.uint8)
+        ver, prep = self._prepared.get("mmoe", (-1, None))
+        pbytes = lib.dmt_mmoe_prepared_bytes(C.byref(mcfg))
+        if prep is None:
+            prep = torch.empty(pbytes, dtype=torch.uint8, device=self.device)
+        if ver != self.params_version:
+            abi.check(lib.dmt_mmoe_prepare_weights(C.byref(mcfg), C.byref(self._mmoe_w), prep.data_ptr(), pbytes,
+                                                   self._stream()))
+            self._prepared["mmoe"] = (self.params_version, prep)
+        d.mmoe_cfg, d.mmoe_w = C.addressof(mcfg), C.addressof(self._mmoe_w)
+        d.mmoe_ws, d.mmoe_ws_bytes, d.mmoe_prepared = mws.data_ptr(), nbytes, prep.data_ptr()
+        bcfg = self._bias_cfg(batch)
+        bias_in = self._buf("bias_in", (batch, plan.bias_width))
+        d.bias_cfg, d.bias_w = C.addressof(bcfg), C.addressof(self._bias_w)
+        d.bias_in, d.bias_ld = bias_in.data_ptr(), bias_in.stride(0)
+        x_ld = (plan.mmoe_in + 7) // 8 * 8
+        xb = self._buf("xb", (batch, x_ld), torch.bfloat16)
+        d.xb, d.xb_ld = xb.data_ptr(), x_ld
+        st["keep"] += [mcfg, mws, prep, bcfg, bias_in, xb]
+        st["desc"], st["xb"] = d, xb
+        # kernel launches per call: bias pool + tower | length classes + tile kernel + tails | dense + pooled |
+        # MMoE layer 0 + fused tail + mixture
+        st["launches"] = (0 if is_predict else 2) + 3 + (1 if d.feature_dim else 0) + 1 + 3
+        self._fwd_states[key] = st
+        return st
+
+    def _fwd_table(self, inputs, st, batch):
+        """Per-call half: the [n_features, 3] pointer table (ids, offsets, weights)."""
+        names = st["names"]
+        packed = inputs.get("__packed__")
+        if packed is not None and "__buffer__" in inputs and not inputs.get("__remap__"):
+            tab, cnt = packed.feature_offsets(names)
+            ok = packed.__dict__.setdefault("_fwd_ok", set())        # validated once per (packed batch, model)
+            if (id(self), batch) not in ok:
+                if any(n + "Wts" in inputs for n in names):
+                    return None
+                item = {n for seq in self.plan.sequences for n in seq.item_features}
+                for i, n in enumerate(names):
+                    if cnt[i, 1] != batch + 1:
+                        raise ValueError("feature %r: offsets has %d entries, batch is %d" % (n, cnt[i, 1], batch))
+                    if n in item and cnt[i, 0] != batch:
+                        raise ValueError("item feature %r must hold exactly one id per sample" % n)
+                ok.add((id(self), batch))
+            buf, wide = inputs["__buffer__"]
+            base, wbase = buf.data_ptr(), (wide.data_ptr() if wide is not None else 0)
+            out = tab.copy()
+            in_wide = (out[:, 0] >> 62) & 1
+            out[:, 0] = (out[:, 0] & ((1 << 62) - 1)) + np.where(in_wide == 1, wbase, base)
+            out[:, 1] += base
+            out[:, 2] = np.where(tab[:, 2] >= 0, tab[:, 2] + base, 0)
+            return out
+        cached = inputs.get("__fwd_table__")
+        if cached is not None and cached[0] is st["names"]:
+            return cached[1]
+        item = {n for seq in self.plan.sequences for n in seq.item_features}
+        out = np.zeros((len(names), 3), dtype=np.int64)
+        for i, n in enumerate(names):
+            sp = self._sparse(inputs, n)
+            if sp.offsets.numel() != batch + 1:
+                raise ValueError("feature %r: offsets has %d entries, batch is %d" % (n, sp.offsets.numel(), batch))
+            if n in item and sp.values.numel() != batch:
+                raise ValueError("item feature %r must hold exactly one id per sample" % n)
+            out[i, 0], out[i, 1] = sp.values.data_ptr(), sp.offsets.data_ptr()
+            out[i, 2] = 0 if sp.weights is None else sp.weights.data_ptr()
+        inputs["__fwd_table__"] = (st["names"], out)      # (the batch object owns its pointers: reused as is)
+        return out
+
+    def _inference_native(self, inputs, feats, batch, is_predict):
+        """One `dmt_forward_bf16` call: descriptor templates patched and the three branches issued natively."""
+        plan = self.plan
+        if inputs.get("__remap__"):
+            return None
+        st = self._fwd_state(batch, is_predict)
+        table = self._fwd_table(inputs, st, batch)
+        if table is None:
+            return None
+        fptr, fbf16 = None, 0
+        if feats is not None:
+            if tuple(feats.shape) != (batch, plan.feature_dim) or feats.dtype not in (torch.float32, torch.bfloat16):
+                raise ValueError("'features' must be fp32 (or bf16) [%d, %d]" % (batch, plan.feature_dim))
+            feats = feats.contiguous()
+            fptr, fbf16 = feats.data_ptr(), 1 if feats.dtype == torch.bfloat16 else 0
+        scores = self._next_scores(batch)
+        abi.check(self.lib.dmt_forward_bf16(C.byref(st["desc"]), table.shape[0], table.ctypes.data, fptr, fbf16,
+                                            scores.data_ptr(), self._stream()))
+        self.launches += st["launches"]
+        self._last = {"x": st["xb"], "batch": batch, "keep": [table, feats, inputs]}
+        logits = scores[:plan.num_tasks]
+        y_rel = tuple(logits[t].view(batch, 1) for t in range(plan.num_tasks))
+        if is_predict:
+            return y_rel
+        return (y_rel, scores[plan.num_tasks].view(batch, 1))
 
     def _next_scores(self, batch):
         """Scores of one call live in ONE [num_tasks + 1, B] buffer (task logits, then y_bias) so that a caller can

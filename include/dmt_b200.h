@@ -317,6 +317,57 @@ DMT_API int dmt_mmoe_fwd_bf16in(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights*
                                 int64_t xb_ld, float* logits, void* workspace, size_t workspace_bytes,
                                 const void* prepared, void* stream);
 
+/* ---- the whole bf16 inference forward as one host call -------------------------------
+ * Replaces mmoe_transformer_unbias.inference (mmoe_transformer_unbias.py:293-316, eval mode) for the bf16 tensor-core
+ * path: the static part of every descriptor is built once (dmt_fwd_desc, all HOST memory, kept alive by the caller);
+ * per call the caller passes one table of feature pointers and the dense block.  The function patches the descriptor
+ * templates, runs the bias branch and the sequences on two library-owned side streams forked from / joined into
+ * `stream`, and issues dmt_stage_dense_features_bf16, dmt_pool_mean_fwd(_bf16), dmt_seq_encode_multi_fwd,
+ * dmt_mmoe_fwd_bf16in and dmt_bias_loss_fwd -- results are exactly those calls'.
+ *   feats   [n_features] ids / offsets / weights (NULL = unit weights) of every CSR feature, device pointers
+ *   scores  [n_tasks + 1][batch]: task logits, then y_bias (not written with is_predict) */
+typedef struct dmt_fwd_feature {
+  const int32_t* ids;
+  const int32_t* offsets;
+  const float* weights;
+} dmt_fwd_feature;
+
+typedef struct dmt_fwd_desc {
+  int32_t batch;
+  int32_t n_seq;
+  int32_t n_pool;                       /* lookups of embedding_combiner (base.py:93-124)                  */
+  int32_t n_bias_pool;                  /* lookups of embedding_combiner_bias (:235-257)                    */
+  int32_t feature_dim;                  /* dense block width (0: none)                                      */
+  int32_t is_predict;                   /* skip the bias branch                                             */
+  int32_t interest_col;                 /* first column of the interest vectors in the MMoE input          */
+  int32_t _pad;
+  const dmt_pool_feat* pool;            /* templates: table / rows / dim / out_col filled                   */
+  const int32_t* pool_feature;          /* lookup i reads feature pool_feature[i] of `feats`                */
+  const dmt_pool_feat* bias_pool;
+  const int32_t* bias_pool_feature;
+  const dmt_seq_cfg* seq_cfg[DMT_MAX_TAIL_SEQS];        /* flags must hold DMT_SEQ_OUT_BF16                 */
+  const dmt_seq_input* seq_in[DMT_MAX_TAIL_SEQS];       /* templates: table / rows / dim filled             */
+  const int32_t* seq_user_feature[DMT_MAX_TAIL_SEQS];   /* pair f of sequence q: user feature index         */
+  const int32_t* seq_item_feature[DMT_MAX_TAIL_SEQS];   /*                       item feature index         */
+  const dmt_seq_weights* seq_w[DMT_MAX_TAIL_SEQS];
+  void* seq_ws[DMT_MAX_TAIL_SEQS];                      /* prepared workspaces (dmt_seq_prepare_weights)    */
+  size_t seq_ws_bytes[DMT_MAX_TAIL_SEQS];
+  const dmt_mmoe_cfg* mmoe_cfg;
+  const dmt_mmoe_weights* mmoe_w;
+  void* mmoe_ws;
+  size_t mmoe_ws_bytes;
+  const void* mmoe_prepared;
+  const dmt_bias_loss_cfg* bias_cfg;
+  const dmt_bias_weights* bias_w;
+  float* bias_in;                       /* [batch, bias_ld] scratch: pooled bias embeddings                 */
+  int64_t bias_ld;
+  void* xb;                             /* [batch, xb_ld] bf16 MMoE input (scratch)                         */
+  int64_t xb_ld;
+} dmt_fwd_desc;
+
+DMT_API int dmt_forward_bf16(const dmt_fwd_desc* desc, int32_t n_features, const dmt_fwd_feature* feats,
+                             const void* features, int32_t features_are_bf16, float* scores, void* stream);
+
 /* ---- A11/A12: bias tower + unbiased multi-task loss -------------------------------
  * Replaces embedding_mlp_bias (mmoe_transformer_unbias.py:259-289, eval mode),
  * cal_ctr_cvr_unibas (run_dnn.py:90-100) and logit_loss_unbias + cal_cross_entropy
