@@ -35,9 +35,16 @@ int fwd_streams(FwdStreams** out) {
   DMT_REQUIRE(dev >= 0 && dev < kMaxDevices, DMT_ERR_INVALID_ARGUMENT, "dmt_forward_bf16: device %d", dev);
   FwdStreams& s = g_fwd[dev];
   if (!s.ready) {
+    // The sequence stream has the highest priority: its persistent tile kernel needs whole SMs, and the short CTAs of
+    // the dense / pooled / bias kernels that start beside it would otherwise keep it from becoming resident (its
+    // duration is set by its LAST CTA to start); with the priority they fill in while it ramps up and as its CTAs
+    // retire instead.
+    int prio_lo = 0, prio_hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetStreamPriorityRange(dmt_forward_bf16)");
     for (int i = 0; i < 2; ++i) {
-      e = cudaStreamCreateWithFlags(&s.side[i], cudaStreamNonBlocking);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithFlags(dmt_forward_bf16)");
+      e = cudaStreamCreateWithPriority(&s.side[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority(dmt_forward_bf16)");
       e = cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming);
       if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreateWithFlags(dmt_forward_bf16)");
     }

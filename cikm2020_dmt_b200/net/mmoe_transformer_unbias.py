@@ -169,7 +169,8 @@ class mmoe_transformer_unbias(object):
     def _seq_side_streams(self, n):
         st = getattr(self, "_side_streams", None)
         if st is None or len(st) < n:
-            st = self._side_streams = [torch.cuda.Stream(self.device) for _ in range(n)]
+            # stream 0 carries the (whole-SM, persistent) sequence kernels: highest priority, see csrc/forward.cu
+            st = self._side_streams = [torch.cuda.Stream(self.device, priority=-1 if i == 0 else 0) for i in range(n)]
         return st
 
     def _ev_pool(self, name):
