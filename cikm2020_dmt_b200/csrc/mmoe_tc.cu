@@ -16,7 +16,7 @@ namespace dmt {
 
 using namespace umma;
 
-constexpr int GBM = 128, GBN = 128, GBK = 64, GSTAGES = 3;
+constexpr int GBM = 128, GBN = 128, GBK = 64, GSTAGES = 3;   // 3 stages = 2 CTAs per SM (6 stages, 1 CTA: slower)
 constexpr int kGemmThreads = 192;
 constexpr int kStageBytes = (GBM * GBK + GBN * GBK) * 2;
 
