@@ -677,7 +677,8 @@ def main():
     # DRAM bytes per launch of the same kernel from the committed ncu capture (when the workload matches)
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            tr = json.load(fh).get("seq_encode_tc_kernel")
+            tr = json.load(fh).get("seq_encode_multi_kernel" if (args.precision == "bf16" and getattr(model, "seq_multi", False))
+                                   else "seq_encode_tc_kernel")
         wl = tr["workload"]
         if (dom in ("seq_encode", "seq_encode_train") and wl["conf"] == args.conf and wl["per_gpu_batch"] == args.batch
                 and wl["precision"] == args.precision and wl["id_mode"] == args.id_mode and not args.small_tables):
