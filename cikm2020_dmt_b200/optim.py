@@ -213,8 +213,9 @@ class TFAdam(object):
                                           self.v_dense.data_ptr(), grad_flat.data_ptr(), grad_flat.numel(),
                                           float(grad_scale), stream))
 
-    def step_table(self, name, sources: List[LookupGrad], lr=None, grad_scale=1.0):
-        """`name` is the TF variable name of the table; `sources` every lookup of this step into it."""
+    def step_table(self, name, sources: List[LookupGrad], lr=None, grad_scale=1.0, ws_name="sorted_ws"):
+        """`name` is the TF variable name of the table; `sources` every lookup of this step into it.  ws_name: the
+        scratch buffer of the segmented reduction (a caller that runs this on a side stream names its own)."""
         table = self.store.tables[name]
         cfg = self._cfg(lr)
         stream = torch.cuda.current_stream(table.device).cuda_stream
@@ -228,7 +229,7 @@ class TFAdam(object):
             abi.check(self.lib.dmt_embed_grad_expand(len(sources), arr, rows, keys.data_ptr(), refs.data_ptr(),
                                                      scale.data_ptr(), stream))
             skeys, perm = torch.sort(keys, stable=True)
-            ws = self.model._scratch("sorted_ws", self.lib.dmt_embed_sorted_workspace_bytes(total, dim))
+            ws = self.model._scratch(ws_name, self.lib.dmt_embed_sorted_workspace_bytes(total, dim))
             abi.check(self.lib.dmt_embed_adam_sorted(C.byref(cfg), table.data_ptr(), self.m_tab[name].data_ptr(),
                                                      self.v_tab[name].data_ptr(), rows, dim, len(sources), arr,
                                                      skeys.data_ptr(), perm.data_ptr(), refs.data_ptr(),

@@ -15,7 +15,9 @@ One process per GPU.  Per step and rank:
 With world == 1 steps 1, 3 and 4's exchange vanish and the tables take the sparse path of optim.TFAdam.
 Host code only; the collectives are torch.distributed (NCCL over NVLink), the arithmetic is the C-ABI library.
 """
+import contextlib
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -27,6 +29,9 @@ from .net.mmoe_transformer_unbias import mmoe_transformer_unbias
 from .optim import LookupGrad, TFAdam
 from .params import ParamStore
 from .shard import RowExchange, RowShard, remap_ids
+
+
+_nullctx = contextlib.nullcontext
 
 
 class Trainer(object):
@@ -80,6 +85,7 @@ class Trainer(object):
                 off += pad4(n)
         self.last_loss = None
         self.last_a2a_bytes = 0           # all-to-all payload of the last step (this rank's sends)
+        self.overlap_push = os.environ.get("DMT_DP_OVERLAP", "1") != "0"   # sharded-table push beside the allreduce
 
     @property
     def allreduce_bytes(self):
@@ -173,12 +179,42 @@ class Trainer(object):
                 self.store.tables[scope] = full
         stream = torch.cuda.current_stream(self.device).cuda_stream
         inv_world = 1.0 / self.world
+        keep = []
+        opt.begin_step()
+        # sharded tables: per-row gradients back to the owners, then sparse Adam on the shard -- on a side stream:
+        # independent of the replicated tables' densify -> allreduce -> Adam below, which runs beside it (all ranks
+        # issue the all-to-all before the allreduce, so the collectives keep one order on NCCL's stream).  The
+        # per-stage timing pass keeps everything on one stream.
+        main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        side = None
+        if main is not None and state and self.model._events is None and self.overlap_push:
+            if getattr(self, "_push_stream", None) is None:
+                self._push_stream = torch.cuda.Stream(self.device)
+            side = self._push_stream
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else _nullctx()):
+            pstream = side.cuda_stream if side is not None else stream
+            for scope, (ex, compact, full) in state.items():
+                srcs = grads.lookups.get(scope, [])
+                dim = full.shape[1]
+                with self._stage("sku_push", 2):
+                    gc = torch.zeros(max(ex.n_valid, 1), dim, dtype=torch.float32, device=self.device)
+                    if srcs and ex.n_valid:
+                        keys, refs, scale, arr = self._expand(srcs, ex.n_valid, pstream)
+                        abi.check(self.lib.dmt_embed_grad_scatter_rows(len(srcs), arr, keys.data_ptr(), refs.data_ptr(),
+                                                                       scale.data_ptr(), keys.numel(), dim, gc.data_ptr(),
+                                                                       pstream))
+                        keep.append((keys, refs, scale, arr, srcs))
+                    recv = ex.push_grads(gc[:ex.n_valid])
+                with self._stage("adam_shard"):
+                    src = [LookupGrad(ex.recv_rows.to(torch.int32), recv, 0, 0)] if recv.shape[0] else []
+                    opt.step_table(scope, src, lr=lr, grad_scale=inv_world, ws_name="sorted_ws_shard")
+                keep.append((gc, recv, src))
         # replicated tables: densify into the allreduce bucket (the bucket's dense part was zeroed and filled by
         # compute_gradients; zero the table part here)
         with self._stage("densify", 3):
             n_dense = self.store.dense.numel()
             self.bucket[n_dense:].zero_()
-            keep = []
             scopes = [k for k in self.replicated if grads.lookups.get(k)]
             n_src = sum(len(grads.lookups[k]) for k in scopes)
             if scopes and (len(scopes) > abi.MAX_ADAM_TABLES or n_src > abi.MAX_MULTI_GRAD_SOURCES or
@@ -226,7 +262,6 @@ class Trainer(object):
         with self._stage("allreduce"):
             if self.world > 1:
                 dist.all_reduce(self.bucket, group=self.group)
-        opt.begin_step()
         with self._stage("adam"):
             opt.step_dense(grads.dense, lr=lr, grad_scale=inv_world)
             cfg = opt._cfg(lr)
@@ -236,22 +271,8 @@ class Trainer(object):
                                                   opt.v_tab[scope].data_ptr(), self.table_grad[scope].data_ptr(),
                                                   t.numel(), inv_world, stream))
                 model.launches += 1
-        # sharded tables: per-row gradients back to the owners, then sparse Adam on the shard
-        for scope, (ex, compact, full) in state.items():
-            srcs = grads.lookups.get(scope, [])
-            dim = full.shape[1]
-            with self._stage("sku_push", 2):
-                gc = torch.zeros(max(ex.n_valid, 1), dim, dtype=torch.float32, device=self.device)
-                if srcs and ex.n_valid:
-                    keys, refs, scale, arr = self._expand(srcs, ex.n_valid, stream)
-                    abi.check(self.lib.dmt_embed_grad_scatter_rows(len(srcs), arr, keys.data_ptr(), refs.data_ptr(),
-                                                                   scale.data_ptr(), keys.numel(), dim, gc.data_ptr(),
-                                                                   stream))
-                    keep.append((keys, refs, scale, arr, srcs))
-                recv = ex.push_grads(gc[:ex.n_valid])
-            with self._stage("adam_shard"):
-                src = [LookupGrad(ex.recv_rows.to(torch.int32), recv, 0, 0)] if recv.shape[0] else []
-                opt.step_table(scope, src, lr=lr, grad_scale=inv_world)
+        if side is not None:
+            main.wait_stream(side)
         model.invalidate_prepared()
         self.last_loss = loss
         self._keep = keep
