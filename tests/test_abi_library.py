@@ -125,6 +125,9 @@ def test_argument_errors_need_no_gpu():
     grow = lib.dmt_seq_encode_workspace_bytes(C.byref(big), 0) - lib.dmt_seq_encode_workspace_bytes(C.byref(cfg), 0)
     sched = lambda b: (b * 4 + 16 + 255) // 256 * 256                            # length-class schedule: perm + counts
     assert grow == (4096 // 128 - 1) * 128 * 128 * 2 + sched(4096) - sched(4)    # one 32 KB image per 128 samples
+    assert lib.dmt_forward_bf16(None, 0, None, None, 0, None, None) == -1 and b"null" in lib.dmt_last_error()
+    assert lib.dmt_stage_dense_features_bf16(None, 0, 4, 8, None, 8, None) == -1
+    assert lib.dmt_pool_mean_fwd_bf16(4, 1, None, None, 8, None) == -1
     rc = lib.dmt_seq_encode_multi_fwd(abi.MAX_TAIL_SEQS + 1, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"n_seq" in lib.dmt_last_error()
     assert lib.dmt_seq_encode_multi_fwd(0, None, None, None, None, None, None, None, None) == 0

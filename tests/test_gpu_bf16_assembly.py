@@ -172,6 +172,49 @@ def test_inference_bf16_assembly_matches_oracle_and_fp32_assembly(compact):
         assert (got[t] - yr1[t]).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("is_predict", [False, True])
+def test_native_forward_driver_equals_the_per_operator_path(is_predict):
+    """dmt_forward_bf16 issues the same entry points as the Python path: bit-identical scores -- for a resident dict
+    batch (pointer table from the tensors) and for a prefetched compact PackedBatch (base + feature_offsets)."""
+    from cikm2020_dmt_b200.data import PackedBatch
+    B = 300
+    plan, tc, host, dev, P, O = _setup("dmt_d64.conf", B, seed=43, precision="bf16")
+    assert tc.fwd_native
+
+    def run(inputs):
+        out = tc.inference(inputs, is_train=False, is_predict=is_predict)
+        torch.cuda.synchronize()
+        return tc.last_scores[:plan.num_tasks + (0 if is_predict else 1)].clone()
+
+    launches0 = tc.launches
+    native = run(dev)
+    assert tc.launches - launches0 == (10 if is_predict else 12)
+    keys = set(plan.all_id_features()) | {"features"}
+    pk = PackedBatch(host, compact=True, keys=keys)
+    staged_native = run(tc.prefetch(pk, views=False))
+    tc.fwd_native = False
+    python = run(dev)
+    staged_python = run(tc.prefetch(pk, views=False))
+    assert torch.equal(native, python)
+    assert torch.equal(staged_native, staged_python)
+    # compact batch: bf16 features / widened uint16 ids -- same ids, features rounded once either way
+    assert (native - staged_native).abs().max().item() < 3e-2
+    # a second batch size gets its own descriptor; a parameter change rebuilds it
+    tc.fwd_native = True
+    plan2, _, host2, dev2, _, _ = _setup("dmt_d64.conf", 64, seed=44, precision="bf16")
+    a = run(dev2)
+    tc.fwd_native = False
+    b = run(dev2)
+    assert torch.equal(a, b)
+    tc.fwd_native = True
+    tc.params.dense.mul_(1.01)
+    tc.invalidate_prepared()
+    c = run(dev)
+    tc.fwd_native = False
+    d = run(dev)
+    assert torch.equal(c, d) and not torch.equal(c, native)
+
+
 def test_new_entries_reject_bad_arguments():
     from cikm2020_dmt_b200 import abi
     lib = abi.load()
@@ -179,3 +222,6 @@ def test_new_entries_reject_bad_arguments():
     assert lib.dmt_pool_mean_fwd_bf16(4, 1, None, None, 8, None) == -1
     cfg = abi.MmoeCfg()
     assert lib.dmt_mmoe_fwd_bf16in(C.byref(cfg), None, None, 8, None, None, 0, None, None) == -1
+    assert lib.dmt_forward_bf16(None, 0, None, None, 0, None, None) == -1
+    desc = abi.FwdDesc()
+    assert lib.dmt_forward_bf16(C.byref(desc), 0, None, None, 0, None, None) == -1
