@@ -539,7 +539,11 @@ class mmoe_transformer_unbias(object):
                                                                 prep.data_ptr(), pbytes, stream))
                 self._prepared["mmoe"] = (self.params_version, prep)
             prep_ptr = prep.data_ptr()
-            launches = cfg.n_layers + 2
+            # fp32 input: conversion + gates, one GEMM per layer, head; bf16 input: the gates ride in the layer-0 GEMM;
+            # hidden_units_bottom = (x, 256, 128) with one tower layer: layers 2 + 3 + tower are one kernel + mixture
+            fused = (cfg.n_layers == 3 and cfg.units[1] == 256 and cfg.units[2] == 128 and cfg.n_tower_layers == 1
+                     and cfg.n_tasks * cfg.tower_units[0] <= 64)
+            launches = (0 if x.dtype == torch.bfloat16 else 1) + (3 if fused else cfg.n_layers + 1)
         fwd = self.lib.dmt_mmoe_fwd_bf16in if x.dtype == torch.bfloat16 else self.lib.dmt_mmoe_fwd
         with self._Stage(self, "mmoe", launches):
             abi.check(fwd(C.byref(cfg), C.byref(self._mmoe_w), x.data_ptr(), x.stride(0),

@@ -93,6 +93,39 @@ def test_demo_records_tensor_core_path_auc_within_1e3():
         assert abs(got.result()["auc"] - want.result()["auc"]) < 1e-3
 
 
+def test_demo_records_bf16_fused_path_auc_within_1e3():
+    """SURVEY 8c for the bf16 route (fused tcgen05 tile kernels, one launch over all sequences, bf16 MMoE assembly,
+    native forward driver): the demo records with the d_model-64 shape those kernels are built for -- logits within
+    the bf16 tolerance, click / order AUC within 1e-3 of the oracle's."""
+    from cikm2020_dmt_b200.data import batch_to
+    from cikm2020_dmt_b200.params import ParamStore
+    from cikm2020_dmt_b200.net.mmoe_transformer_unbias import mmoe_transformer_unbias
+    from cikm2020_dmt_b200 import metrics as M
+    from oracle import dmt_oracle as O
+    conf, plan = make_plan("dmt_demo_d64.conf")
+    assert (plan.d_model, plan.num_heads, plan.d_ff) == (64, 2, 256)
+    host, headers = _demo_batch(conf, plan)
+    store = ParamStore(plan, device="cuda", seed=2).randomize_(3)
+    model = mmoe_transformer_unbias(plan, params=store, precision="bf16")
+    assert model.seq_multi and model.x_bf16 and model.fwd_native
+    dev = batch_to(host, "cuda")
+    (click, order), y_bias = model.inference(dev, is_train=False)
+    loss, probs, _ = model.loss(((click, order), y_bias), dev["mask"], want_probs=True)
+    torch.cuda.synchronize()
+    (rc, ro), rb = O.inference(plan, O.params_from_store(store), host)
+    assert torch.allclose(click.double().cpu(), rc, atol=5e-2, rtol=2e-2)
+    assert torch.allclose(order.double().cpu(), ro, atol=5e-2, rtol=2e-2)
+    p_ctr, p_cvr = O.probabilities(((rc, ro), rb))
+    y_clk, y_ord = M.click_order_labels(host["mask"])
+    for y, got_p, want_p in ((y_clk, probs[0], p_ctr), (y_ord, probs[1], p_cvr)):
+        if not 0 < float(y.sum()) < y.numel():      # a label that never / always fires has no AUC
+            continue
+        got, want = M.StreamingBinaryMetrics(), M.StreamingBinaryMetrics()
+        got.update(y, got_p.cpu())
+        want.update(y, want_p.reshape(-1))
+        assert abs(got.result()["auc"] - want.result()["auc"]) < 1e-3
+
+
 def test_checkpoint_resume_is_exact(tmp_path):
     from cikm2020_dmt_b200 import checkpoint as CK
     from cikm2020_dmt_b200.data import synthetic_batch, batch_to
