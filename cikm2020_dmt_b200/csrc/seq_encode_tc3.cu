@@ -141,23 +141,12 @@ struct Tc2Layout {
   static constexpr int tCtx = 192;                      // [192,256): untouched by the next tile's X Wqkv
 };
 
-#define T2_TICK(idx)                                                    \
-  do {                                                                  \
-    if (a.dbg && tid == 0) {                                            \
-      const long long _now = clock64();                                 \
-      atomicAdd(a.dbg + (idx), (unsigned long long)(_now - t_last));    \
-      t_last = _now;                                                    \
-    }                                                                   \
-  } while (0)
-
-// KW: key columns of the score window the softmax actually visits (>= the longest sequence; 64-row slots only)
-
 // =====================================================================================================================
-// v3: the same per-tile program with every token row split across TWO threads (warps w and w + 4 of a group share
-// TMEM lane quarter w): 2 groups x 256 threads = 16 warps per SM at 128 registers.  v2 is limited by the dependent-
-// issue rate of 2 warps per scheduler (issue slots 30 % busy, no pipe above 40 %); v3 halves every thread's share
-// of the epilogues (half hf owns head hf / feature columns [32 hf, 32 hf + 32) / 4 of the 8 gather chunks) and
-// doubles the warps the schedulers can pick from.  LayerNorm and the decoder scores need the whole row: the two
+// The per-tile program: every token row is split across TWO threads (warps w and w + 4 of a group share
+// TMEM lane quarter w): 2 groups x 256 threads = 16 warps per SM at 128 registers.  One thread per row (v2, removed)
+// was limited by the dependent-issue rate of 2 warps per scheduler (issue slots 30 % busy, no pipe above 40 %); here
+// every thread has half the epilogue work (half hf owns head hf / feature columns [32 hf, 32 hf + 32) / 4 of the 8
+// gather chunks) and the schedulers have twice the warps to pick from.  LayerNorm and the decoder scores need the whole row: the two
 // halves exchange partial sums through 2 KB of (otherwise unused) shared memory inside the Q region.
 // TMEM plan per group (256 columns):  X Wqkv [0,192) -> S_0 [0,128) | S_1 [128,256) -> P_h in place [128h, +64),
 // O_h [128h+64, +32) -> A W1 [0,256) -> H packed by half hf IN PLACE inside ITS OWN 128 accumulator columns:
@@ -165,641 +154,18 @@ struct Tc2Layout {
 // =====================================================================================================================
 constexpr int kT3Threads = 512;
 
-template <int SLOT, int KW>
-__global__ void __launch_bounds__(kT3Threads, 1) seq_encode_tc3_kernel(const __grid_constant__ SeqTcArgs a) {
-  using L = Tc2Layout<SLOT>;
-  static_assert(KW % 8 == 0 && KW <= L::CW && (SLOT == 64 || KW == L::CW), "key window");
-  constexpr int D = kD, DFF = kDFF, H = kH, DK = kDK, KC = kKC, ROWB = kROWB;
-  constexpr int NS = L::NS, CW = L::CW, W = L::W, NR = L::NR, PPS = L::PPS;
-  constexpr int HC = KC / 2;                          // gather chunks per half
-  constexpr int tFF2 = 64;                            // H W2 accumulator (v3 plan)
-  constexpr int oExLN = 6144, oExSc = 4096;           // exchange scratch inside the Q region (see Tc2Layout aliases)
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[2], cbars[2], wbar;        // per group: phase MMAs | context MMA; weights landed
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int slen_s[2][2][NS];
-  __shared__ ChunkDesc sd[KC];
-  // partial-softmax maxima | denominators of the group's last tile.  NOT inside the Q image like the other decoder
-  // scratch: the two read-out warps read them in the shadow of the next tile's X Wqkv, and the first of them to
-  // finish goes on to rewrite the Q image
-  __shared__ float mxs_s[2][32];
-
-  const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, row = gt & 127, hf = gt >> 7;
-  const int wq = (gt >> 5) & 3, lane = tid & 31;      // wq: warp inside the half = TMEM lane quarter
-  uint8_t* gbase = smem + L::oGrp + grp * L::szGrp;
-  uint8_t* sXA = gbase + L::gXA;
-  uint8_t* sQ = gbase + L::gQ;
-  uint8_t* sK = gbase + L::gK;
-  float* fv = reinterpret_cast<float*>(smem + L::oFV);
-  const uint4* spos = reinterpret_cast<const uint4*>(smem + L::oPos);
-  uint64_t* bar = &bars[grp];
-  uint64_t* cbar = &cbars[grp];
-  const int B = a.cfg.batch;
-  const uint32_t bar_id = 1 + grp;
-
-  if (tid < 32) tmem_alloc(&tmem_base_s, 512);
-  if (tid < KC) {
-    const int f = a.chunk_feat[tid];
-    sd[tid].ids = a.in.ids[f];
-    sd[tid].offs = a.in.offsets[f];
-    sd[tid].item_ids = a.in.item_ids[f];
-    sd[tid].tab = a.in.table[f] + a.chunk_off[tid];
-    sd[tid].rows = a.in.rows[f];
-    sd[tid].dim = a.in.dim[f];
-    sd[tid].dup = (tid > 0 && (tid % HC) != 0 && f == a.chunk_feat[tid - 1]) ? 1 : 0;   // dup only inside a half
-  }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&cbars[0], 1);
-    mbar_init(&cbars[1], 1);
-    mbar_init(&wbar, 1);
-    mbar_fence_init();
-    // the 88 KB of weight images: one bulk async copy; only the MMA-issuing threads ever wait for it, so it
-    // overlaps the first tile's gather
-    mbar_expect_tx(&wbar, L::oGrp);
-    bulk_g2s(smem + L::oWqkv, a.prepared, L::oGrp, &wbar);
-  }
-  {
-    for (int i = tid; i < D; i += kT3Threads) {
-      fv[L::vBQKV + i] = a.bq[i];
-      fv[L::vBQKV + D + i] = a.bk[i];
-      fv[L::vBQKV + 2 * D + i] = a.bv[i];
-      fv[L::vB2 + i] = a.b2[i];
-      fv[L::vLN + 0 * D + i] = a.ln1_g[i];
-      fv[L::vLN + 1 * D + i] = a.ln1_b[i];
-      fv[L::vLN + 2 * D + i] = a.ln2_g[i];
-      fv[L::vLN + 3 * D + i] = a.ln2_b[i];
-    }
-    for (int i = tid; i < DFF; i += kT3Threads) fv[L::vB1 + i] = a.b1[i];
-    uint4* pdst = reinterpret_cast<uint4*>(smem + L::oPos);
-    for (int i = tid; i < a.cfg.maxlen * KC; i += kT3Threads) {
-      const float4 p0 = ldg4(a.pos + i * 8), p1 = ldg4(a.pos + i * 8 + 4);
-      const float f[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-      pdst[i] = f8_to_bf16(f);
-    }
-  }
-  fence_proxy_async();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = tmem_base_s + grp * 256;
-  const uint32_t aXA = smem_u32(sXA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(gbase + L::gV);
-  const uint32_t dHi = desc_hi(128, kLayoutNone), dHiV = desc_hi(ROWB, kLayoutNone);
-  const uint32_t dXA = desc_lo(aXA, ROWB), dQ = desc_lo(aQ, ROWB), dK = desc_lo(aK, ROWB);
-  const uint32_t dWqkv = desc_lo(smem_u32(smem + L::oWqkv), 3 * D * 16), dW1 = desc_lo(smem_u32(smem + L::oW1), DFF * 16),
-                 dW2 = desc_lo(smem_u32(smem + L::oW2), D * 16);
-  const __nv_bfloat16* gDec = a.prepared + prep_off_dec(D, DFF);
-  const uint4* gG = reinterpret_cast<const uint4*>(gDec);
-  const float* gGb = reinterpret_cast<const float*>(gDec + (size_t)H * D * D + (size_t)D * D);
-  const float sqrt_d = sqrtf((float)D);
-  const float sl2 = (1.0f / sqrtf((float)DK)) * 1.4426950408889634f;
-  const int32_t* const len_offs = a.in.offsets[a.cfg.n_feats - 1];
-  const int lmax = a.cfg.maxlen < SLOT ? a.cfg.maxlen : SLOT;
-  const int zp = a.cfg.zero_pad ? 1 : 0;
-  const int slot = row / SLOT, tpos = row % SLOT;
-  const int c0h = hf * HC;                             // first gather chunk / 8-column group of this half
-  uint32_t phase = 0;
-  // exchange slots: [row][half] pairs of floats
-  float2* exLN = reinterpret_cast<float2*>(sQ + oExLN);
-  float2* exSc = reinterpret_cast<float2*>(sQ + oExSc);
-
-  // ---- software-pipelined gather: this thread loads chunks c0h .. c0h+HC-1 of its token row ----
-  int pf_o0[HC], pf_o1[HC], pf_id[HC];
-  int pf_l0 = 0, pf_l1 = 0, pf_len = 0;
-  bool pf_valid = false;
-  f8 pf_e[HC];
-  int pf_tid = kInvalidId;
-  float4 pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_t1 = pf_t0;
-
-  auto stage_offsets = [&](int nt) {
-    pf_l0 = pf_l1 = 0;
-    pf_tid = kInvalidId;
-#pragma unroll
-    for (int k = 0; k < HC; ++k) pf_o0[k] = pf_o1[k] = 0;
-    if (nt >= a.n_tiles) return;
-    const int b = nt * NS + slot;
-    if (b < B) {
-      pf_l0 = __ldg(len_offs + b);
-      pf_l1 = __ldg(len_offs + b + 1);
-#pragma unroll
-      for (int k = 0; k < HC; ++k) {
-        if (k > 0 && sd[c0h + k].dup) {
-          pf_o0[k] = pf_o0[k - 1];
-          pf_o1[k] = pf_o1[k - 1];
-        } else {
-          const int32_t* of = sd[c0h + k].offs;
-          pf_o0[k] = __ldg(of + b);
-          pf_o1[k] = __ldg(of + b + 1);
-        }
-      }
-    }
-    if (gt < NS * KC) {
-      const int bt = nt * NS + gt / KC;
-      if (bt < B) pf_tid = __ldg(sd[gt % KC].item_ids + bt);
-    }
-  };
-  auto stage_ids = [&](int nt, int par) {
-    pf_len = min(pf_l1 - pf_l0, lmax);
-    pf_valid = tpos < pf_len;
-    if (tpos == 0 && hf == 0) slen_s[grp][par][slot] = pf_len;
-#pragma unroll
-    for (int k = 0; k < HC; ++k) {
-      pf_id[k] = kInvalidId;
-      if (pf_valid) {
-        if (k > 0 && sd[c0h + k].dup) pf_id[k] = pf_id[k - 1];
-        else pf_id[k] = (tpos < pf_o1[k] - pf_o0[k]) ? __ldg(sd[c0h + k].ids + pf_o0[k] + tpos) : 0;
-      }
-    }
-  };
-  auto stage_rows = [&]() {
-#pragma unroll
-    for (int k = 0; k < HC; ++k) {
-      pf_e[k].lo = make_float4(0.f, 0.f, 0.f, 0.f);
-      pf_e[k].hi = pf_e[k].lo;
-      const int64_t rw = (int64_t)pf_id[k] - zp;
-      if (pf_id[k] != kInvalidId && rw >= 0 && rw < sd[c0h + k].rows)
-        pf_e[k] = ld_stream8(sd[c0h + k].tab + rw * sd[c0h + k].dim);
-    }
-    pf_t0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    pf_t1 = pf_t0;
-    if (gt < NS * KC) {
-      const int c = gt % KC;
-      const int64_t rw = (int64_t)pf_tid - zp;
-      if (pf_tid != kInvalidId && rw >= 0 && rw < sd[c].rows) {
-        const f8 t = ld_stream8(sd[c].tab + rw * sd[c].dim);
-        pf_t0 = t.lo;
-        pf_t1 = t.hi;
-      }
-    }
-  };
-  // decoder contexts of the tile whose first sample is rb0.  The context MMA is issued TRANSPOSED (A = the memory
-  // image read MN-major, B = the 16-row probability image): accumulator row k = feature k, column (part, head), so
-  // the read-out is 16 values in each of 64 lanes (two warps) instead of 64 values in each of 8-16 lanes of one
-  // warp, and the two partial softmaxes of a 64-row slot sit in the same lane (no shuffles).
-  uint32_t cphase = 0;
-  auto ctx_readout = [&](int rb0) {
-    if (gt >= D) return;
-    mbar_wait(cbar, cphase);
-    cphase ^= 1;
-    fence_after_sync();
-    uint32_t c[16];
-    tmem_ld16(tmem_addr(tbase, L::tCtx), c);
-    tmem_ld_wait();
-    const float* mxs = mxs_s[grp];
-    const int kf = gt;                                 // feature column = TMEM lane
-    uint8_t* dst0 = reinterpret_cast<uint8_t*>(a.ctx) + (size_t)(kf >> 3) * (128 * 16) + (kf & 7) * 2;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int b = rb0 + s;
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float num, den;
-        if constexpr (PPS == 2) {
-          const int ia = (2 * s) * H + h, ib = (2 * s + 1) * H + h;
-          const float ma = mxs[ia], mb = mxs[ib];
-          const float m = fmaxf(ma, mb);
-          const float wa = (ma == -INFINITY) ? 0.f : ex2_approx(ma - m), wb = (mb == -INFINITY) ? 0.f : ex2_approx(mb - m);
-          num = __uint_as_float(c[ia]) * wa + __uint_as_float(c[ib]) * wb;
-          den = mxs[NR + ia] * wa + mxs[NR + ib] * wb;
-        } else {
-          num = __uint_as_float(c[s * H + h]);
-          den = mxs[NR + s * H + h];
-        }
-        const float v = den > 0.f ? num / den : 0.f;    // empty sequence: context 0
-        if (b < B)
-          *reinterpret_cast<unsigned short*>(dst0 + (size_t)(b >> 7) * (128 * H * D * 2) + (size_t)(h * KC) * (128 * 16) +
-                                             (size_t)(b & 127) * 16) = __bfloat16_as_ushort(__float2bfloat16(v));
-      }
-    }
-    fence_before_sync();
-  };
-  // concat + sqrt(d) scale + learned position -> bf16, in registers: done early (in an MMA shadow) so that P0 is
-  // four stores
-  uint4 px[HC];
-  auto convert_rows = [&]() {
-#pragma unroll
-    for (int k = 0; k < HC; ++k) {
-      float x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = 0.f;
-      if (pf_valid) {
-        float p[8];
-        bf16x8_to_f(spos[tpos * KC + c0h + k], p);
-        x[0] = fmaf(pf_e[k].lo.x, sqrt_d, p[0]); x[1] = fmaf(pf_e[k].lo.y, sqrt_d, p[1]);
-        x[2] = fmaf(pf_e[k].lo.z, sqrt_d, p[2]); x[3] = fmaf(pf_e[k].lo.w, sqrt_d, p[3]);
-        x[4] = fmaf(pf_e[k].hi.x, sqrt_d, p[4]); x[5] = fmaf(pf_e[k].hi.y, sqrt_d, p[5]);
-        x[6] = fmaf(pf_e[k].hi.z, sqrt_d, p[6]); x[7] = fmaf(pf_e[k].hi.w, sqrt_d, p[7]);
-      }
-      px[k] = f8_to_bf16(x);
-    }
-  };
-  int n_done = 0;
-  const int tile0 = blockIdx.x * 2 + grp, tstride = 2 * gridDim.x;
-  stage_offsets(tile0);
-  stage_ids(tile0, 0);
-  stage_rows();
-  convert_rows();
-
-  long long t_last = clock64();
-  for (int it = 0;; ++it) {
-    const int tile = tile0 + it * tstride;
-    if (tile >= a.n_tiles) break;
-    const int par = it & 1;
-    const int b0 = tile * NS;
-    const int next_tile = tile + tstride;
-
-    // ---- P0: this half's four (already converted) chunks -> X image ----
-#pragma unroll
-    for (int k = 0; k < HC; ++k) *reinterpret_cast<uint4*>(sXA + (c0h + k) * ROWB + row * 16) = px[k];
-    const float4 cur_t0 = pf_t0, cur_t1 = pf_t1;
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(0);
-
-    // ---- P1: [Q|K|V] = X Wqkv ----
-    if (gt == 0) {
-      if (it == 0) mbar_wait(&wbar, 0);              // weight images landed (bulk copy issued in the prologue)
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 3 * D);
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tQKV, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
-                    desc_join(dWqkv + ks * (2 * 3 * D), dHi), idesc, ks > 0);
-      commit(bar);
-    }
-    if (it > 0) ctx_readout(b0 - tstride * NS);
-    stage_offsets(next_tile);
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(1);
-
-    // ---- P2: + bias, bf16 -> Q / K / V images; half hf converts columns [96 hf, 96 hf + 96) ----
-#pragma unroll 1
-    for (int blk = 0; blk < 3; ++blk) {
-      const int n0 = hf * 96 + blk * 32;
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, L::tQKV + n0), r);
-      tmem_ld_wait();
-      const int m = n0 >> 6;                           // 0: Q, 1: K, 2: V image
-      uint8_t* dstm = sQ + m * 16384 + row * 16;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n0 + g * 8;
-        const float4 ba = *reinterpret_cast<const float4*>(fv + L::vBQKV + n);
-        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vBQKV + n + 4);
-        float y[8];
-        y[0] = __uint_as_float(r[g * 8 + 0]) + ba.x; y[1] = __uint_as_float(r[g * 8 + 1]) + ba.y;
-        y[2] = __uint_as_float(r[g * 8 + 2]) + ba.z; y[3] = __uint_as_float(r[g * 8 + 3]) + ba.w;
-        y[4] = __uint_as_float(r[g * 8 + 4]) + bb.x; y[5] = __uint_as_float(r[g * 8 + 5]) + bb.y;
-        y[6] = __uint_as_float(r[g * 8 + 6]) + bb.z; y[7] = __uint_as_float(r[g * 8 + 7]) + bb.w;
-        const int ch = ((n0 & 63) >> 3) + g;
-        *reinterpret_cast<uint4*>(dstm + ch * ROWB) = f8_to_bf16(y);
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(2);
-
-    // ---- P3: S_h = Q_h K_h^T ----
-    if (gt == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-#pragma unroll
-      for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int ks = 0; ks < DK / 16; ++ks) {
-          const uint32_t ch = (h * DK) / 8 + ks * 2;
-          mma_bf16_ss(tbase + L::tS + h * 128, desc_join(dQ + ch * (ROWB / 16), dHi),
-                      desc_join(dK + ch * (ROWB / 16), dHi), idesc, ks > 0);
-        }
-      commit(bar);
-    }
-    stage_ids(next_tile, par ^ 1);
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(3);
-
-    // ---- P4: masked softmax of head hf; unnormalised P_hf packed IN PLACE ----
-    const int len = slen_s[grp][par][slot];
-    float inv_h = 0.f;
-    {
-      const int col0 = (row / CW) * CW;
-      const int lo = (SLOT == CW) ? 0 : slot * SLOT - col0;
-      const uint32_t sbase = tmem_addr(tbase, L::tS + hf * 128);
-      uint32_t r[CW];
-      tmem_ld32(sbase + col0, r);
-      if constexpr (KW >= 48) tmem_ld16(sbase + col0 + 32, r + 32);
-      if constexpr (KW == 56) tmem_ld8(sbase + col0 + 48, r + 48);
-      if constexpr (KW == 64) tmem_ld16(sbase + col0 + 48, r + 48);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < KW; ++j) {
-        const bool ok = (unsigned)(j - lo) < (unsigned)len;
-        const float v = ok ? __uint_as_float(r[j]) : -INFINITY;
-        r[j] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
-      }
-      const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < KW; j += 4) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -mxs));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), sl2, -mxs));
-        const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), sl2, -mxs));
-        const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), sl2, -mxs));
-        s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-        r[j / 2] = pack_bf16x2(e0, e1);                 // (j/2 <= j: the packed words trail the reads)
-        r[j / 2 + 1] = pack_bf16x2(e2, e3);
-      }
-      const float sum = (s0 + s1) + (s2 + s3);
-      inv_h = sum > 0.f ? 1.0f / sum : 0.f;
-#pragma unroll
-      for (int j = KW / 2; j < CW; ++j) r[j] = 0u;
-      if constexpr (CW == 64) {
-        tmem_st32(sbase + col0 / 2, r);
-        tmem_st32(sbase + (32 - col0 / 2), r + 32);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q * 16 == col0 / 2) tmem_st16(sbase + q * 16, r);
-          else tmem_st16(sbase + q * 16, r + 16);
-        }
-      }
-    }
-    if (gt < NS * KC) {
-      float* dv = reinterpret_cast<float*>(gbase + L::gDvec) + (gt / KC) * D + (gt % KC) * 8;
-      *reinterpret_cast<float4*>(dv) = make_float4(cur_t0.x * sqrt_d, cur_t0.y * sqrt_d, cur_t0.z * sqrt_d, cur_t0.w * sqrt_d);
-      *reinterpret_cast<float4*>(dv + 4) = make_float4(cur_t1.x * sqrt_d, cur_t1.y * sqrt_d, cur_t1.z * sqrt_d, cur_t1.w * sqrt_d);
-    }
-    tmem_st_wait();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(4);
-
-    // ---- P5: O_h = P_h V_h ----
-    if (gt == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, DK, false, true);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const uint32_t dV = desc_lo(aV + ((h * DK) / 8) * ROWB, 128);
-#pragma unroll
-        for (int ks = 0; ks < 128 / 16; ++ks)
-          mma_bf16_ts(tbase + L::tO + h * 128, tbase + L::tS + h * 128 + ks * 8,
-                      desc_join(dV + ks * (256 / 16), dHiV), idesc, ks > 0);
-      }
-      commit(bar);
-    }
-    // folded decoder queries qt[s][n] = dvec[s] . G[n] + g[n]: thread (n = row, hf) computes the samples s = hf,
-    // hf + 2, ...; the contraction is split between the shadows of the P.V and the H.W2 MMAs
-    constexpr int NSH = NS / 2;
-    float qacc[NSH];
-    auto qt_part = [&](int jc0) {
-      const float* dvs = reinterpret_cast<const float*>(gbase + L::gDvec);
-#pragma unroll
-      for (int jc = jc0; jc < jc0 + KC / 2; ++jc) {
-        float w[8];
-        bf16x8_to_f(__ldg(gG + jc * (H * D) + row), w);
-#pragma unroll
-        for (int s = 0; s < NSH; ++s) {
-          const float4 d0 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8);
-          const float4 d1 = *reinterpret_cast<const float4*>(dvs + (2 * s + hf) * D + jc * 8 + 4);
-          qacc[s] = fmaf(d0.x, w[0], fmaf(d0.y, w[1], fmaf(d0.z, w[2], fmaf(d0.w, w[3], qacc[s]))));
-          qacc[s] = fmaf(d1.x, w[4], fmaf(d1.y, w[5], fmaf(d1.z, w[6], fmaf(d1.w, w[7], qacc[s]))));
-        }
-      }
-    };
-    {
-      const float gb = __ldg(gGb + row);
-#pragma unroll
-      for (int s = 0; s < NSH; ++s) qacc[s] = gb;
-      qt_part(0);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(5);
-
-    // ---- P6: A = LN(O + X): half hf owns columns [32 hf, 32 hf + 32) = head hf ----
-    {
-      float y[DK];
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, L::tO + hf * 128), r);
-#pragma unroll
-      for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
-      tmem_ld_wait();
-      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < DK; e += 2) {
-        y[e] = fmaf(__uint_as_float(r[e]), inv_h, y[e]);
-        y[e + 1] = fmaf(__uint_as_float(r[e + 1]), inv_h, y[e + 1]);
-        s0 += y[e]; s1 += y[e + 1];
-        q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
-      }
-      exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
-      named_sync(bar_id, 256);
-      const float2 o = exLN[row * 2 + (hf ^ 1)];
-      const float mean = ((s0 + s1) + o.x) * (1.0f / D);
-      const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
-      const float rstd = 1.0f / sqrtf(var + kLnEps);
-      const float* g = fv + L::vLN + 0 * D + hf * DK;
-      const float* bt = fv + L::vLN + 1 * D + hf * DK;
-#pragma unroll
-      for (int e = 0; e < DK; e += 4) {
-        const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
-        y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
-        y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
-        y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
-        y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
-      }
-#pragma unroll
-      for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sXA + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(6);
-
-    // ---- P7: hidden = A W1 ----
-    if (gt == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, DFF);
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks)
-        mma_bf16_ss(tbase + L::tFF1, desc_join(dXA + ks * (2 * ROWB / 16), dHi),
-                    desc_join(dW1 + ks * (2 * DFF), dHi), idesc, ks > 0);
-      commit(bar);
-    }
-    stage_rows();
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(7);
-
-    // ---- P8: relu(+b1): half hf packs accumulator columns [128 hf, 128 hf + 128) into [128 hf, 128 hf + 64) ----
-#pragma unroll 1
-    for (int blk = 0; blk < 4; ++blk) {
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 32), r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 bb = *reinterpret_cast<const float4*>(fv + L::vB1 + hf * 128 + blk * 32 + g * 4);
-        pk[g * 2] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4]) + bb.x, 0.f), fmaxf(__uint_as_float(r[g * 4 + 1]) + bb.y, 0.f));
-        pk[g * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(r[g * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[g * 4 + 3]) + bb.w, 0.f));
-      }
-      tmem_st16(tmem_addr(tbase, L::tFF1 + hf * 128 + blk * 16), pk);
-    }
-    tmem_st_wait();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(8);
-
-    // ---- P9: F = H W2; the K = 256 A operand is two 64-column pieces of tensor memory ----
-    if (gt == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, D);
-#pragma unroll
-      for (int ks = 0; ks < DFF / 16; ++ks)
-        mma_bf16_ts(tbase + tFF2, tbase + L::tFF1 + (ks / 8) * 128 + (ks % 8) * 8, desc_join(dW2 + ks * (2 * D), dHi),
-                    idesc, ks > 0);
-      commit(bar);
-    }
-    convert_rows();                                      // next tile's rows (requested in P7) -> bf16 registers
-    {
-      qt_part(KC / 2);
-      float* qt = reinterpret_cast<float*>(gbase + L::gQt);
-#pragma unroll
-      for (int s = 0; s < NSH; ++s) qt[(2 * s + hf) * (H * D) + row] = qacc[s];
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    fence_after_sync();
-    T2_TICK(9);                                          // (qt is read after P10's LayerNorm-exchange barrier)
-
-    // ---- P10: memory = LN(F + b2 + A); decoder scores; partial softmax of head hf; images for the context MMA ----
-    {
-      float y[DK];
-      uint32_t r[32];
-      tmem_ld32(tmem_addr(tbase, tFF2 + hf * DK), r);
-#pragma unroll
-      for (int c = 0; c < HC; ++c) bf16x8_to_f(*reinterpret_cast<const uint4*>(sXA + (c0h + c) * ROWB + row * 16), y + c * 8);
-      tmem_ld_wait();
-      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < DK; e += 2) {
-        y[e] += __uint_as_float(r[e]) + fv[L::vB2 + hf * DK + e];
-        y[e + 1] += __uint_as_float(r[e + 1]) + fv[L::vB2 + hf * DK + e + 1];
-        s0 += y[e]; s1 += y[e + 1];
-        q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1);
-      }
-      exLN[row * 2 + hf] = make_float2(s0 + s1, q0 + q1);
-      named_sync(bar_id, 256);
-      {
-        const float2 o = exLN[row * 2 + (hf ^ 1)];
-        const float mean = ((s0 + s1) + o.x) * (1.0f / D);
-        const float var = fmaxf(((q0 + q1) + o.y) * (1.0f / D) - mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + kLnEps);
-        const float* g = fv + L::vLN + 2 * D + hf * DK;
-        const float* bt = fv + L::vLN + 3 * D + hf * DK;
-#pragma unroll
-        for (int e = 0; e < DK; e += 4) {
-          const float4 gg = *reinterpret_cast<const float4*>(g + e), bb = *reinterpret_cast<const float4*>(bt + e);
-          y[e] = fmaf(gg.x, (y[e] - mean) * rstd, bb.x);
-          y[e + 1] = fmaf(gg.y, (y[e + 1] - mean) * rstd, bb.y);
-          y[e + 2] = fmaf(gg.z, (y[e + 2] - mean) * rstd, bb.z);
-          y[e + 3] = fmaf(gg.w, (y[e + 3] - mean) * rstd, bb.w);
-        }
-      }
-      // memory image: this half's four chunks
-#pragma unroll
-      for (int c = 0; c < HC; ++c) *reinterpret_cast<uint4*>(sK + (c0h + c) * ROWB + row * 16) = f8_to_bf16(y + c * 8);
-      // partial decoder scores over this half's 32 columns, both heads; exchanged with the other half
-      const float* qt = reinterpret_cast<const float*>(gbase + L::gQt) + slot * (H * D) + hf * DK;
-      float pu[H];
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < DK; k += 4) {
-          const float4 q = *reinterpret_cast<const float4*>(qt + h * D + k);
-          a0 = fmaf(y[k], q.x, a0); a1 = fmaf(y[k + 1], q.y, a1);
-          a0 = fmaf(y[k + 2], q.z, a0); a1 = fmaf(y[k + 3], q.w, a1);
-        }
-        pu[h] = a0 + a1;
-      }
-      exSc[row * 2 + hf] = make_float2(pu[0], pu[1]);
-      named_sync(bar_id, 256);
-      const float2 os = exSc[row * 2 + (hf ^ 1)];
-      // this half finishes head hf
-      const float dot = (hf == 0 ? pu[0] + os.x : pu[1] + os.y);
-      const float u = (tpos < len) ? dot * sl2 : -INFINITY;
-      const int part = (SLOT >= 32) ? wq : (wq * (32 / W) + lane / W);
-      float m = u;
-#pragma unroll
-      for (int o = W / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      float e = (tpos < len) ? ex2_approx(u - m) : 0.f;
-      e = __bfloat162float(__float2bfloat16(e));
-      float dsum = e;
-#pragma unroll
-      for (int o = W / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-      if ((lane % W) == 0) {
-        mxs_s[grp][part * H + hf] = m;
-        mxs_s[grp][NR + part * H + hf] = dsum;
-      }
-      // transposed probabilities: rows (p, hf) for every part p, column = this token
-      const unsigned short eb = __bfloat16_as_ushort(__float2bfloat16(e));
-      uint8_t* pd = gbase + L::gPd + (row >> 3) * 256 + (row & 7) * 2 + hf * 16;
-#pragma unroll
-      for (int p = 0; p < NR / H; ++p)
-        *reinterpret_cast<unsigned short*>(pd + p * (H * 16)) = (p == part) ? eb : (unsigned short)0;
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    named_sync(bar_id, 256);
-    T2_TICK(10);
-
-    // ---- P11: context MMA, transposed: D[feature][(part, head)] = sum_t M_t[feature] e_t  (A = memory image read
-    //      MN-major, B = the compact probability image); read out in the shadow of the next tile's X Wqkv ----
-    if (gt == 0) {
-      fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 16, true, false);
-      const uint32_t dPd = desc_lo(smem_u32(gbase + L::gPd), 256), dM = desc_lo(aK, 128);
-#pragma unroll
-      for (int ks = 0; ks < 128 / 16; ++ks)
-        mma_bf16_ss(tbase + L::tCtx, desc_join(dM + ks * (256 / 16), dHiV), desc_join(dPd + ks * (2 * 256 / 16), dHi),
-                    idesc, ks > 0);
-      commit(cbar);
-    }
-    n_done = it + 1;
-    T2_TICK(11);
-  }
-
-  if (n_done > 0) ctx_readout((tile0 + (n_done - 1) * tstride) * NS);
-  fence_before_sync();
-  __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem_base_s, 512);
-}
-
 // =====================================================================================================================
 // One launch for ALL behaviour sequences, with length-bucketed tiles (round 2).
 //
-// The per-sequence launches above pad every sample to the slot size of the batch's LONGEST sequence (64 rows for
-// dmt.conf's 50-token histories although the mean length is 34: ~47 % of every MMA / softmax / LayerNorm row is
-// padding) and pay the pipeline ramp (weight images, first gather, last read-out) and the wave quantisation of a
-// persistent grid three times.  Here `seq_bucket_kernel` first orders the samples of every sequence by length class
+// Round 1 launched this kernel once per sequence and padded every sample to the slot size of the batch's LONGEST
+// sequence (64 rows for dmt.conf's 50-token histories although the mean length is 34: ~47 % of every MMA / softmax /
+// LayerNorm row was padding), paying the pipeline ramp (weight images, first gather, last read-out) and the wave
+// quantisation of a persistent grid three times.  Now `seq_bucket_kernel` first orders the samples of every sequence by length class
 // (> 32 | 17..32 | <= 16 tokens; `perm`, `counts` in the per-sequence workspace -- no host round trip), and ONE
 // persistent kernel walks the concatenated tile list of all (sequence, class) SEGMENTS: 2 / 4 / 8 samples per 128-row
 // tile.  Global tile g belongs to tile group (g mod 2*gridDim.x); a group runs the per-tile program of the segment's
-// slot size (the three instantiations of the generic lambda below: same memory plan, same tensor-memory plan), drains
+// slot size (the three instantiations of the generic lambda below: same memory plan, same tensor-memory plan; KW = the
+// key columns of the score window the softmax of a 64-row slot visits, >= the longest sequence), drains
 // its software pipeline at a segment boundary and, at a SEQUENCE boundary, the whole CTA swaps the 88 KB of weight
 // images / biases / positions / gather descriptors.
 // =====================================================================================================================
@@ -910,7 +276,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
   __shared__ uint32_t tmem_base_s;
   __shared__ int slen_s[2][2][8];
   __shared__ ChunkDesc sd[KC];
-  __shared__ float mxs_s[2][32];                      // (see seq_encode_tc3_kernel)
+  // partial-softmax maxima | denominators of the group's last tile.  NOT inside the Q image like the other decoder
+  // scratch: the read-out warps read them in the shadow of the next tile's X Wqkv, and the first of them to finish goes
+  // on to rewrite the Q image
+  __shared__ float mxs_s[2][32];
 
   const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, row = gt & 127, hf = gt >> 7;
   const int wq = (gt >> 5) & 3, lane = tid & 31;      // wq: warp inside the half = TMEM lane quarter
@@ -1793,29 +1162,6 @@ int launch_tails(const TailBatch& tb, cudaStream_t st) {
   return DMT_OK;
 }
 
-template <int SLOT, int KW>
-int launch_tc2(const SeqTcArgs& a, bool defer_tail, cudaStream_t st) {
-  using L = Tc2Layout<SLOT>;
-  const int total = L::oPos + a.cfg.maxlen * kD * 2 + 64;
-  const int sms = sm_count_cached();
-  const int pairs = (a.n_tiles + 1) / 2;
-  const int grid = pairs < sms ? pairs : sms;
-  {
-    auto kern = seq_encode_tc3_kernel<SLOT, KW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_encode_tc3_kernel)");
-    kern<<<grid, kT3Threads, total, st>>>(a);
-    DMT_CUDA_LAUNCH_CHECK("seq_encode_tc3_kernel");
-  }
-  if (defer_tail) return DMT_OK;
-  TailBatch tb;
-  tb.a[0] = a;
-  tb.n_seq = 1;
-  tb.first_tile[0] = 0;
-  tb.first_tile[1] = (a.cfg.batch + 127) / 128;
-  return launch_tails(tb, st);
-}
-
 }  // namespace
 
 // shared-memory budget of the v2 kernel: the position table is the only size that depends on the configuration
@@ -1825,27 +1171,6 @@ bool seq_tc2_supported(const dmt_seq_cfg* cfg) {
 
 // decoder contexts: one bf16 A-operand image (128 samples x H*D) per tail tile
 size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg) { return (size_t)((cfg->batch + 127) / 128) * (128 * kH * kD * 2) + 256; }
-
-int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st) {
-  const dmt_seq_cfg* cfg = &a.cfg;
-  const bool defer = (cfg->flags & DMT_SEQ_DEFER_TAIL) != 0;
-  int slot = cfg->slot_len > 0 ? cfg->slot_len : cfg->maxlen;
-  if (slot > cfg->maxlen) slot = cfg->maxlen;
-  DMT_REQUIRE(slot <= 64, DMT_ERR_UNSUPPORTED_SHAPE, "dmt_seq_encode_fwd(bf16): sequences longer than 64 (%d)", slot);
-  if (slot <= 16) {
-    a.n_tiles = (cfg->batch + 7) / 8;
-    return launch_tc2<16, 32>(a, defer, st);
-  }
-  if (slot <= 32) {
-    a.n_tiles = (cfg->batch + 3) / 4;
-    return launch_tc2<32, 32>(a, defer, st);
-  }
-  a.n_tiles = (cfg->batch + 1) / 2;
-  const int lmax = cfg->maxlen < 64 ? cfg->maxlen : 64;   // no key beyond the longest possible sequence
-  if (lmax <= 48) return launch_tc2<64, 48>(a, defer, st);
-  if (lmax <= 56) return launch_tc2<64, 56>(a, defer, st);
-  return launch_tc2<64, 64>(a, defer, st);
-}
 
 // dmt_seq_tail_fwd: the deferred tails of several sequences, one launch
 int seq_tails_launch(int n, const SeqTcArgs* args, cudaStream_t st) {
@@ -1901,7 +1226,7 @@ size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg) { return ((size_t)cfg->batch *
 
 // dmt_seq_encode_multi_fwd: every behaviour sequence of the step -- length classes, ONE tile-kernel launch, one tail
 // launch
-int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, cudaStream_t st) {
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaStream_t st) {
   SeqMultiArgs m;
   BucketArgs ba;
   memset(&m, 0, sizeof(m));
@@ -1942,6 +1267,7 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, c
   kern<<<grid, kT3Threads, total, st>>>(m);
   if (timed) cudaEventRecord(g_seq_timer.e1[g_seq_timer.n++], st);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_multi_kernel");
+  if (defer_tail) return DMT_OK;
   return seq_tails_launch(n, args, st);
 }
 

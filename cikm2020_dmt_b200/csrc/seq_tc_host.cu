@@ -91,13 +91,12 @@ size_t seq_tc_prepared_bytes(const dmt_seq_cfg* cfg) {
   return (prep_total(cfg->d_model, cfg->d_ff, cfg->num_heads) * 2 + 511) / 256 * 256;
 }
 
-// v2 (seq_encode_tc3.cu)
+// seq_encode_tc3.cu
 bool seq_tc2_supported(const dmt_seq_cfg* cfg);
 size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg);
-int seq_encode_tc2_launch(SeqTcArgs& a, cudaStream_t st);
 
 size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg);
-int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, cudaStream_t st);
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaStream_t st);
 
 // workspace = [prepared weight images | decoder-context images | length-class schedule (perm, counts)]
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg) {
@@ -176,14 +175,16 @@ int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* con
     fill_args(cfgs[i], ins[i], ws[i], outs[i], out_lds[i], workspaces[i], args[i]);
     scheds[i] = static_cast<uint8_t*>(workspaces[i]) + seq_tc_prepared_bytes(cfgs[i]) + seq_tc2_ctx_bytes(cfgs[i]);
   }
-  return seq_encode_multi_launch(n, args, scheds, st);
+  return seq_encode_multi_launch(n, args, scheds, false, st);
 }
 
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
                          int64_t out_ld, void* workspace, cudaStream_t st) {
+  // one sequence = a one-sequence launch of the multi-sequence kernel (length classes included)
   SeqTcArgs a;
   fill_args(cfg, in, w, out, out_ld, workspace, a);
-  return seq_encode_tc2_launch(a, st);
+  void* sched = static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg) + seq_tc2_ctx_bytes(cfg);
+  return seq_encode_multi_launch(1, &a, &sched, (cfg->flags & DMT_SEQ_DEFER_TAIL) != 0, st);
 }
 
 }  // namespace dmt

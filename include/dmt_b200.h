@@ -97,7 +97,7 @@ typedef struct dmt_ff_weights {
 
 /* dmt_seq_cfg.flags (bf16 path): leave the decoder tail (ctx Wv + residual -> LN -> FF -> LN) of this call to a
  * later dmt_seq_tail_fwd, which runs the tails of several sequences as ONE launch.  Without the bit,
- * dmt_seq_encode_fwd is self-contained. */
+ * dmt_seq_encode_fwd is self-contained (three launches: length classes, tile kernel, tails). */
 #define DMT_SEQ_DEFER_TAIL 1
 /* dmt_seq_cfg.flags: the caller guarantees that NO sequence of the batch is longer than min(slot_len, maxlen) (it
  * knows the lengths: they came through its host memory).  Lets the training pipeline cut whole-sample tiles out of
@@ -120,9 +120,11 @@ typedef struct dmt_seq_cfg {
                            (base.py:87-89); 0: index i reads row i                    */
   int32_t n_feats;      /* pairs in this sequence's attention_embed group             */
   int32_t precision;    /* dmt_precision                                              */
-  int32_t slot_len;     /* upper bound on the sequence lengths in THIS batch (0 = maxlen);
-                           the bf16 path packs 128/slot samples per tile (slot = 16/32/64)
-                           and truncates longer sequences to it                        */
+  int32_t slot_len;     /* upper bound on the sequence lengths in THIS batch (0 = maxlen): sizes the
+                           slot tiles of the training pipeline's tensor-core attention (with
+                           DMT_SEQ_LEN_EXACT).  The bf16 inference kernels no longer need it: they
+                           pick a 16 / 32 / 64-row slot per SAMPLE on the device and truncate
+                           sequences longer than maxlen, like the reference's position table  */
   int32_t flags;        /* DMT_SEQ_* bits (0 = none)                                 */
   /* training entry points only (dmt_seq_encode_fwd_train / _bwd): transformer_dropout_rate applied at the
      encoder input, the decoder input and the attention probabilities (TransformerModel.py:101,151;
@@ -576,9 +578,12 @@ DMT_API int dmt_selftest_tf32_wgrad(const float* P, int64_t ldp, const float* Q,
 DMT_API int dmt_selftest_tf32_colsum(const float* X, int64_t ldx, int64_t T, int32_t W, float* out,
                                      int32_t accumulate, void* scratch, void* stream);
 
-/* Diagnostics: when `device_counters` (16 x uint64 on the device) is non-NULL, the bf16 sequence kernel
- * adds the SM cycles thread 0 of every CTA spends in each of its phases (gather-convert, QKV MMA, QKV
- * epilogue, ... decoder).  Pass NULL to switch it off.  Process-wide debug switch, not for production. */
+/* Diagnostics: when `device_counters` (2048 x uint64 on the device, zeroed by the caller) is non-NULL, the bf16
+ * sequence kernel runs its instrumented instantiation: [16 q + phase] SM cycles thread 0 of every CTA spends in each
+ * phase of sequence q (gather-convert, QKV MMA, QKV epilogue, ... decoder; 12 = pipeline prime, 13 = drain, 14 = tiles,
+ * 15 = sequence prologue), [64 + cta] cycles of the whole CTA, [320 + cta] / [576 + cta] %globaltimer at entry / exit,
+ * [1024 + 128 group + 16 tile + phase] the phase timeline of both tile groups of CTA 0 (first six tiles).  Pass NULL
+ * to switch it off.  Process-wide debug switch, not for production. */
 DMT_API int dmt_debug_seq_profile(void* device_counters);
 /* diagnostics: CUDA events around every seq_encode_multi_kernel launch (on its launch stream) while enabled;
  * _read waits for them and returns their summed duration and count (then keeps collecting). */
