@@ -743,8 +743,9 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(out_host[0].numel() * 4), "ms_per_step": ms_e2e / args.steps,
-                "format": ("compact pinned batch: uint16 ids for vocabularies < 65536, bf16 features, inference keys "
-                           "only; widened on the device by dmt_widen_u16 (1 launch, copy stream)") if compact else
+                "format": ("compact pinned batch: ids in the narrowest byte width (1: time buckets, 2: vocabularies "
+                           "< 65536, 3: Sku / Brand / Shopid < 2^24), bf16 features, inference keys only; widened on the "
+                           "device by dmt_widen_ids (1 launch, copy stream)") if compact else
                           "int32 ids + fp32 features, one pinned buffer",
                 "pinned_numa_node": numa_node,
                 "pipeline": "prefetch two batches deep (three rotating device buffers): step i+2's packed batch is "

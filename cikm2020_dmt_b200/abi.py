@@ -110,6 +110,10 @@ class WidenDesc(C.Structure):
     _fields_ = [("src", _fp), ("dst", _fp), ("n", C.c_int64)]
 
 
+class WidenIdsDesc(C.Structure):
+    _fields_ = [("src", _fp), ("dst", _fp), ("n", C.c_int64), ("bytes", C.c_int32), ("_pad", C.c_int32)]
+
+
 class AdamCfg(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
                 ("step", C.c_int32), ("kind", C.c_int32)]
@@ -196,6 +200,7 @@ PROTOTYPES = {
     "dmt_adam_rows_untouched_multi": (C.c_int, [C.POINTER(AdamCfg), C.c_int32, C.POINTER(AdamTable), _fp]),
     "dmt_build_digest": (C.c_char_p, []),
     "dmt_widen_u16": (C.c_int, [C.c_int32, C.POINTER(WidenDesc), _fp]),
+    "dmt_widen_ids": (C.c_int, [C.c_int32, C.POINTER(WidenIdsDesc), _fp]),
     "dmt_copy_dense_features_bf16": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, C.c_int64, _fp]),
     "dmt_debug_seq_profile": (C.c_int, [_fp]),
     "dmt_debug_seq_timer": (C.c_int, [C.c_int32]),

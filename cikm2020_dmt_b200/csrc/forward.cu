@@ -15,6 +15,8 @@
 // No device work of its own: results are those of the individual calls.
 #include <string.h>
 
+#include <mutex>
+
 #include "dmt_common.cuh"
 
 namespace dmt {
@@ -27,6 +29,7 @@ struct FwdStreams {
 };
 constexpr int kMaxDevices = 64;
 FwdStreams g_fwd[kMaxDevices];
+std::mutex g_fwd_mutex;      // guards the lazy creation; the streams themselves serve ONE caller per device at a time
 
 int fwd_streams(FwdStreams** out) {
   int dev = 0;
@@ -34,6 +37,7 @@ int fwd_streams(FwdStreams** out) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice(dmt_forward_bf16)");
   DMT_REQUIRE(dev >= 0 && dev < kMaxDevices, DMT_ERR_INVALID_ARGUMENT, "dmt_forward_bf16: device %d", dev);
   FwdStreams& s = g_fwd[dev];
+  std::lock_guard<std::mutex> lock(g_fwd_mutex);
   if (!s.ready) {
     // The sequence stream has the highest priority: its persistent tile kernel needs whole SMs, and the short CTAs of
     // the dense / pooled / bias kernels that start beside it would otherwise keep it from becoming resident (its

@@ -38,6 +38,59 @@ __global__ void __launch_bounds__(256) widen_u16_kernel(const __grid_constant__ 
   }
 }
 
+struct WidenIdsArgs {
+  dmt_widen_ids_desc d[DMT_MAX_WIDEN];
+  int32_t n;
+};
+
+// 1- / 2- / 3-byte little-endian ids -> int32: blockIdx.y = array; a thread widens 16 consecutive ids (16 / 32 / 48
+// source bytes as 16-byte loads, four 16-byte stores); arrays start on 256-byte boundaries; the ragged tail is bytewise.
+__global__ void __launch_bounds__(256) widen_ids_kernel(const __grid_constant__ WidenIdsArgs a) {
+  const dmt_widen_ids_desc& d = a.d[blockIdx.y];
+  const int nb = d.bytes;
+  const int64_t groups = d.n >> 4;
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(d.src);
+  int4* __restrict__ dst = reinterpret_cast<int4*>(d.dst);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    uint32_t w[12];
+    int id[16];
+    if (nb == 1) {
+      const uint4 v = __ldcs(src + g);
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) id[i] = (int)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    } else if (nb == 2) {
+      const uint4 v0 = __ldcs(src + 2 * g), v1 = __ldcs(src + 2 * g + 1);
+      w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) id[i] = (int)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    } else {
+      const uint4 v0 = __ldcs(src + 3 * g), v1 = __ldcs(src + 3 * g + 1), v2 = __ldcs(src + 3 * g + 2);
+      w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+      w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                      // 4 ids = 3 words
+        const uint32_t a0 = w[3 * q], a1 = w[3 * q + 1], a2 = w[3 * q + 2];
+        id[4 * q + 0] = (int)(a0 & 0xffffffu);
+        id[4 * q + 1] = (int)((a0 >> 24) | ((a1 & 0xffffu) << 8));
+        id[4 * q + 2] = (int)((a1 >> 16) | ((a2 & 0xffu) << 16));
+        id[4 * q + 3] = (int)(a2 >> 8);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[4 * g + q] = make_int4(id[4 * q], id[4 * q + 1], id[4 * q + 2], id[4 * q + 3]);
+  }
+  if (blockIdx.x == 0) {
+    const uint8_t* __restrict__ sb = reinterpret_cast<const uint8_t*>(d.src);
+    for (int64_t t = (groups << 4) + threadIdx.x; t < d.n; t += blockDim.x) {
+      uint32_t v = 0;
+      for (int k = 0; k < nb; ++k) v |= (uint32_t)sb[t * nb + k] << (8 * k);
+      d.dst[t] = (int32_t)v;
+    }
+  }
+}
+
 // one warp per row; a lane converts 2 consecutive columns per trip (bf16x2 in, two fp32 out)
 __global__ void __launch_bounds__(256)
 copy_dense_bf16_kernel(const __nv_bfloat16* __restrict__ src, int batch, int dim, float* __restrict__ dst, int64_t ld) {
@@ -129,6 +182,35 @@ int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* stream) 
     if (bx > 64) bx = 64;                    // id arrays are <= a few 100 k entries: grid-stride beyond
     dmt::widen_u16_kernel<<<dim3((unsigned)bx, (unsigned)a.n), 256, 0, st>>>(a);
     DMT_CUDA_LAUNCH_CHECK("widen_u16_kernel");
+  }
+  return DMT_OK;
+}
+
+int dmt_widen_ids(int32_t n_arrays, const dmt_widen_ids_desc* arrays, void* stream) {
+  DMT_REQUIRE(n_arrays >= 0 && (arrays || n_arrays == 0), DMT_ERR_INVALID_ARGUMENT, "dmt_widen_ids: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n_arrays; base += DMT_MAX_WIDEN) {
+    dmt::WidenIdsArgs a;
+    a.n = n_arrays - base < DMT_MAX_WIDEN ? n_arrays - base : DMT_MAX_WIDEN;
+    int64_t longest = 0;
+    for (int i = 0; i < a.n; ++i) {
+      const dmt_widen_ids_desc& d = arrays[base + i];
+      DMT_REQUIRE(d.n >= 0 && ((d.src && d.dst) || d.n == 0), DMT_ERR_INVALID_ARGUMENT,
+                  "dmt_widen_ids: array %d is incomplete", base + i);
+      DMT_REQUIRE(d.bytes >= 1 && d.bytes <= 3, DMT_ERR_INVALID_ARGUMENT, "dmt_widen_ids: array %d: %d bytes per id",
+                  base + i, d.bytes);
+      DMT_REQUIRE((((uintptr_t)d.src | (uintptr_t)d.dst) & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
+                  "dmt_widen_ids: array %d is not 16-byte aligned", base + i);
+      a.d[i] = d;
+      if (d.n > longest) longest = d.n;
+    }
+    for (int i = a.n; i < DMT_MAX_WIDEN; ++i) a.d[i] = dmt_widen_ids_desc{nullptr, nullptr, 0, 1, 0};
+    if (longest == 0) continue;
+    int64_t bx = ((longest >> 4) + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    dmt::widen_ids_kernel<<<dim3((unsigned)bx, (unsigned)a.n), 256, 0, st>>>(a);
+    DMT_CUDA_LAUNCH_CHECK("widen_ids_kernel");
   }
   return DMT_OK;
 }

@@ -245,13 +245,14 @@ class PackedBatch:
     ALIGN = 256
 
     def __init__(self, batch: Dict, pin=True, compact=False, keys=None):
-        """compact: ship id arrays whose ids all fit 16 bits (category / time-bucket vocabularies) as uint16 and
+        """compact: ship id arrays in the narrowest byte width that holds their ids -- 1 byte (time buckets), 2 bytes
+        (category vocabularies < 65536), 3 bytes (Sku / Brand / Shopid: < 2^24) -- and
         fp32 `features` as bf16 -- for the bf16 tensor-core path, which rounds the features to bf16 before its
-        first GEMM anyway.  `to()` widens the ids back to int32 on the device (dmt_widen_u16, one launch per
+        first GEMM anyway.  `to()` widens the ids back to int32 on the device (dmt_widen_ids, one launch per
         batch) and hands `features` over as a bf16 tensor.  keys: only these entries are packed (an inference
         batch needs neither `label` nor the propensity arrays)."""
         self.layout = []          # (key, kind, dtype, shape, byte offset); kind in {t, v, o, w}
-        self.narrow = {}          # byte offset of a uint16-stored id array -> (byte offset in the wide buffer, n)
+        self.narrow = {}          # byte offset of a narrow id array -> (byte offset in the wide buffer, n, bytes per id)
         self.wide_bytes = 0
         self.compact = bool(compact)
         blobs, seen, off = [], {}, 0
@@ -265,9 +266,14 @@ class PackedBatch:
                 return
             stored, logical = t, t.dtype
             if compact and kind == "v" and t.dtype == torch.int32 and t.numel() > 0 and \
-                    int(t.min()) >= 0 and int(t.max()) < 65536:
-                stored = torch.from_numpy(t.numpy().astype(np.uint16))
-                self.narrow[off] = (self.wide_bytes, t.numel())
+                    int(t.min()) >= 0 and int(t.max()) < (1 << 24):
+                # the narrowest little-endian width that holds every id: 1 byte (time buckets), 2 (categories),
+                # 3 (Sku / Brand / Shopid: vocabularies < 2^24)
+                top = int(t.max())
+                nb = 1 if top < 256 else (2 if top < 65536 else 3)
+                raw = np.ascontiguousarray(t.numpy().astype("<u4")).view(np.uint8).reshape(-1, 4)
+                stored = torch.from_numpy(np.ascontiguousarray(raw[:, :nb]).reshape(-1))
+                self.narrow[off] = (self.wide_bytes, t.numel(), nb)
                 self.wide_bytes += (t.numel() * 4 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
             elif compact and kind == "t" and key == "features" and t.dtype == torch.float32:
                 stored = t.to(torch.bfloat16)
@@ -338,7 +344,7 @@ class PackedBatch:
         return self._fast
 
     def unpack(self, buf: torch.Tensor, wide: Optional[torch.Tensor] = None) -> Dict:
-        """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device).  uint16-stored id arrays
+        """Views over `buf` (a uint8 tensor holding a copy of `self.host`, on any device).  narrow id arrays
         of a compact batch are views of `wide` (the buffer `to()` widened them into) or, without it (host side),
         converted copies."""
         out, parts = {}, {}
@@ -367,11 +373,13 @@ class PackedBatch:
                 for d in shape:
                     n *= d
                 if o in self.narrow and kind == "v":
-                    wo, _ = self.narrow[o]
+                    wo, _, nb = self.narrow[o]
                     if wide is not None:
                         t = wide[wo:wo + 4 * n].view(torch.int32).view(shape)
-                    else:
-                        t = buf[o:o + 2 * n].view(torch.uint16).to(torch.int32).view(shape)
+                    else:       # host side: bytes -> int32
+                        b = buf[o:o + nb * n].cpu().numpy().reshape(-1, nb).astype(np.uint32)
+                        v = sum(b[:, k] << (8 * k) for k in range(nb)) if n else np.zeros(0, np.uint32)
+                        t = torch.from_numpy(v.astype(np.int32)).view(shape)
                 else:
                     nb = n * torch.empty((), dtype=dtype).element_size()
                     t = buf[o:o + nb].view(dtype).view(shape)
@@ -385,7 +393,7 @@ class PackedBatch:
 
     def feature_offsets(self, names):
         """[len(names), 3] int64 byte offsets of (ids, offsets, weights) of the CSR features `names` inside the packed
-        buffer -- ids of a uint16-stored array: inside the WIDE buffer, flagged by bit 62; no weights: -1 -- plus the
+        buffer -- ids of a narrow-stored array: inside the WIDE buffer, flagged by bit 62; no weights: -1 -- plus the
         element counts [len(names), 2] (ids, offsets).  Computed once per batch when the data loader builds it; the
         native forward driver (dmt_forward_bf16) turns it into its pointer table with one vector add per call."""
         key = tuple(names)
@@ -444,7 +452,7 @@ class PackedBatch:
 
     def to(self, device, out: Optional[torch.Tensor] = None, views: bool = True,
            wide: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> Dict:
-        """One async copy of the pinned buffer into `out` (+, for a compact batch, ONE dmt_widen_u16 launch that
+        """One async copy of the pinned buffer into `out` (+, for a compact batch, ONE dmt_widen_ids launch that
         restores the int32 id arrays into `wide`); both are enqueued on the current stream (`stream` = its raw
         handle, looked up when omitted)."""
         if out is None:
@@ -457,7 +465,7 @@ class PackedBatch:
         return self.unpack(out, wide) if views else self.unpack_ptrs(out, wide)
 
     def widen(self, buf: torch.Tensor, wide: torch.Tensor, stream: Optional[int] = None):
-        """uint16 id arrays of `buf` -> int32 arrays in `wide` (C-ABI kernel; there is no host fallback)."""
+        """1- / 2- / 3-byte id arrays of `buf` -> int32 arrays in `wide` (C-ABI kernel; there is no host fallback)."""
         from . import abi
         if wide.numel() < self.wide_bytes:
             raise ValueError("wide buffer holds %d bytes, the batch needs %d" % (wide.numel(), self.wide_bytes))
@@ -465,12 +473,12 @@ class PackedBatch:
         descs = self._widen_cache.get(key)
         if descs is None:
             items = sorted(self.narrow.items())
-            descs = (abi.WidenDesc * len(items))()
-            for i, (o, (wo, n)) in enumerate(items):
-                descs[i].src, descs[i].dst, descs[i].n = key[0] + o, key[1] + wo, n
+            descs = (abi.WidenIdsDesc * len(items))()
+            for i, (o, (wo, n, nb)) in enumerate(items):
+                descs[i].src, descs[i].dst, descs[i].n, descs[i].bytes = key[0] + o, key[1] + wo, n, nb
             if len(self._widen_cache) > 8:
                 self._widen_cache.clear()
             self._widen_cache[key] = descs
         if stream is None:
             stream = torch.cuda.current_stream(buf.device).cuda_stream
-        abi.check(abi.load().dmt_widen_u16(len(descs), descs, stream))
+        abi.check(abi.load().dmt_widen_ids(len(descs), descs, stream))

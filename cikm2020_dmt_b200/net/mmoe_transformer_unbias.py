@@ -863,8 +863,10 @@ class mmoe_transformer_unbias(object):
             out[:, 1] += base
             out[:, 2] = np.where(tab[:, 2] >= 0, tab[:, 2] + base, 0)
             return out
+        # a resident batch keeps its pointer table; it is rebuilt when any feature entry has been replaced since
+        stamp = tuple(id(inputs.get(n)) for n in names) + tuple(id(inputs.get(n + "Wts")) for n in names)
         cached = inputs.get("__fwd_table__")
-        if cached is not None and cached[0] is st["names"]:
+        if cached is not None and cached[0] == stamp:
             return cached[1]
         item = {n for seq in self.plan.sequences for n in seq.item_features}
         out = np.zeros((len(names), 3), dtype=np.int64)
@@ -876,7 +878,7 @@ class mmoe_transformer_unbias(object):
                 raise ValueError("item feature %r must hold exactly one id per sample" % n)
             out[i, 0], out[i, 1] = sp.values.data_ptr(), sp.offsets.data_ptr()
             out[i, 2] = 0 if sp.weights is None else sp.weights.data_ptr()
-        inputs["__fwd_table__"] = (st["names"], out)      # (the batch object owns its pointers: reused as is)
+        inputs["__fwd_table__"] = (stamp, out)
         return out
 
     def _inference_native(self, inputs, feats, batch, is_predict):

@@ -288,6 +288,16 @@ typedef struct dmt_widen_desc {
   int64_t n;
 } dmt_widen_desc;
 DMT_API int dmt_widen_u16(int32_t n_arrays, const dmt_widen_desc* arrays, void* stream);
+/* the general form: every array carries its own width -- 1 byte (vocabularies < 256: the time buckets), 2 bytes
+ * (< 65536) or 3 bytes little-endian (< 2^24: Sku, Brand, Shopid) per id */
+typedef struct dmt_widen_ids_desc {
+  const void* src;
+  int32_t* dst;
+  int64_t n;
+  int32_t bytes;
+  int32_t _pad;
+} dmt_widen_ids_desc;
+DMT_API int dmt_widen_ids(int32_t n_arrays, const dmt_widen_ids_desc* arrays, void* stream);
 /* bf16 [batch, dim] (dense) -> fp32 columns [0, dim) of out (row stride out_ld); same role as
  * dmt_copy_dense_features (base.py:95-96) */
 DMT_API int dmt_copy_dense_features_bf16(const void* features_bf16, int32_t batch, int32_t dim,
@@ -326,6 +336,8 @@ DMT_API int dmt_mmoe_fwd_bf16in(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights*
  * templates, runs the bias branch and the sequences on two library-owned side streams forked from / joined into
  * `stream`, and issues dmt_stage_dense_features_bf16, dmt_pool_mean_fwd(_bf16), dmt_seq_encode_multi_fwd,
  * dmt_mmoe_fwd_bf16in and dmt_bias_loss_fwd -- results are exactly those calls'.
+ * One caller per device at a time: the two side streams and their events belong to the device, not to the call (two
+ * host threads that drive the same GPU must serialise their calls or use the per-operator entry points).
  *   feats   [n_features] ids / offsets / weights (NULL = unit weights) of every CSR feature, device pointers
  *   scores  [n_tasks + 1][batch]: task logits, then y_bias (not written with is_predict) */
 typedef struct dmt_fwd_feature {

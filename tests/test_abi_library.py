@@ -47,12 +47,12 @@ def test_struct_layouts_match_header(tmp_path):
                "dmt_pool_feat": abi.PoolFeat, "dmt_mmoe_cfg": abi.MmoeCfg, "dmt_mmoe_weights": abi.MmoeWeights,
                "dmt_bias_loss_cfg": abi.BiasLossCfg, "dmt_bias_weights": abi.BiasWeights,
                "dmt_dense": abi.Dense, "dmt_attn_weights": abi.AttnWeights, "dmt_ff_weights": abi.FFWeights,
-               "dmt_fwd_feature": abi.FwdFeature, "dmt_fwd_desc": abi.FwdDesc}
+               "dmt_fwd_feature": abi.FwdFeature, "dmt_fwd_desc": abi.FwdDesc, "dmt_widen_ids_desc": abi.WidenIdsDesc}
     probes = {"dmt_seq_cfg": ["precision", "n_feats", "flags", "dropout_seed"], "dmt_seq_input": ["ids", "item_ids", "dim"],
               "dmt_seq_weights": ["dec_attn", "ff"], "dmt_pool_feat": ["weights", "out_col"],
               "dmt_mmoe_cfg": ["n_tasks", "tower_units", "precision"], "dmt_mmoe_weights": ["gate", "tower_out"],
               "dmt_bias_loss_cfg": ["ctr_rel", "weight_ecvr", "loss_weight"],
-              "dmt_fwd_feature": ["weights"],
+              "dmt_fwd_feature": ["weights"], "dmt_widen_ids_desc": ["n", "bytes"],
               "dmt_fwd_desc": ["pool", "seq_in", "seq_ws_bytes", "mmoe_ws_bytes", "bias_ld", "xb_ld"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void){"]
     for name in structs:

@@ -217,6 +217,49 @@ def test_native_forward_driver_equals_the_per_operator_path(is_predict):
     assert torch.equal(c, d) and not torch.equal(c, native)
 
 
+@pytest.mark.parametrize("nbytes", [1, 2, 3])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4099, 70001])
+def test_widen_ids_bit_exact(nbytes, n):
+    """dmt_widen_ids: 1- / 2- / 3-byte little-endian ids -> int32, vector body + bytewise tail."""
+    import numpy as np
+    from cikm2020_dmt_b200 import abi
+    lib = abi.load()
+    rng = np.random.default_rng(n * 7 + nbytes)
+    ids = rng.integers(0, 1 << (8 * nbytes), size=n, dtype=np.int64).astype(np.int32)
+    if n:
+        ids[0], ids[-1] = (1 << (8 * nbytes)) - 1, 0
+    raw = np.ascontiguousarray(ids.astype("<u4")).view(np.uint8).reshape(-1, 4)[:, :nbytes].reshape(-1)
+    src = torch.zeros(max(raw.size, 1) + 64, dtype=torch.uint8)
+    src[:raw.size] = torch.from_numpy(np.ascontiguousarray(raw))
+    src = src.cuda()
+    dst = torch.full((n + 8,), -5, dtype=torch.int32, device="cuda")
+    desc = (abi.WidenIdsDesc * 1)()
+    desc[0].src, desc[0].dst, desc[0].n, desc[0].bytes = src.data_ptr(), dst.data_ptr(), n, nbytes
+    abi.check(lib.dmt_widen_ids(1, desc, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:n].cpu(), torch.from_numpy(ids))
+    assert bool((dst[n:] == -5).all())
+
+
+def test_compact_batch_with_24_bit_ids_matches_wide_batch():
+    """Sku / Brand ids beyond 16 bits travel as 3 bytes: the staged batch equals the wide one id for id."""
+    from cikm2020_dmt_b200.data import PackedBatch, SparseIds, synthetic_batch
+    rows = {"Sku": 5000000, "Brand": 190000, "Shopid": 230000, "Cid3": 12000, "Cid2": 500}
+    conf, plan = make_plan("dmt_d64.conf", rows=rows)
+    host = synthetic_batch(plan, 129, seed=5, table_rows=rows)
+    keys = set(plan.all_id_features()) | {"features"}
+    packed = PackedBatch(host, compact=True, keys=keys)
+    widths = sorted({v[2] for v in packed.narrow.values()})
+    assert widths == [1, 2, 3]
+    staged = packed.to("cuda")
+    torch.cuda.synchronize()
+    for k in keys:
+        v = host[k]
+        if isinstance(v, SparseIds):
+            assert torch.equal(staged[k].values.cpu(), v.values), k
+            assert torch.equal(staged[k].offsets.cpu(), v.offsets), k
+
+
 def test_new_entries_reject_bad_arguments():
     from cikm2020_dmt_b200 import abi
     lib = abi.load()
@@ -225,5 +268,8 @@ def test_new_entries_reject_bad_arguments():
     cfg = abi.MmoeCfg()
     assert lib.dmt_mmoe_fwd_bf16in(C.byref(cfg), None, None, 8, None, None, 0, None, None) == -1
     assert lib.dmt_forward_bf16(None, 0, None, None, 0, None, None) == -1
+    bad = (abi.WidenIdsDesc * 1)()
+    bad[0].src, bad[0].dst, bad[0].n, bad[0].bytes = 16, 16, 4, 4
+    assert lib.dmt_widen_ids(1, bad, None) == -1
     desc = abi.FwdDesc()
     assert lib.dmt_forward_bf16(C.byref(desc), 0, None, None, 0, None, None) == -1

@@ -174,9 +174,9 @@ def test_packed_batch_pointer_staging_matches_views():
 
 
 def test_compact_packed_batch_host_roundtrip():
-    """PackedBatch(compact=True): small-vocabulary id arrays are stored as uint16, `features` as bf16, only the
-    requested keys are packed; the host-side unpack returns the original ids / offsets and the RNE-rounded features,
-    and `max_len` (the row-slot bound handed to the kernels) is unchanged."""
+    """PackedBatch(compact=True): id arrays are stored in the narrowest byte width that holds them (1: time buckets,
+    2: vocabularies < 65536, 3: < 2^24), `features` as bf16, only the requested keys are packed; the host-side unpack
+    returns the original ids / offsets and the RNE-rounded features, and `max_len` is unchanged."""
     import torch
     from conftest import make_plan
     from cikm2020_dmt_b200.data import PackedBatch, SparseIds, synthetic_batch
@@ -189,8 +189,10 @@ def test_compact_packed_batch_host_roundtrip():
     assert packed.nbytes < wide.nbytes and packed.wide_bytes > 0
     out = packed.unpack(packed.host)
     assert set(out) == keys                                    # label / mask were not packed
-    narrow_keys = {k for k, kind, dt, shape, o in packed.layout if kind == "v" and o in packed.narrow}
-    assert "clk_seq_c2_7d_50" in narrow_keys and "clk_seq_sku_7d_50" not in narrow_keys    # Sku ids need > 16 bits
+    width = {k: packed.narrow[o][2] for k, kind, dt, shape, o in packed.layout if kind == "v" and o in packed.narrow}
+    assert width["clk_seq_ts_7d_50"] == 1 and width["clk_seq_c2_7d_50"] == 1       # 23 buckets / 60 categories
+    assert width["clk_seq_c3_7d_50"] == 2 and width["clk_seq_shop_7d_50"] == 2     # 300 / 900 rows
+    assert width["clk_seq_sku_7d_50"] == 3 and width["clk_seq_brand_7d_50"] == 3   # 200000 / 70000 rows: > 16 bits
     for k in keys:
         v = host[k]
         if isinstance(v, SparseIds):
