@@ -100,7 +100,7 @@ class FwdDesc(C.Structure):
                 ("seq_ws_bytes", C.c_size_t * MAX_TAIL_SEQS),
                 ("mmoe_cfg", _fp), ("mmoe_w", _fp), ("mmoe_ws", _fp), ("mmoe_ws_bytes", C.c_size_t),
                 ("mmoe_prepared", _fp), ("bias_cfg", _fp), ("bias_w", _fp), ("bias_in", _fp), ("bias_ld", C.c_int64),
-                ("xb", _fp), ("xb_ld", C.c_int64)]
+                ("xb", _fp), ("xb_ld", C.c_int64), ("inputs_ready", _fp)]
 
 
 MAX_WIDEN = 64

@@ -20,6 +20,10 @@
 #include "dmt_common.cuh"
 
 namespace dmt {
+int seq_encode_multi_checked(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                             const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                             void* const* workspaces, const size_t* workspace_bytes, cudaEvent_t wait_before_encode,
+                             void* stream);
 namespace {
 
 struct FwdStreams {
@@ -124,7 +128,16 @@ extern "C" int dmt_forward_bf16(const dmt_fwd_desc* d, int32_t n_features, const
   // ---- behaviour sequences ----
   if (d->n_seq > 0) {
     cudaStream_t s0 = fs->side[0];
-    DMT_CUDA_TRY(cudaStreamWaitEvent(s0, fs->fork, 0), "cudaStreamWaitEvent(dmt_forward_bf16)");
+    // With an `inputs_ready` event (a prefetched batch) the length-class kernel -- it only reads the batch's offsets
+    // and writes this stream's own schedule buffers -- does not wait for the caller's stream: it runs as soon as the
+    // previous call's tails are done, under the previous call's MMoE.  The tile kernel then waits for the fork.
+    cudaEvent_t late_wait = nullptr;
+    if (d->inputs_ready) {
+      DMT_CUDA_TRY(cudaStreamWaitEvent(s0, (cudaEvent_t)d->inputs_ready, 0), "cudaStreamWaitEvent(dmt_forward_bf16)");
+      late_wait = fs->fork;
+    } else {
+      DMT_CUDA_TRY(cudaStreamWaitEvent(s0, fs->fork, 0), "cudaStreamWaitEvent(dmt_forward_bf16)");
+    }
     dmt_seq_input in[DMT_MAX_TAIL_SEQS];
     const dmt_seq_input* ins[DMT_MAX_TAIL_SEQS];
     float* outs[DMT_MAX_TAIL_SEQS];
@@ -148,7 +161,7 @@ extern "C" int dmt_forward_bf16(const dmt_fwd_desc* d, int32_t n_features, const
       outs[q] = reinterpret_cast<float*>(static_cast<uint16_t*>(d->xb) + d->interest_col + (int64_t)q * d->seq_cfg[q]->d_model);
       lds[q] = d->xb_ld;
     }
-    rc = dmt_seq_encode_multi_fwd(d->n_seq, d->seq_cfg, ins, d->seq_w, outs, lds, d->seq_ws, d->seq_ws_bytes, s0);
+    rc = seq_encode_multi_checked(d->n_seq, d->seq_cfg, ins, d->seq_w, outs, lds, d->seq_ws, d->seq_ws_bytes, late_wait, s0);
     if (rc != DMT_OK) return rc;
     DMT_CUDA_TRY(cudaEventRecord(fs->join[0], s0), "cudaEventRecord(dmt_forward_bf16)");
   }

@@ -19,7 +19,8 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
                          int64_t out_ld, void* workspace, cudaStream_t st);
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg);
 int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
-                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st);
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaEvent_t wait_before_encode,
+                 cudaStream_t st);
 int seq_timer_enable(int on);
 int seq_timer_read(float* total_ms, int32_t* launches);
 int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
@@ -109,9 +110,15 @@ int dmt_seq_tail_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_se
   return dmt::seq_tc_tails(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, (cudaStream_t)stream);
 }
 
-int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+}  // extern "C"
+
+// shared by dmt_seq_encode_multi_fwd and dmt_forward_bf16 (forward.cu), which passes the event its sequence stream
+// waits for between the length-class kernel and the tile kernel
+namespace dmt {
+int seq_encode_multi_checked(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
                              const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
-                             void* const* workspaces, const size_t* workspace_bytes, void* stream) {
+                             void* const* workspaces, const size_t* workspace_bytes, cudaEvent_t wait_before_encode,
+                             void* stream) {
   DMT_REQUIRE(n_seq >= 0 && n_seq <= DMT_MAX_TAIL_SEQS, DMT_ERR_INVALID_ARGUMENT,
               "dmt_seq_encode_multi_fwd: n_seq=%d (max %d)", n_seq, DMT_MAX_TAIL_SEQS);
   if (n_seq == 0) return DMT_OK;
@@ -133,7 +140,16 @@ int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, cons
     DMT_REQUIRE(((uintptr_t)workspaces[i] & 15) == 0, DMT_ERR_INVALID_ARGUMENT,
                 "dmt_seq_encode_multi_fwd: sequence %d: unaligned workspace", i);
   }
-  return dmt::seq_tc_multi(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, (cudaStream_t)stream);
+  return dmt::seq_tc_multi(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, wait_before_encode, (cudaStream_t)stream);
+}
+}  // namespace dmt
+
+extern "C" {
+
+int dmt_seq_encode_multi_fwd(int32_t n_seq, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins,
+                             const dmt_seq_weights* const* ws, float* const* outs, const int64_t* out_lds,
+                             void* const* workspaces, const size_t* workspace_bytes, void* stream) {
+  return dmt::seq_encode_multi_checked(n_seq, cfgs, ins, ws, outs, out_lds, workspaces, workspace_bytes, nullptr, stream);
 }
 
 size_t dmt_seq_saved_bytes(const dmt_seq_cfg* cfg, int64_t n_tokens) {

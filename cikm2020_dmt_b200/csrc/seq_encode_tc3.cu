@@ -1226,7 +1226,11 @@ size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg) { return ((size_t)cfg->batch *
 
 // dmt_seq_encode_multi_fwd: every behaviour sequence of the step -- length classes, ONE tile-kernel launch, one tail
 // launch
-int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaStream_t st) {
+// wait_before_encode (optional): the stream waits for this event AFTER the length-class kernel -- which only reads the
+// batch's offsets -- and before the tile kernel (dmt_forward_bf16: the classes of step i + 1 are formed while step i's
+// MMoE still runs)
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaEvent_t wait_before_encode,
+                            cudaStream_t st) {
   SeqMultiArgs m;
   BucketArgs ba;
   memset(&m, 0, sizeof(m));
@@ -1263,6 +1267,10 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, b
   }
   seq_bucket_kernel<<<n, 1024, 0, st>>>(ba);
   DMT_CUDA_LAUNCH_CHECK("seq_bucket_kernel");
+  if (wait_before_encode) {
+    e = cudaStreamWaitEvent(st, wait_before_encode, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(seq_encode_multi_launch)");
+  }
   if (timed) cudaEventRecord(g_seq_timer.e0[g_seq_timer.n], st);
   kern<<<grid, kT3Threads, total, st>>>(m);
   if (timed) cudaEventRecord(g_seq_timer.e1[g_seq_timer.n++], st);

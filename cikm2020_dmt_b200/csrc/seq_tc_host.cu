@@ -96,7 +96,8 @@ bool seq_tc2_supported(const dmt_seq_cfg* cfg);
 size_t seq_tc2_ctx_bytes(const dmt_seq_cfg* cfg);
 
 size_t seq_tc_sched_bytes(const dmt_seq_cfg* cfg);
-int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaStream_t st);
+int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, bool defer_tail, cudaEvent_t wait_before_encode,
+                            cudaStream_t st);
 
 // workspace = [prepared weight images | decoder-context images | length-class schedule (perm, counts)]
 size_t seq_tc_workspace_bytes(const dmt_seq_cfg* cfg) {
@@ -168,14 +169,15 @@ int seq_tc_tails(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* con
 }
 
 int seq_tc_multi(int n, const dmt_seq_cfg* const* cfgs, const dmt_seq_input* const* ins, const dmt_seq_weights* const* ws,
-                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaStream_t st) {
+                 float* const* outs, const int64_t* out_lds, void* const* workspaces, cudaEvent_t wait_before_encode,
+                 cudaStream_t st) {
   SeqTcArgs args[DMT_MAX_TAIL_SEQS];
   void* scheds[DMT_MAX_TAIL_SEQS];
   for (int i = 0; i < n; ++i) {
     fill_args(cfgs[i], ins[i], ws[i], outs[i], out_lds[i], workspaces[i], args[i]);
     scheds[i] = static_cast<uint8_t*>(workspaces[i]) + seq_tc_prepared_bytes(cfgs[i]) + seq_tc2_ctx_bytes(cfgs[i]);
   }
-  return seq_encode_multi_launch(n, args, scheds, false, st);
+  return seq_encode_multi_launch(n, args, scheds, false, wait_before_encode, st);
 }
 
 int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const dmt_seq_weights* w, float* out,
@@ -184,7 +186,7 @@ int seq_encode_tc_launch(const dmt_seq_cfg* cfg, const dmt_seq_input* in, const 
   SeqTcArgs a;
   fill_args(cfg, in, w, out, out_ld, workspace, a);
   void* sched = static_cast<uint8_t*>(workspace) + seq_tc_prepared_bytes(cfg) + seq_tc2_ctx_bytes(cfg);
-  return seq_encode_multi_launch(1, &a, &sched, (cfg->flags & DMT_SEQ_DEFER_TAIL) != 0, st);
+  return seq_encode_multi_launch(1, &a, &sched, (cfg->flags & DMT_SEQ_DEFER_TAIL) != 0, nullptr, st);
 }
 
 }  // namespace dmt

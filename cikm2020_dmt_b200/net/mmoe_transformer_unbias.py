@@ -897,6 +897,8 @@ class mmoe_transformer_unbias(object):
             feats = feats.contiguous()
             fptr, fbf16 = feats.data_ptr(), 1 if feats.dtype == torch.bfloat16 else 0
         scores = self._next_scores(batch)
+        ready = inputs.get("__ready__")       # prefetched batch: the copy's event (the length classes may start early)
+        st["desc"].inputs_ready = ready.cuda_event if ready is not None else None
         abi.check(self.lib.dmt_forward_bf16(C.byref(st["desc"]), table.shape[0], table.ctypes.data, fptr, fbf16,
                                             scores.data_ptr(), self._stream()))
         self.launches += st["launches"]

@@ -377,6 +377,10 @@ typedef struct dmt_fwd_desc {
   int64_t bias_ld;
   void* xb;                             /* [batch, xb_ld] bf16 MMoE input (scratch)                         */
   int64_t xb_ld;
+  void* inputs_ready;                   /* optional cudaEvent_t: the batch's arrays are on the device once it
+                                           has fired (the prefetch copy).  Set per call; lets the length classes
+                                           of this call be formed under the previous call's MMoE.  NULL: the
+                                           inputs are ordered by `stream` like everything else                 */
 } dmt_fwd_desc;
 
 DMT_API int dmt_forward_bf16(const dmt_fwd_desc* desc, int32_t n_features, const dmt_fwd_feature* feats,

@@ -53,7 +53,7 @@ def test_struct_layouts_match_header(tmp_path):
               "dmt_mmoe_cfg": ["n_tasks", "tower_units", "precision"], "dmt_mmoe_weights": ["gate", "tower_out"],
               "dmt_bias_loss_cfg": ["ctr_rel", "weight_ecvr", "loss_weight"],
               "dmt_fwd_feature": ["weights"], "dmt_widen_ids_desc": ["n", "bytes"],
-              "dmt_fwd_desc": ["pool", "seq_in", "seq_ws_bytes", "mmoe_ws_bytes", "bias_ld", "xb_ld"]}
+              "dmt_fwd_desc": ["pool", "seq_in", "seq_ws_bytes", "mmoe_ws_bytes", "bias_ld", "xb_ld", "inputs_ready"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void){"]
     for name in structs:
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

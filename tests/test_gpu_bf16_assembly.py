@@ -172,6 +172,19 @@ def test_inference_bf16_assembly_matches_oracle_and_fp32_assembly(compact):
         assert (got[t] - yr1[t]).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("B", [1, 2, 129])
+def test_bf16_inference_small_and_ragged_batches(B):
+    """One sample, two samples, one sample past a 128-row tile: every kernel of the bf16 route has a partial last tile."""
+    plan, tc, host, dev, P, O = _setup("dmt_d64.conf", B, seed=50 + B, precision="bf16")
+    (yr, yb) = tc.inference(dev, is_train=False)
+    torch.cuda.synchronize()
+    (wr, wb) = O.inference(plan, P, host, is_train=False)
+    for t in range(2):
+        err = (yr[t].double().cpu() - wr[t]).abs()
+        assert bool((err <= 5e-2 + 2e-2 * wr[t].abs()).all()), err.max().item()
+    assert (yb.double().cpu() - wb).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("is_predict", [False, True])
 def test_native_forward_driver_equals_the_per_operator_path(is_predict):
     """dmt_forward_bf16 issues the same entry points as the Python path: bit-identical scores -- for a resident dict
