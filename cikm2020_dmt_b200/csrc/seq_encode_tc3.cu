@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(1024) seq_bucket_kernel(const __grid_constant_
   __shared__ int wsum[32][3];
   __shared__ int tot_s[3];
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  griddep_launch();      // the tile kernel behind this one may set itself up (TMEM, barriers, first weight images)
   const int B = ba.batch[q], maxlen = ba.maxlen[q];
   const int32_t* offs = ba.offs[q];
   const int per = (B + 1023) / 1024;
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
         if (nt >= n_tiles) return;
         const int si = nt * NS + slot;
         if (si < seg_cnt) {
-          const int b = __ldg(perm + seg_base + si);
+          const int b = __ldcg(perm + seg_base + si);
           pf_l0 = __ldg(len_offs + b);
           pf_l1 = __ldg(len_offs + b + 1);
 #pragma unroll
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
         }
         if (gt < NS * KC) {
           const int st = nt * NS + gt / KC;
-          if (st < seg_cnt) pf_tid = __ldg(sd[gt % KC].item_ids + __ldg(perm + seg_base + st));
+          if (st < seg_cnt) pf_tid = __ldg(sd[gt % KC].item_ids + __ldcg(perm + seg_base + st));
         }
       };
       auto stage_ids = [&](int nt, int par) {
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           const int si = rb0 + s;
-          const int b = si < seg_cnt ? __ldg(perm + seg_base + si) : -1;
+          const int b = si < seg_cnt ? __ldcg(perm + seg_base + si) : -1;
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             float num, den;
@@ -928,7 +929,11 @@ __global__ void __launch_bounds__(kT3Threads, 1) seq_encode_multi_kernel(const _
       if (DBG && dbgp && tid == 0) atomicAdd(dbgp + 14, (unsigned long long)n_done);
     };
 
-    const int c64 = __ldg(m.counts[q]), c32 = __ldg(m.counts[q] + 1), c16 = __ldg(m.counts[q] + 2);
+    // Dependent launch: perm / counts are seq_bucket_kernel's output, written while this grid may already be running --
+    // they are read with coherent loads (ld.global.cg), never through the read-only path, whose loads the compiler may
+    // hoist above the wait and the hardware may serve from a stale line.
+    if (q == 0) griddep_wait();
+    const int c64 = __ldcg(m.counts[q]), c32 = __ldcg(m.counts[q] + 1), c16 = __ldcg(m.counts[q] + 2);
     run_segment(ic<64>{}, ic<56>{}, c64, 0);
     run_segment(ic<32>{}, ic<32>{}, c32, c64);
     run_segment(ic<16>{}, ic<32>{}, c16, c64 + c32);
@@ -1154,6 +1159,9 @@ __global__ void __launch_bounds__(128, 1) seq_tail_kernel(const __grid_constant_
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// (A programmatic dependent launch behind the tile kernel was measured and dropped: the early tail CTAs -- 113 KB of
+// shared memory and all of tensor memory each -- take the SMs that the dense / pooled kernels fill while the tile
+// kernel's last CTAs retire: 337 -> 347 us per step.)
 int launch_tails(const TailBatch& tb, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(seq_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailLayout::total);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_tail_kernel)");
@@ -1272,7 +1280,13 @@ int seq_encode_multi_launch(int n, const SeqTcArgs* args, void* const* scheds, b
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(seq_encode_multi_launch)");
   }
   if (timed) cudaEventRecord(g_seq_timer.e0[g_seq_timer.n], st);
-  kern<<<grid, kT3Threads, total, st>>>(m);
+  if (!timed && !wait_before_encode) {
+    // directly behind the length-class kernel: programmatic dependent launch, the prologue of sequence 0 runs beside it
+    e = launch_pdl(kern, dim3(grid), dim3(kT3Threads), (size_t)total, st, m);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(seq_encode_multi_kernel)");
+  } else {
+    kern<<<grid, kT3Threads, total, st>>>(m);
+  }
   if (timed) cudaEventRecord(g_seq_timer.e1[g_seq_timer.n++], st);
   DMT_CUDA_LAUNCH_CHECK("seq_encode_multi_kernel");
   if (defer_tail) return DMT_OK;
